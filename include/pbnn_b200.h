@@ -1,0 +1,144 @@
+/*
+ * pbnn_b200 -- C ABI of the B200-native (sm_100a) implementation of pbnn's data-parallel hot path:
+ * many independent SG-MCMC chains / ensemble members advancing over small MLPs.
+ *
+ * Every entry point replaces a Python-level interface of the reference (bstaber/pbnn); the
+ * reference has no native boundary of its own (it is pure Python over JAX/BlackJAX), so each
+ * function cites the reference call it stands in for.  This is the boundary a `jax.ffi` /
+ * ctypes / cffi binding attaches to.
+ *
+ * Conventions
+ *  - all data pointers are DEVICE pointers (cudaMalloc'd / torch CUDA tensors), float32 / uint32 /
+ *    int32, C-contiguous; `stream` is a cudaStream_t passed as void* (NULL = default stream);
+ *  - no allocation, no hidden global state, re-entrant across streams;
+ *  - return 0 on success, a negative PBNN_E* code otherwise; pbnn_last_error() gives the text
+ *    (thread-local);
+ *  - parameters are FLAT vectors in jax.flatten_util.ravel_pytree order of the Flax tree
+ *    {"Dense_k": {"bias": (out,), "kernel": (in,out)}} (bias first, kernel row-major [in][out]);
+ *  - rng keys are legacy uint32[2] threefry2x32 keys, jax_threefry_partitionable=True semantics;
+ *  - chain c of a call == one reference call with (keys[c], theta[c]); chains never interact.
+ */
+#ifndef PBNN_B200_H
+#define PBNN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PBNN_MAX_LAYERS 8
+
+#define PBNN_OK 0
+#define PBNN_EINVAL (-1)   /* bad argument                                   */
+#define PBNN_ETOOBIG (-2)  /* model / batch does not fit the resident engine */
+#define PBNN_ECUDA (-3)    /* CUDA runtime error                             */
+
+#define PBNN_ACT_RELU 0
+#define PBNN_ACT_TANH 1
+
+/* minibatch semantics of the SG samplers */
+#define PBNN_MB_REFERENCE_FIXED 0 /* the draw the reference's traced lax.scan re-uses for all steps */
+#define PBNN_MB_PER_STEP 1        /* a fresh draw of the same generator at every step               */
+
+/* Describes `pbnn.models.MLP` (src/pbnn/models.py:9-35, generalised to a list of widths) together with
+ * `homoscedastic_loglike_fn` / `logprior_fn` (benchmark/pipelines/logprobs.py:6-17). */
+typedef struct pbnn_mlp_spec {
+  int32_t n_layers;                  /* number of Dense layers, 1..PBNN_MAX_LAYERS            */
+  int32_t dims[PBNN_MAX_LAYERS + 1]; /* dims[0]=input width d, dims[l+1]=features of Dense_l  */
+  int32_t activation;                /* PBNN_ACT_RELU | PBNN_ACT_TANH (hidden layers)         */
+  float noise_level;                 /* sigma of the Gaussian likelihood                      */
+  float prior_scale;                 /* std of the N(0, s^2) prior; the reference uses 1      */
+} pbnn_mlp_spec;
+
+int pbnn_version(void);
+const char* pbnn_last_error(void);
+/* number of parameters P of the flat vector; <0 on invalid spec */
+int pbnn_num_params(const pbnn_mlp_spec* spec);
+/* launch plan the library would use: out[0]=threads per CTA, out[1]=batch-tile rows,
+ * out[2]=dynamic shared memory bytes, out[3]=padded parameter count.  `rows` is the minibatch size
+ * (or N for full-batch HMC / M for predict), `n_state` the number of resident parameter-sized arrays. */
+int pbnn_plan_query(const pbnn_mlp_spec* spec, int rows, int n_state, int32_t out[4]);
+
+/* ---- jax.random primitives (jax/_src/prng.py, random.py); test hooks + key plumbing --------------- */
+/* jax.random.split: out[c][i] = threefry(keys[c], (0, i)).  out: [C][n][2] */
+int pbnn_threefry_split(const uint32_t* keys, int C, int n, uint32_t* out, void* stream);
+/* jax.random.bits(key, (n,), uint32).  out: [C][n] */
+int pbnn_threefry_bits(const uint32_t* keys, int C, int n, uint32_t* out, void* stream);
+/* jax.random.uniform / normal float32.  out: [C][n] */
+int pbnn_threefry_uniform(const uint32_t* keys, int C, int n, float* out, void* stream);
+int pbnn_threefry_normal(const uint32_t* keys, int C, int n, float* out, void* stream);
+/* indices of the `draw`-th (1-based) `next(batch_labeled_data(...))` (src/pbnn/utils/data.py:47-78):
+ * key <- split(key)[1] `draw` times, then randint(key,(B,),0,N).  out: [C][B] int32 */
+int pbnn_minibatch_indices(const uint32_t* keys, int C, int draw, int B, int N, int32_t* out, void* stream);
+/* jax.random.permutation(key, N) (stable sort by fresh random bits, ceil(3 ln N / ln(2^32-1)) rounds).
+ * out: [C][N] int32 ; workspace: at least 3*C*N uint64 (device). */
+int pbnn_permutation(const uint32_t* keys, int C, int N, int32_t* out, void* workspace, void* stream);
+
+/* ---- samplers -------------------------------------------------------------------------------------- */
+/* Common arguments of the SG samplers:
+ *   X [N][d], y [N][s]           training data (row major)
+ *   idx                          optional explicit minibatch indices [C][idx_steps][B] (idx_steps 1 or T);
+ *                                NULL = generated on device from keys[c] according to `mb_mode`
+ *   keys [C][2]                  the `rng_key` of each chain (split(rng_key,T)[t] is derived on device)
+ *   theta [C][P]                 in: init_positions, out: final positions
+ *   step_sizes [n_step_sizes]    1 value (constant) or T values (scheduled_sgld: langevin.py:143-204)
+ *   t0                           index of the first step (keys[t0+t] are used) -- exact resume
+ *   thin, burnin                 trace keeps steps t>=burnin with (t-burnin)%thin==0
+ *   trace [C][T_out][P]          optional (NULL = keep only the final state)
+ *   flags [C]                    optional; bit0 set if the chain became non-finite
+ */
+
+/* pbnn.mcmc.sgld (src/pbnn/mcmc/langevin.py:21-78) over blackjax.sgld */
+int pbnn_sgld_run(const pbnn_mlp_spec* spec, const float* X, const float* y, int N, const int32_t* idx,
+                  int idx_steps, int mb_mode, int B, const uint32_t* keys, float* theta, const float* step_sizes,
+                  int n_step_sizes, int64_t t0, int T, int C, int thin, int burnin, float* trace, uint32_t* flags,
+                  void* stream);
+
+/* pbnn.mcmc.pSGLD (langevin.py:81-140; sgmcmc/psgld.py:25-48; sgmcmc/diffusions.py:33-60).
+ * g,V [C][P]: logprob_grad / square_avg of pSGLDState; if has_state==0 they are initialised on device
+ * from the init draw (psgld.init) and written back at the end (resume). */
+int pbnn_psgld_run(const pbnn_mlp_spec* spec, const float* X, const float* y, int N, const int32_t* idx,
+                   int idx_steps, int mb_mode, int B, const uint32_t* keys, float* theta, float* g, float* V,
+                   int has_state, float alpha, const float* step_sizes, int n_step_sizes, int64_t t0, int T, int C,
+                   int thin, int burnin, float* trace, uint32_t* flags, void* stream);
+
+/* pbnn.mcmc.sghmc (src/pbnn/mcmc/hamiltonian.py:80-140) over blackjax.sghmc(grad_fn, L, alpha=0.01, beta=0) */
+int pbnn_sghmc_run(const pbnn_mlp_spec* spec, const float* X, const float* y, int N, const int32_t* idx,
+                   int idx_steps, int mb_mode, int B, const uint32_t* keys, float* theta, int L, float alpha,
+                   float beta, const float* step_sizes, int n_step_sizes, int64_t t0, int T, int C, int thin,
+                   int burnin, float* trace, uint32_t* flags, void* stream);
+
+/* pbnn.mcmc.hmc (hamiltonian.py:18-77) over blackjax.hmc with the full-batch target
+ * logprior + sum_i loglik_i (benchmark/pipelines/hmc.py:59-62).
+ *   inv_mass [P] (flat order), logp [C] out (log density of the final state), accept_count [C] out,
+ *   info_delta [C][num_samples] / info_accept [C][num_samples] optional per-iteration diagnostics. */
+int pbnn_hmc_run(const pbnn_mlp_spec* spec, const float* X, const float* y, int N, const uint32_t* keys,
+                 float* theta, const float* inv_mass, float step_size, int L, int64_t t0, int num_samples, int C,
+                 int thin, int burnin, float* trace, float* logp, int32_t* accept_count, float* info_delta,
+                 int32_t* info_accept, uint32_t* flags, void* stream);
+
+/* inner loop of pbnn.deep_ensembles.deep_ensembles_fn (src/pbnn/deep_ensembles.py:59-75): n_steps Adam
+ * (optax.adam defaults) steps on -logposterior for C members at once.
+ *   idx [C][n_steps][B] minibatch rows (permutation-derived, see pbnn_permutation)
+ *   m, v [C][P] Adam moments (in/out), count0 = steps already taken */
+int pbnn_adam_ensemble_run(const pbnn_mlp_spec* spec, const float* X, const float* y, int N, const int32_t* idx,
+                           int n_steps, int B, float* theta, float* m, float* v, int count0, float lr, float b1,
+                           float b2, float eps, int C, uint32_t* flags, void* stream);
+
+/* predict_fn (langevin.py:75-76) + moments (metrics_prediction_intervals.py:188; variance = ddof 0 extension).
+ *   samples [S][P], Xtest [M][d];  preds [S][M][s] optional; sum / sumsq [M][s] optional (sum_s f, sum_s f^2);
+ *   workspace: float[2 * nchunk * M * s] with nchunk = pbnn_predict_chunks(S) when sum/sumsq requested. */
+int pbnn_predict_chunks(int S);
+int pbnn_predict(const pbnn_mlp_spec* spec, const float* samples, int S, const float* Xtest, int M, float* preds,
+                 float* sum, float* sumsq, float* workspace, void* stream);
+
+/* gradient of the (scaled) log-posterior estimator for C positions on explicit minibatches -- test hook for
+ * blackjax grad_estimator == src/pbnn/utils/misc.py:34-55.  idx [C][B]; grad [C][P]; loglik [C] optional. */
+int pbnn_grad_estimator(const pbnn_mlp_spec* spec, const float* X, const float* y, int N, const int32_t* idx, int B,
+                        const float* theta, int C, float* grad, float* loglik, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PBNN_B200_H */

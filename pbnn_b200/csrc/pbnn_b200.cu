@@ -1,0 +1,226 @@
+// pbnn_b200: CUDA (sm_100a) backend + C ABI.  Build: see __graft_entry__.build().
+//
+// Kernels
+//   pb_sg_kernel<ALGO,ACT>   fused chain-step kernel: one CTA per chain / ensemble member, persistent over
+//                            all T steps (forward, backward, drift, threefry noise, trace) -- SGLD, pSGLD,
+//                            SGHMC, Adam, and the grad_estimator test hook
+//   pb_hmc_kernel<ACT>       full-batch leapfrog + Metropolis accept, one CTA per chain
+//   pb_predict_kernel<ACT>   posterior predictive over (test-row tile) x (sample chunk)
+//   pb_rng_kernel / pb_mbidx_kernel / pb_perm_kernel   jax.random primitives
+#include <cuda_runtime.h>
+
+#include "pbnn_engine.cuh"
+
+// ------------------------------------------------------------------------------------------------
+template <int ALGO, int ACT>
+__global__ void __launch_bounds__(PB_MAX_NT, 2)
+pb_sg_kernel(const __grid_constant__ PbPlan pl, const __grid_constant__ PbSgArgs a) {
+  extern __shared__ __align__(16) float pb_smem[];
+  pb_sg_chain<ALGO, ACT>(pl, a, pb_smem, (int)blockIdx.x, (int)blockDim.x);
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(PB_MAX_NT, 2)
+pb_hmc_kernel(const __grid_constant__ PbPlan pl, const __grid_constant__ PbHmcArgs a) {
+  extern __shared__ __align__(16) float pb_smem[];
+  pb_hmc_chain<ACT>(pl, a, pb_smem, (int)blockIdx.x, (int)blockDim.x);
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(PB_MAX_NT, 2)
+pb_predict_kernel(const __grid_constant__ PbPlan pl, const __grid_constant__ PbPredArgs a) {
+  extern __shared__ __align__(16) float pb_smem[];
+  pb_predict_block<ACT>(pl, a, pb_smem, (int)blockIdx.x, (int)blockIdx.y, (int)blockDim.x);
+}
+
+__global__ void pb_predict_reduce_kernel(const float* __restrict__ part, int nchunk, int n, float* __restrict__ sum,
+                                         float* __restrict__ sumsq) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float a = 0.f, q = 0.f;
+  for (int ch = 0; ch < nchunk; ++ch) {
+    a += part[(size_t)ch * 2 * n + i];
+    q += part[(size_t)ch * 2 * n + n + i];
+  }
+  sum[i] = a;
+  sumsq[i] = q;
+}
+
+// kind: 0 split, 1 bits, 2 uniform, 3 normal
+__global__ void pb_rng_kernel(int kind, const uint32_t* __restrict__ keys, int C, int n, void* __restrict__ out) {
+  const size_t total = (size_t)C * n;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e / n);
+    const uint32_t i = (uint32_t)(e - (size_t)c * n);
+    PbKey k;
+    k.k0 = keys[2 * c];
+    k.k1 = keys[2 * c + 1];
+    if (kind == 0) {
+      const PbKey o = pb_split_at(k, i);
+      reinterpret_cast<uint32_t*>(out)[2 * e] = o.k0;
+      reinterpret_cast<uint32_t*>(out)[2 * e + 1] = o.k1;
+    } else if (kind == 1) {
+      reinterpret_cast<uint32_t*>(out)[e] = pb_bits_at(k, i);
+    } else if (kind == 2) {
+      reinterpret_cast<float*>(out)[e] = fmaxf(0.f, pb_bits_to_uniform(pb_bits_at(k, i)));
+    } else {
+      reinterpret_cast<float*>(out)[e] = pb_normal_at(k, i);
+    }
+  }
+}
+
+__global__ void pb_mbidx_kernel(const uint32_t* __restrict__ keys, int draw, int B, int N, uint32_t mult,
+                                int32_t* __restrict__ out) {
+  const int c = blockIdx.x;
+  PbKey k;
+  k.k0 = keys[2 * c];
+  k.k1 = keys[2 * c + 1];
+  for (int i = 0; i < draw; ++i) k = pb_split_at(k, 1u);
+  const PbKey k1 = pb_split_at(k, 0u), k2 = pb_split_at(k, 1u);
+  for (int b = threadIdx.x; b < B; b += blockDim.x)
+    out[(size_t)c * B + b] = pb_randint_at(k1, k2, (uint32_t)b, (uint32_t)N, mult);
+}
+
+// jax.random.permutation (jax/_src/random.py::_shuffle): `rounds` x { key, sub = split(key); stable sort by
+// bits(sub) }.  The stable sort is a bitonic sort of the composite (bits << 32 | position), which is a strict
+// total order, so any sorting network reproduces the stable result.  One CTA per key.
+__global__ void __launch_bounds__(1024, 1)
+pb_perm_kernel(const uint32_t* __restrict__ keys, int N, int Np2, int rounds, int use_smem, int32_t* __restrict__ out,
+               unsigned long long* __restrict__ ws) {
+  extern __shared__ __align__(16) unsigned long long pb_sort[];
+  const int c = blockIdx.x;
+  unsigned long long* wsc = ws + (size_t)c * 3 * N;
+  unsigned long long* buf = use_smem ? pb_sort : wsc;
+  int32_t* xa = reinterpret_cast<int32_t*>(wsc + 2 * (size_t)N);
+  int32_t* xb = xa + N;
+  int32_t* res = out + (size_t)c * N;
+  PbKey key;
+  key.k0 = keys[2 * c];
+  key.k1 = keys[2 * c + 1];
+  const int32_t* xold = nullptr;  // nullptr == identity
+  for (int r = 0; r < rounds; ++r) {
+    const PbKey sub = pb_split_at(key, 1u);
+    key = pb_split_at(key, 0u);
+    for (int i = threadIdx.x; i < Np2; i += blockDim.x)
+      buf[i] = i < N ? (((unsigned long long)pb_bits_at(sub, (uint32_t)i) << 32) | (unsigned)i) : ~0ull;
+    __syncthreads();
+    for (int k = 2; k <= Np2; k <<= 1)
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = threadIdx.x; i < Np2; i += blockDim.x) {
+          const int ixj = i ^ j;
+          if (ixj > i) {
+            const unsigned long long a = buf[i], b = buf[ixj];
+            const bool up = (i & k) == 0;
+            if ((a > b) == up) {
+              buf[i] = b;
+              buf[ixj] = a;
+            }
+          }
+        }
+        __syncthreads();
+      }
+    int32_t* xnew = (r == rounds - 1) ? res : ((r & 1) ? xb : xa);
+    for (int jn = threadIdx.x; jn < N; jn += blockDim.x) {
+      const int src = (int)(buf[jn] & 0xFFFFFFFFull);
+      xnew[jn] = xold ? xold[src] : src;
+    }
+    __syncthreads();
+    xold = xnew;
+  }
+  if (rounds == 0)
+    for (int jn = threadIdx.x; jn < N; jn += blockDim.x) res[jn] = jn;
+}
+
+// ------------------------------------------------------------------------------------------------
+// backends
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+#define PB_ERRBUF_DEFINED 1
+
+#define PB_CUDA(call)                                                                         \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess) {                                                                  \
+      snprintf(g_err, sizeof(g_err), "%s failed: %s", #call, cudaGetErrorString(e_)); \
+      return PBNN_ECUDA;                                                                      \
+    }                                                                                         \
+  } while (0)
+
+template <class K, class A>
+static int pb_launch(K kern, const PbPlan& pl, const A& a, dim3 grid, void* stream) {
+  const size_t smem = (size_t)pl.smem_floats * 4;
+  PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, pl.NT, smem, (cudaStream_t)stream>>>(pl, a);
+  PB_CUDA(cudaGetLastError());
+  return PBNN_OK;
+}
+
+template <int ALGO>
+static int pb_sg_dispatch(const PbPlan& pl, const PbSgArgs& a, int C, void* stream) {
+  if (pl.act == PBNN_ACT_RELU) return pb_launch(pb_sg_kernel<ALGO, PBNN_ACT_RELU>, pl, a, dim3(C), stream);
+  return pb_launch(pb_sg_kernel<ALGO, PBNN_ACT_TANH>, pl, a, dim3(C), stream);
+}
+
+static int pb_backend_sg(int algo, const PbPlan& pl, const PbSgArgs& a, int C, void* stream) {
+  switch (algo) {
+    case PB_ALGO_SGLD: return pb_sg_dispatch<PB_ALGO_SGLD>(pl, a, C, stream);
+    case PB_ALGO_PSGLD: return pb_sg_dispatch<PB_ALGO_PSGLD>(pl, a, C, stream);
+    case PB_ALGO_SGHMC: return pb_sg_dispatch<PB_ALGO_SGHMC>(pl, a, C, stream);
+    case PB_ALGO_ADAM: return pb_sg_dispatch<PB_ALGO_ADAM>(pl, a, C, stream);
+    default: return pb_sg_dispatch<PB_ALGO_GRAD>(pl, a, C, stream);
+  }
+}
+
+static int pb_backend_hmc(const PbPlan& pl, const PbHmcArgs& a, int C, void* stream) {
+  if (pl.act == PBNN_ACT_RELU) return pb_launch(pb_hmc_kernel<PBNN_ACT_RELU>, pl, a, dim3(C), stream);
+  return pb_launch(pb_hmc_kernel<PBNN_ACT_TANH>, pl, a, dim3(C), stream);
+}
+
+static int pb_backend_predict(const PbPlan& pl, const PbPredArgs& a, int mtiles, float* sum, float* sumsq,
+                              void* stream) {
+  const dim3 grid(mtiles, a.nchunk);
+  int rc;
+  if (pl.act == PBNN_ACT_RELU) rc = pb_launch(pb_predict_kernel<PBNN_ACT_RELU>, pl, a, grid, stream);
+  else rc = pb_launch(pb_predict_kernel<PBNN_ACT_TANH>, pl, a, grid, stream);
+  if (rc) return rc;
+  if (sum) {
+    const int n = a.M * pl.s;
+    pb_predict_reduce_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(a.part, a.nchunk, n, sum, sumsq);
+    PB_CUDA(cudaGetLastError());
+  }
+  return PBNN_OK;
+}
+
+static int pb_backend_rng(int kind, const uint32_t* keys, int C, int n, void* out, void* stream) {
+  const size_t total = (size_t)C * n;
+  size_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  pb_rng_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(kind, keys, C, n, out);
+  PB_CUDA(cudaGetLastError());
+  return PBNN_OK;
+}
+
+static int pb_backend_mbidx(const uint32_t* keys, int C, int draw, int B, int N, uint32_t mult, int32_t* out,
+                            void* stream) {
+  pb_mbidx_kernel<<<C, 128, 0, (cudaStream_t)stream>>>(keys, draw, B, N, mult, out);
+  PB_CUDA(cudaGetLastError());
+  return PBNN_OK;
+}
+
+static int pb_perm_rounds(int N) {
+  return (int)ceil(3.0 * log((double)(N > 1 ? N : 1)) / log(4294967295.0));
+}
+
+static int pb_backend_perm(const uint32_t* keys, int C, int N, int32_t* out, void* ws, void* stream) {
+  int Np2 = 1;
+  while (Np2 < N) Np2 <<= 1;
+  const size_t bytes = (size_t)Np2 * 8;
+  const int use_smem = bytes <= 200 * 1024;
+  if (use_smem) PB_CUDA(cudaFuncSetAttribute(pb_perm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  pb_perm_kernel<<<C, 1024, use_smem ? bytes : 0, (cudaStream_t)stream>>>(keys, N, Np2, pb_perm_rounds(N), use_smem,
+                                                                          out, (unsigned long long*)ws);
+  PB_CUDA(cudaGetLastError());
+  return PBNN_OK;
+}
+
+#include "pbnn_api.inc"
