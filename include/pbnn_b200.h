@@ -63,6 +63,8 @@ int pbnn_plan_query(const pbnn_mlp_spec* spec, int rows, int n_state, int32_t ou
 /* ---- jax.random primitives (jax/_src/prng.py, random.py); test hooks + key plumbing --------------- */
 /* jax.random.split: out[c][i] = threefry(keys[c], (0, i)).  out: [C][n][2] */
 int pbnn_threefry_split(const uint32_t* keys, int C, int n, uint32_t* out, void* stream);
+/* jax.random.fold_in(key, data) = threefry(key, (0, data)).  out: [C][2] */
+int pbnn_threefry_fold_in(const uint32_t* keys, int C, uint32_t data, uint32_t* out, void* stream);
 /* jax.random.bits(key, (n,), uint32).  out: [C][n] */
 int pbnn_threefry_bits(const uint32_t* keys, int C, int n, uint32_t* out, void* stream);
 /* jax.random.uniform / normal float32.  out: [C][n] */
@@ -102,6 +104,16 @@ int pbnn_psgld_run(const pbnn_mlp_spec* spec, const float* X, const float* y, in
                    int idx_steps, int mb_mode, int B, const uint32_t* keys, float* theta, float* g, float* V,
                    int has_state, float alpha, const float* step_sizes, int n_step_sizes, int64_t t0, int T, int C,
                    int thin, int burnin, float* trace, uint32_t* flags, void* stream);
+
+/* pbnn.mcmc.kernels.psgld(grad_estimator_fn, alpha) -> SamplingAlgorithm(init_fn, step_fn)
+ * (src/pbnn/mcmc/kernels.py:80-94; sgmcmc/psgld.py:25-48): BlackJAX-style single transitions on an EXPLICIT
+ * minibatch Xb [B][d], yb [B][s] shared by the C positions; `data_size` is the N of the N*mean(loglik) estimator.
+ * init: g = grad(theta, batch), V = g^2.  step: keys[c] is used directly as the transition's rng_key. */
+int pbnn_psgld_init(const pbnn_mlp_spec* spec, const float* Xb, const float* yb, int B, int data_size,
+                    const float* theta, float* g, float* V, int C, void* stream);
+int pbnn_psgld_step(const pbnn_mlp_spec* spec, const float* Xb, const float* yb, int B, int data_size,
+                    const uint32_t* keys, float* theta, float* g, float* V, float alpha, float step_size, int C,
+                    void* stream);
 
 /* pbnn.mcmc.sghmc (src/pbnn/mcmc/hamiltonian.py:80-140) over blackjax.sghmc(grad_fn, L, alpha=0.01, beta=0) */
 int pbnn_sghmc_run(const pbnn_mlp_spec* spec, const float* X, const float* y, int N, const int32_t* idx,

@@ -162,7 +162,7 @@ def randint(key, n: int, minval: int, maxval: int) -> np.ndarray:
     lo = random_bits(k2, n).astype(np.uint64)
     span = (maxval - minval) if maxval > minval else 1
     mult = (1 << 16) % span
-    mult = (mult * mult) % span
+    mult = ((mult * mult) & _M32) % span  # lax.mul in uint32: wraps to 0 when span > 2**16 (as JAX does)
     with np.errstate(over="ignore"):
         off = (((hi % span) * mult) & _M32) + (lo % span)  # uint32 wrap-around arithmetic
         off = (off & _M32) % span

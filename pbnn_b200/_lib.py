@@ -43,6 +43,7 @@ PROTOTYPES = {
     "pbnn_num_params": (c_int, [_SPEC]),
     "pbnn_plan_query": (c_int, [_SPEC, c_int, c_int, POINTER(c_int32 * 4)]),
     "pbnn_threefry_split": (c_int, [_P, c_int, c_int, _P, _P]),
+    "pbnn_threefry_fold_in": (c_int, [_P, c_int, ctypes.c_uint32, _P, _P]),
     "pbnn_threefry_bits": (c_int, [_P, c_int, c_int, _P, _P]),
     "pbnn_threefry_uniform": (c_int, [_P, c_int, c_int, _P, _P]),
     "pbnn_threefry_normal": (c_int, [_P, c_int, c_int, _P, _P]),
@@ -52,6 +53,8 @@ PROTOTYPES = {
                               c_int, c_int, _P, _P, _P]),
     "pbnn_psgld_run": (c_int, [_SPEC, _P, _P, c_int, _P, c_int, c_int, c_int, _P, _P, _P, _P, c_int, c_float, _P, c_int,
                                c_int64, c_int, c_int, c_int, c_int, _P, _P, _P]),
+    "pbnn_psgld_init": (c_int, [_SPEC, _P, _P, c_int, c_int, _P, _P, _P, c_int, _P]),
+    "pbnn_psgld_step": (c_int, [_SPEC, _P, _P, c_int, c_int, _P, _P, _P, _P, c_float, c_float, c_int, _P]),
     "pbnn_sghmc_run": (c_int, [_SPEC, _P, _P, c_int, _P, c_int, c_int, c_int, _P, _P, c_int, c_float, c_float, _P, c_int,
                                c_int64, c_int, c_int, c_int, c_int, _P, _P, _P]),
     "pbnn_hmc_run": (c_int, [_SPEC, _P, _P, c_int, _P, _P, _P, c_float, c_int, c_int64, c_int, c_int, c_int, c_int, _P,

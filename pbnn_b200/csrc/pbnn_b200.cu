@@ -46,8 +46,19 @@ __global__ void pb_predict_reduce_kernel(const float* __restrict__ part, int nch
   sumsq[i] = q;
 }
 
-// kind: 0 split, 1 bits, 2 uniform, 3 normal
+// kind: 0 split, 1 bits, 2 uniform, 3 normal, 4 fold_in (n carries the 32-bit datum)
 __global__ void pb_rng_kernel(int kind, const uint32_t* __restrict__ keys, int C, int n, void* __restrict__ out) {
+  if (kind == 4) {
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
+      PbKey k;
+      k.k0 = keys[2 * c];
+      k.k1 = keys[2 * c + 1];
+      const PbKey o = pb_split_at(k, (uint32_t)n);
+      reinterpret_cast<uint32_t*>(out)[2 * c] = o.k0;
+      reinterpret_cast<uint32_t*>(out)[2 * c + 1] = o.k1;
+    }
+    return;
+  }
   const size_t total = (size_t)C * n;
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)(e / n);
@@ -192,7 +203,7 @@ static int pb_backend_predict(const PbPlan& pl, const PbPredArgs& a, int mtiles,
 }
 
 static int pb_backend_rng(int kind, const uint32_t* keys, int C, int n, void* out, void* stream) {
-  const size_t total = (size_t)C * n;
+  const size_t total = kind == 4 ? (size_t)C : (size_t)C * n;
   size_t blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   pb_rng_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(kind, keys, C, n, out);

@@ -156,6 +156,11 @@ struct PbSgArgs {
   const int32_t* idx;
   int idx_steps;
   int mb_mode, which_draw, init_draw;
+  int contig;      // minibatch = rows 0..B-1 of X (BlackJAX-style explicit batch)
+  int direct_key;  // keys[c] IS the step key (kernel-level API) instead of split(keys[c], T)[t]
+  int data_size;   // likelihood scale numerator if > 0 (else N)
+  int no_theta_store;
+  float const_step;  // step size when step_sizes == NULL
   int B;
   uint32_t randint_mult;
   const uint32_t* keys;

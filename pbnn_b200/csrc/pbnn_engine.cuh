@@ -504,7 +504,7 @@ PB_DEV void pb_gen_indices(const PbSmem& S, int B, int N, uint32_t mult, int nt)
 
 PB_DEV void pb_copy_indices(const PbSmem& S, const int32_t* src, int B, int nt) {
   PB_PHASE
-  for (int b = tid; b < B; b += nt) S.idx[b] = src[b];
+  for (int b = tid; b < B; b += nt) S.idx[b] = src ? src[b] : b;  // nullptr: rows 0..B-1
   PB_ENDPHASE
 }
 
@@ -551,10 +551,10 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
   PB_ENDPHASE
 
   const bool single_tile = B <= pl.BT;
-  const bool explicit_idx = a.idx != nullptr;
+  const bool explicit_idx = a.idx != nullptr || a.contig;
   const bool per_step =
       explicit_idx ? (a.idx_steps > 1 || ALGO == PB_ALGO_ADAM) : (a.mb_mode == PBNN_MB_PER_STEP);
-  const int32_t* cidx = explicit_idx ? a.idx + (size_t)c * a.idx_steps * B : nullptr;
+  const int32_t* cidx = a.idx ? a.idx + (size_t)c * a.idx_steps * B : nullptr;
   int gen_pos = 0;  // how many draws of the generator have been consumed (uniform across threads)
 
   if (ALGO == PB_ALGO_GRAD) {
@@ -609,11 +609,11 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
 
   for (int t = 0; t < a.T; ++t) {
     const long long tg = a.t0 + t;
-    const PbKey kt = pb_split_at(ck, (uint32_t)tg);  // split(rng_key, T)[t]
-    const float eps = a.step_sizes ? a.step_sizes[t < a.n_step_sizes ? t : a.n_step_sizes - 1] : 0.f;
+    const PbKey kt = a.direct_key ? ck : pb_split_at(ck, (uint32_t)tg);  // split(rng_key, T)[t]
+    const float eps = a.step_sizes ? a.step_sizes[t < a.n_step_sizes ? t : a.n_step_sizes - 1] : a.const_step;
     if (per_step) {
       if (explicit_idx) {
-        pb_copy_indices(S, cidx + (size_t)t * B, B, nt);
+        pb_copy_indices(S, cidx ? cidx + (size_t)t * B : nullptr, B, nt);
       } else {
         pb_gen_advance(S, 1, nt);
         pb_gen_indices(S, B, a.N, a.randint_mult, nt);
@@ -689,7 +689,7 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
     }
   }
 
-  pb_store_state(pl, TH, a.theta + cP, S.scu + 2, nt);
+  if (!a.no_theta_store) pb_store_state(pl, TH, a.theta + cP, S.scu + 2, nt);
   if (ALGO == PB_ALGO_PSGLD || ALGO == PB_ALGO_ADAM) {
     pb_store_state(pl, ALGO == PB_ALGO_PSGLD ? G : A1, a.aux1 + cP, nullptr, nt);
     pb_store_state(pl, ALGO == PB_ALGO_PSGLD ? A1 : A2, a.aux2 + cP, nullptr, nt);

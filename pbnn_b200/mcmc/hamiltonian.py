@@ -1,0 +1,44 @@
+"""Hamiltonian-family wrappers with the signatures of src/pbnn/mcmc/hamiltonian.py (hmc :31-39, sghmc :80-91)."""
+from __future__ import annotations
+
+import torch
+
+from ..logprobs import FullBatchLogPosterior, require_specs
+from ..ops import default_ops
+from ._common import chain_layout, make_predict_fn, make_ravel_fn, positions_tree
+
+
+def hmc(logprob_fn, init_positions, num_samples, step_size, inverse_mass_matrix, num_integration_steps, rng_key, *,
+        thin=1, burnin=0, return_info=False):
+    """pbnn.mcmc.hmc (hamiltonian.py:31-77) over blackjax.hmc.  ``logprob_fn`` must be a
+    ``FullBatchLogPosterior`` (the closure of benchmark/pipelines/hmc.py:59-62 as a spec object)."""
+    if not isinstance(logprob_fn, FullBatchLogPosterior):
+        raise TypeError("logprob_fn must be a pbnn_b200.logprobs.FullBatchLogPosterior (got %r); arbitrary "
+                        "callables cannot be compiled to the CUDA path" % (type(logprob_fn).__name__,))
+    ops = default_ops()
+    flat, layers, keys, batched = chain_layout(init_positions, rng_key)
+    spec = logprob_fn.flat_spec()
+    if tuple(spec.layers) != tuple(layers):
+        raise ValueError(f"init_positions widths {layers} do not match the network {spec.layers}")
+    res = ops.hmc(spec, logprob_fn.X, logprob_fn.y, flat, keys, int(num_samples), float(step_size),
+                  inverse_mass_matrix, int(num_integration_steps), thin=thin, burnin=burnin, info=return_info)
+    out = (positions_tree(res["trace"], layers, batched), make_ravel_fn(layers), make_predict_fn(layers))
+    if return_info:
+        info = {"acceptance_rate": res["accept_count"].to(torch.float32) / max(1, int(num_samples)),
+                "delta_energy": res["delta"], "is_accepted": res["accept"], "logdensity": res["logp"],
+                "flags": res["flags"]}
+        return out + (info,)
+    return out
+
+
+def sghmc(X, y, loglikelihood_fn, logprior_fn, init_positions, batch_size, step_size, num_iterations,
+          num_integration_steps, rng_key, *, thin=1, burnin=0, minibatch_mode="reference_fixed", alpha=0.01, beta=0.0):
+    """pbnn.mcmc.sghmc (hamiltonian.py:80-140) over blackjax.sghmc(grad_fn, L) (alpha=0.01, beta=0 defaults)."""
+    require_specs(loglikelihood_fn, logprior_fn)
+    ops = default_ops()
+    flat, layers, keys, batched = chain_layout(init_positions, rng_key)
+    spec = loglikelihood_fn.flat_spec(layers[0], logprior_fn)
+    res = ops.sghmc(spec, X, y, flat, keys, int(batch_size), step_size, int(num_iterations),
+                    int(num_integration_steps), alpha=alpha, beta=beta, minibatch_mode=minibatch_mode, thin=thin,
+                    burnin=burnin)
+    return positions_tree(res["trace"], layers, batched), make_ravel_fn(layers), make_predict_fn(layers)

@@ -36,6 +36,8 @@ class FlatSpec:
 
 
 def trace_len(T: int, thin: int, burnin: int) -> int:
+    if thin < 1 or burnin < 0:
+        raise ValueError("need thin >= 1 and burnin >= 0")
     return (T - burnin + thin - 1) // thin if T > burnin else 0
 
 
@@ -136,6 +138,13 @@ class Ops:
         k = self._keys(keys)
         out = self._empty((k.shape[0], n, 2), self.i32)
         check(self.lib, self.lib.pbnn_threefry_split(self._ptr(k), k.shape[0], n, self._ptr(out), self._stream()), "split")
+        return out
+
+    def fold_in(self, keys, data: int):
+        k = self._keys(keys)
+        out = self._empty((k.shape[0], 2), self.i32)
+        check(self.lib, self.lib.pbnn_threefry_fold_in(self._ptr(k), k.shape[0], int(data) & 0xFFFFFFFF, self._ptr(out),
+                                                       self._stream()), "fold_in")
         return out
 
     def bits(self, keys, n: int):
@@ -319,6 +328,12 @@ class Ops:
 
 
 _DEFAULT: Optional[Ops] = None
+
+
+def set_default_ops(ops: Optional[Ops]) -> None:
+    """Test hook: lets the CPU test-suite drive the host-side API through the kernel-logic emulator."""
+    global _DEFAULT
+    _DEFAULT = ops
 
 
 def default_ops() -> Ops:

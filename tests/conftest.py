@@ -1,0 +1,35 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu")
+
+
+@pytest.fixture(scope="session")
+def emu_ops():
+    """Kernel-logic emulator (same kernel bodies compiled by g++; test infrastructure only)."""
+    from emu_ops import EmuOps
+    return EmuOps()
+
+
+@pytest.fixture(scope="session")
+def cuda_ops():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from pbnn_b200.ops import default_ops
+    return default_ops()
+
+
+@pytest.fixture(params=["emu", pytest.param("cuda", marks=pytest.mark.gpu)])
+def ops(request):
+    """Parity tests run twice: against the emulator here (CPU), against the CUDA library on the GPU box."""
+    return request.getfixturevalue(request.param + "_ops")

@@ -69,6 +69,12 @@ static int pb_backend_predict(const PbPlan& pl, const PbPredArgs& a, int mtiles,
 static int pb_backend_rng(int kind, const uint32_t* keys, int C, int n, void* out, void*) {
   for (int c = 0; c < C; ++c) {
     PbKey k{keys[2 * c], keys[2 * c + 1]};
+    if (kind == 4) {
+      const PbKey o = pb_split_at(k, (uint32_t)n);
+      ((uint32_t*)out)[2 * c] = o.k0;
+      ((uint32_t*)out)[2 * c + 1] = o.k1;
+      continue;
+    }
     for (int i = 0; i < n; ++i) {
       const size_t e = (size_t)c * n + i;
       if (kind == 0) {
