@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py -- chain-steps/sec of the B200-native pbnn hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload hmc_cfg2] [--impl reference]
+
+One *step* = one pass of the hot path over one batch of synthetic input: a full run of the named configuration's
+job (default `hmc_cfg2`: BASELINE.json configs[1], 256 chains x 200 HMC iterations x L=20 full-batch leapfrogs on a
+13-50-1 MLP, N=506).  `value` = chain-steps/s with inputs resident in HBM (CUDA events, max over ranks);
+`e2e` = the same through the public sampler call with pinned HOST buffers (H2D of data/positions/keys and D2H of
+the positions inside the timed region).  Chains shard over ranks with no data-path collective (weak scaling); the
+only exchange is an all_gather of the predictive moments after the timed region.
+
+`--impl reference` times the CPU restatement of the reference (oracle/c, OpenMP over chains, all host threads) on
+the same config -- JAX / BlackJAX are not installable here, see DESIGN.md.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+# ------------------------------------------------------------------------------------------------ workloads
+# algorithmic FLOPs per gradient evaluation: 6*B*W - 2*B*d*h1, W = sum in*out
+WORKLOADS = {
+    # BASELINE.json configs[1]
+    "hmc_cfg2": dict(algo="hmc", layers=(13, 50, 1), act=0, N=506, B=506, C=256, T=200, L=20, step=1e-3, M=1024),
+    # BASELINE.json configs[0] shape, many chains
+    "sgld_cfg1": dict(algo="sgld", layers=(8, 50, 1), act=0, N=1030, B=32, C=1, T=100_000, L=1, step=1e-5, M=1024),
+    "sgld_cfg1x": dict(algo="sgld", layers=(8, 50, 1), act=0, N=1030, B=32, C=2048, T=2000, L=1, step=1e-5, M=1024),
+    # BASELINE.json configs[2]
+    "psgld_cfg3": dict(algo="psgld", layers=(9, 100, 100, 1), act=0, N=45730, B=128, C=1024, T=200, L=1, step=2e-8,
+                       M=1024),
+    "sgld_cfg3": dict(algo="sgld", layers=(9, 100, 100, 1), act=0, N=45730, B=128, C=1024, T=200, L=1, step=2e-8,
+                      M=1024),
+    "sghmc_cfg3": dict(algo="sghmc", layers=(9, 100, 100, 1), act=0, N=45730, B=128, C=1024, T=20, L=10, step=1e-9,
+                       M=1024),
+    # BASELINE.json configs[3]
+    "adam_cfg4": dict(algo="adam", layers=(8, 50, 50, 1), act=0, N=9568, B=32, C=512, T=299 * 2, L=1, step=1e-2,
+                      M=1024),
+}
+
+
+def grad_flops(layers, B):
+    W = sum(i * o for i, o in zip(layers[:-1], layers[1:]))
+    return 6 * B * W - 2 * B * layers[0] * layers[1]
+
+
+def num_params(layers):
+    return sum(o * (i + 1) for i, o in zip(layers[:-1], layers[1:]))
+
+
+def step_flops(w):
+    """algorithmic FLOPs of one bench step (all chains), RNG integer work excluded."""
+    per_chain_step = w["L"] * grad_flops(w["layers"], w["B"]) + 6 * num_params(w["layers"])
+    return per_chain_step * w["C"] * w["T"]
+
+
+def make_inputs(w, rank, world):
+    from oracle import pbnn_oracle as o  # synthetic data + key derivation shared with the tests (checker side)
+    X, y, Xt, _ = o.synthetic_regression(w["N"], w["layers"][0], 0, M=w["M"])
+    sp = o.MlpSpec(tuple(w["layers"]), w["act"], 0.1)
+    keys_all = o.split(o.PRNGKey(0), w["C"] * world)
+    keys = keys_all[rank * w["C"]:(rank + 1) * w["C"]]
+    th0 = o.init_positions(sp, keys)
+    return X, y, Xt, keys, th0
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        hi = [s for s, p in zip(sm, pw) if p >= 0.5 * max(pw)] or sm
+        return {"sm_mhz": statistics.median(hi), "sm_max_mhz": max(mx), "power_w_max": max(pw),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arms
+def cpu_run(w, n_chains, n_iters, seed_rank=0):
+    """Run the C restatement on a bounded sample: n_chains chains x n_iters sampler iterations.  Returns seconds."""
+    from oracle import c_oracle as co
+    from oracle import pbnn_oracle as o
+    X, y, _, _, _ = make_inputs(dict(w, C=1), 0, 1)
+    sp = o.MlpSpec(tuple(w["layers"]), w["act"], 0.1)
+    keys = o.split(o.PRNGKey(0), n_chains)
+    th0 = o.init_positions(sp, keys)
+    t0 = time.perf_counter()
+    if w["algo"] == "hmc":
+        co.hmc_run(w["layers"], w["act"], 0.1, X, y, th0, keys, n_iters, w["step"], np.ones(sp.num_params, np.float32),
+                   w["L"], trace=False)
+    elif w["algo"] == "adam":
+        idx = np.random.default_rng(0).integers(0, w["N"], (n_chains, n_iters, w["B"])).astype(np.int32)
+        co.adam_run(w["layers"], w["act"], 0.1, X, y, th0, idx, w["step"])
+    else:
+        co.sg_run(w["layers"], w["act"], 0.1, w["algo"], X, y, th0, w["B"], w["step"], n_iters, keys, L=w["L"],
+                  alpha=0.95 if w["algo"] == "psgld" else 0.01, trace=False)
+    return time.perf_counter() - t0
+
+
+def cpu_sample_plan(w, target_s):
+    """Size a bounded sample of the workload for ~target_s seconds of CPU work on all host threads."""
+    from oracle import c_oracle as co
+    cores = co.num_threads()
+    n_chains = min(w["C"], max(1, cores) * 2)
+    probe_iters = max(1, min(w["T"], int(2e8 / max(1, w["L"] * grad_flops(w["layers"], w["B"])))))
+    dt = cpu_run(w, n_chains, probe_iters)
+    rate = n_chains * probe_iters / dt  # chain-steps/s
+    iters = int(max(probe_iters, min(w["T"], target_s * rate / n_chains)))
+    return cores, n_chains, iters
+
+
+def cpu_baseline(w, target_s=12.0):
+    cores, n_chains, iters = cpu_sample_plan(w, target_s)
+    dt = cpu_run(w, n_chains, iters)
+    return {"value": n_chains * iters / dt, "unit": "chain-steps/s", "cores": cores, "kind": "port",
+            "sample": f"{n_chains} chains x {iters} iterations of {w['name']} (C restatement of the reference, OpenMP over "
+                      f"chains; JAX/BlackJAX not installable)", "seconds": dt}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def gpu_step_fn(ops, w, fs, X, y, th0, keys, keep_trace=True):
+    import torch
+    a = w["algo"]
+    if a == "hmc":
+        minv = torch.ones(fs.num_params, device="cuda")
+        return lambda: ops.hmc(fs, X, y, th0, keys, w["T"], w["step"], minv, w["L"], keep_trace=keep_trace)
+    if a == "sgld":
+        return lambda: ops.sgld(fs, X, y, th0, keys, w["B"], w["step"], w["T"], keep_trace=False)
+    if a == "psgld":
+        return lambda: ops.psgld(fs, X, y, th0, keys, w["B"], w["step"], w["T"], 0.95, keep_trace=False)
+    if a == "sghmc":
+        return lambda: ops.sghmc(fs, X, y, th0, keys, w["B"], w["step"], w["T"], w["L"], keep_trace=False)
+    if a == "adam":
+        idx = torch.randint(0, w["N"], (w["C"], w["T"], w["B"]), dtype=torch.int32, device="cuda")
+        return lambda: ops.adam_ensemble(fs, X, y, th0, idx, w["step"])
+    raise ValueError(a)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="hmc_cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--iters", type=int, default=0, help="override iterations per step (profiling runs)")
+    ap.add_argument("--chains", type=int, default=0, help="override chains per GPU (profiling runs)")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3  # timing rule: W >= 3
+    w = dict(WORKLOADS[args.workload], name=args.workload)
+    if args.iters > 0:
+        w["T"] = args.iters
+    if args.chains > 0:
+        w["C"] = args.chains
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    base = {"metric": "chain-steps/sec", "unit": "chain-steps/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic (UCI-shaped regression, seeded; SURVEY.md 8d)",
+            "config": {"workload": f"{args.workload}: {w['algo']} MLP {'-'.join(map(str, w['layers']))} relu, N={w['N']}, "
+                                   f"batch={w['B']}, {w['C']} chains/GPU x {w['T']} iterations x L={w['L']} per step",
+                       "chains_per_gpu": w["C"], "iterations_per_step": w["T"], "leapfrogs": w["L"],
+                       "l2": "flushed (256 MiB write) before every timed step"}}
+
+    # ---------------------------------------------------------------- reference arm (CPU restatement)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cores, n_chains, iters = cpu_sample_plan(w, 8.0)
+        for _ in range(min(args.warmup, 1)):
+            cpu_run(w, n_chains, max(1, iters // 4))
+        t = [cpu_run(w, n_chains, iters) for _ in range(args.steps)]
+        total = sum(t)
+        v = args.steps * n_chains * iters / total
+        cb = {"value": v, "unit": "chain-steps/s", "cores": cores, "kind": "port",
+              "sample": f"each step = {n_chains} chains x {iters} iterations of {args.workload} (C restatement of the "
+                        f"reference, OpenMP over chains on all host threads; JAX/BlackJAX not installable here)"}
+        out = dict(base, impl="reference", value=v, ms_per_step=1e3 * total / args.steps, cpu_baseline=cb,
+                   e2e={"value": v, "unit": "chain-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                   gpu_launches=0)
+        print(json.dumps(out))
+        return
+
+    # ---------------------------------------------------------------- B200 arm
+    import torch
+    import torch.distributed as dist
+    from pbnn_b200.ops import FlatSpec, default_ops
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ops = default_ops()
+    fs = FlatSpec(tuple(w["layers"]), w["act"], 0.1)
+    Xh, yh, Xth, keysh, th0h = make_inputs(w, rank, world)
+    X, y, Xt = (ops._as(a, torch.float32) for a in (Xh, yh, Xth))
+    keys, th0 = ops._keys(keysh), ops._as(th0h, torch.float32)
+    step = gpu_step_fn(ops, w, fs, X, y, th0, keys)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, K, W):
+        for _ in range(W):
+            fn()
+        barrier()
+        evs = []
+        for _ in range(K):
+            flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            evs.append((a, b))
+        barrier()
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_total = timed(step, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    chain_steps = w["C"] * w["T"] * world
+    value = args.steps * chain_steps / (ms_total * 1e-3)
+    ms_per_step = ms_total / args.steps
+
+    # end-to-end: public call with pinned host buffers; H2D of inputs and D2H of the result inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a.view(np.int32) if a.dtype == np.uint32 else a)).pin_memory()
+        hX, hy, hk, ht = pin(Xh), pin(yh), pin(keysh), pin(th0h)
+        P = fs.num_params
+        res_shape = (w["C"], w["T"] if w["algo"] == "hmc" else 1, P)
+        hout = torch.empty(res_shape, dtype=torch.float32).pin_memory()
+        h2d = sum(t.numel() * t.element_size() for t in (hX, hy, hk, ht))
+        d2h = hout.numel() * 4
+
+        def e2e_step():
+            dX, dy = hX.to("cuda", non_blocking=True), hy.to("cuda", non_blocking=True)
+            dk, dt_ = hk.to("cuda", non_blocking=True), ht.to("cuda", non_blocking=True)
+            r = gpu_step_fn(ops, w, fs, dX, dy, dt_, dk)()
+            src = r["trace"] if (w["algo"] == "hmc" and r.get("trace") is not None) else r["theta"].unsqueeze(1)
+            hout.copy_(src, non_blocking=True)
+
+        ms_e2e = timed(e2e_step, args.steps, args.warmup)
+        e2e = {"value": args.steps * chain_steps / (ms_e2e * 1e-3), "unit": "chain-steps/s",
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
+               "api": "pbnn_b200.ops (C ABI) with pinned host buffers; positions returned to the host"}
+
+    # the single exchange step: predictive moments of each rank's final states, all_gather'ed (not in the timed region)
+    last = step()
+    final = last["theta"]
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    mom = ops.predict(fs, final, Xt, want_preds=False, want_moments=True)
+    local = torch.stack([mom["sum"], mom["sumsq"]])
+    if world > 1:
+        gathered = [torch.empty_like(local) for _ in range(world)]
+        dist.all_gather(gathered, local)
+        tot = torch.stack(gathered).sum(0)
+    else:
+        tot = local
+    torch.cuda.synchronize()
+    S_tot = w["C"] * world
+    pm = tot[0] / S_tot
+    pv = (tot[1] / S_tot - pm * pm).clamp_min(0)
+    exchange_ms = 1e3 * (time.perf_counter() - t0)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        flops = step_flops(w)
+        achieved = flops / (ms_per_step * 1e-3) / 1e12
+        sm_max = (clocks or {}).get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0
+        peak_nominal = 148 * 128 * 2 * sm_max * 1e6 / 1e12
+        trace_bytes = w["C"] * w["T"] * fs.num_params * 4 if w["algo"] == "hmc" else 0
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        roofline = {"bound": "fma", "achieved": achieved, "peak": peak_nominal, "unit": "TFLOP/s",
+                    "frac": achieved / peak_nominal, "traffic": None,
+                    "peak_source": f"FP32 FMA: 148 SM x 128 lanes x 2 x {sm_max:.0f} MHz (the kernel is FP32-FMA bound, "
+                                   f"neither HBM nor tensor; DESIGN.md)",
+                    "kernel": "pb_hmc_kernel" if w["algo"] == "hmc" else "pb_sg_kernel",
+                    "algorithmic_flops_per_launch": flops,
+                    "hbm": {"achieved": trace_bytes / (ms_per_step * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                            "frac": trace_bytes / (ms_per_step * 1e-3) / 1e9 / hbm_peak,
+                            "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback"}}
+        out = dict(base, value=value, ms_per_step=ms_per_step, clocks=clocks, roofline=roofline, gpu_launches=args.steps,
+                   exchange={"what": "predictive moments (sum, sumsq over chains) all_gather", "ms": exchange_ms,
+                             "pred_mean_abs": float(pm.abs().mean()), "pred_var_mean": float(pv.mean())},
+                   chains_finite=bool(torch.isfinite(final).all().item()))
+        if w["algo"] == "hmc":
+            out["hmc_accept_rate"] = float(last["accept_count"].float().mean().item() / w["T"])
+        if e2e:
+            out["e2e"] = e2e
+        if not args.no_cpu_baseline and world == 1:
+            out["cpu_baseline"] = cpu_baseline(w)
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -11,11 +11,22 @@
 
 #include "pbnn_engine.cuh"
 
+#if defined(PB_PROFILE)
+#define PB_PROF_START                                                  \
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {        \
+    pb_prof_last = clock64();                                          \
+    pb_prof_tag = 0;                                                   \
+  }
+#else
+#define PB_PROF_START
+#endif
+
 // ------------------------------------------------------------------------------------------------
 template <int ALGO, int ACT>
 __global__ void __launch_bounds__(PB_MAX_NT, 2)
 pb_sg_kernel(const __grid_constant__ PbPlan pl, const __grid_constant__ PbSgArgs a) {
   extern __shared__ __align__(16) float pb_smem[];
+  PB_PROF_START
   pb_sg_chain<ALGO, ACT>(pl, a, pb_smem, (int)blockIdx.x, (int)blockDim.x);
 }
 
@@ -23,6 +34,7 @@ template <int ACT>
 __global__ void __launch_bounds__(PB_MAX_NT, 2)
 pb_hmc_kernel(const __grid_constant__ PbPlan pl, const __grid_constant__ PbHmcArgs a) {
   extern __shared__ __align__(16) float pb_smem[];
+  PB_PROF_START
   pb_hmc_chain<ACT>(pl, a, pb_smem, (int)blockIdx.x, (int)blockDim.x);
 }
 
@@ -235,3 +247,14 @@ static int pb_backend_perm(const uint32_t* keys, int C, int N, int32_t* out, voi
 }
 
 #include "pbnn_api.inc"
+
+#if defined(PB_PROFILE)
+// profiling build only: per-phase cycle totals [0..31] and phase counts [32..63] of CTA 0; resets the counters
+extern "C" int pbnn_debug_profile(unsigned long long out[64]) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, pb_prof_cycles, sizeof(unsigned long long) * 64);
+  unsigned long long zero[64] = {0};
+  cudaMemcpyToSymbol(pb_prof_cycles, zero, sizeof(zero));
+  return 0;
+}
+#endif

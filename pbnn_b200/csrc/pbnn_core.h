@@ -12,12 +12,16 @@
 
 #define PB_SMEM_LIMIT_BYTES (227 * 1024)
 #define PB_MAX_NT 256
+#define PB_SCR_FLOATS (1024 + 64 + 128 + 128)  // reduction scratch, second level, llbuf[128], fbuf[128]
+#define PB_GPART_BUDGET_BYTES (24 * 1024)      // split-K partial gradient buffers
 
 // One Dense layer in the resident (shared-memory) layout.
 //   W_aug : rows x wp floats, rows = roundup4(in+1); row r<in is kernel row r, row `in` is the bias,
 //           remaining rows and the columns >= out are zero pads that are never updated.
 //   wp    : pitch, multiple of 4 with wp % 8 == 4 so that 8 consecutive rows hit 8 distinct 16-byte
 //           bank groups (conflict-free LDS.128 in the k-contiguous GEMMs).
+//   dw_ni : lane layout of the weight-gradient GEMM: 8 -> warp tile 32(in) x 16(out), 4 -> 16(in) x 32(out)
+//   dw_ks : split-K factor of that GEMM (slices > 0 accumulate into partial buffers)
 struct PbLayer {
   int in, out;
   int inA;   // in + 1
@@ -25,17 +29,20 @@ struct PbLayer {
   int wp;
   int soff;  // float offset of W_aug inside a resident parameter array
   int fb, fw;  // flat (ravel_pytree) offsets of bias and kernel
+  int dw_ni, dw_ks;
 };
 
 struct PbPlan {
   int nl, act, P, Ps;
   int d, s;
   PbLayer L[PBNN_MAX_LAYERS];
-  int BT, ap;                      // batch-tile rows (multiple of 32) and activation pitch (BT + 4)
-  int aoff[PBNN_MAX_LAYERS + 2];   // A_0 (input tile, feature-major) .. A_nl (output / dZ_last), then yT
-  int arows[PBNN_MAX_LAYERS + 2];
-  int nstate;                      // resident parameter-sized arrays
-  int off_act, off_scr, off_idx, off_scal;
+  int BT, ap;                     // batch-tile rows (multiple of 32) and activation pitch (BT + 4)
+  int aoff[PBNN_MAX_LAYERS + 2];  // tile buffers A_0 .. A_nl, then yT (A_0 / yT have 0 rows when res_rows > 0)
+  int res_rows;                   // > 0: all input rows of a gradient evaluation are resident, feature-major
+  int xp, off_xres, off_yres;     //      X^T_aug [r4(d+1)][xp], y^T [r4(s)][xp], xp = roundup(rows, BT) + 4
+  int nstate;                     // resident parameter-sized arrays
+  int ksmax, off_gpart;           // (ksmax - 1) partial gradient arrays for split-K
+  int off_act, off_scr, off_acc, off_idx, off_scal;
   int idx_cap;
   int smem_floats;
   int NT;
@@ -59,10 +66,85 @@ static inline int pb_num_params(const pbnn_mlp_spec* sp) {
   return P > (1L << 26) ? -1 : (int)P;
 }
 
+// choose the lane layout / split-K of every weight-gradient GEMM for `nw` warps and batch tile `bt`
+static inline void pb_plan_dw(PbPlan* pl, int nw, int bt, int kcap) {
+  pl->ksmax = 1;
+  const int ks_env = pb_env_int("PBNN_DW_KS", 0);
+  for (int l = 0; l < pl->nl; ++l) {
+    PbLayer& Ly = pl->L[l];
+    int best_ni = 8, best_ks = 1;
+    long best = -1;
+    for (int ni = 8; ni >= 4; ni -= 4) {
+      const int ti = ni * 4, to = (32 / ni) * 4;
+      const int tiles = ((Ly.inA + ti - 1) / ti) * ((Ly.out + to - 1) / to);
+      for (int ks = 1; ks <= 8; ks *= 2) {
+        if (bt % (4 * ks)) continue;
+        if (ks > 1 && (size_t)(ks - 1) * pl->Ps * 4 > PB_GPART_BUDGET_BYTES) continue;
+        if (ks > kcap || (ks_env > 0 && ks > ks_env)) continue;
+        const long rounds = (tiles * ks + nw - 1) / nw;
+        const long cost = rounds * (bt / ks + 6) + (ks > 1 ? 4 : 0);
+        if (best < 0 || cost < best) {
+          best = cost;
+          best_ni = ni;
+          best_ks = ks;
+        }
+      }
+    }
+    Ly.dw_ni = best_ni;
+    Ly.dw_ks = best_ks;
+    if (best_ks > pl->ksmax) pl->ksmax = best_ks;
+  }
+}
+
+#define PB_PLAN_RES 1
+#define PB_PLAN_ACC 2
+
+// shared-memory layout for one candidate configuration
+static inline void pb_layout(PbPlan* pl, const pbnn_mlp_spec* sp, int rows, int nstate, int bt, int res, int kcap,
+                             int want_acc) {
+  const int ap = bt + 4;
+  pl->BT = bt;
+  pl->ap = ap;
+  pb_plan_dw(pl, pl->NT / 32, bt, kcap);
+  int off = nstate * pl->Ps;
+  pl->off_gpart = off;
+  off += (pl->ksmax - 1) * pl->Ps;
+  pl->off_act = off;
+  for (int l = 0; l <= pl->nl + 1; ++l) {
+    int r;
+    if (l < pl->nl) r = pb_r4(sp->dims[l] + 1);
+    else if (l == pl->nl) r = pl->s == 1 ? 1 : pb_r4(pl->s);  // A_nl: output / dZ_last (rank-1 path: one row)
+    else r = pl->s;                                            // yT
+    if (res && (l == 0 || l == pl->nl + 1)) r = 0;
+    pl->aoff[l] = off;
+    off += r * ap;
+  }
+  pl->res_rows = 0;
+  if (res) {
+    pl->res_rows = rows;
+    pl->xp = ((rows + bt - 1) / bt) * bt + 4;
+    pl->off_xres = off;
+    off += pb_r4(pl->d + 1) * pl->xp;
+    pl->off_yres = off;
+    off += pl->s * pl->xp;
+  }
+  pl->off_scr = off;
+  off += PB_SCR_FLOATS;
+  pl->off_acc = off;
+  if (want_acc) off += 2 * pb_r4(pl->s) * ap;  // predictive accumulators
+  pl->off_idx = off;
+  off += pl->idx_cap;
+  pl->off_scal = off;
+  off += 32;
+  pl->smem_floats = off;
+}
+
 // rows: rows per gradient evaluation (minibatch B, N for HMC, M for predict); nstate: resident
-// parameter-sized arrays; idx_cap: ints reserved for the minibatch index list.
-static inline int pb_build_plan(const pbnn_mlp_spec* sp, int rows, int nstate, int idx_cap, PbPlan* pl, char* err,
-                                size_t errn) {
+// parameter-sized arrays; idx_cap: ints reserved for the minibatch index list; flags: PB_PLAN_RES = try to keep
+// all `rows` input rows resident in shared memory (feature-major) instead of streaming tiles, PB_PLAN_ACC =
+// reserve the predictive accumulators; chains_hint: number of CTAs of the launch (occupancy target).
+static inline int pb_build_plan(const pbnn_mlp_spec* sp, int rows, int nstate, int idx_cap, int flags,
+                                int chains_hint, PbPlan* pl, char* err, size_t errn) {
   memset(pl, 0, sizeof(*pl));
   const int P = pb_num_params(sp);
   if (P < 0) {
@@ -113,33 +195,26 @@ static inline int pb_build_plan(const pbnn_mlp_spec* sp, int rows, int nstate, i
     snprintf(err, errn, "PBNN_NW out of range");
     return PBNN_EINVAL;
   }
-  int bt = pb_r32(rows);
-  if (bt > 128) bt = 128;
+  const int want_res = (flags & PB_PLAN_RES) && !pb_env_int("PBNN_NO_RESIDENT", 0);
+  int maxbt = pb_r32(rows);
+  if (maxbt > 128) maxbt = 128;
   const int forced = pb_env_int("PBNN_BT", 0);
-  if (forced > 0) bt = pb_r32(forced) > 128 ? 128 : pb_r32(forced);
-  for (; bt >= 32; bt -= 32) {
-    const int ap = bt + 4;
-    int off = nstate * pl->Ps;
-    pl->off_act = off;
-    for (int l = 0; l <= pl->nl + 1; ++l) {
-      int r;
-      if (l < pl->nl) r = pb_r4(sp->dims[l] + 1);
-      else r = pb_r4(pl->s);  // A_nl (output / dZ_last) and yT
-      pl->aoff[l] = off;
-      pl->arows[l] = r;
-      off += r * ap;
+  if (forced > 0) maxbt = pb_r32(forced) > 128 ? 128 : pb_r32(forced);
+  // Two passes: first try to stay under half an SM's shared memory so that two CTAs are co-resident (more warps to
+  // hide the latency of the short dependent phases) when there are more chains than SMs; then the full SM.
+  const size_t lim2 = (size_t)(228 * 1024) / 2 - 1024, lim1 = PB_SMEM_LIMIT_BYTES;
+  const int two = (chains_hint > 148 || pb_env_int("PBNN_TWO_CTA", 0)) && !pb_env_int("PBNN_ONE_CTA", 0);
+  for (int pass = two ? 0 : 1; pass < 2; ++pass) {
+    const size_t limit = pass == 0 ? lim2 : lim1;
+    for (int bt = maxbt; bt >= 32; bt -= 32) {
+      if (pass == 0 && bt < (maxbt < 64 ? maxbt : 64)) break;
+      for (int res = want_res ? 1 : 0; res >= 0; --res)
+        for (int kcap = 8; kcap >= 1; kcap /= 2) {
+          pb_layout(pl, sp, rows, nstate, bt, res, kcap, (flags & PB_PLAN_ACC) != 0);
+          if ((size_t)pl->smem_floats * 4 <= limit) return PBNN_OK;
+        }
+      if (forced > 0) break;
     }
-    pl->off_scr = off;
-    off += 1024 + 64 + 128 + 128 + 2 * pb_r4(pl->s) * ap;  // reduction scratch, llbuf, fbuf, predictive accumulators
-    pl->off_idx = off;
-    off += pl->idx_cap;
-    pl->off_scal = off;
-    off += 32;
-    pl->smem_floats = off;
-    pl->BT = bt;
-    pl->ap = ap;
-    if ((size_t)off * 4 <= PB_SMEM_LIMIT_BYTES) return PBNN_OK;
-    if (forced > 0) break;
   }
   snprintf(err, errn,
            "model does not fit the shared-memory resident engine (P=%d, %d resident arrays need %zu bytes > %d)", P,

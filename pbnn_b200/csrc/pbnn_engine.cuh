@@ -9,12 +9,15 @@
 //
 // Data layout in shared memory (floats), see pb_build_plan():
 //   nstate x [Ps]   resident parameter-sized arrays; layer l is W_aug[rows][wp] with the bias as row `in`
-//   A_0..A_nl       activations, FEATURE-MAJOR: A_l[feature][b], pitch ap = BT+4; A_l has a constant
+//   gpart           (ksmax-1) x [Ps] partial weight gradients of the split-K slices
+//   A_1..A_nl       activations, FEATURE-MAJOR: A_l[feature][b], pitch ap = BT+4; A_l has a constant
 //                   ones-row at index dims[l] so the bias and its gradient fall out of the GEMMs
-//   yT              targets, feature-major
+//   X^T_aug, y^T    all input rows of one gradient evaluation, feature-major, resident (pitch xp); a batch
+//                   tile is a column window of it.  (Fallback when they do not fit: A_0 / yT tile buffers
+//                   streamed from global memory.)
 // Three register-tiled FP32 GEMMs (4x4 outputs per thread, LDS.128 operands, conflict-free by pitch):
 //   fwd : A_{l+1}[o][b] = act( sum_k W[k][o] * A_l[k][b] )            (k-major both operands)
-//   dW  : G[i][o]      += sum_b A_l[i][b] * dZ[o][b]                 (dot form, both k-contiguous)
+//   dW  : G[i][o]      += sum_b A_l[i][b] * dZ[o][b]                 (dot form, both k-contiguous, split-K)
 //   dH  : A_l[i][b]     = act'(A_l[i][b]) * sum_o W[i][o] * dZ[o][b]  (in place)
 #pragma once
 #include "pbnn_core.h"
@@ -31,10 +34,31 @@ struct float4 {
 #define PB_PHASE            \
   {                         \
     const int tid = threadIdx.x;
+#if defined(PB_PROFILE)
+// per-phase cycle accounting of CTA 0 (profiling build only, -DPB_PROFILE): PB_TAG(n) names the phases that follow
+__device__ unsigned long long pb_prof_cycles[64];
+__device__ unsigned long long pb_prof_last;
+__device__ int pb_prof_tag;
+#define PB_TAG(n)                                          \
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) pb_prof_tag = (n);
+#define PB_ENDPHASE                                                      \
+  }                                                                      \
+  __syncthreads();                                                       \
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {          \
+    const unsigned long long now_ = clock64();                           \
+    pb_prof_cycles[pb_prof_tag & 63] += now_ - pb_prof_last;             \
+    pb_prof_cycles[32 + (pb_prof_tag & 31)] += 1;                        \
+    pb_prof_last = now_;                                                 \
+  }
+#else
 #define PB_ENDPHASE \
   }                 \
   __syncthreads();
+#endif
 #define PB_ATOMIC_OR(p, v) atomicOr((p), (v))
+#endif
+#ifndef PB_TAG
+#define PB_TAG(n)
 #endif
 
 PB_DEV float4 pb_ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
@@ -52,32 +76,35 @@ PB_DEV float pb_actgrad(float h) {  // derivative expressed through the activati
   return ACT == PBNN_ACT_RELU ? (h > 0.f ? 1.f : 0.f) : 1.f - h * h;
 }
 
-struct PbSmem {
-  float* st[8];
-  float* A[PBNN_MAX_LAYERS + 2];
-  float* yT;
-  float* scr;    // [1024 + 64] reduction scratch
-  float* llbuf;  // [128] per-row log-likelihood terms
-  float* fbuf;   // [128] network outputs of the tile (s == 1)
-  float* acc;    // [2 * r4(s) * ap] predictive accumulators
-  int* idx;
-  float* sc;     // 32 scalar slots
-  uint32_t* scu;
-};
+// shared-memory views (no pointer arrays: dynamic indexing would push them to local memory)
+PB_DEV float* pb_state(const PbPlan& pl, float* sm, int i) { return sm + i * pl.Ps; }
+PB_DEV float* pb_A(const PbPlan& pl, float* sm, int l) { return sm + pl.aoff[l]; }
+PB_DEV float* pb_scr(const PbPlan& pl, float* sm) { return sm + pl.off_scr; }
+PB_DEV float* pb_llbuf(const PbPlan& pl, float* sm) { return sm + pl.off_scr + 1024 + 64; }
+PB_DEV float* pb_fbuf(const PbPlan& pl, float* sm) { return sm + pl.off_scr + 1024 + 64 + 128; }
+PB_DEV float* pb_acc(const PbPlan& pl, float* sm) { return sm + pl.off_acc; }
+PB_DEV int* pb_idx(const PbPlan& pl, float* sm) { return reinterpret_cast<int*>(sm + pl.off_idx); }
+PB_DEV float* pb_sc(const PbPlan& pl, float* sm) { return sm + pl.off_scal; }
+PB_DEV uint32_t* pb_scu(const PbPlan& pl, float* sm) { return reinterpret_cast<uint32_t*>(sm + pl.off_scal); }
 
-PB_DEV PbSmem pb_carve(const PbPlan& pl, float* sm) {
-  PbSmem S;
-  for (int i = 0; i < 8; ++i) S.st[i] = sm + (i < pl.nstate ? i : 0) * pl.Ps;
-  for (int l = 0; l <= pl.nl; ++l) S.A[l] = sm + pl.aoff[l];
-  S.yT = sm + pl.aoff[pl.nl + 1];
-  S.scr = sm + pl.off_scr;
-  S.llbuf = S.scr + 1024 + 64;
-  S.fbuf = S.llbuf + 128;
-  S.acc = S.fbuf + 128;
-  S.idx = reinterpret_cast<int*>(sm + pl.off_idx);
-  S.sc = sm + pl.off_scal;
-  S.scu = reinterpret_cast<uint32_t*>(sm + pl.off_scal);
-  return S;
+// input tile `tile` of the current gradient evaluation: pointer + pitch of X^T_aug and y^T
+struct PbTile {
+  const float* x;
+  const float* y;
+  int px, py;
+};
+PB_DEV PbTile pb_tile(const PbPlan& pl, float* sm, int tile) {
+  PbTile t;
+  if (pl.res_rows > 0) {
+    t.x = sm + pl.off_xres + tile * pl.BT;
+    t.y = sm + pl.off_yres + tile * pl.BT;
+    t.px = t.py = pl.xp;
+  } else {
+    t.x = sm + pl.aoff[0];
+    t.y = sm + pl.aoff[pl.nl + 1];
+    t.px = t.py = pl.ap;
+  }
+  return t;
 }
 
 // visit every real parameter: f(resident_index, flat_index).  Consecutive tid -> consecutive columns,
@@ -102,7 +129,7 @@ PB_DEV void pb_for_each_param(const PbPlan& pl, int tid, int nt, F f) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// GEMMs (per-thread bodies; warp w owns warp-tiles w, w+NW, ...)
+// GEMMs (per-thread bodies; warp w owns work units w, w+NW, ...)
 // ------------------------------------------------------------------------------------------------
 #define PB_FMA4x4(acc, w, h)                                                         \
   acc[0][0] += w.x * h.x; acc[0][1] += w.x * h.y; acc[0][2] += w.x * h.z; acc[0][3] += w.x * h.w; \
@@ -110,10 +137,13 @@ PB_DEV void pb_for_each_param(const PbPlan& pl, int tid, int nt, F f) {
   acc[2][0] += w.z * h.x; acc[2][1] += w.z * h.y; acc[2][2] += w.z * h.z; acc[2][3] += w.z * h.w; \
   acc[3][0] += w.w * h.x; acc[3][1] += w.w * h.y; acc[3][2] += w.w * h.z; acc[3][3] += w.w * h.w;
 
+#define PB_ZERO4x4(acc)           \
+  _Pragma("unroll") for (int i_ = 0; i_ < 4; ++i_) _Pragma("unroll") for (int j_ = 0; j_ < 4; ++j_) acc[i_][j_] = 0.f;
+
 // warp tile: 16 outputs (4 lane-groups x 4) x 32 batch rows (8 lane-groups x 4)
 template <int ACT, bool IDENT>
-PB_DEV void pb_gemm_fwd(const PbLayer& Ly, const float* W, const float* Ain, float* Aout, int ap, int BT, int tid,
-                        int nt) {
+PB_DEV void pb_gemm_fwd(const PbLayer& Ly, const float* W, const float* Ain, int pin, float* Aout, int pout, int BT,
+                        int tid, int nt) {
   const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
   const int lm = lane & 7, ln = lane >> 3;
   const int tiles_b = BT >> 5, tiles_o = (Ly.out + 15) >> 4;
@@ -124,16 +154,13 @@ PB_DEV void pb_gemm_fwd(const PbLayer& Ly, const float* W, const float* Ain, flo
     const float* wptr = W + pb_min(o0, wp - 4);
     const float* aptr = Ain + b0;
     float acc[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    PB_ZERO4x4(acc)
 #pragma unroll 2
     for (int k = 0; k < K; k += 4) {
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
         const float4 w = pb_ld4(wptr + (k + kk) * wp);
-        const float4 h = pb_ld4(aptr + (k + kk) * ap);
+        const float4 h = pb_ld4(aptr + (k + kk) * pin);
         PB_FMA4x4(acc, w, h)
       }
     }
@@ -148,39 +175,42 @@ PB_DEV void pb_gemm_fwd(const PbLayer& Ly, const float* W, const float* Ain, flo
           v.x = pb_act<ACT>(acc[j][0]); v.y = pb_act<ACT>(acc[j][1]);
           v.z = pb_act<ACT>(acc[j][2]); v.w = pb_act<ACT>(acc[j][3]);
         }
-        pb_st4(Aout + o * ap + b0, v);
+        pb_st4(Aout + o * pout + b0, v);
       }
     }
   }
 }
 
-#define PB_DOT4(a, d) (a.x * d.x + a.y * d.y + a.z * d.z + a.w * d.w)
-
-// warp tile: 32 input rows (8 lanes, interleaved by 8) x 16 outputs (4 lanes, interleaved by 4)
-PB_DEV void pb_gemm_dw(const PbLayer& Ly, const float* Ain, const float* dZ, float* G, int ap, int BT, bool first,
-                       int tid, int nt) {
+// Weight gradient.  Lane layout NI x NO (8x4 or 4x8): thread (li, lo) owns rows li + NI*j and columns
+// lo + NO*j (j < 4), i.e. a warp tile of 4*NI input rows x 4*NO outputs; <= 8 distinct consecutive rows per
+// LDS.128 => one wavefront each.  The batch (K) range is split into Ly.dw_ks slices; slice 0 accumulates into G,
+// slice k > 0 into the partial array k-1 (summed by pb_reduce_gparts once per gradient evaluation).
+template <int NI>
+PB_DEV void pb_gemm_dw(const PbLayer& Ly, const float* Ain, int pin, const float* dZ, int pz, float* G, float* Gpart,
+                       int Ps, int BT, bool first, int tid, int nt) {
+  constexpr int NO = 32 / NI, TI = 4 * NI, TO = 4 * NO;
   const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
-  const int li = lane & 7, lo = lane >> 3;
-  const int tiles_i = (Ly.inA + 31) >> 5, tiles_o = (Ly.out + 15) >> 4;
-  for (int wt = warp; wt < tiles_i * tiles_o; wt += nw) {
-    const int ti = wt / tiles_o, to = wt - ti * tiles_o;
+  const int li = lane % NI, lo = lane / NI;
+  const int tiles_i = (Ly.inA + TI - 1) / TI, tiles_o = (Ly.out + TO - 1) / TO;
+  const int ks = Ly.dw_ks, kchunk = BT / ks;
+  const int units = tiles_i * tiles_o * ks;
+  for (int u = warp; u < units; u += nw) {
+    const int t = u / ks, kslice = u - t * ks;
+    const int ti = t / tiles_o, to = t - ti * tiles_o;
     const float* ap_[4];
     const float* dp_[4];
     int ir[4], oc[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      ir[j] = ti * 32 + li + 8 * j;
-      oc[j] = to * 16 + lo + 4 * j;
-      ap_[j] = Ain + pb_min(ir[j], Ly.inA - 1) * ap;
-      dp_[j] = dZ + pb_min(oc[j], Ly.out - 1) * ap;
+      ir[j] = ti * TI + li + NI * j;
+      oc[j] = to * TO + lo + NO * j;
+      ap_[j] = Ain + pb_min(ir[j], Ly.inA - 1) * pin + kslice * kchunk;
+      dp_[j] = dZ + pb_min(oc[j], Ly.out - 1) * pz + kslice * kchunk;
     }
     float acc[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    PB_ZERO4x4(acc)
 #pragma unroll 2
-    for (int b = 0; b < BT; b += 4) {
+    for (int b = 0; b < kchunk; b += 4) {
       float4 a[4], d[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -197,12 +227,13 @@ PB_DEV void pb_gemm_dw(const PbLayer& Ly, const float* Ain, const float* dZ, flo
           acc[i][j] += a[i].w * d[j].w;
         }
     }
+    float* dst = (kslice == 0 ? G : Gpart + (kslice - 1) * Ps) + Ly.soff;
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j)
         if (ir[i] < Ly.inA && oc[j] < Ly.out) {
-          float* g = G + Ly.soff + ir[i] * Ly.wp + oc[j];
+          float* g = dst + ir[i] * Ly.wp + oc[j];
           *g = first ? acc[i][j] : (*g + acc[i][j]);
         }
   }
@@ -228,10 +259,7 @@ PB_DEV void pb_gemm_dh(const PbLayer& Ly, const float* W, const float* dZ, float
     }
     const float* dptr = dZ + b0;
     float acc[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    PB_ZERO4x4(acc)
 #pragma unroll 2
     for (int o = 0; o < Ko; o += 4) {
       float4 w[4], d[4];
@@ -267,91 +295,120 @@ PB_DEV void pb_gemm_dh(const PbLayer& Ly, const float* W, const float* dZ, float
 // tile-level passes
 // ------------------------------------------------------------------------------------------------
 
-// zero the activation region, set the ones-rows.  (pads of the resident arrays are zeroed by the loaders)
-PB_DEV void pb_init_acts(const PbPlan& pl, const PbSmem& S, float* sm, int nt) {
+// zero everything behind the resident state arrays, then set the ones-rows
+PB_DEV void pb_init_acts(const PbPlan& pl, float* sm, int nt) {
   PB_PHASE
-  for (int i = pl.off_act + tid; i < pl.off_idx; i += nt) sm[i] = 0.f;
+  for (int i = pl.off_gpart + tid; i < pl.off_idx; i += nt) sm[i] = 0.f;
   PB_ENDPHASE
   PB_PHASE
-  for (int l = 0; l < pl.nl; ++l) {
-    float* row = S.A[l] + pl.L[l].in * pl.ap;
+  for (int l = 1; l < pl.nl; ++l) {
+    float* row = pb_A(pl, sm, l) + pl.L[l].in * pl.ap;
+    for (int b = tid; b < pl.BT; b += nt) row[b] = 1.f;
+  }
+  if (pl.res_rows > 0) {
+    float* row = sm + pl.off_xres + pl.d * pl.xp;
+    for (int b = tid; b < pl.xp; b += nt) row[b] = 1.f;
+  } else {
+    float* row = pb_A(pl, sm, 0) + pl.d * pl.ap;
     for (int b = tid; b < pl.BT; b += nt) row[b] = 1.f;
   }
   PB_ENDPHASE
 }
 
-// gather BT rows into the feature-major input tile: A_0[k][b] = X[row(b)][k]
-PB_DEV void pb_load_tile(const PbPlan& pl, const PbSmem& S, const float* X, const float* y, const int* idxs,
-                         int row0, int nvalid, bool with_y, int nt) {
+// gather `nrows` rows, feature-major, into buffer (xdst, ydst) of pitch `pitch` with `cap` columns:
+// xdst[k][b] = X[row(b)][k]; columns >= nrows are zeroed.  row(b) = idxs ? idxs[row0+b] : row0+b
+PB_DEV void pb_gather_rows(const PbPlan& pl, float* xdst, float* ydst, int pitch, int cap, const float* X,
+                           const float* y, const int* idxs, int row0, int nrows, int nt) {
+  PB_TAG(10)
   PB_PHASE
-  const int d = pl.d, s = pl.s, ap = pl.ap;
-  for (int item = tid; item < pl.BT * d; item += nt) {
+  const int d = pl.d, s = pl.s;
+  for (int item = tid; item < cap * d; item += nt) {
     const int b = item / d, k = item - b * d;
     float v = 0.f;
-    if (b < nvalid) {
+    if (b < nrows) {
       const int row = idxs ? idxs[row0 + b] : row0 + b;
       v = X[(size_t)row * d + k];
     }
-    S.A[0][k * ap + b] = v;
+    xdst[k * pitch + b] = v;
   }
-  if (with_y)
-    for (int item = tid; item < pl.BT * s; item += nt) {
+  if (y)
+    for (int item = tid; item < cap * s; item += nt) {
       const int b = item / s, o = item - b * s;
       float v = 0.f;
-      if (b < nvalid) {
+      if (b < nrows) {
         const int row = idxs ? idxs[row0 + b] : row0 + b;
         v = y[(size_t)row * s + o];
       }
-      S.yT[o * ap + b] = v;
+      ydst[o * pitch + b] = v;
     }
   PB_ENDPHASE
 }
 
-// forward through all layers for the resident tile.  want_r: also form the scaled residual
-// r = (y - f) * scale (the cotangent of the last layer) into A_nl and the per-row log-likelihood terms.
+// make all rows of the evaluation resident (res plans) -- once for a fixed minibatch / the full data set
+PB_DEV void pb_load_resident(const PbPlan& pl, float* sm, const float* X, const float* y, const int* idxs, int nrows,
+                             int nt) {
+  pb_gather_rows(pl, sm + pl.off_xres, sm + pl.off_yres, pl.xp, pl.xp - 4, X, y, idxs, 0, nrows, nt);
+}
+
+// forward through all layers for one tile.  want_r: also form the scaled residual r = (y - f) * scale (the
+// cotangent of the last layer) into A_nl and the per-row log-likelihood terms.
 template <int ACT>
-PB_DEV void pb_forward_tile(const PbPlan& pl, const PbSmem& S, const float* TH, int nvalid, float scale, bool want_r,
-                            bool first, int nt) {
+PB_DEV void pb_forward_tile(const PbPlan& pl, float* sm, const float* TH, const PbTile& T, int nvalid, float scale,
+                            bool want_r, bool first, int nt) {
   const int ap = pl.ap, BT = pl.BT;
   for (int l = 0; l < pl.nl - 1; ++l) {
+    PB_TAG(1)
     PB_PHASE
-    pb_gemm_fwd<ACT, false>(pl.L[l], TH + pl.L[l].soff, S.A[l], S.A[l + 1], ap, BT, tid, nt);
+    pb_gemm_fwd<ACT, false>(pl.L[l], TH + pl.L[l].soff, l == 0 ? T.x : pb_A(pl, sm, l), l == 0 ? T.px : ap,
+                            pb_A(pl, sm, l + 1), ap, BT, tid, nt);
     PB_ENDPHASE
   }
-  const PbLayer& Ly = pl.L[pl.nl - 1];
-  const float* Ain = S.A[pl.nl - 1];
-  float* Aout = S.A[pl.nl];
+  const int ll_ = pl.nl - 1;
+  const PbLayer& Ly = pl.L[ll_];
+  const float* Ain = ll_ == 0 ? T.x : pb_A(pl, sm, ll_);
+  const int pin = ll_ == 0 ? T.px : ap;
+  float* Aout = pb_A(pl, sm, pl.nl);
+  float* scr = pb_scr(pl, sm);
+  float* llbuf = pb_llbuf(pl, sm);
   if (pl.s == 1) {
     // f[b] = sum_k W[k] * A[k][b]; the k-range is split over NT/BT thread groups
     const int KS = (nt / BT) > 0 ? (nt / BT) : 1;
     const int chunk = (Ly.inA + KS - 1) / KS;
+    PB_TAG(2)
     PB_PHASE
     const float* W = TH + Ly.soff;
     for (int item = tid; item < BT * KS; item += nt) {
       const int ks = item / BT, b = item - ks * BT;
       const int k1 = pb_min(Ly.inA, (ks + 1) * chunk);
-      float a = 0.f;
-      for (int k = ks * chunk; k < k1; ++k) a += W[k * Ly.wp] * Ain[k * ap + b];
-      S.scr[ks * BT + b] = a;
+      float a0 = 0.f, a1 = 0.f;
+      int k = ks * chunk;
+      for (; k + 1 < k1; k += 2) {
+        a0 += W[k * Ly.wp] * Ain[k * pin + b];
+        a1 += W[(k + 1) * Ly.wp] * Ain[(k + 1) * pin + b];
+      }
+      if (k < k1) a0 += W[k * Ly.wp] * Ain[k * pin + b];
+      scr[ks * BT + b] = a0 + a1;
     }
     PB_ENDPHASE
+    PB_TAG(3)
     PB_PHASE
+    float* fbuf = pb_fbuf(pl, sm);
     for (int b = tid; b < BT; b += nt) {
       float f = 0.f;
-      for (int ks = 0; ks < KS; ++ks) f += S.scr[ks * BT + b];
-      S.fbuf[b] = f;
+      for (int ks = 0; ks < KS; ++ks) f += scr[ks * BT + b];
+      fbuf[b] = f;
       if (want_r) {
         const bool valid = b < nvalid;
-        const float res = S.yT[b] - f;
+        const float res = T.y[b] - f;
         Aout[b] = valid ? res * scale : 0.f;
         const float ll = valid ? -0.5f * res * res * pl.inv_s2 : 0.f;
-        S.llbuf[b] = first ? ll : S.llbuf[b] + ll;
+        llbuf[b] = first ? ll : llbuf[b] + ll;
       }
     }
     PB_ENDPHASE
   } else {
     PB_PHASE
-    pb_gemm_fwd<ACT, true>(Ly, TH + Ly.soff, Ain, Aout, ap, BT, tid, nt);
+    pb_gemm_fwd<ACT, true>(Ly, TH + Ly.soff, Ain, pin, Aout, ap, BT, tid, nt);
     PB_ENDPHASE
     if (want_r) {
       PB_PHASE
@@ -359,11 +416,11 @@ PB_DEV void pb_forward_tile(const PbPlan& pl, const PbSmem& S, const float* TH, 
         const bool valid = b < nvalid;
         float ll = 0.f;
         for (int o = 0; o < pl.s; ++o) {
-          const float res = S.yT[o * ap + b] - Aout[o * ap + b];
+          const float res = T.y[o * T.py + b] - Aout[o * ap + b];
           Aout[o * ap + b] = valid ? res * scale : 0.f;
           ll += valid ? -0.5f * res * res * pl.inv_s2 : 0.f;
         }
-        S.llbuf[b] = first ? ll : S.llbuf[b] + ll;
+        llbuf[b] = first ? ll : llbuf[b] + ll;
       }
       PB_ENDPHASE
     }
@@ -372,23 +429,35 @@ PB_DEV void pb_forward_tile(const PbPlan& pl, const PbSmem& S, const float* TH, 
 
 // backward through all layers; G accumulates sum_b r[b] * df_b/dtheta (first: overwrite).
 template <int ACT>
-PB_DEV void pb_backward_tile(const PbPlan& pl, const PbSmem& S, const float* TH, float* G, bool first, int nt) {
+PB_DEV void pb_backward_tile(const PbPlan& pl, float* sm, const float* TH, float* G, const PbTile& T, bool first,
+                             int nt) {
   const int ap = pl.ap, BT = pl.BT;
+  float* Gpart = sm + pl.off_gpart;
   for (int l = pl.nl - 1; l >= 0; --l) {
     const PbLayer& Ly = pl.L[l];
-    float* Ain = S.A[l];
-    const float* dZ = S.A[l + 1];
+    const float* Ain = l == 0 ? T.x : pb_A(pl, sm, l);
+    const int pin = l == 0 ? T.px : ap;
+    const float* dZ = pb_A(pl, sm, l + 1);
     if (l == pl.nl - 1 && pl.s == 1) {
-      // rank-1 last layer: one thread per input row k: G[k] += <r, A[k][:]>, then A[k][:] becomes dZ_{l-1}
+      // rank-1 last layer: G[k] += <r, A[k][:]> and (l > 0) A[k][:] <- r * W[k] * act'(A[k][:]) = dZ_{l-1}.
+      // work item = (row k, column segment); consecutive lanes take consecutive rows (conflict-free LDS.128)
+      int SEG = 1;
+      while (SEG * 2 * Ly.inA <= nt && SEG * 2 * 4 <= BT && SEG < 8) SEG *= 2;
+      const int seglen = BT / SEG;
+      float* scr = pb_scr(pl, sm);
+      PB_TAG(4)
       PB_PHASE
-      for (int k = tid; k < Ly.inA; k += nt) {
-        float* row = Ain + k * ap;
+      for (int item = tid; item < Ly.inA * SEG; item += nt) {
+        const int seg = item / Ly.inA, k = item - seg * Ly.inA;
+        const float* rowc = Ain + k * pin + seg * seglen;
+        float* roww = pb_A(pl, sm, l) + k * ap + seg * seglen;  // only dereferenced when l > 0
+        const float* rp = dZ + seg * seglen;
         const float wk = TH[Ly.soff + k * Ly.wp];
         const bool prop = (l > 0) && (k < Ly.in);
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-        for (int b = 0; b < BT; b += 4) {
-          const float4 r = pb_ld4(dZ + b);
-          const float4 h = pb_ld4(row + b);
+        for (int b = 0; b < seglen; b += 4) {
+          const float4 r = pb_ld4(rp + b);
+          const float4 h = pb_ld4(rowc + b);
           a0 += r.x * h.x; a1 += r.y * h.y; a2 += r.z * h.z; a3 += r.w * h.w;
           if (prop) {
             float4 v;
@@ -396,57 +465,84 @@ PB_DEV void pb_backward_tile(const PbPlan& pl, const PbSmem& S, const float* TH,
             v.y = r.y * wk * pb_actgrad<ACT>(h.y);
             v.z = r.z * wk * pb_actgrad<ACT>(h.z);
             v.w = r.w * wk * pb_actgrad<ACT>(h.w);
-            pb_st4(row + b, v);
+            pb_st4(roww + b, v);
           }
         }
-        const float a = (a0 + a1) + (a2 + a3);
+        scr[seg * Ly.inA + k] = (a0 + a1) + (a2 + a3);
+      }
+      PB_ENDPHASE
+      PB_TAG(5)
+      PB_PHASE
+      for (int k = tid; k < Ly.inA; k += nt) {
+        float a = 0.f;
+        for (int seg = 0; seg < SEG; ++seg) a += scr[seg * Ly.inA + k];
         float* g = G + Ly.soff + k * Ly.wp;
         *g = first ? a : (*g + a);
       }
       PB_ENDPHASE
     } else {
+      PB_TAG(6)
       PB_PHASE
-      pb_gemm_dw(Ly, Ain, dZ, G, ap, BT, first, tid, nt);
+      if (Ly.dw_ni == 8) pb_gemm_dw<8>(Ly, Ain, pin, dZ, ap, G, Gpart, pl.Ps, BT, first, tid, nt);
+      else pb_gemm_dw<4>(Ly, Ain, pin, dZ, ap, G, Gpart, pl.Ps, BT, first, tid, nt);
       PB_ENDPHASE
       if (l > 0) {
+        PB_TAG(7)
         PB_PHASE
-        pb_gemm_dh<ACT>(Ly, TH + Ly.soff, dZ, Ain, ap, BT, tid, nt);
+        pb_gemm_dh<ACT>(Ly, TH + Ly.soff, dZ, pb_A(pl, sm, l), ap, BT, tid, nt);
         PB_ENDPHASE
       }
     }
   }
 }
 
-// likelihood part of the gradient over `nrows` rows (minibatch via idxs, or contiguous rows from row0).
-// If `resident` the single tile already sits in A_0 / yT (fixed minibatch, nrows <= BT).
+// likelihood part of the gradient over `nrows` rows.  Resident plans: the rows must already be resident
+// (pb_load_resident).  Streaming plans: tiles are gathered from global memory (idxs, or contiguous rows); a single
+// already-loaded tile can be re-used with tile_loaded = true.
 template <int ACT>
-PB_DEV void pb_grad_rows(const PbPlan& pl, const PbSmem& S, const float* TH, float* G, const float* X, const float* y,
-                         const int* idxs, int row0, int nrows, float scale, bool resident, int nt) {
+PB_DEV void pb_grad_rows(const PbPlan& pl, float* sm, const float* TH, float* G, const float* X, const float* y,
+                         const int* idxs, int nrows, float scale, bool tile_loaded, int nt) {
   const int ntiles = (nrows + pl.BT - 1) / pl.BT;
   for (int tile = 0; tile < ntiles; ++tile) {
     const int nvalid = pb_min(pl.BT, nrows - tile * pl.BT);
-    if (!resident) pb_load_tile(pl, S, X, y, idxs, row0 + tile * pl.BT, nvalid, true, nt);
-    pb_forward_tile<ACT>(pl, S, TH, nvalid, scale, true, tile == 0, nt);
-    pb_backward_tile<ACT>(pl, S, TH, G, tile == 0, nt);
+    if (pl.res_rows == 0 && !tile_loaded)
+      pb_gather_rows(pl, pb_A(pl, sm, 0), pb_A(pl, sm, pl.nl + 1), pl.ap, pl.BT, X, y, idxs, tile * pl.BT, nvalid, nt);
+    const PbTile T = pb_tile(pl, sm, tile);
+    pb_forward_tile<ACT>(pl, sm, TH, T, nvalid, scale, true, tile == 0, nt);
+    pb_backward_tile<ACT>(pl, sm, TH, G, T, tile == 0, nt);
   }
+  PB_TAG(9)
+  if (pl.ksmax > 1) {
+    PB_TAG(8)
+    PB_PHASE
+    const float* Gpart = sm + pl.off_gpart;
+    for (int i = tid; i < pl.Ps; i += nt) {
+      float a = G[i];
+      for (int k = 0; k < pl.ksmax - 1; ++k) a += Gpart[k * pl.Ps + i];
+      G[i] = a;
+    }
+    PB_ENDPHASE
+  }
+  PB_TAG(0)
 }
 
 // deterministic block sums of K (<=4) quantities whose per-thread partials sit in scr[k*256 + tid]
-PB_DEV void pb_block_sums(const PbSmem& S, int K, float* dst, int nt) {
+PB_DEV void pb_block_sums(const PbPlan& pl, float* sm, int K, float* dst, int nt) {
   const int nw = nt >> 5;
+  float* scr = pb_scr(pl, sm);
   PB_PHASE
   if (tid < K * nw) {
     const int k = tid / nw, w = tid - k * nw;
-    const float* p = S.scr + k * 256 + w * 32;
+    const float* p = scr + k * 256 + w * 32;
     float a = 0.f;
     for (int i = 0; i < 32; ++i) a += p[i];
-    S.scr[1024 + k * 8 + w] = a;
+    scr[1024 + k * 8 + w] = a;
   }
   PB_ENDPHASE
   PB_PHASE
   if (tid < K) {
     float a = 0.f;
-    for (int w = 0; w < nw; ++w) a += S.scr[1024 + tid * 8 + w];
+    for (int w = 0; w < nw; ++w) a += scr[1024 + tid * 8 + w];
     dst[tid] = a;
   }
   PB_ENDPHASE
@@ -479,32 +575,36 @@ PB_DEV void pb_store_state(const PbPlan& pl, const float* src, float* dst_flat, 
 // ------------------------------------------------------------------------------------------------
 // minibatch index generation (src/pbnn/utils/data.py:69-78): key <- split(key)[1]; randint(key,(B,),0,N)
 // ------------------------------------------------------------------------------------------------
-PB_DEV void pb_gen_advance(const PbSmem& S, int times, int nt) {
+PB_DEV void pb_gen_advance(const PbPlan& pl, float* sm, int times, int nt) {
   PB_PHASE
   if (tid == 0) {
+    uint32_t* scu = pb_scu(pl, sm);
     PbKey k;
-    k.k0 = S.scu[0];
-    k.k1 = S.scu[1];
+    k.k0 = scu[0];
+    k.k1 = scu[1];
     for (int i = 0; i < times; ++i) k = pb_split_at(k, 1u);
-    S.scu[0] = k.k0;
-    S.scu[1] = k.k1;
+    scu[0] = k.k0;
+    scu[1] = k.k1;
   }
   PB_ENDPHASE
 }
 
-PB_DEV void pb_gen_indices(const PbSmem& S, int B, int N, uint32_t mult, int nt) {
+PB_DEV void pb_gen_indices(const PbPlan& pl, float* sm, int B, int N, uint32_t mult, int nt) {
   PB_PHASE
+  const uint32_t* scu = pb_scu(pl, sm);
+  int* idx = pb_idx(pl, sm);
   PbKey k;
-  k.k0 = S.scu[0];
-  k.k1 = S.scu[1];
+  k.k0 = scu[0];
+  k.k1 = scu[1];
   const PbKey k1 = pb_split_at(k, 0u), k2 = pb_split_at(k, 1u);
-  for (int b = tid; b < B; b += nt) S.idx[b] = pb_randint_at(k1, k2, (uint32_t)b, (uint32_t)N, mult);
+  for (int b = tid; b < B; b += nt) idx[b] = pb_randint_at(k1, k2, (uint32_t)b, (uint32_t)N, mult);
   PB_ENDPHASE
 }
 
-PB_DEV void pb_copy_indices(const PbSmem& S, const int32_t* src, int B, int nt) {
+PB_DEV void pb_copy_indices(const PbPlan& pl, float* sm, const int32_t* src, int B, int nt) {
   PB_PHASE
-  for (int b = tid; b < B; b += nt) S.idx[b] = src ? src[b] : b;  // nullptr: rows 0..B-1
+  int* idx = pb_idx(pl, sm);
+  for (int b = tid; b < B; b += nt) idx[b] = src ? src[b] : b;  // nullptr: rows 0..B-1
   PB_ENDPHASE
 }
 
@@ -519,18 +619,20 @@ PB_DEV void pb_copy_indices(const PbSmem& S, const int32_t* src, int B, int nt) 
 // ------------------------------------------------------------------------------------------------
 template <int ALGO, int ACT>
 PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, int nt) {
-  const PbSmem S = pb_carve(pl, sm);
-  float* TH = S.st[0];
-  float* G = S.st[1];
-  float* A1 = S.st[2];
-  float* A2 = S.st[3];
+  float* TH = pb_state(pl, sm, 0);
+  float* G = pb_state(pl, sm, 1);
+  float* A1 = pb_state(pl, sm, pl.nstate > 2 ? 2 : 0);
+  float* A2 = pb_state(pl, sm, pl.nstate > 3 ? 3 : 0);
+  float* sc = pb_sc(pl, sm);
+  uint32_t* scu = pb_scu(pl, sm);
+  const int* sidx = pb_idx(pl, sm);
   const int P = pl.P, B = a.B;
   const size_t cP = (size_t)c * P;
   PbKey ck;
   ck.k0 = a.keys ? a.keys[2 * c] : 0u;
   ck.k1 = a.keys ? a.keys[2 * c + 1] : 0u;
 
-  pb_init_acts(pl, S, sm, nt);
+  pb_init_acts(pl, sm, nt);
   pb_load_state(pl, TH, a.theta + cP, nt);
   pb_load_state(pl, G, nullptr, nt);
   if (ALGO == PB_ALGO_PSGLD) {
@@ -544,12 +646,13 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
   }
   PB_PHASE
   if (tid == 0) {
-    S.scu[0] = ck.k0;
-    S.scu[1] = ck.k1;
-    S.scu[2] = 0u;
+    scu[0] = ck.k0;
+    scu[1] = ck.k1;
+    scu[2] = 0u;
   }
   PB_ENDPHASE
 
+  const bool res = pl.res_rows > 0;
   const bool single_tile = B <= pl.BT;
   const bool explicit_idx = a.idx != nullptr || a.contig;
   const bool per_step =
@@ -558,16 +661,20 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
   int gen_pos = 0;  // how many draws of the generator have been consumed (uniform across threads)
 
   if (ALGO == PB_ALGO_GRAD) {
-    pb_copy_indices(S, cidx, B, nt);
-    pb_grad_rows<ACT>(pl, S, TH, G, a.X, a.y, S.idx, 0, B, a.scale, false, nt);
+    pb_copy_indices(pl, sm, cidx, B, nt);
+    if (res) pb_load_resident(pl, sm, a.X, a.y, sidx, B, nt);
+    pb_grad_rows<ACT>(pl, sm, TH, G, a.X, a.y, sidx, B, a.scale, false, nt);
     PB_PHASE
     pb_for_each_param(pl, tid, nt, [&](int si, int fi) { a.aux1[cP + fi] = G[si] - TH[si] * pl.inv_pv; });
-    S.scr[tid] = 0.f;
-    for (int b = tid; b < pl.BT; b += nt) S.scr[tid] += S.llbuf[b];
+    float* scr = pb_scr(pl, sm);
+    const float* llbuf = pb_llbuf(pl, sm);
+    float v = 0.f;
+    for (int b = tid; b < pl.BT; b += nt) v += llbuf[b];
+    scr[tid] = v;
     PB_ENDPHASE
-    pb_block_sums(S, 1, S.sc + 8, nt);
+    pb_block_sums(pl, sm, 1, sc + 8, nt);
     PB_PHASE
-    if (tid == 0 && a.aux2) a.aux2[c] = S.sc[8];
+    if (tid == 0 && a.aux2) a.aux2[c] = sc[8];
     PB_ENDPHASE
     return;
   }
@@ -575,13 +682,14 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
   // pSGLD init (psgld.py:25-29): g0 = grad(theta0, draw #init_draw), V0 = g0^2
   if (ALGO == PB_ALGO_PSGLD && !a.has_state) {
     if (explicit_idx) {
-      pb_copy_indices(S, cidx, B, nt);
+      pb_copy_indices(pl, sm, cidx, B, nt);
     } else {
-      pb_gen_advance(S, a.init_draw - gen_pos, nt);
+      pb_gen_advance(pl, sm, a.init_draw - gen_pos, nt);
       gen_pos = a.init_draw;
-      pb_gen_indices(S, B, a.N, a.randint_mult, nt);
+      pb_gen_indices(pl, sm, B, a.N, a.randint_mult, nt);
     }
-    pb_grad_rows<ACT>(pl, S, TH, G, a.X, a.y, S.idx, 0, B, a.scale, false, nt);
+    if (res) pb_load_resident(pl, sm, a.X, a.y, sidx, B, nt);
+    pb_grad_rows<ACT>(pl, sm, TH, G, a.X, a.y, sidx, B, a.scale, false, nt);
     PB_PHASE
     for (int i = tid; i < pl.Ps; i += nt) {
       const float g = G[i] - TH[i] * pl.inv_pv;
@@ -592,19 +700,25 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
   }
 
   // the minibatch the traced loop re-uses (quirk Q1), or the state before the first per-step draw
+  bool tile_loaded = false;
   if (!per_step) {
     if (explicit_idx) {
-      pb_copy_indices(S, cidx, B, nt);
+      pb_copy_indices(pl, sm, cidx, B, nt);
     } else {
-      pb_gen_advance(S, a.which_draw - gen_pos, nt);
+      pb_gen_advance(pl, sm, a.which_draw - gen_pos, nt);
       gen_pos = a.which_draw;
-      pb_gen_indices(S, B, a.N, a.randint_mult, nt);
+      pb_gen_indices(pl, sm, B, a.N, a.randint_mult, nt);
     }
-    if (single_tile) pb_load_tile(pl, S, a.X, a.y, S.idx, 0, B, true, nt);
+    if (res) {
+      pb_load_resident(pl, sm, a.X, a.y, sidx, B, nt);
+    } else if (single_tile) {
+      pb_gather_rows(pl, pb_A(pl, sm, 0), pb_A(pl, sm, pl.nl + 1), pl.ap, pl.BT, a.X, a.y, sidx, 0, B, nt);
+      tile_loaded = true;
+    }
   } else if (!explicit_idx) {
     // per-step mode: draw #1 is consumed by kern.init (langevin.py:60), step t uses draw t0 + t + 2
     const long long skip = 1 + a.t0 - gen_pos;
-    pb_gen_advance(S, (int)skip, nt);
+    pb_gen_advance(pl, sm, (int)skip, nt);
   }
 
   for (int t = 0; t < a.T; ++t) {
@@ -613,16 +727,16 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
     const float eps = a.step_sizes ? a.step_sizes[t < a.n_step_sizes ? t : a.n_step_sizes - 1] : a.const_step;
     if (per_step) {
       if (explicit_idx) {
-        pb_copy_indices(S, cidx ? cidx + (size_t)t * B : nullptr, B, nt);
+        pb_copy_indices(pl, sm, cidx ? cidx + (size_t)t * B : nullptr, B, nt);
       } else {
-        pb_gen_advance(S, 1, nt);
-        pb_gen_indices(S, B, a.N, a.randint_mult, nt);
+        pb_gen_advance(pl, sm, 1, nt);
+        pb_gen_indices(pl, sm, B, a.N, a.randint_mult, nt);
       }
+      if (res) pb_load_resident(pl, sm, a.X, a.y, sidx, B, nt);
     }
-    const bool resident = single_tile && !per_step;
 
     if (ALGO == PB_ALGO_SGLD) {
-      pb_grad_rows<ACT>(pl, S, TH, G, a.X, a.y, S.idx, 0, B, a.scale, resident, nt);
+      pb_grad_rows<ACT>(pl, sm, TH, G, a.X, a.y, sidx, B, a.scale, tile_loaded, nt);
       const float ns = sqrtf(2.0f * eps);
       PB_PHASE
       pb_for_each_param(pl, tid, nt, [&](int si, int fi) {
@@ -638,7 +752,7 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
         TH[si] = TH[si] + eps * pre * G[si] + sqrtf(2.0f * pre * eps) * pb_normal_at(kt, (uint32_t)fi);
       });
       PB_ENDPHASE
-      pb_grad_rows<ACT>(pl, S, TH, G, a.X, a.y, S.idx, 0, B, a.scale, resident, nt);
+      pb_grad_rows<ACT>(pl, sm, TH, G, a.X, a.y, sidx, B, a.scale, tile_loaded, nt);
       PB_PHASE
       for (int i = tid; i < pl.Ps; i += nt) {
         const float g = G[i] - TH[i] * pl.inv_pv;
@@ -654,7 +768,7 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
       const float fric = 1.0f - a.alpha;
       for (int l = 0; l < a.L; ++l) {
         const PbKey kl = pb_split_at(kt, (uint32_t)l);  // split(keys[t], L)[l]
-        pb_grad_rows<ACT>(pl, S, TH, G, a.X, a.y, S.idx, 0, B, a.scale, resident, nt);
+        pb_grad_rows<ACT>(pl, sm, TH, G, a.X, a.y, sidx, B, a.scale, tile_loaded, nt);
         PB_PHASE
         pb_for_each_param(pl, tid, nt, [&](int si, int fi) {
           const float th = TH[si], p = A1[si];
@@ -665,7 +779,7 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
         PB_ENDPHASE
       }
     } else if (ALGO == PB_ALGO_ADAM) {
-      pb_grad_rows<ACT>(pl, S, TH, G, a.X, a.y, S.idx, 0, B, a.scale, false, nt);
+      pb_grad_rows<ACT>(pl, sm, TH, G, a.X, a.y, sidx, B, a.scale, false, nt);
       const float cnt = (float)(a.count0 + t + 1);
       const float bc1 = 1.0f - powf(a.b1, cnt), bc2 = 1.0f - powf(a.b2, cnt);
       PB_PHASE
@@ -689,13 +803,13 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
     }
   }
 
-  if (!a.no_theta_store) pb_store_state(pl, TH, a.theta + cP, S.scu + 2, nt);
+  if (!a.no_theta_store) pb_store_state(pl, TH, a.theta + cP, scu + 2, nt);
   if (ALGO == PB_ALGO_PSGLD || ALGO == PB_ALGO_ADAM) {
     pb_store_state(pl, ALGO == PB_ALGO_PSGLD ? G : A1, a.aux1 + cP, nullptr, nt);
     pb_store_state(pl, ALGO == PB_ALGO_PSGLD ? A1 : A2, a.aux2 + cP, nullptr, nt);
   }
   PB_PHASE
-  if (tid == 0 && a.flags) a.flags[c] = S.scu[2];
+  if (tid == 0 && a.flags) a.flags[c] = scu[2];
   PB_ENDPHASE
 }
 
@@ -706,32 +820,34 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
 // scalar slots: sc[8]=loglik sum, sc[9]=sum theta'^2, sc[10]=KE, sc[12]=logp(current), sc[13]=KE0,
 //               scu[14]=accept flag, scu[15]=accept count
 // ------------------------------------------------------------------------------------------------
-template <int ACT>
-PB_DEV void pb_hmc_logp_reduce(const PbPlan& pl, const PbSmem& S, const float* TH, const float* PM, const float* MI,
+PB_DEV void pb_hmc_logp_reduce(const PbPlan& pl, float* sm, const float* TH, const float* PM, const float* MI,
                                int nt) {
   PB_PHASE
+  float* scr = pb_scr(pl, sm);
+  const float* llbuf = pb_llbuf(pl, sm);
   float ll = 0.f, t2 = 0.f, ke = 0.f;
-  for (int b = tid; b < pl.BT; b += nt) ll += S.llbuf[b];
+  for (int b = tid; b < pl.BT; b += nt) ll += llbuf[b];
   for (int i = tid; i < pl.Ps; i += nt) {
     t2 += TH[i] * TH[i];
     ke += (MI[i] * PM[i]) * PM[i];
   }
-  S.scr[tid] = ll;
-  S.scr[256 + tid] = t2;
-  S.scr[512 + tid] = ke;
+  scr[tid] = ll;
+  scr[256 + tid] = t2;
+  scr[512 + tid] = ke;
   PB_ENDPHASE
-  pb_block_sums(S, 3, S.sc + 8, nt);
+  pb_block_sums(pl, sm, 3, pb_sc(pl, sm) + 8, nt);
 }
 
 template <int ACT>
 PB_DEV void pb_hmc_chain(const PbPlan& pl, const PbHmcArgs& a, float* sm, int c, int nt) {
-  const PbSmem S = pb_carve(pl, sm);
-  float* TH = S.st[0];
-  float* G = S.st[1];
-  float* PM = S.st[2];
-  float* TH0 = S.st[3];
-  float* G0 = S.st[4];
-  float* MI = S.st[5];
+  float* TH = pb_state(pl, sm, 0);
+  float* G = pb_state(pl, sm, 1);
+  float* PM = pb_state(pl, sm, 2);
+  float* TH0 = pb_state(pl, sm, 3);
+  float* G0 = pb_state(pl, sm, 4);
+  float* MI = pb_state(pl, sm, 5);
+  float* sc = pb_sc(pl, sm);
+  uint32_t* scu = pb_scu(pl, sm);
   const int P = pl.P;
   const size_t cP = (size_t)c * P;
   PbKey ck;
@@ -739,20 +855,21 @@ PB_DEV void pb_hmc_chain(const PbPlan& pl, const PbHmcArgs& a, float* sm, int c,
   ck.k1 = a.keys[2 * c + 1];
   const float eps = a.step_size, heps = a.step_size * 0.5f;
 
-  pb_init_acts(pl, S, sm, nt);
+  pb_init_acts(pl, sm, nt);
   pb_load_state(pl, TH, a.theta + cP, nt);
   pb_load_state(pl, G, nullptr, nt);
   pb_load_state(pl, PM, nullptr, nt);
   pb_load_state(pl, MI, a.inv_mass, nt);
+  if (pl.res_rows > 0) pb_load_resident(pl, sm, a.X, a.y, nullptr, a.N, nt);
   PB_PHASE
   if (tid == 0) {
-    S.scu[2] = 0u;
-    S.scu[15] = 0u;
+    scu[2] = 0u;
+    scu[15] = 0u;
   }
   PB_ENDPHASE
 
   // init: (logp, grad) at theta0
-  pb_grad_rows<ACT>(pl, S, TH, G, a.X, a.y, nullptr, 0, a.N, pl.inv_s2, false, nt);
+  pb_grad_rows<ACT>(pl, sm, TH, G, a.X, a.y, nullptr, a.N, pl.inv_s2, false, nt);
   PB_PHASE
   for (int i = tid; i < pl.Ps; i += nt) {
     const float g = G[i] - TH[i] * pl.inv_pv;
@@ -761,15 +878,16 @@ PB_DEV void pb_hmc_chain(const PbPlan& pl, const PbHmcArgs& a, float* sm, int c,
     TH0[i] = TH[i];
   }
   PB_ENDPHASE
-  pb_hmc_logp_reduce<ACT>(pl, S, TH, PM, MI, nt);
+  pb_hmc_logp_reduce(pl, sm, TH, PM, MI, nt);
   PB_PHASE
-  if (tid == 0) S.sc[12] = (-0.5f * pl.inv_pv * S.sc[9] - (float)P * pl.logprior_const) + S.sc[8];
+  if (tid == 0) sc[12] = (-0.5f * pl.inv_pv * sc[9] - (float)P * pl.logprior_const) + sc[8];
   PB_ENDPHASE
 
   for (int s = 0; s < a.S; ++s) {
     const PbKey ks = pb_split_at(ck, (uint32_t)(a.t0 + s));
     const PbKey km = pb_split_at(ks, 0u), ka = pb_split_at(ks, 1u);
     // momentum ~ sqrt(1/Minv) * N(0, I); proposal starts at the current state
+    PB_TAG(11)
     PB_PHASE
     float ke = 0.f;
     pb_for_each_param(pl, tid, nt, [&](int si, int fi) {
@@ -780,11 +898,12 @@ PB_DEV void pb_hmc_chain(const PbPlan& pl, const PbHmcArgs& a, float* sm, int c,
       TH[si] = TH0[si];
       G[si] = G0[si];
     });
-    S.scr[tid] = ke;
+    pb_scr(pl, sm)[tid] = ke;
     PB_ENDPHASE
-    pb_block_sums(S, 1, S.sc + 13, nt);
+    pb_block_sums(pl, sm, 1, sc + 13, nt);
 
     for (int l = 0; l < a.L; ++l) {
+      PB_TAG(12)
       PB_PHASE
       for (int i = tid; i < pl.Ps; i += nt) {
         const float p = PM[i] + heps * G[i];
@@ -792,7 +911,8 @@ PB_DEV void pb_hmc_chain(const PbPlan& pl, const PbHmcArgs& a, float* sm, int c,
         TH[i] = TH[i] + eps * (MI[i] * p);
       }
       PB_ENDPHASE
-      pb_grad_rows<ACT>(pl, S, TH, G, a.X, a.y, nullptr, 0, a.N, pl.inv_s2, false, nt);
+      pb_grad_rows<ACT>(pl, sm, TH, G, a.X, a.y, nullptr, a.N, pl.inv_s2, false, nt);
+      PB_TAG(13)
       PB_PHASE
       for (int i = tid; i < pl.Ps; i += nt) {
         const float g = G[i] - TH[i] * pl.inv_pv;
@@ -801,21 +921,23 @@ PB_DEV void pb_hmc_chain(const PbPlan& pl, const PbHmcArgs& a, float* sm, int c,
       }
       PB_ENDPHASE
     }
-    pb_hmc_logp_reduce<ACT>(pl, S, TH, PM, MI, nt);
+    PB_TAG(14)
+    pb_hmc_logp_reduce(pl, sm, TH, PM, MI, nt);
+    PB_TAG(15)
     PB_PHASE
     if (tid == 0) {
-      const float lp1 = (-0.5f * pl.inv_pv * S.sc[9] - (float)P * pl.logprior_const) + S.sc[8];
-      const float e0 = -S.sc[12] + 0.5f * S.sc[13];
-      const float e1 = -lp1 + 0.5f * S.sc[10];
+      const float lp1 = (-0.5f * pl.inv_pv * sc[9] - (float)P * pl.logprior_const) + sc[8];
+      const float e0 = -sc[12] + 0.5f * sc[13];
+      const float e1 = -lp1 + 0.5f * sc[10];
       float delta = e0 - e1;
       if (delta != delta) delta = -INFINITY;
       const float pacc = fminf(1.0f, expf(delta));
       const float u = fmaxf(0.0f, pb_bits_to_uniform(pb_bits_at(ka, 0u)));
       const bool acc = u < pacc;
-      S.scu[14] = acc ? 1u : 0u;
+      scu[14] = acc ? 1u : 0u;
       if (acc) {
-        S.sc[12] = lp1;
-        S.scu[15] += 1u;
+        sc[12] = lp1;
+        scu[15] += 1u;
       }
       if (a.info_delta) a.info_delta[(size_t)c * a.S + s] = delta;
       if (a.info_accept) a.info_accept[(size_t)c * a.S + s] = acc ? 1 : 0;
@@ -823,8 +945,9 @@ PB_DEV void pb_hmc_chain(const PbPlan& pl, const PbHmcArgs& a, float* sm, int c,
     PB_ENDPHASE
     const bool emit = a.trace && s >= a.burnin && ((s - a.burnin) % a.thin) == 0;
     float* dst = emit ? a.trace + ((size_t)c * a.S_out + (size_t)((s - a.burnin) / a.thin)) * P : nullptr;
+    PB_TAG(16)
     PB_PHASE
-    const bool acc = S.scu[14] != 0u;
+    const bool acc = scu[14] != 0u;
     if (acc)
       for (int i = tid; i < pl.Ps; i += nt) {
         TH0[i] = TH[i];
@@ -834,12 +957,12 @@ PB_DEV void pb_hmc_chain(const PbPlan& pl, const PbHmcArgs& a, float* sm, int c,
     PB_ENDPHASE
   }
 
-  pb_store_state(pl, TH0, a.theta + cP, S.scu + 2, nt);
+  pb_store_state(pl, TH0, a.theta + cP, scu + 2, nt);
   PB_PHASE
   if (tid == 0) {
-    if (a.logp) a.logp[c] = S.sc[12];
-    if (a.accept_count) a.accept_count[c] = (int32_t)S.scu[15];
-    if (a.flags) a.flags[c] = S.scu[2];
+    if (a.logp) a.logp[c] = sc[12];
+    if (a.accept_count) a.accept_count[c] = (int32_t)scu[15];
+    if (a.flags) a.flags[c] = scu[2];
   }
   PB_ENDPHASE
 }
@@ -850,27 +973,27 @@ PB_DEV void pb_hmc_chain(const PbPlan& pl, const PbHmcArgs& a, float* sm, int c,
 // ------------------------------------------------------------------------------------------------
 template <int ACT>
 PB_DEV void pb_predict_block(const PbPlan& pl, const PbPredArgs& a, float* sm, int mt, int ch, int nt) {
-  const PbSmem S = pb_carve(pl, sm);
-  float* TH = S.st[0];
+  float* TH = pb_state(pl, sm, 0);
+  float* acc = pb_acc(pl, sm);
   const int ap = pl.ap, BT = pl.BT, s = pl.s, P = pl.P;
   const int row0 = mt * BT;
   const int nvalid = pb_min(BT, a.M - row0);
   const int accn = pb_r4dev(s) * ap;
-  pb_init_acts(pl, S, sm, nt);
-  PB_PHASE
-  for (int i = tid; i < 2 * accn; i += nt) S.acc[i] = 0.f;
-  PB_ENDPHASE
-  pb_load_tile(pl, S, a.Xtest, nullptr, nullptr, row0, nvalid, false, nt);
+  pb_init_acts(pl, sm, nt);
+  pb_gather_rows(pl, pb_A(pl, sm, 0), nullptr, pl.ap, pl.BT, a.Xtest, nullptr, nullptr, row0, nvalid, nt);
+  const PbTile T = pb_tile(pl, sm, 0);
   const int s0 = ch * a.chunk, s1 = pb_min(a.S, s0 + a.chunk);
   for (int smp = s0; smp < s1; ++smp) {
     pb_load_state(pl, TH, a.samples + (size_t)smp * P, nt);
-    pb_forward_tile<ACT>(pl, S, TH, nvalid, 0.f, false, true, nt);
+    pb_forward_tile<ACT>(pl, sm, TH, T, nvalid, 0.f, false, true, nt);
     PB_PHASE
+    const float* fbuf = pb_fbuf(pl, sm);
+    const float* Aout = pb_A(pl, sm, pl.nl);
     for (int item = tid; item < s * BT; item += nt) {
       const int o = item / BT, b = item - o * BT;
-      const float f = (s == 1) ? S.fbuf[b] : S.A[pl.nl][o * ap + b];
-      S.acc[o * ap + b] += f;
-      S.acc[accn + o * ap + b] += f * f;
+      const float f = (s == 1) ? fbuf[b] : Aout[o * ap + b];
+      acc[o * ap + b] += f;
+      acc[accn + o * ap + b] += f * f;
       if (a.preds && b < nvalid) a.preds[((size_t)smp * a.M + row0 + b) * s + o] = f;
     }
     PB_ENDPHASE
@@ -881,8 +1004,8 @@ PB_DEV void pb_predict_block(const PbPlan& pl, const PbPredArgs& a, float* sm, i
       const int b = item / s, o = item - b * s;
       if (b < nvalid) {
         const size_t base = ((size_t)ch * 2) * a.M * s + (size_t)(row0 + b) * s + o;
-        a.part[base] = S.acc[o * ap + b];
-        a.part[base + (size_t)a.M * s] = S.acc[accn + o * ap + b];
+        a.part[base] = acc[o * ap + b];
+        a.part[base + (size_t)a.M * s] = acc[accn + o * ap + b];
       }
     }
     PB_ENDPHASE

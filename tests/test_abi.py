@@ -1,0 +1,72 @@
+"""The C-ABI library builds for sm_100a, loads, and exports every symbol include/pbnn_b200.h declares (no compute
+calls: there is no GPU here).  Also checks that the product has no CPU fallback."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def cuda_lib_path():
+    import __graft_entry__ as g
+    return g.build_cuda()
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "pbnn_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(pbnn_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_are_exported_and_bound(cuda_lib_path):
+    from pbnn_b200 import _lib
+    names = declared_symbols()
+    assert len(names) >= 20
+    lib = ctypes.CDLL(cuda_lib_path)
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/pbnn_b200.h but not exported"
+    assert sorted(_lib.PROTOTYPES) == names, "ctypes prototypes out of sync with the header"
+    bound = _lib.load_library(cuda_lib_path)
+    assert bound.pbnn_version() == 100
+
+
+def test_host_side_calls_without_gpu(cuda_lib_path):
+    """Argument validation and planning are host code: they must work (and fail loudly) without a device."""
+    from pbnn_b200 import _lib
+    lib = _lib.load_library(cuda_lib_path)
+    spec = _lib.make_spec((13, 50, 1), 0, 0.1)
+    assert lib.pbnn_num_params(spec) == 751
+    out = (ctypes.c_int32 * 4)()
+    assert lib.pbnn_plan_query(spec, 506, 6, out) == 0
+    assert out[0] % 32 == 0 and out[1] % 32 == 0 and out[2] <= 227 * 1024
+    big = _lib.make_spec((90, 256, 256, 1), 0, 0.1)
+    assert lib.pbnn_plan_query(big, 128, 2, out) == -2
+    assert b"does not fit" in lib.pbnn_last_error()
+    assert lib.pbnn_sgld_run(spec, None, None, 10, None, 0, 0, 4, None, None, None, 1, 0, 1, 1, 1, 0, None, None, None) == -1
+    bad = _lib.make_spec((13, 50, 1), 7, 0.1)
+    assert lib.pbnn_num_params(bad) == 751 and lib.pbnn_plan_query(bad, 8, 2, out) == -1
+
+
+def test_sass_is_sm100a(cuda_lib_path):
+    out = subprocess.run(["cuobjdump", "-lelf", cuda_lib_path], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_no_cpu_fallback_in_product():
+    """The package must not import the oracle, and must refuse to run without CUDA."""
+    import torch
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "pbnn_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.replace("for the oracle", "").replace("the oracle", ""), (dirpath, f)
+    from pbnn_b200.ops import Ops
+    if not torch.cuda.is_available():
+        import numpy as np
+        from pbnn_b200.ops import FlatSpec
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            Ops().normal(np.array([0, 1], np.uint32), 4)

@@ -1,0 +1,155 @@
+"""The pbnn-compatible Python surface (same names / argument order as src/pbnn/mcmc/*.py and deep_ensembles.py).
+Runs against the emulator on the CPU box and against the CUDA library under -m gpu."""
+import numpy as np
+import pytest
+
+import pbnn_b200
+from oracle import pbnn_oracle as o
+from pbnn_b200 import logprobs, pytree
+from pbnn_b200.mcmc import hmc, kernels, pSGLD, predictive_moments, scheduled_sgld, sghmc, sgld
+from pbnn_b200.models import MLP
+from pbnn_b200.ops import set_default_ops
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def npy(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.fixture
+def api(ops):
+    set_default_ops(ops)
+    yield ops
+    set_default_ops(None)
+
+
+def setup(C=None, layers=(8, 50, 1), act="relu", N=200):
+    X, y = o.synthetic_regression(N, layers[0], 3)
+    net = MLP.from_widths(layers, act)
+    sp = o.MlpSpec(layers, o.RELU if act == "relu" else o.TANH, 0.1)
+    key = o.PRNGKey(7) if C is None else o.split(o.PRNGKey(7), C)
+    th0 = o.init_positions(sp, key)
+    tree = {k: {kk: vv if C is not None else vv[0] for kk, vv in v.items()} for k, v in o.to_pytree(sp, th0).items()}
+    lik = logprobs.GaussianMLPLikelihood(net, 0.1)
+    return X, y, net, sp, key, th0, tree, lik, logprobs.StdNormalPrior()
+
+
+def test_sgld_single_chain_signature(api):
+    X, y, net, sp, key, th0, tree, lik, prior = setup()
+    positions, ravel_fn, predict_fn = sgld(X, y, lik, prior, tree, 32, 1e-5, 8, key)
+    assert set(positions) == {"Dense_0", "Dense_1"}
+    assert tuple(positions["Dense_0"]["kernel"].shape) == (8, 8, 50)      # leading T, Flax layout (in, out)
+    assert tuple(positions["Dense_1"]["bias"].shape) == (8, 1)
+    flat = ravel_fn(positions)
+    assert tuple(flat.shape) == (8, sp.num_params)
+    ref = o.sgld(sp, X, y, th0, 32, 1e-5, 8, key)
+    assert rel(npy(flat), ref[0]) <= 1e-5
+    preds = predict_fn(net, positions, X[:20])
+    assert tuple(preds.shape) == (8, 20, 1)
+    assert rel(npy(preds), o.predict(sp, ref[0], X[:20])) <= 1e-5
+    mean, var = predictive_moments(net, positions, X[:20])
+    assert rel(npy(mean), o.predict(sp, ref[0], X[:20]).mean(0)) <= 1e-5
+
+
+def test_samplers_batched_chains(api):
+    C = 3
+    X, y, net, sp, keys, th0, tree, lik, prior = setup(C, layers=(9, 20, 20, 1), act="tanh")
+    pos, ravel_fn, _ = pSGLD(X, y, lik, prior, tree, 40, 1e-6, 5, 0.95, keys)
+    assert tuple(pos["Dense_1"]["kernel"].shape) == (C, 5, 20, 20)
+    assert rel(npy(ravel_fn(pos)), o.psgld(sp, X, y, th0, 40, 1e-6, 5, 0.95, keys)) <= 1e-5
+    pos, ravel_fn, _ = sghmc(X, y, lik, prior, tree, 40, 1e-9, 3, 2, keys)
+    assert rel(npy(ravel_fn(pos)), o.sghmc(sp, X, y, th0, 40, 1e-9, 3, 2, keys)) <= 1e-5
+    sched = lambda t: 1e-5 / (1 + t)
+    pos, ravel_fn, _ = scheduled_sgld(X, y, lik, prior, tree, 40, sched, 4, keys)
+    th, ref = th0.copy(), []
+    for t in range(4):
+        th = o.sgld(sp, X, y, th, 40, np.float32(sched(t + 1)), 1, keys, t0=t)[:, 0]
+        ref.append(th)
+    assert rel(npy(ravel_fn(pos)), np.stack(ref, 1)) <= 1e-5
+    logprob = logprobs.FullBatchLogPosterior(lik, prior, X, y)
+    minv = np.ones(sp.num_params, np.float32)
+    pos, ravel_fn, predict_fn, info = hmc(logprob, tree, 3, 1e-4, minv, 4, keys, return_info=True)
+    ref, rinfo = o.hmc(sp, X, y, th0, 3, 1e-4, minv, 4, keys, return_info=True)
+    assert np.array_equal(npy(info["is_accepted"]).astype(bool), rinfo["accept"])
+    assert rel(npy(ravel_fn(pos)), ref) <= 1e-5
+
+
+def test_density_objects_are_callable_and_checked(api):
+    X, y, net, sp, key, th0, tree, lik, prior = setup()
+    lp = float(prior(tree))
+    assert abs(lp - float(o.logprior(sp, th0)[0])) < 1e-3
+    ll = float(lik(tree, (X[:16], y[:16])))
+    ll_ref, _ = o.loglik_and_grad(sp, th0, X[:16], y[:16], 1.0)
+    assert abs(ll - float(ll_ref[0])) <= 1e-4 * abs(float(ll_ref[0]))
+    full = logprobs.FullBatchLogPosterior(lik, prior, X, y)
+    ref = o.logposterior_full(sp, th0, X, y)[0][0]
+    assert abs(float(full(tree)) - ref) <= 1e-4 * abs(ref)
+    with pytest.raises(TypeError):
+        sgld(X, y, lambda p, d: 0.0, prior, tree, 32, 1e-5, 2, key)
+    with pytest.raises(TypeError):
+        sgld(X, y, lik, lambda p: 0.0, tree, 32, 1e-5, 2, key)
+    with pytest.raises(TypeError):
+        hmc(lambda p: 0.0, tree, 2, 1e-3, np.ones(sp.num_params), 2, key)
+
+
+def test_blackjax_style_psgld_kernel(api):
+    """kernels.psgld(grad_estimator_fn, alpha) -> SamplingAlgorithm(init, step) (kernels.py:80-94)."""
+    X, y, net, sp, key, th0, tree, lik, prior = setup(layers=(8, 12, 1))
+    N, B = len(X), 16
+    grad_fn = kernels.grad_estimator(prior, lik, N)
+    kern = kernels.psgld(grad_fn, 0.9)
+    batch = (X[:B], y[:B])
+    state = kern.init(tree, batch)
+    g_ref = o.grad_estimator(sp, th0, X[:B], y[:B], N)
+    assert state.step == 0
+    assert rel(npy(pytree.ravel(state.logprob_grad)), g_ref[0]) <= 1e-5
+    assert rel(npy(pytree.ravel(state.square_avg)), g_ref[0] ** 2) <= 2e-5
+    step_key = o.split(key, 3)[2]
+    new = kern.step(step_key, state, (X[B:2 * B], y[B:2 * B]), 1e-6)
+    G = 1.0 / (np.sqrt(g_ref ** 2) + 1e-6)
+    th1 = th0 + np.float32(1e-6) * G * g_ref + np.sqrt(2 * G * np.float32(1e-6)) * o.normal(step_key, sp.num_params)
+    assert new.step == 1
+    assert rel(npy(pytree.ravel(new.position)), th1[0]) <= 1e-5
+    g1 = o.grad_estimator(sp, th1.astype(np.float32), X[B:2 * B], y[B:2 * B], N)
+    assert rel(npy(pytree.ravel(new.logprob_grad)), g1[0]) <= 1e-4
+    assert rel(npy(pytree.ravel(new.square_avg)), 0.9 * g_ref[0] ** 2 + 0.1 * g1[0] ** 2) <= 1e-4
+
+
+def test_deep_ensembles(api):
+    layers = (8, 10, 10, 1)
+    X, y = o.synthetic_regression(96, 8, 3)
+    net = MLP(10, 1)  # reference MLP: two equal hidden layers (models.py:19-35)
+    assert net.widths(8) == layers
+    sp = o.MlpSpec(layers, o.RELU, 0.1)
+    lik, prior = logprobs.GaussianMLPLikelihood(net, 0.1), logprobs.StdNormalPrior()
+    K, B, E = 3, 16, 1
+    key = o.PRNGKey(11)
+    init = o.init_positions(sp, o.split(o.PRNGKey(5), K))
+    params, ravel_fn, predict_fn = pbnn_b200.deep_ensembles_fn(X, y, lik, prior, net, B, E, 1e-3, K, key,
+                                                              init_params=o.to_pytree(sp, init))
+    assert tuple(params["Dense_1"]["kernel"].shape) == (K, 10, 10)
+    mk = [k for k, _ in o.ensemble_member_keys(key, K)]
+    ref = o.deep_ensembles(sp, X, y, init, B, E, 1e-3, mk)
+    assert rel(npy(ravel_fn(params)), ref) <= 2e-5
+    assert tuple(predict_fn(net, params, X[:5]).shape) == (K, 5, 1)
+    # default initialisation path (Flax-style N(0, 0.01^2) init on device): runs and is finite
+    params2, _, _ = pbnn_b200.deep_ensembles_fn(X, y, lik, prior, net, B, 0, 1e-3, 2, key)
+    flat2 = npy(pytree.ravel(params2))
+    assert np.isfinite(flat2).all() and flat2.shape == (2, sp.num_params)
+
+
+def test_flax_style_init_and_apply(api):
+    net = MLP(6, 1)
+    x = np.zeros((4,), np.float32)
+    p = net.init(o.PRNGKey(1), x)["params"]
+    flat = npy(pytree.ravel(p))
+    assert flat.shape == (4 * 6 + 6 + 6 * 6 + 6 + 6 + 1,)
+    assert 0.003 < flat.std() < 0.03  # normal(stddev=0.01) for kernels and biases (models.py:19-22)
+    X = o.synthetic_regression(9, 4, 0)[0]
+    out = net.apply({"params": p}, X)
+    sp = o.MlpSpec((4, 6, 6, 1), o.RELU, 0.1)
+    assert rel(npy(out), o.predict(sp, flat[None], X)[0]) <= 1e-5
