@@ -33,7 +33,7 @@ import numpy as np  # noqa: E402
 # algorithmic FLOPs per gradient evaluation: 6*B*W - 2*B*d*h1, W = sum in*out
 WORKLOADS = {
     # BASELINE.json configs[1]
-    "hmc_cfg2": dict(algo="hmc", layers=(13, 50, 1), act=0, N=506, B=506, C=256, T=200, L=20, step=1e-3, M=1024),
+    "hmc_cfg2": dict(algo="hmc", layers=(13, 50, 1), act=0, N=506, B=506, C=256, T=200, L=20, step=5e-4, M=1024),
     # BASELINE.json configs[0] shape, many chains
     "sgld_cfg1": dict(algo="sgld", layers=(8, 50, 1), act=0, N=1030, B=32, C=1, T=100_000, L=1, step=1e-5, M=1024),
     "sgld_cfg1x": dict(algo="sgld", layers=(8, 50, 1), act=0, N=1030, B=32, C=2048, T=2000, L=1, step=1e-5, M=1024),

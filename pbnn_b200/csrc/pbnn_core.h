@@ -42,6 +42,8 @@ struct PbPlan {
   int xp, off_xres, off_yres;     //      X^T_aug [r4(d+1)][xp], y^T [r4(s)][xp], xp = roundup(rows, BT) + 4
   int nstate;                     // resident parameter-sized arrays
   int ksmax, off_gpart;           // (ksmax - 1) partial gradient arrays for split-K
+  int h1, h1_dp;                  // fused one-hidden-layer path: X row-major [rows][4*h1_dp], per-warp partial grads
+  int off_xr, off_yr, off_hpart;
   int off_act, off_scr, off_acc, off_idx, off_scal;
   int idx_cap;
   int smem_floats;
@@ -101,15 +103,40 @@ static inline void pb_plan_dw(PbPlan* pl, int nw, int bt, int kcap) {
 
 // shared-memory layout for one candidate configuration
 static inline void pb_layout(PbPlan* pl, const pbnn_mlp_spec* sp, int rows, int nstate, int bt, int res, int kcap,
-                             int want_acc) {
+                             int want_acc, int h1) {
   const int ap = bt + 4;
   pl->BT = bt;
   pl->ap = ap;
+  pl->h1 = h1;
   pb_plan_dw(pl, pl->NT / 32, bt, kcap);
+  if (h1) pl->ksmax = 1;
   int off = nstate * pl->Ps;
   pl->off_gpart = off;
   off += (pl->ksmax - 1) * pl->Ps;
   pl->off_act = off;
+  if (h1) {
+    // fused path: no activation buffers; X row-major with the ones column, y, one partial gradient per warp
+    for (int l = 0; l <= pl->nl + 1; ++l) pl->aoff[l] = off;
+    pl->res_rows = rows;
+    pl->h1_dp = pb_r4(pl->d + 1) / 4;
+    pl->xp = 0;
+    pl->off_xres = pl->off_yres = off;
+    pl->off_xr = off;
+    off += rows * 4 * pl->h1_dp;
+    pl->off_yr = off;
+    off += pb_r4(rows);
+    pl->off_hpart = off;
+    off += (pl->NT / 32) * pl->Ps;
+    pl->off_scr = off;
+    off += PB_SCR_FLOATS;
+    pl->off_acc = off;
+    pl->off_idx = off;
+    off += pl->idx_cap;
+    pl->off_scal = off;
+    off += 32;
+    pl->smem_floats = off;
+    return;
+  }
   for (int l = 0; l <= pl->nl + 1; ++l) {
     int r;
     if (l < pl->nl) r = pb_r4(sp->dims[l] + 1);
@@ -198,6 +225,12 @@ static inline int pb_build_plan(const pbnn_mlp_spec* sp, int rows, int nstate, i
   const int want_res = (flags & PB_PLAN_RES) && !pb_env_int("PBNN_NO_RESIDENT", 0);
   int maxbt = pb_r32(rows);
   if (maxbt > 128) maxbt = 128;
+  // fused one-hidden-layer path (scalar output, H <= 64, d+1 <= 16, all rows resident); CUDA only (warp shuffles)
+  int h1_ok = want_res && pl->nl == 2 && pl->s == 1 && sp->dims[1] <= 64 && pl->d + 1 <= 16 &&
+              !(flags & PB_PLAN_ACC) && !pb_env_int("PBNN_NO_H1", 0);
+#if defined(PB_EMU)
+  h1_ok = 0;
+#endif
   const int forced = pb_env_int("PBNN_BT", 0);
   if (forced > 0) maxbt = pb_r32(forced) > 128 ? 128 : pb_r32(forced);
   // Two passes: first try to stay under half an SM's shared memory so that two CTAs are co-resident (more warps to
@@ -208,9 +241,13 @@ static inline int pb_build_plan(const pbnn_mlp_spec* sp, int rows, int nstate, i
     const size_t limit = pass == 0 ? lim2 : lim1;
     for (int bt = maxbt; bt >= 32; bt -= 32) {
       if (pass == 0 && bt < (maxbt < 64 ? maxbt : 64)) break;
+      if (h1_ok && bt == maxbt) {
+        pb_layout(pl, sp, rows, nstate, bt, 1, 1, 0, 1);
+        if ((size_t)pl->smem_floats * 4 <= limit) return PBNN_OK;
+      }
       for (int res = want_res ? 1 : 0; res >= 0; --res)
         for (int kcap = 8; kcap >= 1; kcap /= 2) {
-          pb_layout(pl, sp, rows, nstate, bt, res, kcap, (flags & PB_PLAN_ACC) != 0);
+          pb_layout(pl, sp, rows, nstate, bt, res, kcap, (flags & PB_PLAN_ACC) != 0, 0);
           if ((size_t)pl->smem_floats * 4 <= limit) return PBNN_OK;
         }
       if (forced > 0) break;

@@ -56,6 +56,7 @@ __device__ int pb_prof_tag;
   __syncthreads();
 #endif
 #define PB_ATOMIC_OR(p, v) atomicOr((p), (v))
+#define PB_ENDPHASE_RAW { PB_ENDPHASE
 #endif
 #ifndef PB_TAG
 #define PB_TAG(n)
@@ -300,6 +301,7 @@ PB_DEV void pb_init_acts(const PbPlan& pl, float* sm, int nt) {
   PB_PHASE
   for (int i = pl.off_gpart + tid; i < pl.off_idx; i += nt) sm[i] = 0.f;
   PB_ENDPHASE
+  if (pl.h1) return;  // fused path: no activation buffers, the loader writes the ones column
   PB_PHASE
   for (int l = 1; l < pl.nl; ++l) {
     float* row = pb_A(pl, sm, l) + pl.L[l].in * pl.ap;
@@ -347,6 +349,23 @@ PB_DEV void pb_gather_rows(const PbPlan& pl, float* xdst, float* ydst, int pitch
 // make all rows of the evaluation resident (res plans) -- once for a fixed minibatch / the full data set
 PB_DEV void pb_load_resident(const PbPlan& pl, float* sm, const float* X, const float* y, const int* idxs, int nrows,
                              int nt) {
+  if (pl.h1) {
+    // fused path: row-major X_aug[b][4*dp] = (x_b, 1, 0...), y[b]
+    PB_TAG(10)
+    PB_PHASE
+    const int xpitch = 4 * pl.h1_dp, d = pl.d;
+    float* Xr = sm + pl.off_xr;
+    float* yr = sm + pl.off_yr;
+    for (int item = tid; item < nrows * xpitch; item += nt) {
+      const int b = item / xpitch, k = item - b * xpitch;
+      float v = k == d ? 1.f : 0.f;
+      if (k < d) v = X[(size_t)(idxs ? idxs[b] : b) * d + k];
+      Xr[item] = v;
+    }
+    for (int b = tid; b < nrows; b += nt) yr[b] = y[(size_t)(idxs ? idxs[b] : b)];
+    PB_ENDPHASE
+    return;
+  }
   pb_gather_rows(pl, sm + pl.off_xres, sm + pl.off_yres, pl.xp, pl.xp - 4, X, y, idxs, 0, nrows, nt);
 }
 
@@ -526,6 +545,150 @@ PB_DEV void pb_grad_rows(const PbPlan& pl, float* sm, const float* TH, float* G,
   PB_TAG(0)
 }
 
+#if !defined(PB_EMU)
+#ifndef PB_H1_NP
+#define PB_H1_NP 2  // rows in flight per warp in the fused path (register budget: 128 regs at 2 CTAs/SM)
+#endif
+PB_DEV float pb_warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;  // xor butterfly: every lane ends with the bit-identical sum
+}
+
+// Fused gradient for one-hidden-layer nets with a scalar output (BASELINE configs 0 and 1: 8-50-1, 13-50-1).
+// Warp-autonomous: each warp owns a contiguous slice of the rows; lane j keeps the input weights of hidden units
+// 2j, 2j+1 and their gradient accumulators in registers.  Rows are processed NP at a time so that the NP warp
+// all-reduces (the long dependent chains) overlap: per row broadcast LDS.128 of x, 2 dot products, one all-reduce
+// for f, then x is re-read (broadcast, one wavefront) for the rank-1 gradient accumulation.  No activation ever
+// touches shared memory and there is no CTA barrier until the per-warp partial gradients are summed in a fixed
+// order (deterministic).  DP = float4 chunks per augmented input row (compile time: no branches in the row loop).
+template <int ACT, int DP>
+PB_DEV void pb_grad_h1_t(const PbPlan& pl, float* sm, const float* TH, float* G, int nrows, float scale, int nt) {
+  PB_TAG(1)
+  constexpr int NP = PB_H1_NP, KD = 4 * DP;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+  const PbLayer& L0 = pl.L[0];
+  const PbLayer& L1 = pl.L[1];
+  const int H = L0.out, wp = L0.wp;
+  const float* Xr = sm + pl.off_xr;
+  const float* yr = sm + pl.off_yr;
+  float* hpart = sm + pl.off_hpart;
+  float* part = hpart + warp * pl.Ps;
+  float* llbuf = pb_llbuf(pl, sm);
+  const int j0 = 2 * lane;
+  const bool ok0 = j0 < H, ok1 = j0 + 1 < H;
+  float W0[KD], W1[KD], a0[KD], a1[KD];
+#pragma unroll
+  for (int k = 0; k < KD; ++k) {
+    const float* wr = TH + L0.soff + k * wp;
+    W0[k] = ok0 ? wr[j0] : 0.f;
+    W1[k] = ok1 ? wr[j0 + 1] : 0.f;
+    a0[k] = 0.f;
+    a1[k] = 0.f;
+  }
+  const float v0 = ok0 ? TH[L1.soff + j0 * L1.wp] : 0.f;
+  const float v1 = ok1 ? TH[L1.soff + (j0 + 1) * L1.wp] : 0.f;
+  const float b2 = TH[L1.soff + H * L1.wp];
+  float av0 = 0.f, av1 = 0.f, ab = 0.f, ll = 0.f;
+  const int per = (nrows + nw - 1) / nw;
+  const int n0 = warp * per, n1 = pb_min(nrows, n0 + per);
+  for (int n = n0; n < n1; n += NP) {
+    float h0[NP], h1[NP], pf[NP];
+    int row[NP];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      row[p] = pb_min(n + p, n1 - 1);
+      const float* xp_ = Xr + row[p] * KD;
+      float za = 0.f, zb = 0.f, zc = 0.f, zd = 0.f;
+#pragma unroll
+      for (int c = 0; c < DP; ++c) {
+        const float4 t = pb_ld4(xp_ + 4 * c);
+        za += t.x * W0[4 * c];     zc += t.x * W1[4 * c];
+        zb += t.y * W0[4 * c + 1]; zd += t.y * W1[4 * c + 1];
+        za += t.z * W0[4 * c + 2]; zc += t.z * W1[4 * c + 2];
+        zb += t.w * W0[4 * c + 3]; zd += t.w * W1[4 * c + 3];
+      }
+      h0[p] = pb_act<ACT>(za + zb);
+      h1[p] = pb_act<ACT>(zc + zd);
+      pf[p] = h0[p] * v0 + h1[p] * v1;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int p = 0; p < NP; ++p) pf[p] += __shfl_xor_sync(0xffffffffu, pf[p], o);
+    }
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      const bool valid = n + p < n1;
+      const float res = yr[row[p]] - (pf[p] + b2);
+      const float r = valid ? res * scale : 0.f;
+      ll += valid ? -0.5f * res * res * pl.inv_s2 : 0.f;
+      const float dz0 = r * v0 * pb_actgrad<ACT>(h0[p]), dz1 = r * v1 * pb_actgrad<ACT>(h1[p]);
+      const float* xp_ = Xr + row[p] * KD;
+#pragma unroll
+      for (int c = 0; c < DP; ++c) {
+        const float4 t = pb_ld4(xp_ + 4 * c);
+        a0[4 * c] += t.x * dz0;     a1[4 * c] += t.x * dz1;
+        a0[4 * c + 1] += t.y * dz0; a1[4 * c + 1] += t.y * dz1;
+        a0[4 * c + 2] += t.z * dz0; a1[4 * c + 2] += t.z * dz1;
+        a0[4 * c + 3] += t.w * dz0; a1[4 * c + 3] += t.w * dz1;
+      }
+      av0 += r * h0[p];
+      av1 += r * h1[p];
+      ab += r;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < KD; ++k)
+    if (k < L0.inA) {
+      if (ok0) part[L0.soff + k * wp + j0] = a0[k];
+      if (ok1) part[L0.soff + k * wp + j0 + 1] = a1[k];
+    }
+  if (ok0) part[L1.soff + j0 * L1.wp] = av0;
+  if (ok1) part[L1.soff + (j0 + 1) * L1.wp] = av1;
+  if (lane == 0) {
+    part[L1.soff + H * L1.wp] = ab;
+    llbuf[warp] = ll;
+  }
+  if (tid >= nw && tid < 128) llbuf[tid] = 0.f;
+  PB_ENDPHASE_RAW
+  PB_TAG(8)
+  for (int i = 4 * tid; i < pl.Ps; i += 4 * nt) {  // Ps is a multiple of 4; fixed summation order over the warps
+    float4 a = pb_ld4(hpart + i);
+    for (int w = 1; w < nw; ++w) {
+      const float4 b = pb_ld4(hpart + w * pl.Ps + i);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    pb_st4(G + i, a);
+  }
+  PB_ENDPHASE_RAW
+  PB_TAG(0)
+}
+
+template <int ACT>
+PB_DEV void pb_grad_h1(const PbPlan& pl, float* sm, const float* TH, float* G, int nrows, float scale, int nt) {
+  switch (pl.h1_dp) {
+    case 1: pb_grad_h1_t<ACT, 1>(pl, sm, TH, G, nrows, scale, nt); break;
+    case 2: pb_grad_h1_t<ACT, 2>(pl, sm, TH, G, nrows, scale, nt); break;
+    case 3: pb_grad_h1_t<ACT, 3>(pl, sm, TH, G, nrows, scale, nt); break;
+    default: pb_grad_h1_t<ACT, 4>(pl, sm, TH, G, nrows, scale, nt); break;
+  }
+}
+#endif
+
+// likelihood gradient over the rows of one evaluation: fused one-hidden-layer path or the tiled GEMM engine
+template <int ACT>
+PB_DEV void pb_grad(const PbPlan& pl, float* sm, const float* TH, float* G, const float* X, const float* y,
+                    const int* idxs, int nrows, float scale, bool tile_loaded, int nt) {
+#if !defined(PB_EMU)
+  if (pl.h1) {
+    pb_grad_h1<ACT>(pl, sm, TH, G, nrows, scale, nt);
+    return;
+  }
+#endif
+  pb_grad_rows<ACT>(pl, sm, TH, G, X, y, idxs, nrows, scale, tile_loaded, nt);
+}
+
 // deterministic block sums of K (<=4) quantities whose per-thread partials sit in scr[k*256 + tid]
 PB_DEV void pb_block_sums(const PbPlan& pl, float* sm, int K, float* dst, int nt) {
   const int nw = nt >> 5;
@@ -663,7 +826,7 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
   if (ALGO == PB_ALGO_GRAD) {
     pb_copy_indices(pl, sm, cidx, B, nt);
     if (res) pb_load_resident(pl, sm, a.X, a.y, sidx, B, nt);
-    pb_grad_rows<ACT>(pl, sm, TH, G, a.X, a.y, sidx, B, a.scale, false, nt);
+    pb_grad<ACT>(pl, sm, TH, G, a.X, a.y, sidx, B, a.scale, false, nt);
     PB_PHASE
     pb_for_each_param(pl, tid, nt, [&](int si, int fi) { a.aux1[cP + fi] = G[si] - TH[si] * pl.inv_pv; });
     float* scr = pb_scr(pl, sm);
@@ -689,7 +852,7 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
       pb_gen_indices(pl, sm, B, a.N, a.randint_mult, nt);
     }
     if (res) pb_load_resident(pl, sm, a.X, a.y, sidx, B, nt);
-    pb_grad_rows<ACT>(pl, sm, TH, G, a.X, a.y, sidx, B, a.scale, false, nt);
+    pb_grad<ACT>(pl, sm, TH, G, a.X, a.y, sidx, B, a.scale, false, nt);
     PB_PHASE
     for (int i = tid; i < pl.Ps; i += nt) {
       const float g = G[i] - TH[i] * pl.inv_pv;
@@ -736,7 +899,7 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
     }
 
     if (ALGO == PB_ALGO_SGLD) {
-      pb_grad_rows<ACT>(pl, sm, TH, G, a.X, a.y, sidx, B, a.scale, tile_loaded, nt);
+      pb_grad<ACT>(pl, sm, TH, G, a.X, a.y, sidx, B, a.scale, tile_loaded, nt);
       const float ns = sqrtf(2.0f * eps);
       PB_PHASE
       pb_for_each_param(pl, tid, nt, [&](int si, int fi) {
@@ -752,7 +915,7 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
         TH[si] = TH[si] + eps * pre * G[si] + sqrtf(2.0f * pre * eps) * pb_normal_at(kt, (uint32_t)fi);
       });
       PB_ENDPHASE
-      pb_grad_rows<ACT>(pl, sm, TH, G, a.X, a.y, sidx, B, a.scale, tile_loaded, nt);
+      pb_grad<ACT>(pl, sm, TH, G, a.X, a.y, sidx, B, a.scale, tile_loaded, nt);
       PB_PHASE
       for (int i = tid; i < pl.Ps; i += nt) {
         const float g = G[i] - TH[i] * pl.inv_pv;
@@ -768,7 +931,7 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
       const float fric = 1.0f - a.alpha;
       for (int l = 0; l < a.L; ++l) {
         const PbKey kl = pb_split_at(kt, (uint32_t)l);  // split(keys[t], L)[l]
-        pb_grad_rows<ACT>(pl, sm, TH, G, a.X, a.y, sidx, B, a.scale, tile_loaded, nt);
+        pb_grad<ACT>(pl, sm, TH, G, a.X, a.y, sidx, B, a.scale, tile_loaded, nt);
         PB_PHASE
         pb_for_each_param(pl, tid, nt, [&](int si, int fi) {
           const float th = TH[si], p = A1[si];
@@ -779,7 +942,7 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
         PB_ENDPHASE
       }
     } else if (ALGO == PB_ALGO_ADAM) {
-      pb_grad_rows<ACT>(pl, sm, TH, G, a.X, a.y, sidx, B, a.scale, false, nt);
+      pb_grad<ACT>(pl, sm, TH, G, a.X, a.y, sidx, B, a.scale, false, nt);
       const float cnt = (float)(a.count0 + t + 1);
       const float bc1 = 1.0f - powf(a.b1, cnt), bc2 = 1.0f - powf(a.b2, cnt);
       PB_PHASE
@@ -869,7 +1032,7 @@ PB_DEV void pb_hmc_chain(const PbPlan& pl, const PbHmcArgs& a, float* sm, int c,
   PB_ENDPHASE
 
   // init: (logp, grad) at theta0
-  pb_grad_rows<ACT>(pl, sm, TH, G, a.X, a.y, nullptr, a.N, pl.inv_s2, false, nt);
+  pb_grad<ACT>(pl, sm, TH, G, a.X, a.y, nullptr, a.N, pl.inv_s2, false, nt);
   PB_PHASE
   for (int i = tid; i < pl.Ps; i += nt) {
     const float g = G[i] - TH[i] * pl.inv_pv;
@@ -911,7 +1074,7 @@ PB_DEV void pb_hmc_chain(const PbPlan& pl, const PbHmcArgs& a, float* sm, int c,
         TH[i] = TH[i] + eps * (MI[i] * p);
       }
       PB_ENDPHASE
-      pb_grad_rows<ACT>(pl, sm, TH, G, a.X, a.y, nullptr, a.N, pl.inv_s2, false, nt);
+      pb_grad<ACT>(pl, sm, TH, G, a.X, a.y, nullptr, a.N, pl.inv_s2, false, nt);
       PB_TAG(13)
       PB_PHASE
       for (int i = tid; i < pl.Ps; i += nt) {

@@ -29,7 +29,13 @@ def cuda_ops():
     return default_ops()
 
 
-@pytest.fixture(params=["emu", pytest.param("cuda", marks=pytest.mark.gpu)])
-def ops(request):
-    """Parity tests run twice: against the emulator here (CPU), against the CUDA library on the GPU box."""
+@pytest.fixture(params=["emu", pytest.param("cuda", marks=pytest.mark.gpu),
+                        pytest.param("cuda_generic", marks=pytest.mark.gpu)])
+def ops(request, monkeypatch):
+    """Parity tests run against the emulator here (CPU) and against the CUDA library on the GPU box -- there twice:
+    with the default kernel selection (fused one-hidden-layer path where it applies) and with the generic tiled-GEMM
+    engine forced (PBNN_NO_H1=1; the plan is rebuilt on every call, so the environment switch is enough)."""
+    if request.param == "cuda_generic":
+        monkeypatch.setenv("PBNN_NO_H1", "1")
+        return request.getfixturevalue("cuda_ops")
     return request.getfixturevalue(request.param + "_ops")
