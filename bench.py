@@ -44,6 +44,9 @@ WORKLOADS = {
                       M=1024),
     "sghmc_cfg3": dict(algo="sghmc", layers=(9, 100, 100, 1), act=0, N=45730, B=128, C=1024, T=20, L=10, step=1e-9,
                        M=1024),
+    # BASELINE.json configs[4], per-GPU share (1024 of the 8192 chains); state lives in the global workspace
+    "sgld_cfg5": dict(algo="sgld", layers=(90, 256, 256, 1), act=0, N=515345, B=128, C=1024, T=20, L=1, step=1e-9,
+                      M=4096),
     # BASELINE.json configs[3]
     "adam_cfg4": dict(algo="adam", layers=(8, 50, 50, 1), act=0, N=9568, B=32, C=512, T=299 * 2, L=1, step=1e-2,
                       M=1024),
@@ -308,17 +311,9 @@ def main():
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     mom = ops.predict(fs, final, Xt, want_preds=False, want_moments=True)
-    local = torch.stack([mom["sum"], mom["sumsq"]])
-    if world > 1:
-        gathered = [torch.empty_like(local) for _ in range(world)]
-        dist.all_gather(gathered, local)
-        tot = torch.stack(gathered).sum(0)
-    else:
-        tot = local
+    from pbnn_b200 import dist as pdist
+    pm, pv, S_tot = pdist.pooled_moments(mom["sum"], mom["sumsq"], w["C"])  # all_gather over NCCL when world > 1
     torch.cuda.synchronize()
-    S_tot = w["C"] * world
-    pm = tot[0] / S_tot
-    pv = (tot[1] / S_tot - pm * pm).clamp_min(0)
     exchange_ms = 1e3 * (time.perf_counter() - t0)
 
     if rank == 0:

@@ -60,6 +60,17 @@ int pbnn_num_params(const pbnn_mlp_spec* spec);
  * (or N for full-batch HMC / M for predict), `n_state` the number of resident parameter-sized arrays. */
 int pbnn_plan_query(const pbnn_mlp_spec* spec, int rows, int n_state, int32_t out[4]);
 
+/* Workspace.  Models whose parameter-sized state does not fit shared memory (e.g. 90-256-256-1, P = 89 345) keep it in
+ * a caller-provided, 16-byte aligned DEVICE workspace (L2 resident while the chain is advanced).  Returns the bytes the
+ * sampler `op` needs for C chains (0 when everything is resident on chip; pass NULL then), < 0 on error. */
+#define PBNN_OP_SGLD 0
+#define PBNN_OP_PSGLD 1
+#define PBNN_OP_SGHMC 2
+#define PBNN_OP_ADAM 3
+#define PBNN_OP_GRAD 4
+#define PBNN_OP_HMC 5
+int64_t pbnn_workspace_bytes(const pbnn_mlp_spec* spec, int op, int rows, int C);
+
 /* ---- jax.random primitives (jax/_src/prng.py, random.py); test hooks + key plumbing --------------- */
 /* jax.random.split: out[c][i] = threefry(keys[c], (0, i)).  out: [C][n][2] */
 int pbnn_threefry_split(const uint32_t* keys, int C, int n, uint32_t* out, void* stream);
@@ -95,7 +106,7 @@ int pbnn_permutation(const uint32_t* keys, int C, int N, int32_t* out, void* wor
 int pbnn_sgld_run(const pbnn_mlp_spec* spec, const float* X, const float* y, int N, const int32_t* idx,
                   int idx_steps, int mb_mode, int B, const uint32_t* keys, float* theta, const float* step_sizes,
                   int n_step_sizes, int64_t t0, int T, int C, int thin, int burnin, float* trace, uint32_t* flags,
-                  void* stream);
+                  void* workspace, int64_t workspace_bytes, void* stream);
 
 /* pbnn.mcmc.pSGLD (langevin.py:81-140; sgmcmc/psgld.py:25-48; sgmcmc/diffusions.py:33-60).
  * g,V [C][P]: logprob_grad / square_avg of pSGLDState; if has_state==0 they are initialised on device
@@ -103,7 +114,8 @@ int pbnn_sgld_run(const pbnn_mlp_spec* spec, const float* X, const float* y, int
 int pbnn_psgld_run(const pbnn_mlp_spec* spec, const float* X, const float* y, int N, const int32_t* idx,
                    int idx_steps, int mb_mode, int B, const uint32_t* keys, float* theta, float* g, float* V,
                    int has_state, float alpha, const float* step_sizes, int n_step_sizes, int64_t t0, int T, int C,
-                   int thin, int burnin, float* trace, uint32_t* flags, void* stream);
+                   int thin, int burnin, float* trace, uint32_t* flags, void* workspace, int64_t workspace_bytes,
+                   void* stream);
 
 /* pbnn.mcmc.kernels.psgld(grad_estimator_fn, alpha) -> SamplingAlgorithm(init_fn, step_fn)
  * (src/pbnn/mcmc/kernels.py:80-94; sgmcmc/psgld.py:25-48): BlackJAX-style single transitions on an EXPLICIT
@@ -119,7 +131,7 @@ int pbnn_psgld_step(const pbnn_mlp_spec* spec, const float* Xb, const float* yb,
 int pbnn_sghmc_run(const pbnn_mlp_spec* spec, const float* X, const float* y, int N, const int32_t* idx,
                    int idx_steps, int mb_mode, int B, const uint32_t* keys, float* theta, int L, float alpha,
                    float beta, const float* step_sizes, int n_step_sizes, int64_t t0, int T, int C, int thin,
-                   int burnin, float* trace, uint32_t* flags, void* stream);
+                   int burnin, float* trace, uint32_t* flags, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* pbnn.mcmc.hmc (hamiltonian.py:18-77) over blackjax.hmc with the full-batch target
  * logprior + sum_i loglik_i (benchmark/pipelines/hmc.py:59-62).
@@ -128,7 +140,7 @@ int pbnn_sghmc_run(const pbnn_mlp_spec* spec, const float* X, const float* y, in
 int pbnn_hmc_run(const pbnn_mlp_spec* spec, const float* X, const float* y, int N, const uint32_t* keys,
                  float* theta, const float* inv_mass, float step_size, int L, int64_t t0, int num_samples, int C,
                  int thin, int burnin, float* trace, float* logp, int32_t* accept_count, float* info_delta,
-                 int32_t* info_accept, uint32_t* flags, void* stream);
+                 int32_t* info_accept, uint32_t* flags, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* inner loop of pbnn.deep_ensembles.deep_ensembles_fn (src/pbnn/deep_ensembles.py:59-75): n_steps Adam
  * (optax.adam defaults) steps on -logposterior for C members at once.
@@ -136,19 +148,23 @@ int pbnn_hmc_run(const pbnn_mlp_spec* spec, const float* X, const float* y, int 
  *   m, v [C][P] Adam moments (in/out), count0 = steps already taken */
 int pbnn_adam_ensemble_run(const pbnn_mlp_spec* spec, const float* X, const float* y, int N, const int32_t* idx,
                            int n_steps, int B, float* theta, float* m, float* v, int count0, float lr, float b1,
-                           float b2, float eps, int C, uint32_t* flags, void* stream);
+                           float b2, float eps, int C, uint32_t* flags, void* workspace, int64_t workspace_bytes,
+                           void* stream);
 
 /* predict_fn (langevin.py:75-76) + moments (metrics_prediction_intervals.py:188; variance = ddof 0 extension).
  *   samples [S][P], Xtest [M][d];  preds [S][M][s] optional; sum / sumsq [M][s] optional (sum_s f, sum_s f^2);
- *   workspace: float[2 * nchunk * M * s] with nchunk = pbnn_predict_chunks(S) when sum/sumsq requested. */
+ *   workspace: pbnn_predict_workspace_bytes(spec, S, M, want_moments) bytes, 16-byte aligned (partial sums of the
+ *   sample chunks, plus padded parameter copies for models that do not fit shared memory); NULL when that is 0. */
 int pbnn_predict_chunks(int S);
+int64_t pbnn_predict_workspace_bytes(const pbnn_mlp_spec* spec, int S, int M, int want_moments);
 int pbnn_predict(const pbnn_mlp_spec* spec, const float* samples, int S, const float* Xtest, int M, float* preds,
-                 float* sum, float* sumsq, float* workspace, void* stream);
+                 float* sum, float* sumsq, float* workspace, int64_t workspace_bytes, void* stream);
 
 /* gradient of the (scaled) log-posterior estimator for C positions on explicit minibatches -- test hook for
  * blackjax grad_estimator == src/pbnn/utils/misc.py:34-55.  idx [C][B]; grad [C][P]; loglik [C] optional. */
 int pbnn_grad_estimator(const pbnn_mlp_spec* spec, const float* X, const float* y, int N, const int32_t* idx, int B,
-                        const float* theta, int C, float* grad, float* loglik, void* stream);
+                        const float* theta, int C, float* grad, float* loglik, void* workspace, int64_t workspace_bytes,
+                        void* stream);
 
 #ifdef __cplusplus
 }

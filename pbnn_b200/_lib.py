@@ -11,6 +11,7 @@ from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
 
 PBNN_MAX_LAYERS = 8
 ACT_RELU, ACT_TANH = 0, 1
+OP_SGLD, OP_PSGLD, OP_SGHMC, OP_ADAM, OP_GRAD, OP_HMC = range(6)
 MB_REFERENCE_FIXED, MB_PER_STEP = 0, 1
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -49,21 +50,23 @@ PROTOTYPES = {
     "pbnn_threefry_normal": (c_int, [_P, c_int, c_int, _P, _P]),
     "pbnn_minibatch_indices": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P]),
     "pbnn_permutation": (c_int, [_P, c_int, c_int, _P, _P, _P]),
+    "pbnn_workspace_bytes": (c_int64, [_SPEC, c_int, c_int, c_int]),
+    "pbnn_predict_workspace_bytes": (c_int64, [_SPEC, c_int, c_int, c_int]),
     "pbnn_sgld_run": (c_int, [_SPEC, _P, _P, c_int, _P, c_int, c_int, c_int, _P, _P, _P, c_int, c_int64, c_int, c_int,
-                              c_int, c_int, _P, _P, _P]),
+                              c_int, c_int, _P, _P, _P, c_int64, _P]),
     "pbnn_psgld_run": (c_int, [_SPEC, _P, _P, c_int, _P, c_int, c_int, c_int, _P, _P, _P, _P, c_int, c_float, _P, c_int,
-                               c_int64, c_int, c_int, c_int, c_int, _P, _P, _P]),
+                               c_int64, c_int, c_int, c_int, c_int, _P, _P, _P, c_int64, _P]),
     "pbnn_psgld_init": (c_int, [_SPEC, _P, _P, c_int, c_int, _P, _P, _P, c_int, _P]),
     "pbnn_psgld_step": (c_int, [_SPEC, _P, _P, c_int, c_int, _P, _P, _P, _P, c_float, c_float, c_int, _P]),
     "pbnn_sghmc_run": (c_int, [_SPEC, _P, _P, c_int, _P, c_int, c_int, c_int, _P, _P, c_int, c_float, c_float, _P, c_int,
-                               c_int64, c_int, c_int, c_int, c_int, _P, _P, _P]),
+                               c_int64, c_int, c_int, c_int, c_int, _P, _P, _P, c_int64, _P]),
     "pbnn_hmc_run": (c_int, [_SPEC, _P, _P, c_int, _P, _P, _P, c_float, c_int, c_int64, c_int, c_int, c_int, c_int, _P,
-                             _P, _P, _P, _P, _P, _P]),
+                             _P, _P, _P, _P, _P, _P, c_int64, _P]),
     "pbnn_adam_ensemble_run": (c_int, [_SPEC, _P, _P, c_int, _P, c_int, c_int, _P, _P, _P, c_int, c_float, c_float,
-                                       c_float, c_float, c_int, _P, _P]),
+                                       c_float, c_float, c_int, _P, _P, c_int64, _P]),
     "pbnn_predict_chunks": (c_int, [c_int]),
-    "pbnn_predict": (c_int, [_SPEC, _P, c_int, _P, c_int, _P, _P, _P, _P, _P]),
-    "pbnn_grad_estimator": (c_int, [_SPEC, _P, _P, c_int, _P, c_int, _P, c_int, _P, _P, _P]),
+    "pbnn_predict": (c_int, [_SPEC, _P, c_int, _P, c_int, _P, _P, _P, _P, c_int64, _P]),
+    "pbnn_grad_estimator": (c_int, [_SPEC, _P, _P, c_int, _P, c_int, _P, c_int, _P, _P, _P, c_int64, _P]),
 }
 
 

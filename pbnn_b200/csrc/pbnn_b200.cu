@@ -22,27 +22,27 @@
 #endif
 
 // ------------------------------------------------------------------------------------------------
-template <int ALGO, int ACT>
+template <int ALGO, int ACT, bool GS>
 __global__ void __launch_bounds__(PB_MAX_NT, 2)
 pb_sg_kernel(const __grid_constant__ PbPlan pl, const __grid_constant__ PbSgArgs a) {
   extern __shared__ __align__(16) float pb_smem[];
   PB_PROF_START
-  pb_sg_chain<ALGO, ACT>(pl, a, pb_smem, (int)blockIdx.x, (int)blockDim.x);
+  pb_sg_chain<ALGO, ACT, GS>(pl, a, pb_smem, (int)blockIdx.x, (int)blockDim.x);
 }
 
-template <int ACT>
+template <int ACT, bool GS>
 __global__ void __launch_bounds__(PB_MAX_NT, 2)
 pb_hmc_kernel(const __grid_constant__ PbPlan pl, const __grid_constant__ PbHmcArgs a) {
   extern __shared__ __align__(16) float pb_smem[];
   PB_PROF_START
-  pb_hmc_chain<ACT>(pl, a, pb_smem, (int)blockIdx.x, (int)blockDim.x);
+  pb_hmc_chain<ACT, GS>(pl, a, pb_smem, (int)blockIdx.x, (int)blockDim.x);
 }
 
-template <int ACT>
+template <int ACT, bool GS>
 __global__ void __launch_bounds__(PB_MAX_NT, 2)
 pb_predict_kernel(const __grid_constant__ PbPlan pl, const __grid_constant__ PbPredArgs a) {
   extern __shared__ __align__(16) float pb_smem[];
-  pb_predict_block<ACT>(pl, a, pb_smem, (int)blockIdx.x, (int)blockIdx.y, (int)blockDim.x);
+  pb_predict_block<ACT, GS>(pl, a, pb_smem, (int)blockIdx.x, (int)blockIdx.y, (int)blockDim.x);
 }
 
 __global__ void pb_predict_reduce_kernel(const float* __restrict__ part, int nchunk, int n, float* __restrict__ sum,
@@ -154,6 +154,33 @@ pb_perm_kernel(const uint32_t* __restrict__ keys, int N, int Np2, int rounds, in
     for (int jn = threadIdx.x; jn < N; jn += blockDim.x) res[jn] = jn;
 }
 
+// FP32 FMA throughput probe (roofline denominator measured in-run): 16 independent accumulator pairs per thread,
+// `iters` x 32 FMAs each, as scalar FFMA (mode 0) or packed FFMA2 / fma.rn.f32x2 (mode 1).
+__global__ void __launch_bounds__(256, 4) pb_fma_probe_kernel(int mode, int iters, float seed, float* sink) {
+  float2 a[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = make_float2(seed + i + threadIdx.x, seed - i);
+  const float2 m = make_float2(1.0000001f, 0.9999999f), c = make_float2(1e-7f, -1e-7f);
+  if (mode == 0) {
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        a[i].x = fmaf(a[i].x, m.x, c.x);
+        a[i].y = fmaf(a[i].y, m.y, c.y);
+      }
+    }
+  } else {
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) a[i] = __ffma2_rn(a[i], m, c);
+    }
+  }
+  float r = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) r += a[i].x + a[i].y;
+  if (r == 123.456f) sink[0] = r;
+}
+
 // ------------------------------------------------------------------------------------------------
 // backends
 // ------------------------------------------------------------------------------------------------
@@ -180,8 +207,12 @@ static int pb_launch(K kern, const PbPlan& pl, const A& a, dim3 grid, void* stre
 
 template <int ALGO>
 static int pb_sg_dispatch(const PbPlan& pl, const PbSgArgs& a, int C, void* stream) {
-  if (pl.act == PBNN_ACT_RELU) return pb_launch(pb_sg_kernel<ALGO, PBNN_ACT_RELU>, pl, a, dim3(C), stream);
-  return pb_launch(pb_sg_kernel<ALGO, PBNN_ACT_TANH>, pl, a, dim3(C), stream);
+  if (pl.gstate) {
+    if (pl.act == PBNN_ACT_RELU) return pb_launch(pb_sg_kernel<ALGO, PBNN_ACT_RELU, true>, pl, a, dim3(C), stream);
+    return pb_launch(pb_sg_kernel<ALGO, PBNN_ACT_TANH, true>, pl, a, dim3(C), stream);
+  }
+  if (pl.act == PBNN_ACT_RELU) return pb_launch(pb_sg_kernel<ALGO, PBNN_ACT_RELU, false>, pl, a, dim3(C), stream);
+  return pb_launch(pb_sg_kernel<ALGO, PBNN_ACT_TANH, false>, pl, a, dim3(C), stream);
 }
 
 static int pb_backend_sg(int algo, const PbPlan& pl, const PbSgArgs& a, int C, void* stream) {
@@ -195,16 +226,25 @@ static int pb_backend_sg(int algo, const PbPlan& pl, const PbSgArgs& a, int C, v
 }
 
 static int pb_backend_hmc(const PbPlan& pl, const PbHmcArgs& a, int C, void* stream) {
-  if (pl.act == PBNN_ACT_RELU) return pb_launch(pb_hmc_kernel<PBNN_ACT_RELU>, pl, a, dim3(C), stream);
-  return pb_launch(pb_hmc_kernel<PBNN_ACT_TANH>, pl, a, dim3(C), stream);
+  if (pl.gstate) {
+    if (pl.act == PBNN_ACT_RELU) return pb_launch(pb_hmc_kernel<PBNN_ACT_RELU, true>, pl, a, dim3(C), stream);
+    return pb_launch(pb_hmc_kernel<PBNN_ACT_TANH, true>, pl, a, dim3(C), stream);
+  }
+  if (pl.act == PBNN_ACT_RELU) return pb_launch(pb_hmc_kernel<PBNN_ACT_RELU, false>, pl, a, dim3(C), stream);
+  return pb_launch(pb_hmc_kernel<PBNN_ACT_TANH, false>, pl, a, dim3(C), stream);
 }
 
 static int pb_backend_predict(const PbPlan& pl, const PbPredArgs& a, int mtiles, float* sum, float* sumsq,
                               void* stream) {
   const dim3 grid(mtiles, a.nchunk);
   int rc;
-  if (pl.act == PBNN_ACT_RELU) rc = pb_launch(pb_predict_kernel<PBNN_ACT_RELU>, pl, a, grid, stream);
-  else rc = pb_launch(pb_predict_kernel<PBNN_ACT_TANH>, pl, a, grid, stream);
+  if (pl.gstate) {
+    if (pl.act == PBNN_ACT_RELU) rc = pb_launch(pb_predict_kernel<PBNN_ACT_RELU, true>, pl, a, grid, stream);
+    else rc = pb_launch(pb_predict_kernel<PBNN_ACT_TANH, true>, pl, a, grid, stream);
+  } else {
+    if (pl.act == PBNN_ACT_RELU) rc = pb_launch(pb_predict_kernel<PBNN_ACT_RELU, false>, pl, a, grid, stream);
+    else rc = pb_launch(pb_predict_kernel<PBNN_ACT_TANH, false>, pl, a, grid, stream);
+  }
   if (rc) return rc;
   if (sum) {
     const int n = a.M * pl.s;
@@ -247,6 +287,13 @@ static int pb_backend_perm(const uint32_t* keys, int C, int N, int32_t* out, voi
 }
 
 #include "pbnn_api.inc"
+
+// measurement utility (not part of the sampler ABI): launches the FP32 FMA probe; flops = grid*256*iters*64
+extern "C" int pbnn_probe_fp32(int mode, int iters, int ctas, float* sink, void* stream) {
+  pb_fma_probe_kernel<<<ctas, 256, 0, (cudaStream_t)stream>>>(mode, iters, 1.0f, sink);
+  PB_CUDA(cudaGetLastError());
+  return PBNN_OK;
+}
 
 #if defined(PB_PROFILE)
 // profiling build only: per-phase cycle totals [0..31] and phase counts [32..63] of CTA 0; resets the counters

@@ -42,6 +42,7 @@ struct PbPlan {
   int xp, off_xres, off_yres;     //      X^T_aug [r4(d+1)][xp], y^T [r4(s)][xp], xp = roundup(rows, BT) + 4
   int nstate;                     // resident parameter-sized arrays
   int ksmax, off_gpart;           // (ksmax - 1) partial gradient arrays for split-K
+  int gstate;                     // resident arrays live in a global-memory workspace (model too large for smem)
   int h1, h1_dp;                  // fused one-hidden-layer path: X row-major [rows][4*h1_dp], per-warp partial grads
   int off_xr, off_yr, off_hpart;
   int off_act, off_scr, off_acc, off_idx, off_scal;
@@ -103,14 +104,15 @@ static inline void pb_plan_dw(PbPlan* pl, int nw, int bt, int kcap) {
 
 // shared-memory layout for one candidate configuration
 static inline void pb_layout(PbPlan* pl, const pbnn_mlp_spec* sp, int rows, int nstate, int bt, int res, int kcap,
-                             int want_acc, int h1) {
+                             int want_acc, int h1, int gstate = 0) {
   const int ap = bt + 4;
   pl->BT = bt;
   pl->ap = ap;
   pl->h1 = h1;
   pb_plan_dw(pl, pl->NT / 32, bt, kcap);
   if (h1) pl->ksmax = 1;
-  int off = nstate * pl->Ps;
+  pl->gstate = gstate;
+  int off = gstate ? 0 : nstate * pl->Ps;
   pl->off_gpart = off;
   off += (pl->ksmax - 1) * pl->Ps;
   pl->off_act = off;
@@ -237,7 +239,7 @@ static inline int pb_build_plan(const pbnn_mlp_spec* sp, int rows, int nstate, i
   // hide the latency of the short dependent phases) when there are more chains than SMs; then the full SM.
   const size_t lim2 = (size_t)(228 * 1024) / 2 - 1024, lim1 = PB_SMEM_LIMIT_BYTES;
   const int two = (chains_hint > 148 || pb_env_int("PBNN_TWO_CTA", 0)) && !pb_env_int("PBNN_ONE_CTA", 0);
-  for (int pass = two ? 0 : 1; pass < 2; ++pass) {
+  for (int pass = pb_env_int("PBNN_FORCE_GSTATE", 0) ? 2 : (two ? 0 : 1); pass < 2; ++pass) {
     const size_t limit = pass == 0 ? lim2 : lim1;
     for (int bt = maxbt; bt >= 32; bt -= 32) {
       if (pass == 0 && bt < (maxbt < 64 ? maxbt : 64)) break;
@@ -252,6 +254,14 @@ static inline int pb_build_plan(const pbnn_mlp_spec* sp, int rows, int nstate, i
         }
       if (forced > 0) break;
     }
+  }
+  // last resort: parameter-sized arrays in a global-memory workspace (L2 resident), activations in shared memory
+  for (int bt = maxbt; bt >= 32; bt -= 32) {
+    for (int res = want_res ? 1 : 0; res >= 0; --res) {
+      pb_layout(pl, sp, rows, nstate, bt, res, 1, (flags & PB_PLAN_ACC) != 0, 0, 1);
+      if ((size_t)pl->smem_floats * 4 <= lim1) return PBNN_OK;
+    }
+    if (forced > 0) break;
   }
   snprintf(err, errn,
            "model does not fit the shared-memory resident engine (P=%d, %d resident arrays need %zu bytes > %d)", P,
@@ -291,6 +301,7 @@ struct PbSgArgs {
   float lr, b1, b2, eps;
   int count0;
   float scale;  // (N/B) / sigma^2
+  float* ws;    // global workspace [C][nstate][Ps] when plan.gstate
 };
 
 struct PbHmcArgs {
@@ -310,6 +321,7 @@ struct PbHmcArgs {
   float* info_delta;
   int32_t* info_accept;
   uint32_t* flags;
+  float* ws;
 };
 
 struct PbPredArgs {
@@ -320,4 +332,5 @@ struct PbPredArgs {
   float* preds;
   float* part;  // [nchunk][2][M][s] partial sums, or NULL
   int nchunk, chunk;
+  float* ws;
 };

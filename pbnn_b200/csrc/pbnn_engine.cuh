@@ -78,7 +78,12 @@ PB_DEV float pb_actgrad(float h) {  // derivative expressed through the activati
 }
 
 // shared-memory views (no pointer arrays: dynamic indexing would push them to local memory)
-PB_DEV float* pb_state(const PbPlan& pl, float* sm, int i) { return sm + i * pl.Ps; }
+// GS (compile time) = state arrays in the global workspace; keeping it a template parameter lets the compiler see
+// that the resident arrays are shared-memory pointers (LDS/STS instead of generic loads) in the common case
+template <bool GS>
+PB_DEV float* pb_state(const PbPlan& pl, float* sm, float* ws, int i) {
+  return (GS ? ws : sm) + i * pl.Ps;
+}
 PB_DEV float* pb_A(const PbPlan& pl, float* sm, int l) { return sm + pl.aoff[l]; }
 PB_DEV float* pb_scr(const PbPlan& pl, float* sm) { return sm + pl.off_scr; }
 PB_DEV float* pb_llbuf(const PbPlan& pl, float* sm) { return sm + pl.off_scr + 1024 + 64; }
@@ -577,14 +582,19 @@ PB_DEV void pb_grad_h1_t(const PbPlan& pl, float* sm, const float* TH, float* G,
   float* llbuf = pb_llbuf(pl, sm);
   const int j0 = 2 * lane;
   const bool ok0 = j0 < H, ok1 = j0 + 1 < H;
-  float W0[KD], W1[KD], a0[KD], a1[KD];
+  // packed FP32 (Blackwell fma.rn.f32x2 / FFMA2): register pairs (k, k+1) of the weights and accumulators, so the
+  // x pairs coming out of the LDS.128 are used as they are -- half the FMA issue slots of scalar FFMA.
+  // (Measured alternatives, B200: re-reading the weights per row block to afford NP = 4..8 rows in flight is 5-12 %
+  // slower than weights in registers with NP = 2; NP = 4 with weights in registers spills and is 2x slower.)
+  float2 W0[KD / 2], W1[KD / 2], a0[KD / 2], a1[KD / 2];
 #pragma unroll
-  for (int k = 0; k < KD; ++k) {
-    const float* wr = TH + L0.soff + k * wp;
-    W0[k] = ok0 ? wr[j0] : 0.f;
-    W1[k] = ok1 ? wr[j0 + 1] : 0.f;
-    a0[k] = 0.f;
-    a1[k] = 0.f;
+  for (int k = 0; k < KD / 2; ++k) {
+    const float* wr0 = TH + L0.soff + (2 * k) * wp;
+    const float* wr1 = wr0 + wp;
+    W0[k] = make_float2(ok0 ? wr0[j0] : 0.f, ok0 ? wr1[j0] : 0.f);
+    W1[k] = make_float2(ok1 ? wr0[j0 + 1] : 0.f, ok1 ? wr1[j0 + 1] : 0.f);
+    a0[k] = make_float2(0.f, 0.f);
+    a1[k] = make_float2(0.f, 0.f);
   }
   const float v0 = ok0 ? TH[L1.soff + j0 * L1.wp] : 0.f;
   const float v1 = ok1 ? TH[L1.soff + (j0 + 1) * L1.wp] : 0.f;
@@ -599,17 +609,18 @@ PB_DEV void pb_grad_h1_t(const PbPlan& pl, float* sm, const float* TH, float* G,
     for (int p = 0; p < NP; ++p) {
       row[p] = pb_min(n + p, n1 - 1);
       const float* xp_ = Xr + row[p] * KD;
-      float za = 0.f, zb = 0.f, zc = 0.f, zd = 0.f;
+      float2 z0 = make_float2(0.f, 0.f), z1 = make_float2(0.f, 0.f);
 #pragma unroll
       for (int c = 0; c < DP; ++c) {
         const float4 t = pb_ld4(xp_ + 4 * c);
-        za += t.x * W0[4 * c];     zc += t.x * W1[4 * c];
-        zb += t.y * W0[4 * c + 1]; zd += t.y * W1[4 * c + 1];
-        za += t.z * W0[4 * c + 2]; zc += t.z * W1[4 * c + 2];
-        zb += t.w * W0[4 * c + 3]; zd += t.w * W1[4 * c + 3];
+        const float2 lo = make_float2(t.x, t.y), hi = make_float2(t.z, t.w);
+        z0 = __ffma2_rn(lo, W0[2 * c], z0);
+        z1 = __ffma2_rn(lo, W1[2 * c], z1);
+        z0 = __ffma2_rn(hi, W0[2 * c + 1], z0);
+        z1 = __ffma2_rn(hi, W1[2 * c + 1], z1);
       }
-      h0[p] = pb_act<ACT>(za + zb);
-      h1[p] = pb_act<ACT>(zc + zd);
+      h0[p] = pb_act<ACT>(z0.x + z0.y);
+      h1[p] = pb_act<ACT>(z1.x + z1.y);
       pf[p] = h0[p] * v0 + h1[p] * v1;
     }
 #pragma unroll
@@ -624,14 +635,16 @@ PB_DEV void pb_grad_h1_t(const PbPlan& pl, float* sm, const float* TH, float* G,
       const float r = valid ? res * scale : 0.f;
       ll += valid ? -0.5f * res * res * pl.inv_s2 : 0.f;
       const float dz0 = r * v0 * pb_actgrad<ACT>(h0[p]), dz1 = r * v1 * pb_actgrad<ACT>(h1[p]);
+      const float2 d0 = make_float2(dz0, dz0), d1 = make_float2(dz1, dz1);
       const float* xp_ = Xr + row[p] * KD;
 #pragma unroll
       for (int c = 0; c < DP; ++c) {
         const float4 t = pb_ld4(xp_ + 4 * c);
-        a0[4 * c] += t.x * dz0;     a1[4 * c] += t.x * dz1;
-        a0[4 * c + 1] += t.y * dz0; a1[4 * c + 1] += t.y * dz1;
-        a0[4 * c + 2] += t.z * dz0; a1[4 * c + 2] += t.z * dz1;
-        a0[4 * c + 3] += t.w * dz0; a1[4 * c + 3] += t.w * dz1;
+        const float2 lo = make_float2(t.x, t.y), hi = make_float2(t.z, t.w);
+        a0[2 * c] = __ffma2_rn(lo, d0, a0[2 * c]);
+        a1[2 * c] = __ffma2_rn(lo, d1, a1[2 * c]);
+        a0[2 * c + 1] = __ffma2_rn(hi, d0, a0[2 * c + 1]);
+        a1[2 * c + 1] = __ffma2_rn(hi, d1, a1[2 * c + 1]);
       }
       av0 += r * h0[p];
       av1 += r * h1[p];
@@ -639,11 +652,16 @@ PB_DEV void pb_grad_h1_t(const PbPlan& pl, float* sm, const float* TH, float* G,
     }
   }
 #pragma unroll
-  for (int k = 0; k < KD; ++k)
-    if (k < L0.inA) {
-      if (ok0) part[L0.soff + k * wp + j0] = a0[k];
-      if (ok1) part[L0.soff + k * wp + j0 + 1] = a1[k];
+  for (int k = 0; k < KD / 2; ++k) {
+    if (2 * k < L0.inA) {
+      if (ok0) part[L0.soff + (2 * k) * wp + j0] = a0[k].x;
+      if (ok1) part[L0.soff + (2 * k) * wp + j0 + 1] = a1[k].x;
     }
+    if (2 * k + 1 < L0.inA) {
+      if (ok0) part[L0.soff + (2 * k + 1) * wp + j0] = a0[k].y;
+      if (ok1) part[L0.soff + (2 * k + 1) * wp + j0 + 1] = a1[k].y;
+    }
+  }
   if (ok0) part[L1.soff + j0 * L1.wp] = av0;
   if (ok1) part[L1.soff + (j0 + 1) * L1.wp] = av1;
   if (lane == 0) {
@@ -677,11 +695,11 @@ PB_DEV void pb_grad_h1(const PbPlan& pl, float* sm, const float* TH, float* G, i
 #endif
 
 // likelihood gradient over the rows of one evaluation: fused one-hidden-layer path or the tiled GEMM engine
-template <int ACT>
+template <int ACT, bool GS>
 PB_DEV void pb_grad(const PbPlan& pl, float* sm, const float* TH, float* G, const float* X, const float* y,
                     const int* idxs, int nrows, float scale, bool tile_loaded, int nt) {
 #if !defined(PB_EMU)
-  if (pl.h1) {
+  if (!GS && pl.h1) {
     pb_grad_h1<ACT>(pl, sm, TH, G, nrows, scale, nt);
     return;
   }
@@ -780,12 +798,13 @@ PB_DEV void pb_copy_indices(const PbPlan& pl, float* sm, const int32_t* src, int
 //   GRAD  : test hook, one gradient evaluation
 // resident arrays: st[0]=theta, st[1]=g, st[2]=aux (p | V | m), st[3]=aux2 (v)
 // ------------------------------------------------------------------------------------------------
-template <int ALGO, int ACT>
+template <int ALGO, int ACT, bool GS>
 PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, int nt) {
-  float* TH = pb_state(pl, sm, 0);
-  float* G = pb_state(pl, sm, 1);
-  float* A1 = pb_state(pl, sm, pl.nstate > 2 ? 2 : 0);
-  float* A2 = pb_state(pl, sm, pl.nstate > 3 ? 3 : 0);
+  float* ws = a.ws ? a.ws + (size_t)c * pl.nstate * pl.Ps : nullptr;
+  float* TH = pb_state<GS>(pl, sm, ws, 0);
+  float* G = pb_state<GS>(pl, sm, ws, 1);
+  float* A1 = pb_state<GS>(pl, sm, ws, pl.nstate > 2 ? 2 : 0);
+  float* A2 = pb_state<GS>(pl, sm, ws, pl.nstate > 3 ? 3 : 0);
   float* sc = pb_sc(pl, sm);
   uint32_t* scu = pb_scu(pl, sm);
   const int* sidx = pb_idx(pl, sm);
@@ -826,7 +845,7 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
   if (ALGO == PB_ALGO_GRAD) {
     pb_copy_indices(pl, sm, cidx, B, nt);
     if (res) pb_load_resident(pl, sm, a.X, a.y, sidx, B, nt);
-    pb_grad<ACT>(pl, sm, TH, G, a.X, a.y, sidx, B, a.scale, false, nt);
+    pb_grad<ACT, GS>(pl, sm, TH, G, a.X, a.y, sidx, B, a.scale, false, nt);
     PB_PHASE
     pb_for_each_param(pl, tid, nt, [&](int si, int fi) { a.aux1[cP + fi] = G[si] - TH[si] * pl.inv_pv; });
     float* scr = pb_scr(pl, sm);
@@ -852,7 +871,7 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
       pb_gen_indices(pl, sm, B, a.N, a.randint_mult, nt);
     }
     if (res) pb_load_resident(pl, sm, a.X, a.y, sidx, B, nt);
-    pb_grad<ACT>(pl, sm, TH, G, a.X, a.y, sidx, B, a.scale, false, nt);
+    pb_grad<ACT, GS>(pl, sm, TH, G, a.X, a.y, sidx, B, a.scale, false, nt);
     PB_PHASE
     for (int i = tid; i < pl.Ps; i += nt) {
       const float g = G[i] - TH[i] * pl.inv_pv;
@@ -899,7 +918,7 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
     }
 
     if (ALGO == PB_ALGO_SGLD) {
-      pb_grad<ACT>(pl, sm, TH, G, a.X, a.y, sidx, B, a.scale, tile_loaded, nt);
+      pb_grad<ACT, GS>(pl, sm, TH, G, a.X, a.y, sidx, B, a.scale, tile_loaded, nt);
       const float ns = sqrtf(2.0f * eps);
       PB_PHASE
       pb_for_each_param(pl, tid, nt, [&](int si, int fi) {
@@ -915,7 +934,7 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
         TH[si] = TH[si] + eps * pre * G[si] + sqrtf(2.0f * pre * eps) * pb_normal_at(kt, (uint32_t)fi);
       });
       PB_ENDPHASE
-      pb_grad<ACT>(pl, sm, TH, G, a.X, a.y, sidx, B, a.scale, tile_loaded, nt);
+      pb_grad<ACT, GS>(pl, sm, TH, G, a.X, a.y, sidx, B, a.scale, tile_loaded, nt);
       PB_PHASE
       for (int i = tid; i < pl.Ps; i += nt) {
         const float g = G[i] - TH[i] * pl.inv_pv;
@@ -931,7 +950,7 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
       const float fric = 1.0f - a.alpha;
       for (int l = 0; l < a.L; ++l) {
         const PbKey kl = pb_split_at(kt, (uint32_t)l);  // split(keys[t], L)[l]
-        pb_grad<ACT>(pl, sm, TH, G, a.X, a.y, sidx, B, a.scale, tile_loaded, nt);
+        pb_grad<ACT, GS>(pl, sm, TH, G, a.X, a.y, sidx, B, a.scale, tile_loaded, nt);
         PB_PHASE
         pb_for_each_param(pl, tid, nt, [&](int si, int fi) {
           const float th = TH[si], p = A1[si];
@@ -942,7 +961,7 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
         PB_ENDPHASE
       }
     } else if (ALGO == PB_ALGO_ADAM) {
-      pb_grad<ACT>(pl, sm, TH, G, a.X, a.y, sidx, B, a.scale, false, nt);
+      pb_grad<ACT, GS>(pl, sm, TH, G, a.X, a.y, sidx, B, a.scale, false, nt);
       const float cnt = (float)(a.count0 + t + 1);
       const float bc1 = 1.0f - powf(a.b1, cnt), bc2 = 1.0f - powf(a.b2, cnt);
       PB_PHASE
@@ -1001,14 +1020,15 @@ PB_DEV void pb_hmc_logp_reduce(const PbPlan& pl, float* sm, const float* TH, con
   pb_block_sums(pl, sm, 3, pb_sc(pl, sm) + 8, nt);
 }
 
-template <int ACT>
+template <int ACT, bool GS>
 PB_DEV void pb_hmc_chain(const PbPlan& pl, const PbHmcArgs& a, float* sm, int c, int nt) {
-  float* TH = pb_state(pl, sm, 0);
-  float* G = pb_state(pl, sm, 1);
-  float* PM = pb_state(pl, sm, 2);
-  float* TH0 = pb_state(pl, sm, 3);
-  float* G0 = pb_state(pl, sm, 4);
-  float* MI = pb_state(pl, sm, 5);
+  float* ws = a.ws ? a.ws + (size_t)c * pl.nstate * pl.Ps : nullptr;
+  float* TH = pb_state<GS>(pl, sm, ws, 0);
+  float* G = pb_state<GS>(pl, sm, ws, 1);
+  float* PM = pb_state<GS>(pl, sm, ws, 2);
+  float* TH0 = pb_state<GS>(pl, sm, ws, 3);
+  float* G0 = pb_state<GS>(pl, sm, ws, 4);
+  float* MI = pb_state<GS>(pl, sm, ws, 5);
   float* sc = pb_sc(pl, sm);
   uint32_t* scu = pb_scu(pl, sm);
   const int P = pl.P;
@@ -1032,7 +1052,7 @@ PB_DEV void pb_hmc_chain(const PbPlan& pl, const PbHmcArgs& a, float* sm, int c,
   PB_ENDPHASE
 
   // init: (logp, grad) at theta0
-  pb_grad<ACT>(pl, sm, TH, G, a.X, a.y, nullptr, a.N, pl.inv_s2, false, nt);
+  pb_grad<ACT, GS>(pl, sm, TH, G, a.X, a.y, nullptr, a.N, pl.inv_s2, false, nt);
   PB_PHASE
   for (int i = tid; i < pl.Ps; i += nt) {
     const float g = G[i] - TH[i] * pl.inv_pv;
@@ -1074,7 +1094,7 @@ PB_DEV void pb_hmc_chain(const PbPlan& pl, const PbHmcArgs& a, float* sm, int c,
         TH[i] = TH[i] + eps * (MI[i] * p);
       }
       PB_ENDPHASE
-      pb_grad<ACT>(pl, sm, TH, G, a.X, a.y, nullptr, a.N, pl.inv_s2, false, nt);
+      pb_grad<ACT, GS>(pl, sm, TH, G, a.X, a.y, nullptr, a.N, pl.inv_s2, false, nt);
       PB_TAG(13)
       PB_PHASE
       for (int i = tid; i < pl.Ps; i += nt) {
@@ -1134,9 +1154,9 @@ PB_DEV void pb_hmc_chain(const PbPlan& pl, const PbHmcArgs& a, float* sm, int c,
 // predictive: CTA (mt, ch) evaluates samples [ch*chunk, (ch+1)*chunk) on test rows [mt*BT, (mt+1)*BT)
 // (predict_fn, langevin.py:75-76) and accumulates sum_s f, sum_s f^2 for the moments.
 // ------------------------------------------------------------------------------------------------
-template <int ACT>
+template <int ACT, bool GS>
 PB_DEV void pb_predict_block(const PbPlan& pl, const PbPredArgs& a, float* sm, int mt, int ch, int nt) {
-  float* TH = pb_state(pl, sm, 0);
+  float* TH = pb_state<GS>(pl, sm, a.ws ? a.ws + ((size_t)mt * a.nchunk + ch) * pl.Ps : nullptr, 0);
   float* acc = pb_acc(pl, sm);
   const int ap = pl.ap, BT = pl.BT, s = pl.s, P = pl.P;
   const int row0 = mt * BT;

@@ -183,6 +183,15 @@ class Ops:
               "permutation")
         return out
 
+    def _workspace(self, spec, op, rows, C):
+        """Device workspace for models whose state does not fit shared memory (None when not needed)."""
+        need = self.lib.pbnn_workspace_bytes(spec.c_struct(), op, int(rows), int(C))
+        if need < 0:
+            check(self.lib, int(need), "workspace_bytes")
+        if need == 0:
+            return None, 0
+        return self._empty(((need + 3) // 4,), self.f32), int(need)
+
     # ---- samplers ------------------------------------------------------------------------------
     def _sg_common(self, spec, X, y, theta, keys, B, step_size, T, idx, thin, burnin, keep_trace):
         keys = self._keys(keys)
@@ -201,9 +210,11 @@ class Ops:
         keys, C, X, y, th, ix, idx_steps, steps, nsteps, trace, flags = self._sg_common(
             spec, X, y, theta, keys, B, step_size, T, idx, thin, burnin, keep_trace)
         cs = spec.c_struct()
+        ws, wsb = self._workspace(spec, _lib.OP_SGLD, B, C)
         rc = self.lib.pbnn_sgld_run(cs, self._ptr(X), self._ptr(y), X.shape[0], self._ptr(ix), idx_steps,
                                     _MB_MODES[minibatch_mode], B, self._ptr(keys), self._ptr(th), self._ptr(steps),
-                                    nsteps, t0, T, C, thin, burnin, self._ptr(trace), self._ptr(flags), self._stream())
+                                    nsteps, t0, T, C, thin, burnin, self._ptr(trace), self._ptr(flags), self._ptr(ws), wsb,
+                                    self._stream())
         check(self.lib, rc, "sgld")
         return {"theta": th, "trace": trace, "flags": flags}
 
@@ -216,10 +227,11 @@ class Ops:
         else:
             g, V, has = self._theta(state[0], spec, C), self._theta(state[1], spec, C), 1
         cs = spec.c_struct()
+        ws, wsb = self._workspace(spec, _lib.OP_PSGLD, B, C)
         rc = self.lib.pbnn_psgld_run(cs, self._ptr(X), self._ptr(y), X.shape[0], self._ptr(ix), idx_steps,
                                      _MB_MODES[minibatch_mode], B, self._ptr(keys), self._ptr(th), self._ptr(g),
                                      self._ptr(V), has, float(alpha), self._ptr(steps), nsteps, t0, T, C, thin, burnin,
-                                     self._ptr(trace), self._ptr(flags), self._stream())
+                                     self._ptr(trace), self._ptr(flags), self._ptr(ws), wsb, self._stream())
         check(self.lib, rc, "psgld")
         return {"theta": th, "trace": trace, "flags": flags, "grad": g, "square_avg": V}
 
@@ -228,10 +240,11 @@ class Ops:
         keys, C, X, y, th, ix, idx_steps, steps, nsteps, trace, flags = self._sg_common(
             spec, X, y, theta, keys, B, step_size, T, idx, thin, burnin, keep_trace)
         cs = spec.c_struct()
+        ws, wsb = self._workspace(spec, _lib.OP_SGHMC, B, C)
         rc = self.lib.pbnn_sghmc_run(cs, self._ptr(X), self._ptr(y), X.shape[0], self._ptr(ix), idx_steps,
                                      _MB_MODES[minibatch_mode], B, self._ptr(keys), self._ptr(th), int(L), float(alpha),
                                      float(beta), self._ptr(steps), nsteps, t0, T, C, thin, burnin, self._ptr(trace),
-                                     self._ptr(flags), self._stream())
+                                     self._ptr(flags), self._ptr(ws), wsb, self._stream())
         check(self.lib, rc, "sghmc")
         return {"theta": th, "trace": trace, "flags": flags}
 
@@ -252,10 +265,11 @@ class Ops:
         idelta = self._empty((C, num_samples), self.f32) if info else None
         iacc = self._empty((C, num_samples), self.i32) if info else None
         cs = spec.c_struct()
+        ws, wsb = self._workspace(spec, _lib.OP_HMC, X.shape[0], C)
         rc = self.lib.pbnn_hmc_run(cs, self._ptr(X), self._ptr(y), X.shape[0], self._ptr(keys), self._ptr(th),
                                    self._ptr(im), float(step_size), int(L), t0, num_samples, C, thin, burnin,
                                    self._ptr(trace), self._ptr(logp), self._ptr(acc), self._ptr(idelta), self._ptr(iacc),
-                                   self._ptr(flags), self._stream())
+                                   self._ptr(flags), self._ptr(ws), wsb, self._stream())
         check(self.lib, rc, "hmc")
         return {"theta": th, "trace": trace, "flags": flags, "logp": logp, "accept_count": acc, "delta": idelta,
                 "accept": iacc}
@@ -274,10 +288,11 @@ class Ops:
         v = self._zeros(th.shape, self.f32) if v is None else self._theta(v, spec, C)
         flags = self._zeros((C,), self.i32)
         cs = spec.c_struct()
+        ws, wsb = self._workspace(spec, _lib.OP_ADAM, B, C)
         rc = self.lib.pbnn_adam_ensemble_run(cs, self._ptr(X), self._ptr(y), X.shape[0], self._ptr(ix.contiguous()),
                                              n_steps, B, self._ptr(th), self._ptr(m), self._ptr(v), int(count0),
                                              float(lr), float(b1), float(b2), float(eps), C, self._ptr(flags),
-                                             self._stream())
+                                             self._ptr(ws), wsb, self._stream())
         check(self.lib, rc, "adam_ensemble")
         return {"theta": th, "m": m, "v": v, "flags": flags, "count": count0 + n_steps}
 
@@ -291,8 +306,10 @@ class Ops:
         g = self._empty(th.shape, self.f32)
         ll = self._empty((C,), self.f32)
         cs = spec.c_struct()
+        ws, wsb = self._workspace(spec, _lib.OP_GRAD, B, C)
         rc = self.lib.pbnn_grad_estimator(cs, self._ptr(X), self._ptr(y), X.shape[0], self._ptr(ix), B,
-                                          self._ptr(th.contiguous()), C, self._ptr(g), self._ptr(ll), self._stream())
+                                          self._ptr(th.contiguous()), C, self._ptr(g), self._ptr(ll), self._ptr(ws), wsb,
+                                          self._stream())
         check(self.lib, rc, "grad_estimator")
         return g, ll
 
@@ -310,10 +327,14 @@ class Ops:
         ssum = ssq = ws = None
         if want_moments:
             ssum, ssq = self._empty((M, s), self.f32), self._empty((M, s), self.f32)
-            ws = self._empty((2 * max(1, self.lib.pbnn_predict_chunks(S)) * M * s,), self.f32)
         cs = spec.c_struct()
+        wsb = int(self.lib.pbnn_predict_workspace_bytes(cs, S, M, 1 if want_moments else 0))
+        if wsb < 0:
+            check(self.lib, wsb, "predict_workspace_bytes")
+        if wsb > 0:
+            ws = self._empty(((wsb + 3) // 4,), self.f32)
         rc = self.lib.pbnn_predict(cs, self._ptr(smp), S, self._ptr(Xt), M, self._ptr(preds), self._ptr(ssum),
-                                   self._ptr(ssq), self._ptr(ws), self._stream())
+                                   self._ptr(ssq), self._ptr(ws), wsb, self._stream())
         check(self.lib, rc, "predict")
         out = {"preds": preds}
         if want_moments:

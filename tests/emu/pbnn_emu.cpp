@@ -18,8 +18,13 @@ static int pb_backend_sg(int algo, const PbPlan& pl, const PbSgArgs& a, int C, v
     float* p = sm.data();
 #define PB_CASE(ALGO)                                                        \
   case ALGO:                                                                 \
-    if (act == PBNN_ACT_RELU) pb_sg_chain<ALGO, PBNN_ACT_RELU>(pl, a, p, c, pl.NT); \
-    else pb_sg_chain<ALGO, PBNN_ACT_TANH>(pl, a, p, c, pl.NT);               \
+    if (act == PBNN_ACT_RELU) {                                              \
+      if (pl.gstate) pb_sg_chain<ALGO, PBNN_ACT_RELU, true>(pl, a, p, c, pl.NT);  \
+      else pb_sg_chain<ALGO, PBNN_ACT_RELU, false>(pl, a, p, c, pl.NT);      \
+    } else {                                                                 \
+      if (pl.gstate) pb_sg_chain<ALGO, PBNN_ACT_TANH, true>(pl, a, p, c, pl.NT);  \
+      else pb_sg_chain<ALGO, PBNN_ACT_TANH, false>(pl, a, p, c, pl.NT);      \
+    }                                                                        \
     break;
     switch (algo) {
       PB_CASE(PB_ALGO_SGLD)
@@ -37,8 +42,13 @@ static int pb_backend_hmc(const PbPlan& pl, const PbHmcArgs& a, int C, void*) {
 #pragma omp parallel for schedule(dynamic)
   for (int c = 0; c < C; ++c) {
     std::vector<float> sm(pl.smem_floats + 16, std::nanf(""));
-    if (pl.act == PBNN_ACT_RELU) pb_hmc_chain<PBNN_ACT_RELU>(pl, a, sm.data(), c, pl.NT);
-    else pb_hmc_chain<PBNN_ACT_TANH>(pl, a, sm.data(), c, pl.NT);
+    if (pl.act == PBNN_ACT_RELU) {
+      if (pl.gstate) pb_hmc_chain<PBNN_ACT_RELU, true>(pl, a, sm.data(), c, pl.NT);
+      else pb_hmc_chain<PBNN_ACT_RELU, false>(pl, a, sm.data(), c, pl.NT);
+    } else {
+      if (pl.gstate) pb_hmc_chain<PBNN_ACT_TANH, true>(pl, a, sm.data(), c, pl.NT);
+      else pb_hmc_chain<PBNN_ACT_TANH, false>(pl, a, sm.data(), c, pl.NT);
+    }
   }
   return PBNN_OK;
 }
@@ -48,8 +58,13 @@ static int pb_backend_predict(const PbPlan& pl, const PbPredArgs& a, int mtiles,
   for (int mt = 0; mt < mtiles; ++mt)
     for (int ch = 0; ch < a.nchunk; ++ch) {
       std::vector<float> sm(pl.smem_floats + 16, std::nanf(""));
-      if (pl.act == PBNN_ACT_RELU) pb_predict_block<PBNN_ACT_RELU>(pl, a, sm.data(), mt, ch, pl.NT);
-      else pb_predict_block<PBNN_ACT_TANH>(pl, a, sm.data(), mt, ch, pl.NT);
+      if (pl.act == PBNN_ACT_RELU) {
+        if (pl.gstate) pb_predict_block<PBNN_ACT_RELU, true>(pl, a, sm.data(), mt, ch, pl.NT);
+        else pb_predict_block<PBNN_ACT_RELU, false>(pl, a, sm.data(), mt, ch, pl.NT);
+      } else {
+        if (pl.gstate) pb_predict_block<PBNN_ACT_TANH, true>(pl, a, sm.data(), mt, ch, pl.NT);
+        else pb_predict_block<PBNN_ACT_TANH, false>(pl, a, sm.data(), mt, ch, pl.NT);
+      }
     }
   if (sum) {
     const int n = a.M * pl.s;

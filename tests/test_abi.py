@@ -43,10 +43,15 @@ def test_host_side_calls_without_gpu(cuda_lib_path):
     out = (ctypes.c_int32 * 4)()
     assert lib.pbnn_plan_query(spec, 506, 6, out) == 0
     assert out[0] % 32 == 0 and out[1] % 32 == 0 and out[2] <= 227 * 1024
-    big = _lib.make_spec((90, 256, 256, 1), 0, 0.1)
-    assert lib.pbnn_plan_query(big, 128, 2, out) == -2
+    big = _lib.make_spec((90, 256, 256, 1), 0, 0.1)  # state goes to a global workspace, activations stay on chip
+    assert lib.pbnn_plan_query(big, 128, 2, out) == 0
+    assert lib.pbnn_workspace_bytes(big, _lib.OP_SGLD, 128, 10) == 10 * 2 * out[3] * 4 > 0
+    assert lib.pbnn_workspace_bytes(spec, _lib.OP_HMC, 506, 256) == 0
+    huge = _lib.make_spec((3000, 4000, 1), 0, 0.1)
+    assert lib.pbnn_plan_query(huge, 128, 2, out) == -2
     assert b"does not fit" in lib.pbnn_last_error()
-    assert lib.pbnn_sgld_run(spec, None, None, 10, None, 0, 0, 4, None, None, None, 1, 0, 1, 1, 1, 0, None, None, None) == -1
+    assert lib.pbnn_sgld_run(spec, None, None, 10, None, 0, 0, 4, None, None, None, 1, 0, 1, 1, 1, 0, None, None, None,
+                             0, None) == -1
     bad = _lib.make_spec((13, 50, 1), 7, 0.1)
     assert lib.pbnn_num_params(bad) == 751 and lib.pbnn_plan_query(bad, 8, 2, out) == -1
 

@@ -291,6 +291,29 @@ def test_edge_cases_and_errors(ops):
         ops.sghmc(fs, X, y, th0, keys, B, 1e-5, 2, 0)
     with pytest.raises(ValueError):
         ops.sgld(FlatSpec((8, 50, 1), 0, -1.0), X, y, th0, keys, B, 1e-5, 2)
-    big = FlatSpec((90, 256, 256, 1), 0, 0.1)
+    huge = FlatSpec((3000, 4000, 1), 0, 0.1)
     with pytest.raises(MemoryError):
-        ops.plan(big, 128, 2)
+        ops.plan(huge, 128, 2)
+
+
+def test_global_workspace_state_path(ops, monkeypatch):
+    """Models whose state does not fit shared memory keep it in a global workspace (the 90-256-256-1 case); force that
+    path on small nets and check it against the oracle like the resident path."""
+    monkeypatch.setenv("PBNN_FORCE_GSTATE", "1")
+    for layers, act, B in (NETS[0], NETS[2], NETS[3]):
+        X, y, sp, fs, keys, th0 = problem(layers, act)
+        ref = o.sgld(sp, X, y, th0, B, 1e-5, 4, keys)
+        assert rel(npy(ops.sgld(fs, X, y, th0, keys, B, 1e-5, 4)["trace"]), ref) <= RTOL_STEP
+        ref = o.psgld(sp, X, y, th0, B, 1e-6, 3, 0.95, keys)
+        assert rel(npy(ops.psgld(fs, X, y, th0, keys, B, 1e-6, 3, 0.95)["trace"]), ref) <= RTOL_STEP
+        Xt = X[:50]
+        res = ops.predict(fs, th0, Xt, want_preds=True, want_moments=True)
+        F = o.predict(sp, th0.astype(np.float64), Xt.astype(np.float64), dtype=np.float64)
+        assert rel(npy(res["preds"]), F) <= 1e-5 and rel(npy(res["mean"]), F.mean(0)) <= 1e-5
+    layers, act = (4, 6, 6, 1), o.TANH
+    X, y, sp, fs, keys, th0 = problem(layers, act, N=70, scale=0.05)
+    minv = np.ones(sp.num_params, np.float32)
+    ref, info = o.hmc(sp, X, y, th0, 3, 2e-4, minv, 4, keys, return_info=True)
+    out = ops.hmc(fs, X, y, th0, keys, 3, 2e-4, minv, 4, info=True)
+    assert np.array_equal(npy(out["accept"]).astype(bool), info["accept"])
+    assert rel(npy(out["trace"]), ref) <= RTOL_STEP
