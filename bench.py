@@ -147,7 +147,7 @@ def cpu_run(w, n_chains, n_iters, seed_rank=0):
 def cpu_sample_plan(w, target_s):
     """Size a bounded sample of the workload for ~target_s seconds of CPU work on all host threads."""
     from oracle import c_oracle as co
-    cores = co.num_threads()
+    cores = co.use_all_cores()
     n_chains = min(w["C"], max(1, cores) * 2)
     probe_iters = max(1, min(w["T"], int(2e8 / max(1, w["L"] * grad_flops(w["layers"], w["B"])))))
     dt = cpu_run(w, n_chains, probe_iters)
@@ -328,8 +328,15 @@ def main():
         peak_nominal = 148 * 128 * 2 * sm_max * 1e6 / 1e12
         trace_bytes = w["C"] * w["T"] * fs.num_params * 4 if w["algo"] == "hmc" else 0
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(args.workload)
+            if tr and not args.iters and not args.chains:
+                traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+        except (OSError, KeyError, ValueError):
+            pass
         roofline = {"bound": "fma", "achieved": achieved, "peak": peak_nominal, "unit": "TFLOP/s",
-                    "frac": achieved / peak_nominal, "traffic": None,
+                    "frac": achieved / peak_nominal, "traffic": traffic,
                     "peak_source": f"FP32 FMA: 148 SM x 128 lanes x 2 x {sm_max:.0f} MHz (the kernel is FP32-FMA bound, "
                                    f"neither HBM nor tensor; DESIGN.md)",
                     "kernel": "pb_hmc_kernel" if w["algo"] == "hmc" else "pb_sg_kernel",
@@ -337,6 +344,23 @@ def main():
                     "hbm": {"achieved": trace_bytes / (ms_per_step * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                             "frac": trace_bytes / (ms_per_step * 1e-3) / 1e9 / hbm_peak,
                             "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback"}}
+        try:  # practical FP32 ceiling measured in the same run (scalar FFMA and packed FFMA2 probes)
+            import ctypes
+            ops.lib.pbnn_probe_fp32.argtypes = [ctypes.c_int] * 3 + [ctypes.c_void_p] * 2
+            sink = torch.zeros(4, device="cuda")
+            best = 0.0
+            for mode in (0, 1):
+                ops.lib.pbnn_probe_fp32(mode, 200, 148 * 8, sink.data_ptr(), None)
+                ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ea.record()
+                ops.lib.pbnn_probe_fp32(mode, 10000, 148 * 8, sink.data_ptr(), None)
+                eb.record()
+                torch.cuda.synchronize()
+                best = max(best, 148 * 8 * 256 * 10000 * 64 / (ea.elapsed_time(eb) * 1e-3) / 1e12)
+            roofline["peak_measured_fp32_probe"] = best
+            roofline["frac_of_measured"] = achieved / best
+        except Exception as exc:  # noqa: BLE001
+            roofline["peak_measured_fp32_probe"] = None
         out = dict(base, value=value, ms_per_step=ms_per_step, clocks=clocks, roofline=roofline, gpu_launches=args.steps,
                    exchange={"what": "predictive moments (sum, sumsq over chains) all_gather", "ms": exchange_ms,
                              "pred_mean_abs": float(pm.abs().mean()), "pred_var_mean": float(pv.mean())},

@@ -236,6 +236,13 @@ static float logpost_grad(const Spec* s, Work* w, const float* th, const float* 
 }
 
 int pbo_num_params(const Spec* s) { return num_params(s); }
+void pbo_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
 int pbo_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

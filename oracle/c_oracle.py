@@ -59,6 +59,16 @@ def num_threads():
     return lib().pbo_num_threads()
 
 
+def use_all_cores():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU baseline is meant to use every host core it may run on."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    lib().pbo_set_num_threads(c_int(n))
+    return num_threads()
+
+
 def normal(keys, n):
     keys = np.ascontiguousarray(keys, np.uint32).reshape(-1, 2)
     out = np.empty((len(keys), n), np.float32)
