@@ -22,24 +22,24 @@
 #endif
 
 // ------------------------------------------------------------------------------------------------
-template <int ALGO, int ACT, bool GS>
-__global__ void __launch_bounds__(PB_MAX_NT, 2)
+template <int ALGO, int ACT, bool GS, int ENG>
+__global__ void __launch_bounds__(PB_MAX_NT)
 pb_sg_kernel(const __grid_constant__ PbPlan pl, const __grid_constant__ PbSgArgs a) {
   extern __shared__ __align__(16) float pb_smem[];
   PB_PROF_START
-  pb_sg_chain<ALGO, ACT, GS>(pl, a, pb_smem, (int)blockIdx.x, (int)blockDim.x);
+  pb_sg_chain<ALGO, ACT, GS, ENG>(pl, a, pb_smem, (int)blockIdx.x, (int)blockDim.x);
 }
 
-template <int ACT, bool GS>
-__global__ void __launch_bounds__(PB_MAX_NT, 2)
+template <int ACT, bool GS, int ENG>
+__global__ void __launch_bounds__(PB_MAX_NT)
 pb_hmc_kernel(const __grid_constant__ PbPlan pl, const __grid_constant__ PbHmcArgs a) {
   extern __shared__ __align__(16) float pb_smem[];
   PB_PROF_START
-  pb_hmc_chain<ACT, GS>(pl, a, pb_smem, (int)blockIdx.x, (int)blockDim.x);
+  pb_hmc_chain<ACT, GS, ENG>(pl, a, pb_smem, (int)blockIdx.x, (int)blockDim.x);
 }
 
 template <int ACT, bool GS>
-__global__ void __launch_bounds__(PB_MAX_NT, 2)
+__global__ void __launch_bounds__(PB_MAX_NT)
 pb_predict_kernel(const __grid_constant__ PbPlan pl, const __grid_constant__ PbPredArgs a) {
   extern __shared__ __align__(16) float pb_smem[];
   pb_predict_block<ACT, GS>(pl, a, pb_smem, (int)blockIdx.x, (int)blockIdx.y, (int)blockDim.x);
@@ -208,11 +208,15 @@ static int pb_launch(K kern, const PbPlan& pl, const A& a, dim3 grid, void* stre
 template <int ALGO>
 static int pb_sg_dispatch(const PbPlan& pl, const PbSgArgs& a, int C, void* stream) {
   if (pl.gstate) {
-    if (pl.act == PBNN_ACT_RELU) return pb_launch(pb_sg_kernel<ALGO, PBNN_ACT_RELU, true>, pl, a, dim3(C), stream);
-    return pb_launch(pb_sg_kernel<ALGO, PBNN_ACT_TANH, true>, pl, a, dim3(C), stream);
+    if (pl.act == PBNN_ACT_RELU) return pb_launch(pb_sg_kernel<ALGO, PBNN_ACT_RELU, true, 0>, pl, a, dim3(C), stream);
+    return pb_launch(pb_sg_kernel<ALGO, PBNN_ACT_TANH, true, 0>, pl, a, dim3(C), stream);
   }
-  if (pl.act == PBNN_ACT_RELU) return pb_launch(pb_sg_kernel<ALGO, PBNN_ACT_RELU, false>, pl, a, dim3(C), stream);
-  return pb_launch(pb_sg_kernel<ALGO, PBNN_ACT_TANH, false>, pl, a, dim3(C), stream);
+  if (pl.h1) {
+    if (pl.act == PBNN_ACT_RELU) return pb_launch(pb_sg_kernel<ALGO, PBNN_ACT_RELU, false, 1>, pl, a, dim3(C), stream);
+    return pb_launch(pb_sg_kernel<ALGO, PBNN_ACT_TANH, false, 1>, pl, a, dim3(C), stream);
+  }
+  if (pl.act == PBNN_ACT_RELU) return pb_launch(pb_sg_kernel<ALGO, PBNN_ACT_RELU, false, 0>, pl, a, dim3(C), stream);
+  return pb_launch(pb_sg_kernel<ALGO, PBNN_ACT_TANH, false, 0>, pl, a, dim3(C), stream);
 }
 
 static int pb_backend_sg(int algo, const PbPlan& pl, const PbSgArgs& a, int C, void* stream) {
@@ -227,11 +231,15 @@ static int pb_backend_sg(int algo, const PbPlan& pl, const PbSgArgs& a, int C, v
 
 static int pb_backend_hmc(const PbPlan& pl, const PbHmcArgs& a, int C, void* stream) {
   if (pl.gstate) {
-    if (pl.act == PBNN_ACT_RELU) return pb_launch(pb_hmc_kernel<PBNN_ACT_RELU, true>, pl, a, dim3(C), stream);
-    return pb_launch(pb_hmc_kernel<PBNN_ACT_TANH, true>, pl, a, dim3(C), stream);
+    if (pl.act == PBNN_ACT_RELU) return pb_launch(pb_hmc_kernel<PBNN_ACT_RELU, true, 0>, pl, a, dim3(C), stream);
+    return pb_launch(pb_hmc_kernel<PBNN_ACT_TANH, true, 0>, pl, a, dim3(C), stream);
   }
-  if (pl.act == PBNN_ACT_RELU) return pb_launch(pb_hmc_kernel<PBNN_ACT_RELU, false>, pl, a, dim3(C), stream);
-  return pb_launch(pb_hmc_kernel<PBNN_ACT_TANH, false>, pl, a, dim3(C), stream);
+  if (pl.h1) {
+    if (pl.act == PBNN_ACT_RELU) return pb_launch(pb_hmc_kernel<PBNN_ACT_RELU, false, 1>, pl, a, dim3(C), stream);
+    return pb_launch(pb_hmc_kernel<PBNN_ACT_TANH, false, 1>, pl, a, dim3(C), stream);
+  }
+  if (pl.act == PBNN_ACT_RELU) return pb_launch(pb_hmc_kernel<PBNN_ACT_RELU, false, 0>, pl, a, dim3(C), stream);
+  return pb_launch(pb_hmc_kernel<PBNN_ACT_TANH, false, 0>, pl, a, dim3(C), stream);
 }
 
 static int pb_backend_predict(const PbPlan& pl, const PbPredArgs& a, int mtiles, float* sum, float* sumsq,

@@ -11,8 +11,11 @@
 #include "../../include/pbnn_b200.h"
 
 #define PB_SMEM_LIMIT_BYTES (227 * 1024)
-#define PB_MAX_NT 256
-#define PB_SCR_FLOATS (1024 + 64 + 128 + 128)  // reduction scratch, second level, llbuf[128], fbuf[128]
+#ifndef PB_MAX_NT
+#define PB_MAX_NT 512
+#endif
+#define PB_SCR_MAIN (3 * PB_MAX_NT)                       // per-thread partials of up to 3 block reductions
+#define PB_SCR_FLOATS (PB_SCR_MAIN + 64 + 128 + 128)    // + second level [64], llbuf[128], fbuf[128]
 #define PB_GPART_BUDGET_BYTES (24 * 1024)      // split-K partial gradient buffers
 
 // One Dense layer in the resident (shared-memory) layout.
@@ -30,6 +33,7 @@ struct PbLayer {
   int soff;  // float offset of W_aug inside a resident parameter array
   int fb, fw;  // flat (ravel_pytree) offsets of bias and kernel
   int dw_ni, dw_ks;
+  unsigned long long div_out;  // ceil(2^40 / out): q / out == (q * div_out) >> 40 exactly for q < 2^28
 };
 
 struct PbPlan {
@@ -118,6 +122,7 @@ static inline void pb_layout(PbPlan* pl, const pbnn_mlp_spec* sp, int rows, int 
   pl->off_act = off;
   if (h1) {
     // fused path: no activation buffers; X row-major with the ones column, y, one partial gradient per warp
+    if (pl->NT > 256) pl->NT = 256;
     for (int l = 0; l <= pl->nl + 1; ++l) pl->aoff[l] = off;
     pl->res_rows = rows;
     pl->h1_dp = pb_r4(pl->d + 1) / 4;
@@ -212,6 +217,7 @@ static inline int pb_build_plan(const pbnn_mlp_spec* sp, int rows, int nstate, i
     Ly.wp = wp;
     Ly.soff = soff;
     soff += Ly.rows * wp;
+    Ly.div_out = ((1ull << 40) + (unsigned long long)Ly.out - 1) / (unsigned long long)Ly.out;
     Ly.fb = foff;  // ravel_pytree: "bias" < "kernel"
     Ly.fw = foff + Ly.out;
     foff += Ly.out * (Ly.in + 1);
@@ -220,7 +226,7 @@ static inline int pb_build_plan(const pbnn_mlp_spec* sp, int rows, int nstate, i
   pl->nstate = nstate;
   pl->idx_cap = pb_r4(idx_cap);
   pl->NT = 32 * pb_env_int("PBNN_NW", 8);
-  if (pl->NT < 32 || pl->NT > PB_MAX_NT) {
+  if (pl->NT < 32 || pl->NT > PB_MAX_NT || (pl->NT & (pl->NT - 1))) {
     snprintf(err, errn, "PBNN_NW out of range");
     return PBNN_EINVAL;
   }
@@ -239,7 +245,11 @@ static inline int pb_build_plan(const pbnn_mlp_spec* sp, int rows, int nstate, i
   // hide the latency of the short dependent phases) when there are more chains than SMs; then the full SM.
   const size_t lim2 = (size_t)(228 * 1024) / 2 - 1024, lim1 = PB_SMEM_LIMIT_BYTES;
   const int two = (chains_hint > 148 || pb_env_int("PBNN_TWO_CTA", 0)) && !pb_env_int("PBNN_ONE_CTA", 0);
+  // Plans that end up with one CTA per SM anyway (large resident state) run 16 warps instead of 8: the phases are
+  // short dependent sequences, 4 warps per scheduler hide their latency much better than 2.
+  const int nw_env = pb_env_int("PBNN_NW", 0);
   for (int pass = pb_env_int("PBNN_FORCE_GSTATE", 0) ? 2 : (two ? 0 : 1); pass < 2; ++pass) {
+    pl->NT = nw_env > 0 ? 32 * nw_env : (pass == 0 ? 256 : 512);
     const size_t limit = pass == 0 ? lim2 : lim1;
     for (int bt = maxbt; bt >= 32; bt -= 32) {
       if (pass == 0 && bt < (maxbt < 64 ? maxbt : 64)) break;
@@ -256,6 +266,7 @@ static inline int pb_build_plan(const pbnn_mlp_spec* sp, int rows, int nstate, i
     }
   }
   // last resort: parameter-sized arrays in a global-memory workspace (L2 resident), activations in shared memory
+  pl->NT = nw_env > 0 ? 32 * nw_env : 512;
   for (int bt = maxbt; bt >= 32; bt -= 32) {
     for (int res = want_res ? 1 : 0; res >= 0; --res) {
       pb_layout(pl, sp, rows, nstate, bt, res, 1, (flags & PB_PLAN_ACC) != 0, 0, 1);

@@ -67,6 +67,9 @@ PB_DEV void pb_st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 PB_DEV int pb_min(int a, int b) { return a < b ? a : b; }
 PB_DEV int pb_r4dev(int x) { return (x + 3) & ~3; }
 PB_DEV bool pb_finite(float x) { return fabsf(x) <= 3.402823466e+38f; }
+#if defined(PB_EMU)
+static inline float __fdividef(float a, float b) { return a / b; }
+#endif
 
 template <int ACT>
 PB_DEV float pb_act(float z) {
@@ -86,8 +89,8 @@ PB_DEV float* pb_state(const PbPlan& pl, float* sm, float* ws, int i) {
 }
 PB_DEV float* pb_A(const PbPlan& pl, float* sm, int l) { return sm + pl.aoff[l]; }
 PB_DEV float* pb_scr(const PbPlan& pl, float* sm) { return sm + pl.off_scr; }
-PB_DEV float* pb_llbuf(const PbPlan& pl, float* sm) { return sm + pl.off_scr + 1024 + 64; }
-PB_DEV float* pb_fbuf(const PbPlan& pl, float* sm) { return sm + pl.off_scr + 1024 + 64 + 128; }
+PB_DEV float* pb_llbuf(const PbPlan& pl, float* sm) { return sm + pl.off_scr + PB_SCR_MAIN + 64; }
+PB_DEV float* pb_fbuf(const PbPlan& pl, float* sm) { return sm + pl.off_scr + PB_SCR_MAIN + 64 + 128; }
 PB_DEV float* pb_acc(const PbPlan& pl, float* sm) { return sm + pl.off_acc; }
 PB_DEV int* pb_idx(const PbPlan& pl, float* sm) { return reinterpret_cast<int*>(sm + pl.off_idx); }
 PB_DEV float* pb_sc(const PbPlan& pl, float* sm) { return sm + pl.off_scal; }
@@ -132,6 +135,78 @@ PB_DEV void pb_for_each_param(const PbPlan& pl, int tid, int nt, F f) {
       }
     }
   }
+}
+
+// flat (ravel_pytree) index -> index in the resident padded layout
+PB_DEV int pb_flat_to_resident(const PbPlan& pl, int fi) {
+  int l = 0;
+  for (int k = 1; k < pl.nl; ++k)
+    if (fi >= pl.L[k].fb) l = k;
+  const PbLayer& Ly = pl.L[l];
+  int q = fi - Ly.fb;
+  if (q < Ly.out) return Ly.soff + Ly.in * Ly.wp + q;  // bias row
+  q -= Ly.out;
+  const int r = (int)(((unsigned long long)(unsigned)q * Ly.div_out) >> 40);
+  return Ly.soff + r * Ly.wp + (q - r * Ly.out);
+}
+
+// One jax.random.normal(key, (P,))[flat] per parameter handed to f(resident_index, flat_index, z), iterating over the
+// FLAT index (no pad slots, coalesced trace order).  The threefry2x32 + erf_inv chains of ILP parameters are
+// evaluated together: a single chain is ~250 cycles of dependent integer ops, so instruction-level parallelism
+// (not more warps) is what hides its latency.
+template <int ILP, class F>
+PB_DEV void pb_flat_normal_ilp(const PbPlan& pl, int tid, int nt, PbKey key, F f) {
+  for (int p0 = tid; p0 < pl.P; p0 += ILP * nt) {
+    int si[ILP];
+    float z[ILP];
+#pragma unroll
+    for (int j = 0; j < ILP; ++j) {
+      const int fi = p0 + j * nt;
+      si[j] = fi < pl.P ? pb_flat_to_resident(pl, fi) : -1;
+    }
+#pragma unroll
+    for (int j = 0; j < ILP; ++j) z[j] = pb_normal_at(key, (uint32_t)(p0 + j * nt));
+#pragma unroll
+    for (int j = 0; j < ILP; ++j)
+      if (si[j] >= 0) f(si[j], p0 + j * nt, z[j]);
+  }
+}
+
+// Large nets: iterate over the padded resident index instead (pad slots are a few % there, and the flat -> resident
+// mapping per element costs more than they do); 4 chains in flight as above.
+template <class F>
+PB_DEV void pb_padded_normal_ilp4(const PbPlan& pl, int tid, int nt, PbKey key, F f) {
+  for (int l = 0; l < pl.nl; ++l) {
+    const PbLayer& Ly = pl.L[l];
+    const int total = Ly.inA * Ly.wp;
+    const float inv_wp = 1.0f / (float)Ly.wp;
+    for (int e0 = tid; e0 < total; e0 += 4 * nt) {
+      int si[4], fi[4];
+      float z[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int e = e0 + j * nt;
+        const int r = (int)(((float)e + 0.5f) * inv_wp);  // exact: (e + .5)/wp is >= .5/wp away from an integer
+        const int c = e - r * Ly.wp;
+        const bool ok = e < total && c < Ly.out;
+        si[j] = ok ? Ly.soff + e : -1;
+        fi[j] = (r < Ly.in) ? (Ly.fw + r * Ly.out + c) : (Ly.fb + c);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) z[j] = pb_normal_at(key, (uint32_t)fi[j]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (si[j] >= 0) f(si[j], fi[j], z[j]);
+    }
+  }
+}
+
+template <class F>
+PB_DEV void pb_for_each_param_normal(const PbPlan& pl, int tid, int nt, PbKey key, F f) {
+  if (pl.P > 16 * nt) pb_padded_normal_ilp4(pl, tid, nt, key, f);
+  else if (pl.P > 3 * nt) pb_flat_normal_ilp<4>(pl, tid, nt, key, f);
+  else if (pl.P > nt) pb_flat_normal_ilp<2>(pl, tid, nt, key, f);
+  else pb_flat_normal_ilp<1>(pl, tid, nt, key, f);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -695,11 +770,13 @@ PB_DEV void pb_grad_h1(const PbPlan& pl, float* sm, const float* TH, float* G, i
 #endif
 
 // likelihood gradient over the rows of one evaluation: fused one-hidden-layer path or the tiled GEMM engine
-template <int ACT, bool GS>
+// ENG selects the gradient engine at COMPILE time (0 = tiled GEMM engine, 1 = fused one-hidden-layer path): separate
+// kernels keep the code of each small (the HMC kernel lost 5 % when unrelated unrolled code was inlined into it).
+template <int ACT, int ENG>
 PB_DEV void pb_grad(const PbPlan& pl, float* sm, const float* TH, float* G, const float* X, const float* y,
                     const int* idxs, int nrows, float scale, bool tile_loaded, int nt) {
 #if !defined(PB_EMU)
-  if (!GS && pl.h1) {
+  if (ENG == 1) {
     pb_grad_h1<ACT>(pl, sm, TH, G, nrows, scale, nt);
     return;
   }
@@ -707,23 +784,23 @@ PB_DEV void pb_grad(const PbPlan& pl, float* sm, const float* TH, float* G, cons
   pb_grad_rows<ACT>(pl, sm, TH, G, X, y, idxs, nrows, scale, tile_loaded, nt);
 }
 
-// deterministic block sums of K (<=4) quantities whose per-thread partials sit in scr[k*256 + tid]
+// deterministic block sums of K (<=3) quantities whose per-thread partials sit in scr[k*PB_MAX_NT + tid]
 PB_DEV void pb_block_sums(const PbPlan& pl, float* sm, int K, float* dst, int nt) {
   const int nw = nt >> 5;
   float* scr = pb_scr(pl, sm);
   PB_PHASE
   if (tid < K * nw) {
     const int k = tid / nw, w = tid - k * nw;
-    const float* p = scr + k * 256 + w * 32;
+    const float* p = scr + k * PB_MAX_NT + w * 32;
     float a = 0.f;
     for (int i = 0; i < 32; ++i) a += p[i];
-    scr[1024 + k * 8 + w] = a;
+    scr[PB_SCR_MAIN + k * 16 + w] = a;
   }
   PB_ENDPHASE
   PB_PHASE
   if (tid < K) {
     float a = 0.f;
-    for (int w = 0; w < nw; ++w) a += scr[1024 + tid * 8 + w];
+    for (int w = 0; w < nw; ++w) a += scr[PB_SCR_MAIN + tid * 16 + w];
     dst[tid] = a;
   }
   PB_ENDPHASE
@@ -798,7 +875,7 @@ PB_DEV void pb_copy_indices(const PbPlan& pl, float* sm, const int32_t* src, int
 //   GRAD  : test hook, one gradient evaluation
 // resident arrays: st[0]=theta, st[1]=g, st[2]=aux (p | V | m), st[3]=aux2 (v)
 // ------------------------------------------------------------------------------------------------
-template <int ALGO, int ACT, bool GS>
+template <int ALGO, int ACT, bool GS, int ENG>
 PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, int nt) {
   float* ws = a.ws ? a.ws + (size_t)c * pl.nstate * pl.Ps : nullptr;
   float* TH = pb_state<GS>(pl, sm, ws, 0);
@@ -845,7 +922,7 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
   if (ALGO == PB_ALGO_GRAD) {
     pb_copy_indices(pl, sm, cidx, B, nt);
     if (res) pb_load_resident(pl, sm, a.X, a.y, sidx, B, nt);
-    pb_grad<ACT, GS>(pl, sm, TH, G, a.X, a.y, sidx, B, a.scale, false, nt);
+    pb_grad<ACT, ENG>(pl, sm, TH, G, a.X, a.y, sidx, B, a.scale, false, nt);
     PB_PHASE
     pb_for_each_param(pl, tid, nt, [&](int si, int fi) { a.aux1[cP + fi] = G[si] - TH[si] * pl.inv_pv; });
     float* scr = pb_scr(pl, sm);
@@ -871,7 +948,7 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
       pb_gen_indices(pl, sm, B, a.N, a.randint_mult, nt);
     }
     if (res) pb_load_resident(pl, sm, a.X, a.y, sidx, B, nt);
-    pb_grad<ACT, GS>(pl, sm, TH, G, a.X, a.y, sidx, B, a.scale, false, nt);
+    pb_grad<ACT, ENG>(pl, sm, TH, G, a.X, a.y, sidx, B, a.scale, false, nt);
     PB_PHASE
     for (int i = tid; i < pl.Ps; i += nt) {
       const float g = G[i] - TH[i] * pl.inv_pv;
@@ -918,23 +995,23 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
     }
 
     if (ALGO == PB_ALGO_SGLD) {
-      pb_grad<ACT, GS>(pl, sm, TH, G, a.X, a.y, sidx, B, a.scale, tile_loaded, nt);
+      pb_grad<ACT, ENG>(pl, sm, TH, G, a.X, a.y, sidx, B, a.scale, tile_loaded, nt);
       const float ns = sqrtf(2.0f * eps);
       PB_PHASE
-      pb_for_each_param(pl, tid, nt, [&](int si, int fi) {
+      pb_for_each_param_normal(pl, tid, nt, kt, [&](int si, int fi, float z) {
         const float th = TH[si];
         const float g = G[si] - th * pl.inv_pv;
-        TH[si] = th + eps * g + ns * pb_normal_at(kt, (uint32_t)fi);
+        TH[si] = th + eps * g + ns * z;
       });
       PB_ENDPHASE
     } else if (ALGO == PB_ALGO_PSGLD) {
       PB_PHASE
-      pb_for_each_param(pl, tid, nt, [&](int si, int fi) {
+      pb_for_each_param_normal(pl, tid, nt, kt, [&](int si, int fi, float z) {
         const float pre = 1.0f / (sqrtf(A1[si]) + 1e-6f);
-        TH[si] = TH[si] + eps * pre * G[si] + sqrtf(2.0f * pre * eps) * pb_normal_at(kt, (uint32_t)fi);
+        TH[si] = TH[si] + eps * pre * G[si] + sqrtf(2.0f * pre * eps) * z;
       });
       PB_ENDPHASE
-      pb_grad<ACT, GS>(pl, sm, TH, G, a.X, a.y, sidx, B, a.scale, tile_loaded, nt);
+      pb_grad<ACT, ENG>(pl, sm, TH, G, a.X, a.y, sidx, B, a.scale, tile_loaded, nt);
       PB_PHASE
       for (int i = tid; i < pl.Ps; i += nt) {
         const float g = G[i] - TH[i] * pl.inv_pv;
@@ -944,26 +1021,26 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
       PB_ENDPHASE
     } else if (ALGO == PB_ALGO_SGHMC) {
       PB_PHASE
-      pb_for_each_param(pl, tid, nt, [&](int si, int fi) { A1[si] = pb_normal_at(kt, (uint32_t)fi); });
+      pb_for_each_param_normal(pl, tid, nt, kt, [&](int si, int fi, float z) { A1[si] = z; });
       PB_ENDPHASE
       const float ns = sqrtf(2.0f * eps * (a.alpha - a.beta));
       const float fric = 1.0f - a.alpha;
       for (int l = 0; l < a.L; ++l) {
         const PbKey kl = pb_split_at(kt, (uint32_t)l);  // split(keys[t], L)[l]
-        pb_grad<ACT, GS>(pl, sm, TH, G, a.X, a.y, sidx, B, a.scale, tile_loaded, nt);
+        pb_grad<ACT, ENG>(pl, sm, TH, G, a.X, a.y, sidx, B, a.scale, tile_loaded, nt);
         PB_PHASE
-        pb_for_each_param(pl, tid, nt, [&](int si, int fi) {
+        pb_for_each_param_normal(pl, tid, nt, kl, [&](int si, int fi, float z) {
           const float th = TH[si], p = A1[si];
           const float g = G[si] - th * pl.inv_pv;
           TH[si] = th + p;
-          A1[si] = fric * p + eps * g + ns * pb_normal_at(kl, (uint32_t)fi);
+          A1[si] = fric * p + eps * g + ns * z;
         });
         PB_ENDPHASE
       }
     } else if (ALGO == PB_ALGO_ADAM) {
-      pb_grad<ACT, GS>(pl, sm, TH, G, a.X, a.y, sidx, B, a.scale, false, nt);
+      pb_grad<ACT, ENG>(pl, sm, TH, G, a.X, a.y, sidx, B, a.scale, false, nt);
       const float cnt = (float)(a.count0 + t + 1);
-      const float bc1 = 1.0f - powf(a.b1, cnt), bc2 = 1.0f - powf(a.b2, cnt);
+      const float ibc1 = 1.0f / (1.0f - powf(a.b1, cnt)), ibc2 = 1.0f / (1.0f - powf(a.b2, cnt));
       PB_PHASE
       for (int i = tid; i < pl.Ps; i += nt) {
         const float th = TH[i];
@@ -972,7 +1049,7 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
         const float v = (1.0f - a.b2) * (g * g) + a.b2 * A2[i];
         A1[i] = m;
         A2[i] = v;
-        TH[i] = th + (-a.lr) * ((m / bc1) / (sqrtf(v / bc2) + a.eps));
+        TH[i] = th + (-a.lr) * __fdividef(m * ibc1, sqrtf(v * ibc2) + a.eps);
       }
       PB_ENDPHASE
     }
@@ -1014,13 +1091,13 @@ PB_DEV void pb_hmc_logp_reduce(const PbPlan& pl, float* sm, const float* TH, con
     ke += (MI[i] * PM[i]) * PM[i];
   }
   scr[tid] = ll;
-  scr[256 + tid] = t2;
-  scr[512 + tid] = ke;
+  scr[PB_MAX_NT + tid] = t2;
+  scr[2 * PB_MAX_NT + tid] = ke;
   PB_ENDPHASE
   pb_block_sums(pl, sm, 3, pb_sc(pl, sm) + 8, nt);
 }
 
-template <int ACT, bool GS>
+template <int ACT, bool GS, int ENG>
 PB_DEV void pb_hmc_chain(const PbPlan& pl, const PbHmcArgs& a, float* sm, int c, int nt) {
   float* ws = a.ws ? a.ws + (size_t)c * pl.nstate * pl.Ps : nullptr;
   float* TH = pb_state<GS>(pl, sm, ws, 0);
@@ -1052,7 +1129,7 @@ PB_DEV void pb_hmc_chain(const PbPlan& pl, const PbHmcArgs& a, float* sm, int c,
   PB_ENDPHASE
 
   // init: (logp, grad) at theta0
-  pb_grad<ACT, GS>(pl, sm, TH, G, a.X, a.y, nullptr, a.N, pl.inv_s2, false, nt);
+  pb_grad<ACT, ENG>(pl, sm, TH, G, a.X, a.y, nullptr, a.N, pl.inv_s2, false, nt);
   PB_PHASE
   for (int i = tid; i < pl.Ps; i += nt) {
     const float g = G[i] - TH[i] * pl.inv_pv;
@@ -1073,9 +1150,12 @@ PB_DEV void pb_hmc_chain(const PbPlan& pl, const PbHmcArgs& a, float* sm, int c,
     PB_TAG(11)
     PB_PHASE
     float ke = 0.f;
+    // (plain iterator: the momentum draw is 1/L of the work and the unrolled ILP variants cost the HMC kernel 5 %
+    // through code size -- measured)
     pb_for_each_param(pl, tid, nt, [&](int si, int fi) {
+      const float z = pb_normal_at(km, (uint32_t)fi);
       const float mi = MI[si];
-      const float p = sqrtf(1.0f / mi) * pb_normal_at(km, (uint32_t)fi);
+      const float p = sqrtf(1.0f / mi) * z;
       PM[si] = p;
       ke += (mi * p) * p;
       TH[si] = TH0[si];
@@ -1094,7 +1174,7 @@ PB_DEV void pb_hmc_chain(const PbPlan& pl, const PbHmcArgs& a, float* sm, int c,
         TH[i] = TH[i] + eps * (MI[i] * p);
       }
       PB_ENDPHASE
-      pb_grad<ACT, GS>(pl, sm, TH, G, a.X, a.y, nullptr, a.N, pl.inv_s2, false, nt);
+      pb_grad<ACT, ENG>(pl, sm, TH, G, a.X, a.y, nullptr, a.N, pl.inv_s2, false, nt);
       PB_TAG(13)
       PB_PHASE
       for (int i = tid; i < pl.Ps; i += nt) {

@@ -19,11 +19,11 @@ static int pb_backend_sg(int algo, const PbPlan& pl, const PbSgArgs& a, int C, v
 #define PB_CASE(ALGO)                                                        \
   case ALGO:                                                                 \
     if (act == PBNN_ACT_RELU) {                                              \
-      if (pl.gstate) pb_sg_chain<ALGO, PBNN_ACT_RELU, true>(pl, a, p, c, pl.NT);  \
-      else pb_sg_chain<ALGO, PBNN_ACT_RELU, false>(pl, a, p, c, pl.NT);      \
+      if (pl.gstate) pb_sg_chain<ALGO, PBNN_ACT_RELU, true, 0>(pl, a, p, c, pl.NT);  \
+      else pb_sg_chain<ALGO, PBNN_ACT_RELU, false, 0>(pl, a, p, c, pl.NT);      \
     } else {                                                                 \
-      if (pl.gstate) pb_sg_chain<ALGO, PBNN_ACT_TANH, true>(pl, a, p, c, pl.NT);  \
-      else pb_sg_chain<ALGO, PBNN_ACT_TANH, false>(pl, a, p, c, pl.NT);      \
+      if (pl.gstate) pb_sg_chain<ALGO, PBNN_ACT_TANH, true, 0>(pl, a, p, c, pl.NT);  \
+      else pb_sg_chain<ALGO, PBNN_ACT_TANH, false, 0>(pl, a, p, c, pl.NT);      \
     }                                                                        \
     break;
     switch (algo) {
@@ -43,11 +43,11 @@ static int pb_backend_hmc(const PbPlan& pl, const PbHmcArgs& a, int C, void*) {
   for (int c = 0; c < C; ++c) {
     std::vector<float> sm(pl.smem_floats + 16, std::nanf(""));
     if (pl.act == PBNN_ACT_RELU) {
-      if (pl.gstate) pb_hmc_chain<PBNN_ACT_RELU, true>(pl, a, sm.data(), c, pl.NT);
-      else pb_hmc_chain<PBNN_ACT_RELU, false>(pl, a, sm.data(), c, pl.NT);
+      if (pl.gstate) pb_hmc_chain<PBNN_ACT_RELU, true, 0>(pl, a, sm.data(), c, pl.NT);
+      else pb_hmc_chain<PBNN_ACT_RELU, false, 0>(pl, a, sm.data(), c, pl.NT);
     } else {
-      if (pl.gstate) pb_hmc_chain<PBNN_ACT_TANH, true>(pl, a, sm.data(), c, pl.NT);
-      else pb_hmc_chain<PBNN_ACT_TANH, false>(pl, a, sm.data(), c, pl.NT);
+      if (pl.gstate) pb_hmc_chain<PBNN_ACT_TANH, true, 0>(pl, a, sm.data(), c, pl.NT);
+      else pb_hmc_chain<PBNN_ACT_TANH, false, 0>(pl, a, sm.data(), c, pl.NT);
     }
   }
   return PBNN_OK;
