@@ -39,6 +39,7 @@ NETS = [
     ((9, 20, 20, 1), o.RELU, 200),  # two hidden layers, batch > one tile
     ((5, 7, 3), o.TANH, 16),        # out > 1 (generic last layer)
     ((4, 2), o.RELU, 8),            # single Dense layer
+    ((6, 40, 36, 1), o.TANH, 100),  # wide enough for the 8x8 / 8x4 register-tile GEMMs (batch tile 128)
 ]
 
 
