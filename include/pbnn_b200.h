@@ -100,13 +100,22 @@ int pbnn_permutation(const uint32_t* keys, int C, int N, int32_t* out, void* wor
  *   thin, burnin                 trace keeps steps t>=burnin with (t-burnin)%thin==0
  *   trace [C][T_out][P]          optional (NULL = keep only the final state)
  *   flags [C]                    optional; bit0 set if the chain became non-finite
+ *   cv_grad_center, cv_grad_center_est [C][P]  (sgld, sghmc) optional control variates of blackjax.sgmcmc.gradients
+ *                                control_variates, as used by sgld_cv / sghmc_cv / *_svrg (langevin.py:207-354,
+ *                                hamiltonian.py:207-359): gradient of the full-data log-posterior at the centring
+ *                                position (pbnn_logposterior_grad) and the minibatch estimate at the centring position
+ *                                (pbnn_grad_estimator on the loop's fixed minibatch); the step uses
+ *                                grad_center + grad_est - grad_center_est.  NULL, NULL = plain estimator.
+ *   temperature                  (sgld, sghmc) 1 in pbnn; 0 turns the step into the plain gradient step of the SGD
+ *                                phase of cyclical_sgld (langevin.py:364-470)
  */
 
 /* pbnn.mcmc.sgld (src/pbnn/mcmc/langevin.py:21-78) over blackjax.sgld */
 int pbnn_sgld_run(const pbnn_mlp_spec* spec, const float* X, const float* y, int N, const int32_t* idx,
                   int idx_steps, int mb_mode, int B, const uint32_t* keys, float* theta, const float* step_sizes,
                   int n_step_sizes, int64_t t0, int T, int C, int thin, int burnin, float* trace, uint32_t* flags,
-                  void* workspace, int64_t workspace_bytes, void* stream);
+                  const float* cv_grad_center, const float* cv_grad_center_est, float temperature, void* workspace,
+                  int64_t workspace_bytes, void* stream);
 
 /* pbnn.mcmc.pSGLD (langevin.py:81-140; sgmcmc/psgld.py:25-48; sgmcmc/diffusions.py:33-60).
  * g,V [C][P]: logprob_grad / square_avg of pSGLDState; if has_state==0 they are initialised on device
@@ -131,7 +140,9 @@ int pbnn_psgld_step(const pbnn_mlp_spec* spec, const float* Xb, const float* yb,
 int pbnn_sghmc_run(const pbnn_mlp_spec* spec, const float* X, const float* y, int N, const int32_t* idx,
                    int idx_steps, int mb_mode, int B, const uint32_t* keys, float* theta, int L, float alpha,
                    float beta, const float* step_sizes, int n_step_sizes, int64_t t0, int T, int C, int thin,
-                   int burnin, float* trace, uint32_t* flags, void* workspace, int64_t workspace_bytes, void* stream);
+                   int burnin, float* trace, uint32_t* flags, const float* cv_grad_center,
+                   const float* cv_grad_center_est, float temperature, void* workspace, int64_t workspace_bytes,
+                   void* stream);
 
 /* pbnn.mcmc.hmc (hamiltonian.py:18-77) over blackjax.hmc with the full-batch target
  * logprior + sum_i loglik_i (benchmark/pipelines/hmc.py:59-62).
@@ -141,6 +152,12 @@ int pbnn_hmc_run(const pbnn_mlp_spec* spec, const float* X, const float* y, int 
                  float* theta, const float* inv_mass, float step_size, int L, int64_t t0, int num_samples, int C,
                  int thin, int burnin, float* trace, float* logp, int32_t* accept_count, float* info_delta,
                  int32_t* info_accept, uint32_t* flags, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* value and gradient of the full-batch log-posterior logprior + sum_i loglik_i (benchmark/pipelines/hmc.py:59-62;
+ * also the `logdensity_grad_estimator(centering_position, data)` of blackjax control_variates) for C positions.
+ * grad [C][P] and/or logp [C]. */
+int pbnn_logposterior_grad(const pbnn_mlp_spec* spec, const float* X, const float* y, int N, const float* theta, int C,
+                           float* grad, float* logp, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* inner loop of pbnn.deep_ensembles.deep_ensembles_fn (src/pbnn/deep_ensembles.py:59-75): n_steps Adam
  * (optax.adam defaults) steps on -logposterior for C members at once.

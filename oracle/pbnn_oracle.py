@@ -511,6 +511,88 @@ def hmc(spec, X, y, theta0, num_samples, step_size, inv_mass, L, keys, *, dtype=
 
 
 # ----------------------------------------------------------------------------------------------
+# control variates / SVRG / cyclical variants
+# blackjax.sgmcmc.gradients.control_variates (1.2.5): g_hat(theta) = g_full(c) + g_mb(theta) - g_mb(c), with
+# g_full(c) = grad_estimator(c, full data) (N * mean over N rows = the full-data log-posterior gradient).
+# ----------------------------------------------------------------------------------------------
+
+def control_variate_terms(spec, X, y, centering, Xb, yb, dtype=np.float32):
+    dt = np.dtype(dtype)
+    c = np.array(centering, dtype=dt)
+    _, g_full = logposterior_full(spec, c, X.astype(dt), y.astype(dt))
+    g_est = grad_estimator(spec, c, Xb, yb, X.shape[0])
+    return g_full, g_est
+
+
+def sgld_cv(spec, X, y, theta0, B, step_size, T, centering, keys, *, batch_keys=None, dtype=np.float32, which_draw=2,
+            temperature=1.0):
+    """src/pbnn/mcmc/langevin.py:207-270.  ``batch_keys``: keys of the minibatch generator when they differ from the
+    step keys (the SVRG outer loop, :273-354)."""
+    keys = _as_keys(keys)
+    dt = np.dtype(dtype)
+    theta = np.array(theta0, dtype=dt).reshape(len(keys), -1)
+    C, P = theta.shape
+    N = X.shape[0]
+    Xb, yb, _ = _fixed_batches(spec, X.astype(dt), y.astype(dt), _as_keys(batch_keys if batch_keys is not None else keys),
+                               B, which_draw)
+    g_c, g_ce = control_variate_terms(spec, X, y, np.array(centering, dtype=dt).reshape(C, P), Xb, yb, dtype)
+    eps = dt.type(np.float32(step_size))
+    ns = dt.type(np.sqrt(np.float32(2.0) * np.float32(temperature) * np.float32(step_size)))
+    out = np.empty((C, T, P), dtype=dt)
+    for t in range(T):
+        g = (g_c + grad_estimator(spec, theta, Xb, yb, N)) - g_ce
+        theta = theta + eps * g + ns * _normals(_step_keys(keys, t), P, dt)
+        out[:, t] = theta
+    return out
+
+
+def sghmc_cv(spec, X, y, theta0, B, step_size, T, centering, L, keys, *, batch_keys=None, alpha=0.01, beta=0.0,
+             dtype=np.float32, which_draw=2):
+    """src/pbnn/mcmc/hamiltonian.py:207-273."""
+    keys = _as_keys(keys)
+    dt = np.dtype(dtype)
+    theta = np.array(theta0, dtype=dt).reshape(len(keys), -1)
+    C, P = theta.shape
+    N = X.shape[0]
+    Xb, yb, _ = _fixed_batches(spec, X.astype(dt), y.astype(dt), _as_keys(batch_keys if batch_keys is not None else keys),
+                               B, which_draw)
+    g_c, g_ce = control_variate_terms(spec, X, y, np.array(centering, dtype=dt).reshape(C, P), Xb, yb, dtype)
+    eps = dt.type(np.float32(step_size))
+    fric = dt.type(1.0) - dt.type(np.float32(alpha))
+    ns = dt.type(np.sqrt(np.float32(2.0) * np.float32(step_size) * (np.float32(alpha) - np.float32(beta))))
+    out = np.empty((C, T, P), dtype=dt)
+    for t in range(T):
+        kt = _step_keys(keys, t)
+        p = _normals(kt, P, dt)
+        for l in range(L):
+            g = (g_c + grad_estimator(spec, theta, Xb, yb, N)) - g_ce
+            xi = _normals(_step_keys(kt, l), P, dt)
+            theta = theta + p
+            p = fric * p + eps * g + ns * xi
+        out[:, t] = theta
+    return out
+
+
+def svrg(algo, spec, X, y, theta0, B, step_size, centering, num_cv, num_svrg, keys, *, L=None, dtype=np.float32):
+    """sgld_svrg (langevin.py:273-354) / sghmc_svrg (hamiltonian.py:276-359): outer keys = split(rng_key, num_svrg);
+    every outer iteration re-centres on the last position; the minibatch generator stays keyed by rng_key."""
+    keys = _as_keys(keys)
+    theta = np.array(theta0, dtype=dtype).reshape(len(keys), -1)
+    c = np.array(centering, dtype=dtype).reshape(theta.shape)
+    outs = []
+    for i in range(num_svrg):
+        ki = _step_keys(keys, i)
+        if algo == "sgld":
+            tr = sgld_cv(spec, X, y, theta, B, step_size, num_cv, c, ki, batch_keys=keys, dtype=dtype)
+        else:
+            tr = sghmc_cv(spec, X, y, theta, B, step_size, num_cv, c, L, ki, batch_keys=keys, dtype=dtype)
+        outs.append(tr)
+        theta = tr[:, -1]
+        c = theta
+    return np.concatenate(outs, axis=1)
+
+
+# ----------------------------------------------------------------------------------------------
 # deep ensembles (src/pbnn/deep_ensembles.py:16-107; optax.adam 0.2.5 defaults)
 # ----------------------------------------------------------------------------------------------
 

@@ -53,13 +53,14 @@ PROTOTYPES = {
     "pbnn_workspace_bytes": (c_int64, [_SPEC, c_int, c_int, c_int]),
     "pbnn_predict_workspace_bytes": (c_int64, [_SPEC, c_int, c_int, c_int]),
     "pbnn_sgld_run": (c_int, [_SPEC, _P, _P, c_int, _P, c_int, c_int, c_int, _P, _P, _P, c_int, c_int64, c_int, c_int,
-                              c_int, c_int, _P, _P, _P, c_int64, _P]),
+                              c_int, c_int, _P, _P, _P, _P, c_float, _P, c_int64, _P]),
+    "pbnn_logposterior_grad": (c_int, [_SPEC, _P, _P, c_int, _P, c_int, _P, _P, _P, c_int64, _P]),
     "pbnn_psgld_run": (c_int, [_SPEC, _P, _P, c_int, _P, c_int, c_int, c_int, _P, _P, _P, _P, c_int, c_float, _P, c_int,
                                c_int64, c_int, c_int, c_int, c_int, _P, _P, _P, c_int64, _P]),
     "pbnn_psgld_init": (c_int, [_SPEC, _P, _P, c_int, c_int, _P, _P, _P, c_int, _P]),
     "pbnn_psgld_step": (c_int, [_SPEC, _P, _P, c_int, c_int, _P, _P, _P, _P, c_float, c_float, c_int, _P]),
     "pbnn_sghmc_run": (c_int, [_SPEC, _P, _P, c_int, _P, c_int, c_int, c_int, _P, _P, c_int, c_float, c_float, _P, c_int,
-                               c_int64, c_int, c_int, c_int, c_int, _P, _P, _P, c_int64, _P]),
+                               c_int64, c_int, c_int, c_int, c_int, _P, _P, _P, _P, c_float, _P, c_int64, _P]),
     "pbnn_hmc_run": (c_int, [_SPEC, _P, _P, c_int, _P, _P, _P, c_float, c_int, c_int64, c_int, c_int, c_int, c_int, _P,
                              _P, _P, _P, _P, _P, _P, c_int64, _P]),
     "pbnn_adam_ensemble_run": (c_int, [_SPEC, _P, _P, c_int, _P, c_int, c_int, _P, _P, _P, c_int, c_float, c_float,

@@ -312,6 +312,9 @@ struct PbSgArgs {
   float lr, b1, b2, eps;
   int count0;
   float scale;  // (N/B) / sigma^2
+  const float* cv_center;      // control variates: gradient of the full-data log-posterior at the centring point [C][P]
+  const float* cv_center_est;  //                   minibatch estimate at the centring point [C][P]
+  float temperature;           // SGLD / SGHMC temperature (1 in pbnn; 0 = plain gradient step)
   float* ws;    // global workspace [C][nstate][Ps] when plan.gstate
 };
 
@@ -333,6 +336,8 @@ struct PbHmcArgs {
   int32_t* info_accept;
   uint32_t* flags;
   float* ws;
+  float* grad_out;  // optional: gradient of the log-posterior at the initial position [C][P]
+  int no_store;     // do not write theta back (value_and_grad only)
 };
 
 struct PbPredArgs {

@@ -1022,11 +1022,14 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
 
     if (ALGO == PB_ALGO_SGLD) {
       pb_grad<ACT, ENG>(pl, sm, TH, G, a.X, a.y, sidx, B, a.scale, tile_loaded, nt);
-      const float ns = sqrtf(2.0f * eps);
+      const float ns = sqrtf(2.0f * a.temperature * eps);
+      const float* cvc = a.cv_center ? a.cv_center + cP : nullptr;
+      const float* cve = a.cv_center ? a.cv_center_est + cP : nullptr;
       PB_PHASE
       pb_for_each_param_normal(pl, tid, nt, kt, [&](int si, int fi, float z) {
         const float th = TH[si];
-        const float g = G[si] - th * pl.inv_pv;
+        float g = G[si] - th * pl.inv_pv;
+        if (cvc) g = (cvc[fi] + g) - cve[fi];  // blackjax control_variates: grad_center + grad_est - grad_center_est
         TH[si] = th + eps * g + ns * z;
       });
       PB_ENDPHASE
@@ -1049,7 +1052,9 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
       PB_PHASE
       pb_for_each_param_normal(pl, tid, nt, kt, [&](int si, int fi, float z) { A1[si] = z; });
       PB_ENDPHASE
-      const float ns = sqrtf(2.0f * eps * (a.alpha - a.beta));
+      const float ns = sqrtf(2.0f * eps * (a.alpha - a.beta) * a.temperature);
+      const float* cvc = a.cv_center ? a.cv_center + cP : nullptr;
+      const float* cve = a.cv_center ? a.cv_center_est + cP : nullptr;
       const float fric = 1.0f - a.alpha;
       for (int l = 0; l < a.L; ++l) {
         const PbKey kl = pb_split_at(kt, (uint32_t)l);  // split(keys[t], L)[l]
@@ -1057,7 +1062,8 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
         PB_PHASE
         pb_for_each_param_normal(pl, tid, nt, kl, [&](int si, int fi, float z) {
           const float th = TH[si], p = A1[si];
-          const float g = G[si] - th * pl.inv_pv;
+          float g = G[si] - th * pl.inv_pv;
+          if (cvc) g = (cvc[fi] + g) - cve[fi];
           TH[si] = th + p;
           A1[si] = fric * p + eps * g + ns * z;
         });
@@ -1137,8 +1143,8 @@ PB_DEV void pb_hmc_chain(const PbPlan& pl, const PbHmcArgs& a, float* sm, int c,
   const int P = pl.P;
   const size_t cP = (size_t)c * P;
   PbKey ck;
-  ck.k0 = a.keys[2 * c];
-  ck.k1 = a.keys[2 * c + 1];
+  ck.k0 = a.keys ? a.keys[2 * c] : 0u;
+  ck.k1 = a.keys ? a.keys[2 * c + 1] : 0u;
   const float eps = a.step_size, heps = a.step_size * 0.5f;
 
   pb_init_acts(pl, sm, nt);
@@ -1167,6 +1173,7 @@ PB_DEV void pb_hmc_chain(const PbPlan& pl, const PbHmcArgs& a, float* sm, int c,
   pb_hmc_logp_reduce(pl, sm, TH, PM, MI, nt);
   PB_PHASE
   if (tid == 0) sc[12] = (-0.5f * pl.inv_pv * sc[9] - (float)P * pl.logprior_const) + sc[8];
+  if (a.grad_out) pb_for_each_param(pl, tid, nt, [&](int si, int fi) { a.grad_out[cP + fi] = G0[si]; });
   PB_ENDPHASE
 
   for (int s = 0; s < a.S; ++s) {
@@ -1246,7 +1253,7 @@ PB_DEV void pb_hmc_chain(const PbPlan& pl, const PbHmcArgs& a, float* sm, int c,
     PB_ENDPHASE
   }
 
-  pb_store_state(pl, TH0, a.theta + cP, scu + 2, nt);
+  if (!a.no_store) pb_store_state(pl, TH0, a.theta + cP, scu + 2, nt);
   PB_PHASE
   if (tid == 0) {
     if (a.logp) a.logp[c] = sc[12];

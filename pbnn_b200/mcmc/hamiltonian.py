@@ -42,3 +42,39 @@ def sghmc(X, y, loglikelihood_fn, logprior_fn, init_positions, batch_size, step_
                     int(num_integration_steps), alpha=alpha, beta=beta, minibatch_mode=minibatch_mode, thin=thin,
                     burnin=burnin)
     return positions_tree(res["trace"], layers, batched), make_ravel_fn(layers), make_predict_fn(layers)
+
+
+def sghmc_cv(X, y, loglikelihood_fn, logprior_fn, init_positions, batch_size, step_size, num_iterations,
+             centering_positions, num_integration_steps, rng_key, *, thin=1, burnin=0):
+    """pbnn.mcmc.sghmc_cv (hamiltonian.py:207-273)."""
+    from .langevin import _cv_terms
+    require_specs(loglikelihood_fn, logprior_fn)
+    ops = default_ops()
+    flat, layers, keys, batched = chain_layout(init_positions, rng_key)
+    cflat, _, _, _ = chain_layout(centering_positions, rng_key)
+    spec = loglikelihood_fn.flat_spec(layers[0], logprior_fn)
+    g_full, g_est, idx = _cv_terms(ops, spec, X, y, cflat, keys, batch_size)
+    res = ops.sghmc(spec, X, y, flat, keys, int(batch_size), step_size, int(num_iterations),
+                    int(num_integration_steps), idx=idx, cv=(g_full, g_est), thin=thin, burnin=burnin)
+    return positions_tree(res["trace"], layers, batched), make_ravel_fn(layers), make_predict_fn(layers)
+
+
+def sghmc_svrg(X, y, loglikelihood_fn, logprior_fn, init_positions, batch_size, step_size, centering_positions,
+               num_cv_iterations, num_svrg_iterations, num_integration_steps, rng_key):
+    """pbnn.mcmc.sghmc_svrg (hamiltonian.py:276-359)."""
+    from .langevin import _cv_terms
+    require_specs(loglikelihood_fn, logprior_fn)
+    ops = default_ops()
+    flat, layers, keys, batched = chain_layout(init_positions, rng_key)
+    cflat, _, _, _ = chain_layout(centering_positions, rng_key)
+    spec = loglikelihood_fn.flat_spec(layers[0], logprior_fn)
+    outer = ops.split(keys, int(num_svrg_iterations))
+    traces, theta, centre = [], flat, cflat
+    for i in range(int(num_svrg_iterations)):
+        g_full, g_est, idx = _cv_terms(ops, spec, X, y, centre, keys, batch_size)
+        res = ops.sghmc(spec, X, y, theta, outer[:, i, :].contiguous(), int(batch_size), step_size,
+                        int(num_cv_iterations), int(num_integration_steps), idx=idx, cv=(g_full, g_est))
+        traces.append(res["trace"])
+        theta = centre = res["theta"]
+    trace = torch.cat(traces, dim=1)
+    return positions_tree(trace, layers, batched), make_ravel_fn(layers), make_predict_fn(layers)

@@ -205,16 +205,22 @@ class Ops:
         flags = self._zeros((C,), self.i32)
         return keys, C, X, y, th, ix, idx_steps, steps, nsteps, trace, flags
 
+    def _cv(self, cv, spec, C):
+        if cv is None:
+            return None, None
+        return self._theta(cv[0], spec, C), self._theta(cv[1], spec, C)
+
     def sgld(self, spec: FlatSpec, X, y, theta, keys, B: int, step_size, T: int, *, idx=None,
-             minibatch_mode="reference_fixed", t0=0, thin=1, burnin=0, keep_trace=True):
+             minibatch_mode="reference_fixed", t0=0, thin=1, burnin=0, keep_trace=True, cv=None, temperature=1.0):
         keys, C, X, y, th, ix, idx_steps, steps, nsteps, trace, flags = self._sg_common(
             spec, X, y, theta, keys, B, step_size, T, idx, thin, burnin, keep_trace)
         cs = spec.c_struct()
         ws, wsb = self._workspace(spec, _lib.OP_SGLD, B, C)
+        cvc, cve = self._cv(cv, spec, C)
         rc = self.lib.pbnn_sgld_run(cs, self._ptr(X), self._ptr(y), X.shape[0], self._ptr(ix), idx_steps,
                                     _MB_MODES[minibatch_mode], B, self._ptr(keys), self._ptr(th), self._ptr(steps),
-                                    nsteps, t0, T, C, thin, burnin, self._ptr(trace), self._ptr(flags), self._ptr(ws), wsb,
-                                    self._stream())
+                                    nsteps, t0, T, C, thin, burnin, self._ptr(trace), self._ptr(flags), self._ptr(cvc),
+                                    self._ptr(cve), float(temperature), self._ptr(ws), wsb, self._stream())
         check(self.lib, rc, "sgld")
         return {"theta": th, "trace": trace, "flags": flags}
 
@@ -236,15 +242,18 @@ class Ops:
         return {"theta": th, "trace": trace, "flags": flags, "grad": g, "square_avg": V}
 
     def sghmc(self, spec: FlatSpec, X, y, theta, keys, B: int, step_size, T: int, L: int, *, alpha=0.01, beta=0.0,
-              idx=None, minibatch_mode="reference_fixed", t0=0, thin=1, burnin=0, keep_trace=True):
+              idx=None, minibatch_mode="reference_fixed", t0=0, thin=1, burnin=0, keep_trace=True, cv=None,
+              temperature=1.0):
         keys, C, X, y, th, ix, idx_steps, steps, nsteps, trace, flags = self._sg_common(
             spec, X, y, theta, keys, B, step_size, T, idx, thin, burnin, keep_trace)
         cs = spec.c_struct()
         ws, wsb = self._workspace(spec, _lib.OP_SGHMC, B, C)
+        cvc, cve = self._cv(cv, spec, C)
         rc = self.lib.pbnn_sghmc_run(cs, self._ptr(X), self._ptr(y), X.shape[0], self._ptr(ix), idx_steps,
                                      _MB_MODES[minibatch_mode], B, self._ptr(keys), self._ptr(th), int(L), float(alpha),
                                      float(beta), self._ptr(steps), nsteps, t0, T, C, thin, burnin, self._ptr(trace),
-                                     self._ptr(flags), self._ptr(ws), wsb, self._stream())
+                                     self._ptr(flags), self._ptr(cvc), self._ptr(cve), float(temperature),
+                                     self._ptr(ws), wsb, self._stream())
         check(self.lib, rc, "sghmc")
         return {"theta": th, "trace": trace, "flags": flags}
 
@@ -312,6 +321,20 @@ class Ops:
                                           self._stream())
         check(self.lib, rc, "grad_estimator")
         return g, ll
+
+    def logposterior_grad(self, spec: FlatSpec, X, y, theta):
+        """(logp [C], grad [C,P]) of the full-batch log-posterior (HMC target; centring gradient of control variates)."""
+        th = self._as(theta, self.f32)
+        th = th.reshape(-1, th.shape[-1]).contiguous()
+        C = th.shape[0]
+        X, y = self._data(X, y, spec)
+        g = self._empty(th.shape, self.f32)
+        lp = self._empty((C,), self.f32)
+        ws, wsb = self._workspace(spec, _lib.OP_HMC, X.shape[0], C)
+        rc = self.lib.pbnn_logposterior_grad(spec.c_struct(), self._ptr(X), self._ptr(y), X.shape[0], self._ptr(th), C,
+                                             self._ptr(g), self._ptr(lp), self._ptr(ws), wsb, self._stream())
+        check(self.lib, rc, "logposterior_grad")
+        return lp, g
 
     def predict(self, spec: FlatSpec, samples, X_test, *, want_preds=True, want_moments=False):
         smp = self._as(samples, self.f32)

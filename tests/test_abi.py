@@ -51,7 +51,7 @@ def test_host_side_calls_without_gpu(cuda_lib_path):
     assert lib.pbnn_plan_query(huge, 128, 2, out) == -2
     assert b"does not fit" in lib.pbnn_last_error()
     assert lib.pbnn_sgld_run(spec, None, None, 10, None, 0, 0, 4, None, None, None, 1, 0, 1, 1, 1, 0, None, None, None,
-                             0, None) == -1
+                             None, 1.0, None, 0, None) == -1
     bad = _lib.make_spec((13, 50, 1), 7, 0.1)
     assert lib.pbnn_num_params(bad) == 751 and lib.pbnn_plan_query(bad, 8, 2, out) == -1
 

@@ -6,7 +6,8 @@ import pytest
 import pbnn_b200
 from oracle import pbnn_oracle as o
 from pbnn_b200 import logprobs, pytree
-from pbnn_b200.mcmc import hmc, kernels, pSGLD, predictive_moments, scheduled_sgld, sghmc, sgld
+from pbnn_b200.mcmc import (cyclical_sgld, hmc, kernels, pSGLD, predictive_moments, scheduled_sgld, sghmc, sghmc_cv,
+                            sghmc_svrg, sgld, sgld_cv, sgld_svrg)
 from pbnn_b200.models import MLP
 from pbnn_b200.ops import set_default_ops
 
@@ -153,3 +154,46 @@ def test_flax_style_init_and_apply(api):
     out = net.apply({"params": p}, X)
     sp = o.MlpSpec((4, 6, 6, 1), o.RELU, 0.1)
     assert rel(npy(out), o.predict(sp, flat[None], X)[0]) <= 1e-5
+
+
+def test_control_variates_and_svrg(api):
+    """sgld_cv / sghmc_cv / sgld_svrg / sghmc_svrg (langevin.py:207-354, hamiltonian.py:207-359)."""
+    C = 2
+    X, y, net, sp, keys, th0, tree, lik, prior = setup(C, layers=(8, 12, 1), act="tanh", N=150)
+    centre = (th0 * 0.5).astype(np.float32)
+    ctree = o.to_pytree(sp, centre)
+    # the two constant terms against the float64 oracle
+    idx = np.stack([o.reference_draw(k, 16, len(X), 2) for k in keys])
+    gf64, ge64 = o.control_variate_terms(sp, X, y, centre, X[idx], y[idx], dtype=np.float64)
+    lp, gf = api.logposterior_grad(lik.flat_spec(8, prior), X, y, centre)
+    assert rel(npy(gf), gf64) <= 1e-5
+    assert rel(npy(lp), o.logposterior_full(sp, centre.astype(np.float64), X.astype(np.float64), y.astype(np.float64))[0]) <= 1e-5
+    pos, ravel_fn, _ = sgld_cv(X, y, lik, prior, tree, 16, 1e-6, 5, ctree, keys)
+    assert rel(npy(ravel_fn(pos)), o.sgld_cv(sp, X, y, th0, 16, 1e-6, 5, centre, keys)) <= 1e-5
+    pos, ravel_fn, _ = sghmc_cv(X, y, lik, prior, tree, 16, 1e-9, 3, ctree, 2, keys)
+    assert rel(npy(ravel_fn(pos)), o.sghmc_cv(sp, X, y, th0, 16, 1e-9, 3, centre, 2, keys)) <= 1e-5
+    pos, ravel_fn, _ = sgld_svrg(X, y, lik, prior, tree, 16, 1e-6, ctree, 3, 2, keys)
+    flat = npy(ravel_fn(pos))
+    assert flat.shape == (C, 6, sp.num_params)
+    assert rel(flat, o.svrg("sgld", sp, X, y, th0, 16, 1e-6, centre, 3, 2, keys)) <= 1e-5
+    pos, ravel_fn, _ = sghmc_svrg(X, y, lik, prior, tree, 16, 1e-9, ctree, 2, 2, 2, keys)
+    assert rel(npy(ravel_fn(pos)), o.svrg("sghmc", sp, X, y, th0, 16, 1e-9, centre, 2, 2, keys, L=2)) <= 1e-5
+
+
+def test_cyclical_sgld_structure(api):
+    """cyclical_sgld (langevin.py:364-470): shapes, burn-in per cycle, temperature-0 SGD phase == plain gradient steps."""
+    X, y, net, sp, key, th0, tree, lik, prior = setup(layers=(8, 12, 1), act="tanh", N=150)
+    pos, ravel_fn, _ = cyclical_sgld(X, y, lik, prior, tree, 16, 1e-6, 2, key, num_sgd_steps=3, num_sgld_steps=5,
+                                     burnin_sgld=2)
+    flat = npy(ravel_fn(pos))
+    assert flat.shape == (2 * 3, sp.num_params) and np.isfinite(flat).all()
+    # SGD phase: theta <- theta + schedule(it) * grad, no noise
+    fs = lik.flat_spec(8, prior)
+    k1 = o.split(key, 2)[1]
+    idx = o.reference_draw(k1, 16, len(X), 1)[None]
+    steps = [0.5 * (np.cos(np.pi * it / 8) + 1) * 1e-6 for it in range(3)]
+    res = api.sgld(fs, X, y, th0, k1, 16, steps, 3, idx=idx, temperature=0.0)
+    th = th0.astype(np.float64)
+    for it in range(3):
+        th = th + np.float32(steps[it]) * o.grad_estimator(sp, th, X[idx].astype(np.float64), y[idx].astype(np.float64), len(X))
+    assert rel(npy(res["theta"]), th) <= 1e-5
