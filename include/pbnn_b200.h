@@ -37,6 +37,13 @@ extern "C" {
 #define PBNN_ACT_RELU 0
 #define PBNN_ACT_TANH 1
 
+/* likelihoods of benchmark/pipelines/logprobs.py:
+ *   homoscedastic  (:12-17)  -sum_o 0.5 (y_o - f_o)^2 / noise_level^2, y has dims[n_layers] columns
+ *   heteroscedastic (:37-42) network outputs (mu, log sigma^2) (dims[n_layers] == 2), y has ONE column:
+ *                            -0.5 log sigma^2 - 0.5 (y - mu)^2 / sigma^2   (noise_level is ignored) */
+#define PBNN_LIK_HOMOSCEDASTIC 0
+#define PBNN_LIK_HETEROSCEDASTIC 1
+
 /* minibatch semantics of the SG samplers */
 #define PBNN_MB_REFERENCE_FIXED 0 /* the draw the reference's traced lax.scan re-uses for all steps */
 #define PBNN_MB_PER_STEP 1        /* a fresh draw of the same generator at every step               */
@@ -49,6 +56,7 @@ typedef struct pbnn_mlp_spec {
   int32_t activation;                /* PBNN_ACT_RELU | PBNN_ACT_TANH (hidden layers)         */
   float noise_level;                 /* sigma of the Gaussian likelihood                      */
   float prior_scale;                 /* std of the N(0, s^2) prior; the reference uses 1      */
+  int32_t likelihood;                /* PBNN_LIK_HOMOSCEDASTIC | PBNN_LIK_HETEROSCEDASTIC       */
 } pbnn_mlp_spec;
 
 int pbnn_version(void);

@@ -200,6 +200,7 @@ class MlpSpec:
     act: int = RELU
     noise_level: float = 0.1
     prior_scale: float = 1.0
+    heteroscedastic: bool = False  # outputs (mu, log sigma^2), logprobs.py:37-42
 
     @property
     def n_layers(self) -> int:
@@ -267,10 +268,17 @@ def loglik_and_grad(spec: MlpSpec, theta: np.ndarray, X: np.ndarray, y: np.ndarr
     C = theta.shape[0]
     f, hs = mlp_forward(spec, theta, X, return_hidden=True)
     yb = np.broadcast_to(y, (C,) + y.shape[-2:]).astype(dt) if y.ndim == 2 else y.astype(dt)
-    inv_s2 = dt.type(1.0) / (dt.type(spec.noise_level) * dt.type(spec.noise_level))
-    res = yb - f
-    ll = -(dt.type(0.5) * res * res * inv_s2).sum(axis=(1, 2))
-    dz = res * inv_s2 * dt.type(scale)  # d(scale*ll)/df
+    if spec.heteroscedastic:
+        mu, ls = f[..., 0], f[..., 1]
+        res = yb[..., 0] - mu
+        e = np.exp(-ls)
+        ll = (-dt.type(0.5) * ls - dt.type(0.5) * res * res * e).sum(axis=1)
+        dz = np.stack([res * e, dt.type(-0.5) + dt.type(0.5) * res * res * e], axis=-1) * dt.type(scale)
+    else:
+        inv_s2 = dt.type(1.0) / (dt.type(spec.noise_level) * dt.type(spec.noise_level))
+        res = yb - f
+        ll = -(dt.type(0.5) * res * res * inv_s2).sum(axis=(1, 2))
+        dz = res * inv_s2 * dt.type(scale)  # d(scale*ll)/df
     g = np.zeros_like(theta)
     params = unravel(spec, theta)
     offs = spec.offsets()

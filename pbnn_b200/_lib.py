@@ -27,6 +27,7 @@ class MlpSpecC(ctypes.Structure):
         ("activation", c_int32),
         ("noise_level", c_float),
         ("prior_scale", c_float),
+        ("likelihood", c_int32),
     ]
 
 
@@ -86,7 +87,10 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
     return lib
 
 
-def make_spec(layers, activation: int, noise_level: float, prior_scale: float = 1.0) -> MlpSpecC:
+LIK_HOMOSCEDASTIC, LIK_HETEROSCEDASTIC = 0, 1
+
+
+def make_spec(layers, activation: int, noise_level: float, prior_scale: float = 1.0, likelihood: int = 0) -> MlpSpecC:
     layers = [int(v) for v in layers]
     if not (2 <= len(layers) <= PBNN_MAX_LAYERS + 1):
         raise ValueError(f"an MLP needs 1..{PBNN_MAX_LAYERS} Dense layers, got widths {layers}")
@@ -97,6 +101,7 @@ def make_spec(layers, activation: int, noise_level: float, prior_scale: float = 
     s.activation = int(activation)
     s.noise_level = float(noise_level)
     s.prior_scale = float(prior_scale)
+    s.likelihood = int(likelihood)
     return s
 
 

@@ -39,6 +39,8 @@ struct PbLayer {
 struct PbPlan {
   int nl, act, P, Ps;
   int d, s;
+  int lik, sy;      // likelihood kind; number of target columns (1 for heteroscedastic, else s)
+  float lik_scale;  // 1/sigma^2 (homoscedastic) or 1
   PbLayer L[PBNN_MAX_LAYERS];
   int BT, ap;                     // batch-tile rows (multiple of 32) and activation pitch (BT + 4)
   int aoff[PBNN_MAX_LAYERS + 2];  // tile buffers A_0 .. A_nl, then yT (A_0 / yT have 0 rows when res_rows > 0)
@@ -148,7 +150,7 @@ static inline void pb_layout(PbPlan* pl, const pbnn_mlp_spec* sp, int rows, int 
     int r;
     if (l < pl->nl) r = pb_r4(sp->dims[l] + 1);
     else if (l == pl->nl) r = pl->s == 1 ? 1 : pb_r4(pl->s);  // A_nl: output / dZ_last (rank-1 path: one row)
-    else r = pl->s;                                            // yT
+    else r = pl->sy;                                           // yT
     if (res && (l == 0 || l == pl->nl + 1)) r = 0;
     pl->aoff[l] = off;
     off += r * ap;
@@ -160,7 +162,7 @@ static inline void pb_layout(PbPlan* pl, const pbnn_mlp_spec* sp, int rows, int 
     pl->off_xres = off;
     off += pb_r4(pl->d + 1) * pl->xp;
     pl->off_yres = off;
-    off += pl->s * pl->xp;
+    off += pl->sy * pl->xp;
   }
   pl->off_scr = off;
   off += PB_SCR_FLOATS;
@@ -189,7 +191,16 @@ static inline int pb_build_plan(const pbnn_mlp_spec* sp, int rows, int nstate, i
     snprintf(err, errn, "unknown activation %d", sp->activation);
     return PBNN_EINVAL;
   }
-  if (!(sp->noise_level > 0.f) || !(sp->prior_scale > 0.f)) {
+  const int hetero = sp->likelihood == PBNN_LIK_HETEROSCEDASTIC;
+  if (sp->likelihood != PBNN_LIK_HOMOSCEDASTIC && !hetero) {
+    snprintf(err, errn, "unknown likelihood %d", sp->likelihood);
+    return PBNN_EINVAL;
+  }
+  if (hetero && sp->dims[sp->n_layers] != 2) {
+    snprintf(err, errn, "the heteroscedastic likelihood needs a network with 2 outputs (mu, log sigma^2)");
+    return PBNN_EINVAL;
+  }
+  if ((!hetero && !(sp->noise_level > 0.f)) || !(sp->prior_scale > 0.f)) {
     snprintf(err, errn, "noise_level and prior_scale must be > 0");
     return PBNN_EINVAL;
   }
@@ -202,7 +213,10 @@ static inline int pb_build_plan(const pbnn_mlp_spec* sp, int rows, int nstate, i
   pl->P = P;
   pl->d = sp->dims[0];
   pl->s = sp->dims[sp->n_layers];
-  pl->inv_s2 = 1.0f / (sp->noise_level * sp->noise_level);
+  pl->lik = sp->likelihood;
+  pl->sy = hetero ? 1 : pl->s;
+  pl->inv_s2 = hetero ? 1.0f : 1.0f / (sp->noise_level * sp->noise_level);
+  pl->lik_scale = pl->inv_s2;
   pl->inv_pv = 1.0f / (sp->prior_scale * sp->prior_scale);
   pl->logprior_const = 0.918938533204672742f + logf(sp->prior_scale);
   int soff = 0, foff = 0;

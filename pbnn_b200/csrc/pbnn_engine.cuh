@@ -429,7 +429,7 @@ PB_DEV void pb_gather_rows(const PbPlan& pl, float* xdst, float* ydst, int pitch
                            const float* y, const int* idxs, int row0, int nrows, int nt) {
   PB_TAG(10)
   PB_PHASE
-  const int d = pl.d, s = pl.s;
+  const int d = pl.d, s = pl.sy;
   for (int item = tid; item < cap * d; item += nt) {
     const int b = item / d, k = item - b * d;
     float v = 0.f;
@@ -540,10 +540,19 @@ PB_DEV void pb_forward_tile(const PbPlan& pl, float* sm, const float* TH, const 
       for (int b = tid; b < BT; b += nt) {
         const bool valid = b < nvalid;
         float ll = 0.f;
-        for (int o = 0; o < pl.s; ++o) {
-          const float res = T.y[o * T.py + b] - Aout[o * ap + b];
-          Aout[o * ap + b] = valid ? res * scale : 0.f;
-          ll += valid ? -0.5f * res * res * pl.inv_s2 : 0.f;
+        if (pl.lik == PBNN_LIK_HETEROSCEDASTIC) {
+          // outputs (mu, log sigma^2): ll = -0.5 ls - 0.5 (y - mu)^2 exp(-ls)   (logprobs.py:37-42)
+          const float mu = Aout[b], ls = Aout[ap + b];
+          const float e = expf(-ls), res = T.y[b] - mu;
+          Aout[b] = valid ? res * e * scale : 0.f;
+          Aout[ap + b] = valid ? (-0.5f + 0.5f * res * res * e) * scale : 0.f;
+          ll = valid ? -0.5f * ls - 0.5f * res * res * e : 0.f;
+        } else {
+          for (int o = 0; o < pl.s; ++o) {
+            const float res = T.y[o * T.py + b] - Aout[o * ap + b];
+            Aout[o * ap + b] = valid ? res * scale : 0.f;
+            ll += valid ? -0.5f * res * res * pl.inv_s2 : 0.f;
+          }
         }
         llbuf[b] = first ? ll : llbuf[b] + ll;
       }

@@ -48,6 +48,34 @@ class GaussianMLPLikelihood:
         return -(0.5 * (y - f) ** 2 / self.noise_level ** 2).sum()
 
 
+@dataclass(frozen=True)
+class HeteroscedasticGaussianMLPLikelihood(GaussianMLPLikelihood):
+    """``heteroscedastic_loglike_fn(parameters, data, network)`` (logprobs.py:37-42): the network has two outputs
+    ``(mu, log sigma^2)``; ``-0.5 log sigma^2 - 0.5 (y - mu)^2 / sigma^2`` per datum (Experiment 3,
+    benchmark/pipelines/experiments.py:149-151)."""
+
+    noise_level: float = 1.0  # unused
+
+    def flat_spec(self, d: int, prior: StdNormalPrior = StdNormalPrior()) -> FlatSpec:
+        from ._lib import LIK_HETEROSCEDASTIC
+        widths = self.network.widths(d)
+        if widths[-1] != 2:
+            raise ValueError("the heteroscedastic likelihood needs a network with out_features=2")
+        return FlatSpec(widths, self.network.act_code, 1.0, float(prior.scale), LIK_HETEROSCEDASTIC)
+
+    def __call__(self, parameters, data):
+        X, y = data
+        f = self.network.apply({"params": parameters}, X)
+        f = f.reshape(-1, 2)
+        y = default_ops()._as(y, torch.float32).reshape(-1)
+        mu, ls = f[:, 0], f[:, 1]
+        return (-0.5 * ls - 0.5 * (y - mu) ** 2 * torch.exp(-ls)).sum()
+
+
+def heteroscedastic_loglike_fn(network: MLP) -> HeteroscedasticGaussianMLPLikelihood:
+    return HeteroscedasticGaussianMLPLikelihood(network)
+
+
 def homoscedastic_loglike_fn(network: MLP, noise_level: float) -> GaussianMLPLikelihood:
     return GaussianMLPLikelihood(network, noise_level)
 

@@ -26,13 +26,18 @@ class FlatSpec:
     activation: int = ACT_RELU
     noise_level: float = 0.1
     prior_scale: float = 1.0
+    likelihood: int = 0  # _lib.LIK_HOMOSCEDASTIC | _lib.LIK_HETEROSCEDASTIC
+
+    @property
+    def target_width(self) -> int:
+        return 1 if self.likelihood == _lib.LIK_HETEROSCEDASTIC else self.layers[-1]
 
     @property
     def num_params(self) -> int:
         return sum(o * (i + 1) for i, o in zip(self.layers[:-1], self.layers[1:]))
 
     def c_struct(self):
-        return make_spec(self.layers, self.activation, self.noise_level, self.prior_scale)
+        return make_spec(self.layers, self.activation, self.noise_level, self.prior_scale, self.likelihood)
 
 
 def trace_len(T: int, thin: int, burnin: int) -> int:
@@ -119,8 +124,8 @@ class Ops:
             raise ValueError(f"X must be (N, {spec.layers[0]}), got {tuple(X.shape)}")
         if y.ndim == 1:
             y = y.reshape(-1, 1)
-        if y.shape != (X.shape[0], spec.layers[-1]):
-            raise ValueError(f"y must be (N, {spec.layers[-1]}), got {tuple(y.shape)}")
+        if y.shape != (X.shape[0], spec.target_width):
+            raise ValueError(f"y must be (N, {spec.target_width}), got {tuple(y.shape)}")
         return X, y
 
     def _idx(self, idx, C, B):

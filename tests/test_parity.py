@@ -270,6 +270,37 @@ def test_adam_ensemble(ops):
     assert rel(npy(b["theta"]), npy(out["theta"])) <= 1e-6
 
 
+def test_heteroscedastic_likelihood(ops):
+    """heteroscedastic_loglike_fn (benchmark/pipelines/logprobs.py:37-42): outputs (mu, log sigma^2), one target."""
+    from pbnn_b200._lib import LIK_HETEROSCEDASTIC
+    layers = (3, 10, 2)
+    X, y = o.synthetic_regression(80, 3, 4)
+    sp = o.MlpSpec(layers, o.TANH, 1.0, heteroscedastic=True)
+    fs = FlatSpec(layers, o.TANH, 1.0, 1.0, LIK_HETEROSCEDASTIC)
+    keys = o.split(o.PRNGKey(8), 3)
+    th0 = (0.3 * np.random.default_rng(3).standard_normal((3, sp.num_params))).astype(np.float32)
+    idx = np.random.default_rng(2).integers(0, 80, (3, 24)).astype(np.int32)
+    g, ll = ops.grad_estimator(fs, X, y, th0, idx)
+    g64 = o.grad_estimator(sp, th0.astype(np.float64), X[idx].astype(np.float64), y[idx].astype(np.float64), 80)
+    ll64, _ = o.loglik_and_grad(sp, th0.astype(np.float64), X[idx].astype(np.float64), y[idx].astype(np.float64), 1.0)
+    assert rel(npy(g), g64) <= 1e-5 and rel(npy(ll), ll64) <= 1e-5
+    # finite-difference check of the oracle's heteroscedastic gradient
+    t = th0[:1].astype(np.float64)
+    f = lambda v: (o.logprior(sp, v) + 80 * o.loglik_and_grad(sp, v, X[idx[0]].astype(np.float64), y[idx[0]].astype(np.float64), 1.0)[0] / 24)[0]
+    fd = np.array([(f(t + 1e-6 * np.eye(sp.num_params)[j]) - f(t - 1e-6 * np.eye(sp.num_params)[j])) / 2e-6
+                   for j in range(sp.num_params)])
+    assert rel(g64[0], fd) <= 1e-6
+    ref = o.sgld(sp, X, y, th0, 24, 1e-4, 5, keys)
+    assert rel(npy(ops.sgld(fs, X, y, th0, keys, 24, 1e-4, 5)["trace"]), ref) <= RTOL_STEP
+    minv = np.ones(sp.num_params, np.float32)
+    ref, info = o.hmc(sp, X, y, th0, 3, 1e-3, minv, 4, keys, return_info=True)
+    out = ops.hmc(fs, X, y, th0, keys, 3, 1e-3, minv, 4, info=True)
+    assert np.array_equal(npy(out["accept"]).astype(bool), info["accept"])
+    assert rel(npy(out["trace"]), ref) <= RTOL_STEP
+    with pytest.raises(ValueError):
+        ops.sgld(FlatSpec((3, 10, 1), o.TANH, 1.0, 1.0, LIK_HETEROSCEDASTIC), X, y, th0[:, :51], keys, 24, 1e-4, 2)
+
+
 # ------------------------------------------------------------------------------------------------ edges / errors
 def test_edge_cases_and_errors(ops):
     layers, act, B = NETS[0]
