@@ -185,6 +185,10 @@ int64_t pbnn_predict_workspace_bytes(const pbnn_mlp_spec* spec, int S, int M, in
 int pbnn_predict(const pbnn_mlp_spec* spec, const float* samples, int S, const float* Xtest, int M, float* preds,
                  float* sum, float* sumsq, float* workspace, int64_t workspace_bytes, void* stream);
 
+/* thinning_fn (src/pbnn/utils/misc.py:58-125): greedy energy-distance thinning of `n` flat positions [n][D] down to
+ * `size` indices, in the reference's order (picks 1..size-1, then the initial pick).  workspace: 3*n + 2064 floats. */
+int pbnn_thinning(const float* positions, int n, int D, int size, int32_t* idx_out, float* workspace, void* stream);
+
 /* gradient of the (scaled) log-posterior estimator for C positions on explicit minibatches -- test hook for
  * blackjax grad_estimator == src/pbnn/utils/misc.py:34-55.  idx [C][B]; grad [C][P]; loglik [C] optional. */
 int pbnn_grad_estimator(const pbnn_mlp_spec* spec, const float* X, const float* y, int N, const int32_t* idx, int B,

@@ -659,6 +659,30 @@ def deep_ensembles(spec, X, y, init_params, B, num_epochs, lr, member_train_keys
 
 
 # ----------------------------------------------------------------------------------------------
+# thinning (src/pbnn/utils/misc.py:58-125)
+# ----------------------------------------------------------------------------------------------
+
+def thinning(positions, size: int, dtype=np.float32):
+    """Greedy energy-distance thinning; returns the indices in the reference's order (picks 1..size-1, then the
+    initial pick appended last, misc.py:121-123)."""
+    X = np.asarray(positions, dtype=dtype)
+    xx = (X * X).sum(1)
+    nrm = np.sqrt(xx)
+    gram = X @ X.T
+    K = nrm[:, None] + nrm[None, :] - np.sqrt(np.clip(xx[:, None] + xx[None, :] - 2 * gram, 0, None))
+    k0_mean = K.mean(axis=1)
+    obj = 2.0 * nrm - 2.0 * k0_mean
+    init = int(np.argmin(obj))
+    idx, picks = init, []
+    for _ in range(1, size):
+        ki = nrm[idx] + nrm - np.sqrt(np.clip(xx[idx] + xx - 2 * (X @ X[idx]), 0, None))
+        obj = obj + 2.0 * ki - 2.0 * k0_mean
+        idx = int(np.argmin(obj))
+        picks.append(idx)
+    return np.array(picks + [init], dtype=np.int32)
+
+
+# ----------------------------------------------------------------------------------------------
 # predictive (predict_fn: langevin.py:75-76; mean: benchmark/pipelines/metrics_prediction_intervals.py:188)
 # ----------------------------------------------------------------------------------------------
 

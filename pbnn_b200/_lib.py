@@ -68,6 +68,7 @@ PROTOTYPES = {
                                        c_float, c_float, c_int, _P, _P, c_int64, _P]),
     "pbnn_predict_chunks": (c_int, [c_int]),
     "pbnn_predict": (c_int, [_SPEC, _P, c_int, _P, c_int, _P, _P, _P, _P, c_int64, _P]),
+    "pbnn_thinning": (c_int, [_P, c_int, c_int, c_int, _P, _P, _P]),
     "pbnn_grad_estimator": (c_int, [_SPEC, _P, _P, c_int, _P, c_int, _P, c_int, _P, _P, _P, c_int64, _P]),
 }
 

@@ -154,6 +154,161 @@ pb_perm_kernel(const uint32_t* __restrict__ keys, int N, int Np2, int rounds, in
     for (int jn = threadIdx.x; jn < N; jn += blockDim.x) res[jn] = jn;
 }
 
+// ------------------------------------------------------------------------------------------------
+// thinning_fn (src/pbnn/utils/misc.py:58-125): greedy energy-distance thinning of a chain.
+//   k(x, y) = |x| + |y| - sqrt(max(x.x + y.y - 2 x.y, 0));  k0_mean[i] = mean_j k(x_i, x_j)
+//   obj = 2|x_i| - 2 k0_mean;  idx_0 = argmin obj;  then size-1 times: obj += 2 k(x_idx, .) - 2 k0_mean, argmin.
+// ------------------------------------------------------------------------------------------------
+__global__ void pb_thin_norm_kernel(const float* __restrict__ X, int n, int D, float* __restrict__ xx) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= n) return;
+  float a = 0.f;
+  for (int k = lane; k < D; k += 32) {
+    const float v = X[(size_t)row * D + k];
+    a += v * v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if (lane == 0) xx[row] = a;
+}
+
+// row sums of the kernel matrix without materialising it: CTA = 64 rows, loops over all column tiles (deterministic
+// order), 4x4 register tiles, operands staged K-major in shared memory
+__global__ void __launch_bounds__(256) pb_thin_rowsum_kernel(const float* __restrict__ X, const float* __restrict__ xx,
+                                                             int n, int D, float* __restrict__ k0sum) {
+  __shared__ __align__(16) float As[16][68], Bs[16][68];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int i0 = blockIdx.x * 64;
+  float rowsum[4] = {0.f, 0.f, 0.f, 0.f};
+  float ni[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) ni[r] = (i0 + ty * 4 + r < n) ? xx[i0 + ty * 4 + r] : 0.f;
+  for (int j0 = 0; j0 < n; j0 += 64) {
+    float acc[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+    for (int k0 = 0; k0 < D; k0 += 16) {
+      for (int e = tid; e < 64 * 16; e += 256) {
+        const int r = e >> 4, k = e & 15;
+        As[k][r] = (i0 + r < n && k0 + k < D) ? X[(size_t)(i0 + r) * D + k0 + k] : 0.f;
+        Bs[k][r] = (j0 + r < n && k0 + k < D) ? X[(size_t)(j0 + r) * D + k0 + k] : 0.f;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+        const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+        const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) acc[r][c] += av[r] * bv[c];
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int j = j0 + tx * 4 + c;
+        if (j < n) {
+          const float nj = xx[j];
+          rowsum[r] += sqrtf(ni[r]) + sqrtf(nj) - sqrtf(fmaxf(ni[r] + nj - 2.0f * acc[r][c], 0.f));
+        }
+      }
+  }
+  // reduce the 16 column-threads of each row (lanes 0..15 / 16..31 of a warp share ty)
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    float v = rowsum[r];
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (tx == 0 && i0 + ty * 4 + r < n) k0sum[i0 + ty * 4 + r] = v;
+  }
+}
+
+// greedy selection, one step = two launches (size-1 dependent argmins: the dependency is carried through `cur`):
+//   update: every warp of the grid takes rows i, i+W, ...: obj[i] += 2 k(x_cur, x_i) - 2 k0_mean[i] (step > 0) and keeps the
+//           CTA's (min, first index); argmin: one CTA reduces the per-CTA partials, records the pick.
+__global__ void __launch_bounds__(256) pb_thin_update_kernel(const float* __restrict__ X, const float* __restrict__ xx,
+                                                             const float* __restrict__ k0sum, int n, int D, int step,
+                                                             const int32_t* __restrict__ cur, float* __restrict__ obj,
+                                                             float* __restrict__ pval, int32_t* __restrict__ pidx) {
+  __shared__ float sval[8];
+  __shared__ int sidx[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gw = blockIdx.x * 8 + warp, nwarps = gridDim.x * 8;
+  const float inv_n = 1.0f / (float)n;
+  float best = INFINITY;
+  int bi = 0x7fffffff;
+  const int c = step > 0 ? cur[0] : 0;
+  const float nc = xx[c];
+  const float* xc = X + (size_t)c * D;
+  for (int i = gw; i < n; i += nwarps) {
+    float v;
+    if (step == 0) {
+      v = 2.0f * sqrtf(xx[i]) - 2.0f * (k0sum[i] * inv_n);
+    } else {
+      const float* xi = X + (size_t)i * D;
+      float a = 0.f;
+      for (int k = lane; k < D; k += 32) a += xc[k] * xi[k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      const float ki = sqrtf(nc) + sqrtf(xx[i]) - sqrtf(fmaxf(nc + xx[i] - 2.0f * a, 0.f));
+      v = obj[i] + 2.0f * ki - 2.0f * (k0sum[i] * inv_n);
+    }
+    if (lane == 0) obj[i] = v;
+    if (v < best) {  // rows ascend within a warp: strict < keeps the first index on ties (jnp.argmin)
+      best = v;
+      bi = i;
+    }
+  }
+  if (lane == 0) {
+    sval[warp] = best;
+    sidx[warp] = bi;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w)
+      if (sval[w] < best || (sval[w] == best && sidx[w] < bi)) {
+        best = sval[w];
+        bi = sidx[w];
+      }
+    pval[blockIdx.x] = best;
+    pidx[blockIdx.x] = bi;
+  }
+}
+
+__global__ void __launch_bounds__(256) pb_thin_argmin_kernel(const float* __restrict__ pval,
+                                                             const int32_t* __restrict__ pidx, int nblocks, int step,
+                                                             int size, int32_t* __restrict__ cur,
+                                                             int32_t* __restrict__ out) {
+  __shared__ float sval[256];
+  __shared__ int sidx[256];
+  float best = INFINITY;
+  int bi = 0x7fffffff;
+  for (int b = threadIdx.x; b < nblocks; b += 256)
+    if (pval[b] < best || (pval[b] == best && pidx[b] < bi)) {
+      best = pval[b];
+      bi = pidx[b];
+    }
+  sval[threadIdx.x] = best;
+  sidx[threadIdx.x] = bi;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int t = 1; t < 256; ++t)
+      if (sval[t] < best || (sval[t] == best && sidx[t] < bi)) {
+        best = sval[t];
+        bi = sidx[t];
+      }
+    cur[0] = bi;
+    // reference order: [picks of steps 1..size-1], then the initial pick appended last (misc.py:121-123)
+    out[step == 0 ? size - 1 : step - 1] = bi;
+  }
+}
+
 // FP32 FMA throughput probe (roofline denominator measured in-run): 16 independent accumulator pairs per thread,
 // `iters` x 32 FMAs each, as scalar FFMA (mode 0) or packed FFMA2 / fma.rn.f32x2 (mode 1).
 __global__ void __launch_bounds__(256, 4) pb_fma_probe_kernel(int mode, int iters, float seed, float* sink) {
@@ -295,6 +450,31 @@ static int pb_backend_perm(const uint32_t* keys, int C, int N, int32_t* out, voi
 }
 
 #include "pbnn_api.inc"
+
+extern "C" int pbnn_thinning(const float* positions, int n, int D, int size, int32_t* idx_out, float* workspace,
+                             void* stream) {
+  if (!positions || !idx_out || !workspace || n < 1 || D < 1 || size < 1 || size > n) {
+    snprintf(g_err, sizeof(g_err), "thinning: need positions, idx_out, workspace, 1 <= size <= n");
+    return PBNN_EINVAL;
+  }
+  float* xx = workspace;
+  float* k0sum = workspace + n;
+  float* obj = workspace + 2 * (size_t)n;
+  float* pval = workspace + 3 * (size_t)n;
+  int32_t* pidx = reinterpret_cast<int32_t*>(workspace + 3 * (size_t)n + 1024);
+  int32_t* cur = reinterpret_cast<int32_t*>(workspace + 3 * (size_t)n + 2048);
+  cudaStream_t st = (cudaStream_t)stream;
+  int nblocks = (n + 7) / 8;
+  if (nblocks > 148 * 4) nblocks = 148 * 4;
+  pb_thin_norm_kernel<<<(n + 7) / 8, 256, 0, st>>>(positions, n, D, xx);
+  pb_thin_rowsum_kernel<<<(n + 63) / 64, 256, 0, st>>>(positions, xx, n, D, k0sum);
+  for (int step = 0; step < size; ++step) {
+    pb_thin_update_kernel<<<nblocks, 256, 0, st>>>(positions, xx, k0sum, n, D, step, cur, obj, pval, pidx);
+    pb_thin_argmin_kernel<<<1, 256, 0, st>>>(pval, pidx, nblocks, step, size, cur, idx_out);
+  }
+  PB_CUDA(cudaGetLastError());
+  return PBNN_OK;
+}
 
 // measurement utility (not part of the sampler ABI): launches the FP32 FMA probe; flops = grid*256*iters*64
 extern "C" int pbnn_probe_fp32(int mode, int iters, int ctas, float* sink, void* stream) {

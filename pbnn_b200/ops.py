@@ -370,6 +370,17 @@ class Ops:
             out.update(sum=ssum, sumsq=ssq, mean=mean, var=(ssq / S - mean * mean).clamp_min(0), count=S)
         return out
 
+    def thinning(self, positions, size: int):
+        """Indices (size,) selected by the greedy energy-distance thinning of ``positions`` (n, D) -- utils/misc.py:58-125."""
+        pos = self._as(positions, self.f32)
+        pos = pos.reshape(pos.shape[0], -1).contiguous()
+        n, D = int(pos.shape[0]), int(pos.shape[1])
+        out = self._empty((int(size),), self.i32)
+        ws = self._empty((3 * n + 2064,), self.f32)
+        rc = self.lib.pbnn_thinning(self._ptr(pos), n, D, int(size), self._ptr(out), self._ptr(ws), self._stream())
+        check(self.lib, rc, "thinning")
+        return out
+
     def plan(self, spec: FlatSpec, rows: int, n_state: int):
         out = (_lib.c_int32 * 4)()
         check(self.lib, self.lib.pbnn_plan_query(spec.c_struct(), rows, n_state, out), "plan_query")

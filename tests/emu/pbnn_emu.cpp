@@ -139,3 +139,37 @@ static int pb_backend_perm(const uint32_t* keys, int C, int N, int32_t* out, voi
 }
 
 #include "../../pbnn_b200/csrc/pbnn_api.inc"
+
+extern "C" int pbnn_thinning(const float* X, int n, int D, int size, int32_t* out, float* ws, void*) {
+  if (!X || !out || !ws || n < 1 || D < 1 || size < 1 || size > n) return PBNN_EINVAL;
+  float* xx = ws;
+  float* k0 = ws + n;
+  float* obj = ws + 2 * (size_t)n;
+  auto dot = [&](int i, int j) {
+    float a = 0.f;
+    for (int k = 0; k < D; ++k) a += X[(size_t)i * D + k] * X[(size_t)j * D + k];
+    return a;
+  };
+  for (int i = 0; i < n; ++i) xx[i] = dot(i, i);
+  for (int i = 0; i < n; ++i) {
+    float s = 0.f;
+    for (int j = 0; j < n; ++j) s += sqrtf(xx[i]) + sqrtf(xx[j]) - sqrtf(fmaxf(xx[i] + xx[j] - 2.0f * dot(i, j), 0.f));
+    k0[i] = s;
+  }
+  int cur = 0;
+  for (int step = 0; step < size; ++step) {
+    for (int i = 0; i < n; ++i) {
+      if (step == 0) obj[i] = 2.0f * sqrtf(xx[i]) - 2.0f * (k0[i] / n);
+      else {
+        const float ki = sqrtf(xx[cur]) + sqrtf(xx[i]) - sqrtf(fmaxf(xx[cur] + xx[i] - 2.0f * dot(cur, i), 0.f));
+        obj[i] = obj[i] + 2.0f * ki - 2.0f * (k0[i] / n);
+      }
+    }
+    int bi = 0;
+    for (int i = 1; i < n; ++i)
+      if (obj[i] < obj[bi]) bi = i;
+    cur = bi;
+    out[step == 0 ? size - 1 : step - 1] = bi;
+  }
+  return PBNN_OK;
+}

@@ -197,3 +197,19 @@ def test_cyclical_sgld_structure(api):
     for it in range(3):
         th = th + np.float32(steps[it]) * o.grad_estimator(sp, th, X[idx].astype(np.float64), y[idx].astype(np.float64), len(X))
     assert rel(npy(res["theta"]), th) <= 1e-5
+
+
+def test_thinning_fn_and_npz_wire_format(api, tmp_path):
+    """Post-processing right after the chain (benchmark/pipelines/sgmcmc.py:172,213-232): burn-in, thinning, predict,
+    savez(positions (S,P), predictions (S,M), time)."""
+    from pbnn_b200.utils import save_results, thinning_fn
+    X, y, net, sp, key, th0, tree, lik, prior = setup(layers=(8, 12, 1), act="tanh", N=150)
+    positions, ravel_fn, predict_fn = sgld(X, y, lik, prior, tree, 16, 1e-5, 60, key, burnin=20)
+    flat = ravel_fn(positions)
+    idx = thinning_fn(flat, 10)
+    assert np.array_equal(npy(idx), o.thinning(npy(flat), 10, dtype=np.float64))
+    thinned = flat[idx.long()]
+    preds = predict_fn(net, pytree.unravel(thinned, (8, 12, 1)), X[:7]).squeeze(-1)
+    save_results(tmp_path / "out.npz", thinned, preds, 1.5)
+    z = np.load(tmp_path / "out.npz")
+    assert z["positions"].shape == (10, sp.num_params) and z["predictions"].shape == (10, 7) and float(z["time"]) == 1.5

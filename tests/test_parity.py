@@ -270,6 +270,17 @@ def test_adam_ensemble(ops):
     assert rel(npy(b["theta"]), npy(out["theta"])) <= 1e-6
 
 
+@pytest.mark.parametrize("n,D,size", [(200, 37, 20), (1000, 501, 50), (65, 3, 65)])
+def test_thinning_matches_reference_order(ops, n, D, size):
+    """thinning_fn (utils/misc.py:58-125): same index sequence as the float64 restatement on generic data."""
+    rng = np.random.default_rng(n)
+    pos = (rng.standard_normal((n, D)) * (1 + rng.random((n, 1)))).astype(np.float32)
+    got = npy(ops.thinning(pos, size))
+    want = o.thinning(pos, size, dtype=np.float64)
+    assert got.shape == (size,) and len(set(got.tolist())) <= size
+    assert np.array_equal(got, want)
+
+
 def test_heteroscedastic_likelihood(ops):
     """heteroscedastic_loglike_fn (benchmark/pipelines/logprobs.py:37-42): outputs (mu, log sigma^2), one target."""
     from pbnn_b200._lib import LIK_HETEROSCEDASTIC
