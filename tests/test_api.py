@@ -213,3 +213,27 @@ def test_thinning_fn_and_npz_wire_format(api, tmp_path):
     save_results(tmp_path / "out.npz", thinned, preds, 1.5)
     z = np.load(tmp_path / "out.npz")
     assert z["positions"].shape == (10, sp.num_params) and z["predictions"].shape == (10, 7) and float(z["time"]) == 1.5
+
+
+def test_map_estimation_train_fn(api):
+    """map_estimation.train_fn (src/pbnn/map_estimation.py:42-108): Adam / SGD on -logposterior, one fixed batch order
+    replayed every epoch."""
+    from pbnn_b200.map_estimation import build_logposterior_estimator_fn, train_fn
+    X, y, net, sp, key, th0, tree, lik, prior = setup(layers=(8, 12, 1), act="tanh", N=96)
+    logpost = build_logposterior_estimator_fn(prior, lik, len(X))
+    batches = np.random.default_rng(0).permutation(96)[:80].reshape(5, 16).astype(np.int32)
+    params = train_fn(logpost, net, {"x": X, "y": y}, 16, 3, 1e-3, key, "adam", init_params=tree, batch_indices=batches)
+    idx = np.tile(batches, (3, 1))[None]
+    ref = o.deep_ensembles(sp, X, y, th0, 16, 0, 1e-3, None, idx=idx)
+    assert rel(npy(pytree.ravel(params)), ref[0]) <= 2e-5
+    params = train_fn(logpost, net, {"x": X, "y": y}, 16, 2, 1e-6, key, "sgd", init_params=tree, batch_indices=batches)
+    th = th0.astype(np.float64)
+    for row in np.tile(batches, (2, 1)):
+        th = th + np.float32(1e-6) * o.grad_estimator(sp, th, X[row][None].astype(np.float64), y[row][None].astype(np.float64), 96)
+    assert rel(npy(pytree.ravel(params)), th[0]) <= 1e-5
+    import torch
+    torch.manual_seed(0)
+    p1 = train_fn(logpost, net, {"x": X, "y": y}, 16, 1, 1e-3, key)  # default init + torch-sampler batch order
+    assert np.isfinite(npy(pytree.ravel(p1))).all()
+    with pytest.raises(TypeError):
+        train_fn(lambda p, b: 0.0, net, {"x": X, "y": y}, 16, 1, 1e-3, key)

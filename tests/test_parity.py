@@ -339,6 +339,24 @@ def test_edge_cases_and_errors(ops):
         ops.plan(huge, 128, 2)
 
 
+def test_streaming_tiles_path(ops, monkeypatch):
+    """Row sets that do not fit shared memory are streamed tile by tile from global memory (large-N HMC, large
+    minibatches); force that path and check it like the resident one."""
+    monkeypatch.setenv("PBNN_NO_RESIDENT", "1")
+    monkeypatch.setenv("PBNN_NO_H1", "1")
+    layers, act, B = NETS[2]
+    X, y, sp, fs, keys, th0 = problem(layers, act)
+    ref = o.sgld(sp, X, y, th0, B, 1e-5, 4, keys)
+    assert rel(npy(ops.sgld(fs, X, y, th0, keys, B, 1e-5, 4)["trace"]), ref) <= RTOL_STEP
+    layers, act = (13, 50, 1), o.RELU
+    X, y, sp, fs, keys, th0 = problem(layers, act, N=300, scale=0.05)
+    minv = np.ones(sp.num_params, np.float32)
+    ref, info = o.hmc(sp, X, y, th0, 3, 2e-4, minv, 4, keys, return_info=True)
+    out = ops.hmc(fs, X, y, th0, keys, 3, 2e-4, minv, 4, info=True)
+    assert np.array_equal(npy(out["accept"]).astype(bool), info["accept"])
+    assert rel(npy(out["trace"]), ref) <= RTOL_STEP
+
+
 def test_global_workspace_state_path(ops, monkeypatch):
     """Models whose state does not fit shared memory keep it in a global workspace (the 90-256-256-1 case); force that
     path on small nets and check it against the oracle like the resident path."""
