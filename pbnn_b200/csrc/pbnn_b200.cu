@@ -38,6 +38,14 @@ pb_hmc_kernel(const __grid_constant__ PbPlan pl, const __grid_constant__ PbHmcAr
   pb_hmc_chain<ACT, GS, ENG>(pl, a, pb_smem, (int)blockIdx.x, (int)blockDim.x);
 }
 
+// tcgen05 engine: 8 epilogue warps + 1 MMA-issue warp, one CTA per SM (the operand buffers need ~200 KB)
+__global__ void __launch_bounds__(288, 1)
+pb_hmc_tc_kernel(const __grid_constant__ PbPlan pl, const __grid_constant__ PbHmcArgs a) {
+  extern __shared__ __align__(16) float pb_smem[];
+  PB_PROF_START
+  pb_hmc_chain<PBNN_ACT_RELU, false, 2>(pl, a, pb_smem, (int)blockIdx.x, (int)blockDim.x);
+}
+
 template <int ACT, bool GS>
 __global__ void __launch_bounds__(PB_MAX_NT)
 pb_predict_kernel(const __grid_constant__ PbPlan pl, const __grid_constant__ PbPredArgs a) {
@@ -389,6 +397,7 @@ static int pb_backend_hmc(const PbPlan& pl, const PbHmcArgs& a, int C, void* str
     if (pl.act == PBNN_ACT_RELU) return pb_launch(pb_hmc_kernel<PBNN_ACT_RELU, true, 0>, pl, a, dim3(C), stream);
     return pb_launch(pb_hmc_kernel<PBNN_ACT_TANH, true, 0>, pl, a, dim3(C), stream);
   }
+  if (pl.tc) return pb_launch(pb_hmc_tc_kernel, pl, a, dim3(C), stream);
   if (pl.h1) {
     if (pl.act == PBNN_ACT_RELU) return pb_launch(pb_hmc_kernel<PBNN_ACT_RELU, false, 1>, pl, a, dim3(C), stream);
     return pb_launch(pb_hmc_kernel<PBNN_ACT_TANH, false, 1>, pl, a, dim3(C), stream);

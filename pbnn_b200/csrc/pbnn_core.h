@@ -51,6 +51,9 @@ struct PbPlan {
   int gstate;                     // resident arrays live in a global-memory workspace (model too large for smem)
   int h1, h1_dp;                  // fused one-hidden-layer path: X row-major [rows][4*h1_dp], per-warp partial grads
   int off_xr, off_yr, off_hpart;
+  // tcgen05 path (one hidden relu layer, scalar output): see pbnn_tc.cuh for the operand layouts
+  int tc, tc_npad;                // tc_npad = rows rounded up to the 128-row MMA tile
+  int off_xa, off_mk, off_z, off_wb, off_w2s, off_tcm;
   int off_act, off_scr, off_acc, off_idx, off_scal;
   int idx_cap;
   int smem_floats;
@@ -107,6 +110,56 @@ static inline void pb_plan_dw(PbPlan* pl, int nw, int bt, int kcap) {
 
 #define PB_PLAN_RES 1
 #define PB_PLAN_ACC 2
+#define PB_PLAN_TC 4  // the caller has a tcgen05 kernel for this op (HMC): allow the tensor-core layout
+
+// tcgen05 operand geometry (floats).  K-major, no swizzle: element (row x, k) at (k/4)*LBO + x*16 B + (k%4)*4 B.
+#define PB_TC_MK_LBO 516   // mask^T  [k = batch row / 4][2 tiles x 64 hidden units (+1 pad row: conflict-free stores)][4]
+#define PB_TC_Z_LBO 260    // Z       [k = batch row / 4][2 tiles x (raw, lo) x 16 inputs (+1 pad row)][4]
+#define PB_TC_MK_FLOATS (32 * PB_TC_MK_LBO)
+#define PB_TC_Z_FLOATS (32 * PB_TC_Z_LBO)
+#define PB_TC_MAX_TILES 7
+
+// shared-memory layout of the tcgen05 plan: state | X (raw, lo) | y | mask | Z | W1 (raw, lo) | w2 | ...
+static inline void pb_layout_tc(PbPlan* pl, int rows, int nstate) {
+  pl->BT = 128;
+  pl->ap = 132;
+  pl->h1 = 1;
+  pl->tc = 1;
+  pl->ksmax = 1;
+  pl->gstate = 0;
+  pl->NT = 288;  // 8 epilogue warps + 1 MMA-issue warp
+  pl->h1_dp = pb_r4(pl->d + 1) / 4;
+  pl->tc_npad = ((rows + 127) / 128) * 128;
+  int off = nstate * pl->Ps;
+  pl->off_gpart = off;
+  pl->off_act = off;
+  for (int l = 0; l <= pl->nl + 1; ++l) pl->aoff[l] = off;
+  pl->res_rows = rows;
+  pl->xp = 0;
+  pl->off_xres = pl->off_yres = pl->off_xr = pl->off_hpart = off;
+  pl->off_xa = off;
+  off += 2 * 16 * pl->tc_npad;
+  pl->off_yr = off;
+  off += pl->tc_npad;
+  pl->off_mk = off;
+  off += PB_TC_MK_FLOATS;
+  pl->off_z = off;
+  off += PB_TC_Z_FLOATS;
+  pl->off_wb = off;
+  off += 2 * 16 * 64;
+  pl->off_w2s = off;
+  off += 128;  // output weights, double-buffered
+  pl->off_tcm = off;         // 5 mbarriers (8 B each) [0..9], TMEM base [12], per-warp residual sums [16..23]
+  off += 32;
+  pl->off_scr = off;
+  off += PB_SCR_FLOATS;
+  pl->off_acc = off;
+  pl->off_idx = off;
+  off += pl->idx_cap;
+  pl->off_scal = off;
+  off += 32;
+  pl->smem_floats = off;
+}
 
 // shared-memory layout for one candidate configuration
 static inline void pb_layout(PbPlan* pl, const pbnn_mlp_spec* sp, int rows, int nstate, int bt, int res, int kcap,
@@ -253,6 +306,13 @@ static inline int pb_build_plan(const pbnn_mlp_spec* sp, int rows, int nstate, i
 #if defined(PB_EMU)
   h1_ok = 0;
 #endif
+  // tcgen05 path: the same nets, relu only (the weight gradient uses the 0/1 activation mask as an exact operand)
+  if (h1_ok && (flags & PB_PLAN_TC) && sp->activation == PBNN_ACT_RELU && !hetero && !pb_env_int("PBNN_NO_TC", 0) &&
+      rows <= 128 * PB_TC_MAX_TILES) {
+    pb_layout_tc(pl, rows, nstate);
+    if ((size_t)pl->smem_floats * 4 <= (size_t)PB_SMEM_LIMIT_BYTES) return PBNN_OK;
+    pl->tc = 0;
+  }
   const int forced = pb_env_int("PBNN_BT", 0);
   if (forced > 0) maxbt = pb_r32(forced) > 128 ? 128 : pb_r32(forced);
   // Two passes: first try to stay under half an SM's shared memory so that two CTAs are co-resident (more warps to

@@ -50,13 +50,25 @@ __device__ int pb_prof_tag;
     pb_prof_cycles[32 + (pb_prof_tag & 31)] += 1;                        \
     pb_prof_last = now_;                                                 \
   }
+// PB_MARK(n): charge the cycles since the last mark / phase end to slot n (subdivides a phase; thread 0 of CTA 0)
+#define PB_MARK(n)                                                       \
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {          \
+    const unsigned long long now_ = clock64();                           \
+    pb_prof_cycles[(n) & 31] += now_ - pb_prof_last;                     \
+    pb_prof_cycles[32 + ((n) & 31)] += 1;                                \
+    pb_prof_last = now_;                                                 \
+  }
 #else
+#define PB_MARK(n)
 #define PB_ENDPHASE \
   }                 \
   __syncthreads();
 #endif
 #define PB_ATOMIC_OR(p, v) atomicOr((p), (v))
 #define PB_ENDPHASE_RAW { PB_ENDPHASE
+#endif
+#ifndef PB_MARK
+#define PB_MARK(n)
 #endif
 #ifndef PB_TAG
 #define PB_TAG(n)
@@ -804,6 +816,8 @@ PB_DEV void pb_grad_h1(const PbPlan& pl, float* sm, const float* TH, float* G, i
 }
 #endif
 
+#include "pbnn_tc.cuh"
+
 // likelihood gradient over the rows of one evaluation: fused one-hidden-layer path or the tiled GEMM engine
 // ENG selects the gradient engine at COMPILE time (0 = tiled GEMM engine, 1 = fused one-hidden-layer path): separate
 // kernels keep the code of each small (the HMC kernel lost 5 % when unrelated unrolled code was inlined into it).
@@ -1161,7 +1175,17 @@ PB_DEV void pb_hmc_chain(const PbPlan& pl, const PbHmcArgs& a, float* sm, int c,
   pb_load_state(pl, G, nullptr, nt);
   pb_load_state(pl, PM, nullptr, nt);
   pb_load_state(pl, MI, a.inv_mass, nt);
-  if (pl.res_rows > 0) pb_load_resident(pl, sm, a.X, a.y, nullptr, a.N, nt);
+  // ENG == 2: tcgen05 engine (pbnn_tc.cuh), its own operand staging; else the resident rows of the scalar engines
+#if !defined(PB_EMU)
+  PbTc tc;
+  if constexpr (ENG == 2) pb_tc_setup(pl, sm, a.X, a.y, a.N, nt, tc);
+#define PB_HMC_GRAD()                                                      \
+  if constexpr (ENG == 2) pb_grad_tc(pl, sm, TH, G, a.N, pl.inv_s2, nt, tc); \
+  else pb_grad<ACT, ENG>(pl, sm, TH, G, a.X, a.y, nullptr, a.N, pl.inv_s2, false, nt);
+#else
+#define PB_HMC_GRAD() pb_grad<ACT, ENG>(pl, sm, TH, G, a.X, a.y, nullptr, a.N, pl.inv_s2, false, nt);
+#endif
+  if (ENG != 2 && pl.res_rows > 0) pb_load_resident(pl, sm, a.X, a.y, nullptr, a.N, nt);
   PB_PHASE
   if (tid == 0) {
     scu[2] = 0u;
@@ -1170,7 +1194,7 @@ PB_DEV void pb_hmc_chain(const PbPlan& pl, const PbHmcArgs& a, float* sm, int c,
   PB_ENDPHASE
 
   // init: (logp, grad) at theta0
-  pb_grad<ACT, ENG>(pl, sm, TH, G, a.X, a.y, nullptr, a.N, pl.inv_s2, false, nt);
+  PB_HMC_GRAD()
   PB_PHASE
   for (int i = tid; i < pl.Ps; i += nt) {
     const float g = G[i] - TH[i] * pl.inv_pv;
@@ -1207,6 +1231,17 @@ PB_DEV void pb_hmc_chain(const PbPlan& pl, const PbHmcArgs& a, float* sm, int c,
     PB_ENDPHASE
     pb_block_sums(pl, sm, 1, sc + 13, nt);
 
+#if !defined(PB_EMU)
+    if constexpr (ENG == 2) {
+      // tcgen05 engine: half-kicks, drift and operand staging are fused into the gradient's readout (pbnn_tc.cuh)
+      const PbTcLeap lf = {PM, MI, eps, heps, pl.inv_pv};
+      if (a.L > 0) {
+        pb_tc_stage_w<true>(pl, sm, TH, G, lf, nt, tc);
+        for (int l = 0; l < a.L - 1; ++l) pb_tc_grad_core<1>(pl, sm, TH, G, a.N, pl.inv_s2, nt, tc, lf);
+        pb_tc_grad_core<2>(pl, sm, TH, G, a.N, pl.inv_s2, nt, tc, lf);
+      }
+    } else
+#endif
     for (int l = 0; l < a.L; ++l) {
       PB_TAG(12)
       PB_PHASE
@@ -1216,7 +1251,7 @@ PB_DEV void pb_hmc_chain(const PbPlan& pl, const PbHmcArgs& a, float* sm, int c,
         TH[i] = TH[i] + eps * (MI[i] * p);
       }
       PB_ENDPHASE
-      pb_grad<ACT, ENG>(pl, sm, TH, G, a.X, a.y, nullptr, a.N, pl.inv_s2, false, nt);
+      PB_HMC_GRAD()
       PB_TAG(13)
       PB_PHASE
       for (int i = tid; i < pl.Ps; i += nt) {
@@ -1270,6 +1305,10 @@ PB_DEV void pb_hmc_chain(const PbPlan& pl, const PbHmcArgs& a, float* sm, int c,
     if (a.flags) a.flags[c] = scu[2];
   }
   PB_ENDPHASE
+#if !defined(PB_EMU)
+  if constexpr (ENG == 2) pb_tc_teardown(pl, sm, tc);
+#endif
+#undef PB_HMC_GRAD
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -1,0 +1,486 @@
+// pbnn_b200: tcgen05 (5th-gen tensor core) gradient engine for one-hidden-layer relu nets with a scalar output
+// (BASELINE configs 0/1: 8-50-1, 13-50-1) -- the full-batch log-likelihood gradient of the HMC leapfrog
+// (reference: jax.value_and_grad(logprob_fn) inside blackjax.hmc, src/pbnn/mcmc/hamiltonian.py:18-77 with
+// benchmark/pipelines/logprobs.py:12-17).
+//
+// FP32 accuracy on TF32 tensor cores.  tcgen05.mma.kind::tf32 reads the top 19 bits of every fp32 operand word, so an
+// operand a is fed as a = hi + lo with hi = the raw word (truncated by the hardware) and lo = a - trunc19(a) (exact in
+// fp32); hi*hi + hi*lo + lo*hi accumulated in the fp32 TMEM accumulator reproduces the fp32 product to ~1e-6 relative
+// (measured by tests/test_umma_experimental.py).  Both GEMMs of the gradient are arranged so that one operand is
+// (nearly) free:
+//
+//   forward   Hpre[b][j]  = sum_i Xaug[b][i] W1aug[i][j]        A = X tile   [128 rows][K=16]   (hi, lo: staged ONCE)
+//                                                               B = W1aug^T  [64 units][K=16]   (hi, lo: per gradient)
+//             3 passes x 2 k-steps per 128-row tile, D = TMEM columns 64(t+1)..64(t+1)+63 of tile t
+//   epilogue  one thread per row (= TMEM lane): h = relu(Hpre), f = w2.h + b2, r = (y - f)/sigma^2, and the relu
+//             MASK m[b][j] = [Hpre > 0] plus Z[b][i] = r_b Xaug[b][i] go back to shared memory as MMA operands
+//   backward  Gm[j][i]    = sum_b m[b][j] Z[b][i]               mask is 0/1: EXACT in tf32, no lo part; Z = hi + lo.
+//             Two 128-row tiles (even tile = warps 0-3, odd tile = warps 4-7) share one MMA per k-step:
+//               A = [mask_even^T ; mask_odd^T]               [2 x 64 units][K = row within the tile]
+//               B = [Z_even hi ; Z_even lo ; Z_odd hi ; Z_odd lo]   [4 x 16 inputs][K]
+//             D (TMEM columns 0..63): lanes 0..63 x columns 0..31 = even tiles (hi | lo), lanes 64..127 x columns
+//             32..63 = odd tiles; the two off-diagonal blocks are cross terms nobody reads.  16 k-steps per round, every
+//             operand byte read from shared memory once (the MMAs of this shape are shared-memory-bandwidth bound).
+//             dW1[i][j] = w2_j Gm[j][i]       dw2_j = sum_b r_b relu(Hpre)[b][j] = sum_i W1aug[i][j] Gm[j][i]
+//             (the second identity: relu(Hpre) = m * (Xaug W1aug), so the output-layer gradient needs no extra GEMM)
+//
+// Operand storage (K-major, SWIZZLE_NONE "interleaved" core matrices of 8 rows x 16 B):
+//   element (row x, k) at (k/4)*LBO + x*16 B + (k%4)*4 B,   SBO (next 8 rows) = 128 B.
+// The mask and Z k-groups are padded by one 16-byte row (LBO = 129 / 65 rows) so that the 32 lanes of a warp (32
+// consecutive batch rows) store to 32 different banks.
+#pragma once
+#if !defined(PB_EMU)
+
+struct PbTc {
+  uint32_t tmem;  // TMEM base address (512 columns allocated)
+  uint32_t ph_f;  // parity of the forward-MMA mbarrier
+  uint32_t ph_d;  // parity of the backward-MMA mbarrier
+  // readout B: this thread's (up to) 4 first-layer weights -- constant over the chain, kept in registers
+  int ridx[4];    // index in the padded resident arrays (a pad slot when the element does not exist)
+  int rwo[4];     // index in the forward B operand Wb / Wl
+  int rgx[4];     // i * 64 + j in the readout scratch
+  uint32_t rok;   // bit u: element u exists
+};
+
+PB_DEV uint32_t pb_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// shared-memory matrix descriptor: SWIZZLE_NONE, sm_100 descriptor version; byte offsets in 16-byte units
+PB_DEV uint64_t pb_umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | ((uint64_t)1 << 46);
+}
+
+// instruction descriptor: D = f32, A = B = tf32, both K-major, dense
+PB_DEV uint32_t pb_umma_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+PB_DEV float pb_trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+PB_DEV void pb_umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// one lane of a converged warp (the compiler keeps tcgen05 issue on the uniform datapath only behind elect.sync;
+// a plain `tid == 0` test wraps every MMA in a divergence loop: measured 90-130 cycles per MMA issued)
+PB_DEV bool pb_elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+  return pred != 0u;
+}
+
+PB_DEV void pb_umma_commit(uint32_t mbar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
+}
+
+PB_DEV void pb_mbar_wait(uint32_t mbar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(done)
+        : "r"(mbar), "r"(parity)
+        : "memory");
+  }
+}
+
+PB_DEV void pb_tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+PB_DEV void pb_tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+PB_DEV void pb_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+PB_DEV void pb_tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+
+PB_DEV void pb_tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+      "[%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+
+PB_DEV void pb_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+PB_DEV uint64_t* pb_tc_mbar(const PbPlan& pl, float* sm, int i) {
+  return reinterpret_cast<uint64_t*>(sm + pl.off_tcm) + i;
+}
+
+// once per chain: X (raw + lo) in the forward A-operand layout, y, mbarriers, TMEM
+PB_DEV void pb_tc_setup(const PbPlan& pl, float* sm, const float* X, const float* y, int nrows, int nt, PbTc& tc) {
+  PB_TAG(10)
+  const int tid = threadIdx.x;
+  const int Npad = pl.tc_npad, d = pl.d;
+  float* Xa = sm + pl.off_xa;
+  float* Xl = Xa + 16 * Npad;
+  float* yr = sm + pl.off_yr;
+  for (int item = tid; item < Npad * 16; item += nt) {
+    const int b = item >> 4, k = item & 15;
+    float v = 0.f;
+    if (b < nrows) v = k < d ? X[(size_t)b * d + k] : (k == d ? 1.f : 0.f);
+    const int o = ((k >> 2) * Npad + b) * 4 + (k & 3);
+    Xa[o] = v;
+    Xl[o] = v - pb_trunc_tf32(v);
+  }
+  for (int b = tid; b < Npad; b += nt) yr[b] = b < nrows ? y[b] : 0.f;
+  if (tid == 0) {
+    for (int i = 0; i < 5; ++i)  // 0..3: forward MMAs of epilogue round i; 4: backward MMAs
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(pb_smem_u32(pb_tc_mbar(pl, sm, i))));
+    asm volatile("fence.mbarrier_init.release.cluster;");
+  }
+  if (tid < 32) {  // TMEM allocation by one full warp: all 512 columns (one CTA per SM: the plan needs > 113 KB)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     pb_smem_u32(sm + pl.off_tcm + 12)),
+                 "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  pb_fence_async_smem();
+  pb_tc_fence_before();
+  PB_ENDPHASE_RAW
+  pb_tc_fence_after();
+  tc.tmem = *reinterpret_cast<const uint32_t*>(sm + pl.off_tcm + 12);
+  tc.ph_f = 0u;
+  tc.ph_d = 0u;
+  tc.rok = 0u;
+  for (int u = 0; u < 4; ++u) {
+    const int e = pb_min(tid + u * nt, 16 * 64 - 1);
+    const int i = e >> 6, j = e & 63;
+    const bool ok = tid + u * nt < 16 * 64 && i < pl.L[0].inA && j < pl.L[0].out;
+    tc.rok |= ok ? (1u << u) : 0u;
+    // missing elements use a pad slot of the output layer (row 0, column 1: always zero and stays zero)
+    tc.ridx[u] = ok ? pl.L[0].soff + i * pl.L[0].wp + j : pl.L[1].soff + 1;
+    tc.rwo[u] = (i >> 2) * 256 + j * 4 + (i & 3);
+    tc.rgx[u] = i * 64 + j;
+  }
+}
+
+PB_DEV void pb_tc_teardown(const PbPlan& pl, float* sm, const PbTc& tc) {
+  pb_tc_fence_before();
+  PB_ENDPHASE_RAW
+  if (threadIdx.x < 32) {
+    pb_tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tc.tmem), "r"(512));
+  }
+}
+
+// leapfrog quantities for the fused readout (MODE 1 / 2 of pb_tc_grad_core)
+struct PbTcLeap {
+  float* PM;        // momentum (padded resident layout)
+  const float* MI;  // inverse mass diagonal
+  float eps, heps, inv_pv;
+};
+
+// W1aug -> forward B operand (raw + lo), w2 -> contiguous vector; with FIRST_PRE the first half-kick + drift of a
+// trajectory (p += eps/2 g; theta += eps Minv p) is applied on the way (same arithmetic as the scalar engines).
+template <bool FIRST_PRE>
+PB_DEV void pb_tc_stage_w(const PbPlan& pl, float* sm, float* TH, const float* G, const PbTcLeap& lf, int nt,
+                          const PbTc& tc) {
+  PB_TAG(1)
+  const int tid = threadIdx.x;
+  const PbLayer& L0 = pl.L[0];
+  const PbLayer& L1 = pl.L[1];
+  const int H = L0.out, wp = L0.wp, inA = L0.inA;
+  float* Wb = sm + pl.off_wb;
+  float* Wl = Wb + 16 * 64;
+  float* w2s = sm + pl.off_w2s + 64 * (int)tc.ph_f;
+  auto upd = [&](int idx) -> float {
+    float th = TH[idx];
+    if (FIRST_PRE) {
+      const float p = lf.PM[idx] + lf.heps * G[idx];
+      lf.PM[idx] = p;
+      th = th + lf.eps * (lf.MI[idx] * p);
+      TH[idx] = th;
+    }
+    return th;
+  };
+#pragma unroll 4
+  for (int e = tid; e < 16 * 64; e += nt) {
+    const int i = e >> 6, j = e & 63;
+    const float v = (i < inA && j < H) ? upd(L0.soff + i * wp + j) : 0.f;
+    const int o = (i >> 2) * 256 + j * 4 + (i & 3);
+    Wb[o] = v;
+    Wl[o] = v - pb_trunc_tf32(v);
+  }
+  if (tid < 64) w2s[tid] = tid < H ? upd(L1.soff + tid * L1.wp) : 0.f;
+  if (FIRST_PRE && tid == 64) upd(L1.soff + H * L1.wp);
+  pb_fence_async_smem();
+  pb_tc_fence_before();
+  PB_ENDPHASE_RAW
+}
+
+// The gradient proper; the forward B operand (Wb, Wl), w2s and TH must be current (pb_tc_stage_w or a MODE 1 call).
+// 288 threads: warps 0-3 own the even 128-row tiles, warps 4-7 the odd ones (warp w reads TMEM lanes 32*(w%4)..+31),
+// warp 8 issues the MMAs.
+//   MODE 0: G <- d loglik / d theta (padded resident layout, pads untouched = 0)
+//   MODE 1: leapfrog interior, fused into the readout: G <- grad log posterior, p += eps/2 G (end of this step),
+//           p += eps/2 G, theta += eps Minv p (start of the next step), next W operands staged
+//   MODE 2: last step of a trajectory: G <- grad log posterior, p += eps/2 G
+// always: llbuf[0..127] <- per-warp log-likelihood partials.
+template <int MODE>
+PB_DEV void pb_tc_grad_core(const PbPlan& pl, float* sm, float* TH, float* G, int nrows, float scale, int nt,
+                            PbTc& tc, const PbTcLeap& lf) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wg = warp >> 2, q = warp & 3;
+  const PbLayer& L0 = pl.L[0];
+  const PbLayer& L1 = pl.L[1];
+  const int H = L0.out, wp = L0.wp, inA = L0.inA, Npad = pl.tc_npad;
+  const int ntiles = Npad >> 7, nrounds = (ntiles + 1) >> 1, nj8 = (H + 7) >> 3;
+  const float* Xa = sm + pl.off_xa;
+  const float* yr = sm + pl.off_yr;
+  float* Wb = sm + pl.off_wb;
+  float* Wl = Wb + 16 * 64;
+  const float* w2s = sm + pl.off_w2s + 64 * (int)tc.ph_f;  // output weights of this evaluation (double-buffered)
+  float* w2nxt = sm + pl.off_w2s + 64 * (int)(tc.ph_f ^ 1u);
+  float* rs = sm + pl.off_tcm + 16;
+  float* gx = sm + pl.off_z;  // readout scratch (even | odd partial sums [2][16][64], dots [2][64]): the Z buffer is
+                              // free once the last backward MMAs are done
+  float* llbuf = pb_llbuf(pl, sm);
+  const uint32_t mb_f0 = pb_smem_u32(pb_tc_mbar(pl, sm, 0)), mb_d = pb_smem_u32(pb_tc_mbar(pl, sm, 4));
+  const float b2 = TH[L1.soff + H * L1.wp];
+  PB_TAG(2)
+  // warp 8 only issues MMAs (one elected lane); warps 0-7 are the epilogue / readout warps
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);  // warp-uniform for the compiler
+  if (warp_u == 8) {
+    pb_tc_fence_after();
+    if (pb_elect_one()) {
+      const uint32_t idesc = pb_umma_idesc_tf32(128, 64);
+      const uint32_t lbo_x = (uint32_t)Npad * 16u;
+      const uint32_t xa = pb_smem_u32(Xa), wb = pb_smem_u32(Wb);
+      // descriptors of k-step 0; the other operands are constant offsets in the 14-bit address field (16-byte units)
+      const uint64_t dxa = pb_umma_desc(xa, lbo_x, 128u), dwb = pb_umma_desc(wb, 1024u, 128u);
+      const uint64_t x_lo = (uint64_t)Npad * 4u;  // + 16 * Npad floats
+      const uint64_t w_lo = 256u;                 // + 16 * 64 floats
+      const uint64_t x_k = (uint64_t)Npad * 2u;   // + 2 k-groups of Npad rows x 16 B
+      const uint64_t w_k = 128u;                  // + 2 k-groups of 64 rows x 16 B
+      const bool k2 = pl.h1_dp > 2;
+      for (int t = 0; t < ntiles; ++t) {
+        const uint32_t dcol = tc.tmem + 64u * (uint32_t)(t + 1);
+        const uint64_t da = dxa + (uint64_t)t * 128u;  // + 128 rows x 16 B
+        pb_umma_tf32(dcol, da, dwb, idesc, 0u);                              // hi * hi
+        if (k2) pb_umma_tf32(dcol, da + x_k, dwb + w_k, idesc, 1u);
+        pb_umma_tf32(dcol, da, dwb + w_lo, idesc, 1u);                       // hi * lo
+        if (k2) pb_umma_tf32(dcol, da + x_k, dwb + w_lo + w_k, idesc, 1u);
+        pb_umma_tf32(dcol, da + x_lo, dwb, idesc, 1u);                       // lo * hi
+        if (k2) pb_umma_tf32(dcol, da + x_lo + x_k, dwb + w_k, idesc, 1u);
+        if ((t & 1) || t == ntiles - 1) pb_umma_commit(mb_f0 + 8u * (uint32_t)(t >> 1));  // one barrier per round
+      }
+    }
+    __syncwarp();
+    PB_MARK(20)
+  }
+
+  // ---- epilogue rounds: two tiles at a time ---------------------------------------------------------------
+  const int bl = q * 32 + lane;
+  float ll = 0.f, rsum = 0.f;
+  for (int round = 0; round < nrounds; ++round) {
+    const int tile = 2 * round + wg;
+    PB_TAG(round == 0 ? 2 : 4)
+    if (warp_u < 8) {
+    pb_mbar_wait(mb_f0 + 8u * (uint32_t)round, tc.ph_f);
+    PB_MARK(21)
+    pb_tc_fence_after();
+    float* zr = sm + pl.off_z + (bl >> 2) * PB_TC_Z_LBO + (wg * 32) * 4 + (bl & 3);
+    if (tile < ntiles) {
+      uint32_t h[64];
+      const uint32_t taddr = tc.tmem + ((uint32_t)(q * 32) << 16) + 64u * (uint32_t)(tile + 1);
+      pb_tmem_ld32(taddr, h);
+      pb_tmem_ld32(taddr + 32u, h + 32);
+      pb_tmem_wait_ld();
+      float f0 = 0.f, f1 = 0.f;
+      // blocks of 8 hidden units behind a (uniform) branch: units >= H are skipped at that granularity
+#pragma unroll
+      for (int c8 = 0; c8 < 8; ++c8)
+        if (c8 < nj8) {
+#pragma unroll
+          for (int j4 = 2 * c8; j4 < 2 * c8 + 2; ++j4) {
+            const float4 w = pb_ld4(w2s + 4 * j4);
+            f0 = fmaf(fmaxf(__uint_as_float(h[4 * j4]), 0.f), w.x, f0);
+            f1 = fmaf(fmaxf(__uint_as_float(h[4 * j4 + 1]), 0.f), w.y, f1);
+            f0 = fmaf(fmaxf(__uint_as_float(h[4 * j4 + 2]), 0.f), w.z, f0);
+            f1 = fmaf(fmaxf(__uint_as_float(h[4 * j4 + 3]), 0.f), w.w, f1);
+          }
+        }
+      const int row = tile * 128 + bl;
+      const bool valid = row < nrows;
+      const float res = yr[row] - ((f0 + f1) + b2);
+      const float r = valid ? res * scale : 0.f;
+      ll += valid ? -0.5f * res * res * pl.inv_s2 : 0.f;
+      rsum += r;
+      float4 x[4];
+#pragma unroll
+      for (int kg = 0; kg < 4; ++kg) x[kg] = pb_ld4(Xa + ((size_t)kg * Npad + row) * 4);
+      if (round > 0) {  // the previous round's backward MMAs have finished reading the mask / Z buffers
+        pb_mbar_wait(mb_d, tc.ph_d);
+        PB_MARK(24)
+      }
+      float* mk = sm + pl.off_mk + (bl >> 2) * PB_TC_MK_LBO + (wg * 64) * 4 + (bl & 3);
+#pragma unroll
+      for (int c8 = 0; c8 < 8; ++c8)
+        if (c8 < nj8) {
+#pragma unroll
+          for (int j = 8 * c8; j < 8 * c8 + 8; ++j) mk[j * 4] = __uint_as_float(h[j]) > 0.f ? 1.f : 0.f;
+        }
+#pragma unroll
+      for (int kg = 0; kg < 4; ++kg) {
+        const float z0 = r * x[kg].x, z1 = r * x[kg].y, z2 = r * x[kg].z, z3 = r * x[kg].w;
+        zr[(4 * kg) * 4] = z0;
+        zr[(4 * kg + 1) * 4] = z1;
+        zr[(4 * kg + 2) * 4] = z2;
+        zr[(4 * kg + 3) * 4] = z3;
+        zr[(16 + 4 * kg) * 4] = z0 - pb_trunc_tf32(z0);
+        zr[(16 + 4 * kg + 1) * 4] = z1 - pb_trunc_tf32(z1);
+        zr[(16 + 4 * kg + 2) * 4] = z2 - pb_trunc_tf32(z2);
+        zr[(16 + 4 * kg + 3) * 4] = z3 - pb_trunc_tf32(z3);
+      }
+    } else {  // odd number of tiles: the odd half of the last round contributes nothing
+      if (round > 0) pb_mbar_wait(mb_d, tc.ph_d);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) zr[i * 4] = 0.f;
+    }
+    PB_MARK(22)
+    pb_fence_async_smem();
+    PB_MARK(25)
+    if (round == nrounds - 1) {
+      ll = pb_warp_sum(ll);
+      rsum = pb_warp_sum(rsum);
+      if (lane == 0) {
+        llbuf[warp] = ll;
+        rs[warp] = rsum;
+      }
+      if (tid >= 8 && tid < 128) llbuf[tid] = 0.f;
+    }
+    }
+    if (round > 0) tc.ph_d ^= 1u;
+    pb_tc_fence_before();
+    PB_ENDPHASE_RAW
+    PB_TAG(5)
+    if (warp_u == 8) {
+      pb_tc_fence_after();
+      if (pb_elect_one()) {
+        const uint32_t idesc = pb_umma_idesc_tf32(128, 64);
+        const uint64_t dm = pb_umma_desc(pb_smem_u32(sm + pl.off_mk), PB_TC_MK_LBO * 4u, 128u);
+        const uint64_t dz = pb_umma_desc(pb_smem_u32(sm + pl.off_z), PB_TC_Z_LBO * 4u, 128u);
+        pb_umma_tf32(tc.tmem, dm, dz, idesc, round == 0 ? 0u : 1u);
+#pragma unroll
+        for (int kb = 1; kb < 16; ++kb)
+          pb_umma_tf32(tc.tmem, dm + (uint64_t)(kb * (2 * PB_TC_MK_LBO * 4 / 16)),
+                       dz + (uint64_t)(kb * (2 * PB_TC_Z_LBO * 4 / 16)), idesc, 1u);
+        pb_umma_commit(mb_d);
+      }
+      __syncwarp();
+      PB_MARK(23)
+    }
+  }
+  tc.ph_f ^= 1u;
+  PB_TAG(3)
+  // ---- readout A (warps 0-3): TMEM lane = hidden unit (lanes 64..127: the odd tiles' partial sums), 16 columns hi +
+  //      16 columns lo -> gx[half][i][j]; partial dot products for the output-layer weights -> gx[2][half][j]
+  if (warp < 4) {
+    pb_mbar_wait(mb_d, tc.ph_d);
+    PB_MARK(24)
+    pb_tc_fence_after();
+    uint32_t g[32];
+    pb_tmem_ld32(tc.tmem + ((uint32_t)(warp * 32) << 16) + (warp >= 2 ? 32u : 0u), g);
+    pb_tmem_wait_ld();
+    pb_tc_fence_before();
+    const int j = tid & 63, half = warp >> 1;
+    float* gh = gx + half * 1024;
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float gm = __uint_as_float(g[i]) + __uint_as_float(g[16 + i]);
+      gh[i * 64 + j] = gm;
+      if (i < inA && j < H) dot = fmaf(TH[L0.soff + i * wp + j], gm, dot);
+    }
+    gx[2048 + half * 64 + j] = dot;
+  }
+  tc.ph_d ^= 1u;
+  PB_ENDPHASE_RAW
+  // ---- readout B (all threads): gradient of the log posterior and, fused, the leapfrog updates + next W operands
+  PB_TAG(6)
+  auto upd = [&](int idx, float gll, float& th_new) -> void {
+    // gll = d loglik / d theta[idx]; MODE 0 stores it, MODE 1/2 apply the half-kick(s) and the drift
+    if (MODE == 0) {
+      G[idx] = gll;
+      return;
+    }
+    const float th = TH[idx];
+    const float gp = gll - th * lf.inv_pv;
+    G[idx] = gp;
+    float p = lf.PM[idx] + lf.heps * gp;
+    if (MODE == 1) {
+      p = p + lf.heps * gp;
+      th_new = th + lf.eps * (lf.MI[idx] * p);
+      TH[idx] = th_new;
+    }
+    lf.PM[idx] = p;
+  };
+  {
+    // up to 4 first-layer weights per thread, branch-free: a missing element works on a zero pad slot with a zero
+    // gradient (every update of it is 0 -> 0); all loads first (the stores may alias for the compiler)
+    float gl[4], th[4], pm[4], mi[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float gsum = gx[tc.rgx[u]] + gx[1024 + tc.rgx[u]];
+      gl[u] = (tc.rok >> u) & 1u ? w2s[tc.rgx[u] & 63] * gsum : 0.f;
+      th[u] = pm[u] = mi[u] = 0.f;
+      if (MODE != 0) {
+        th[u] = TH[tc.ridx[u]];
+        pm[u] = lf.PM[tc.ridx[u]];
+      }
+      if (MODE == 1) mi[u] = lf.MI[tc.ridx[u]];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (MODE == 0) {
+        G[tc.ridx[u]] = gl[u];
+      } else {
+        const float gp = gl[u] - th[u] * lf.inv_pv;
+        G[tc.ridx[u]] = gp;
+        float p = pm[u] + lf.heps * gp;
+        if (MODE == 1) {
+          p = p + lf.heps * gp;
+          const float tn = th[u] + lf.eps * (mi[u] * p);
+          TH[tc.ridx[u]] = tn;
+          Wb[tc.rwo[u]] = tn;
+          Wl[tc.rwo[u]] = tn - pb_trunc_tf32(tn);
+        }
+        lf.PM[tc.ridx[u]] = p;
+      }
+    }
+  }
+  if (tid < H) {  // the output weights are double-buffered: the loop above (other threads) still reads the current ones
+    float w2n = 0.f;
+    upd(L1.soff + tid * L1.wp, gx[2048 + tid] + gx[2048 + 64 + tid], w2n);
+    if (MODE == 1) w2nxt[tid] = w2n;
+  }
+  if (tid == 64) {
+    float a = 0.f, bn = 0.f;
+    for (int w = 0; w < 8; ++w) a += rs[w];
+    upd(L1.soff + H * L1.wp, a, bn);
+  }
+  if (MODE == 1) pb_fence_async_smem();
+  pb_tc_fence_before();
+  PB_ENDPHASE_RAW
+  PB_TAG(0)
+}
+
+// plain gradient (initial point of a chain; pbnn_logposterior_grad)
+PB_DEV void pb_grad_tc(const PbPlan& pl, float* sm, float* TH, float* G, int nrows, float scale, int nt, PbTc& tc) {
+  PbTcLeap lf = {nullptr, nullptr, 0.f, 0.f, 0.f};
+  pb_tc_stage_w<false>(pl, sm, TH, G, lf, nt, tc);
+  pb_tc_grad_core<0>(pl, sm, TH, G, nrows, scale, nt, tc, lf);
+}
+#endif

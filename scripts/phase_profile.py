@@ -22,8 +22,15 @@ step(); ops.lib.pbnn_debug_profile(out)
 a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
 a.record(); step(); b.record(); torch.cuda.synchronize()
 ops.lib.pbnn_debug_profile(out)
+if os.environ.get("PBNN_NO_TC") is None and name.startswith("hmc"):
+    tcn = {1: "tc: W1 split/stage", 2: "tc: fwd MMA wait + epilogue r0", 4: "tc: bwd MMA wait + epilogue r1+", 5: "tc: bwd issue (+next)", 3: "tc: bwd wait + readout A", 6: "tc: readout B (update)",
+           20: "tc mark: fwd issue", 21: "tc mark: fwd wait", 22: "tc mark: epilogue math", 23: "tc mark: bwd issue",
+           24: "tc mark: bwd wait", 25: "tc mark: proxy fence"}
+else:
+    tcn = {}
 names = {11: "hmc momentum", 12: "leapfrog pre", 13: "leapfrog post", 14: "logp reduce", 15: "accept", 16: "copy/emit", 0: "other/elementwise", 1: "fwd gemm", 2: "last fwd A", 3: "last fwd B", 4: "rank1 bwd C1", 5: "rank1 bwd C2",
          6: "dW gemm", 7: "dH gemm", 8: "gpart reduce", 9: "post", 10: "gather rows"}
+names.update(tcn)
 tot = sum(out[i] for i in range(32))
 print(f"{name}: T={w['T']}  kernel {a.elapsed_time(b):.3f} ms; CTA0 accounted {tot} cycles; plan {ops.plan(fs, w['B'], 6 if w['algo']=='hmc' else 3)}")
 for i in range(32):

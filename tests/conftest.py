@@ -30,11 +30,16 @@ def cuda_ops():
 
 
 @pytest.fixture(params=["emu", pytest.param("cuda", marks=pytest.mark.gpu),
+                        pytest.param("cuda_notc", marks=pytest.mark.gpu),
                         pytest.param("cuda_generic", marks=pytest.mark.gpu)])
 def ops(request, monkeypatch):
-    """Parity tests run against the emulator here (CPU) and against the CUDA library on the GPU box -- there twice:
-    with the default kernel selection (fused one-hidden-layer path where it applies) and with the generic tiled-GEMM
-    engine forced (PBNN_NO_H1=1; the plan is rebuilt on every call, so the environment switch is enough)."""
+    """Parity tests run against the emulator here (CPU) and against the CUDA library on the GPU box -- there three
+    times: with the default kernel selection (tcgen05 engine for HMC on one-hidden-layer relu nets, fused FP32 path
+    for the other one-hidden-layer cases), with the tensor-core engine disabled (PBNN_NO_TC=1) and with the generic
+    tiled-GEMM engine forced (PBNN_NO_H1=1; the plan is rebuilt on every call, so the environment switch is enough)."""
+    if request.param == "cuda_notc":
+        monkeypatch.setenv("PBNN_NO_TC", "1")
+        return request.getfixturevalue("cuda_ops")
     if request.param == "cuda_generic":
         monkeypatch.setenv("PBNN_NO_H1", "1")
         return request.getfixturevalue("cuda_ops")

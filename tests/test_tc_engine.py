@@ -1,0 +1,108 @@
+"""tcgen05 HMC engine (pbnn_b200/csrc/pbnn_tc.cuh): parity with the oracle through the C ABI, and plan selection."""
+import numpy as np
+import pytest
+
+from oracle import pbnn_oracle as o
+from pbnn_b200.ops import FlatSpec
+
+pytestmark = pytest.mark.gpu
+
+
+def npy(t):
+    return t.detach().cpu().numpy()
+
+
+def rel(a, b):
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def problem(layers, N, C, seed=3, scale=0.2):
+    X, y = o.synthetic_regression(N, layers[0], seed)
+    sp, fs = o.MlpSpec(tuple(layers), o.RELU, 0.1), FlatSpec(tuple(layers), o.RELU, 0.1)
+    th = (scale * np.random.default_rng(seed).standard_normal((C, sp.num_params))).astype(np.float32)
+    return X, y, sp, fs, th
+
+
+# one tile, an odd number of tiles, a full last tile, the widest / narrowest shapes of the engine, N = 2
+SHAPES = [((13, 50, 1), 506), ((8, 50, 1), 300), ((5, 64, 1), 100), ((15, 33, 1), 640), ((3, 7, 1), 129),
+          ((1, 1, 1), 2), ((2, 64, 1), 256), ((15, 64, 1), 768)]
+
+
+@pytest.mark.parametrize("layers,N", SHAPES)
+def test_tc_gradient_matches_float64(cuda_ops, monkeypatch, layers, N):
+    """3xTF32 split operands: the gradient agrees with the float64 oracle to fp32-summation accuracy (the scalar
+    FP32 engine reaches ~1e-7 on the same inputs, the tolerance here is 5e-6)."""
+    X, y, sp, fs, th = problem(layers, N, 5)
+    lp64, g64 = o.logposterior_full(sp, th.astype(np.float64), X.astype(np.float64), y.astype(np.float64))
+    lp, g = cuda_ops.logposterior_grad(fs, X, y, th)
+    assert rel(npy(g), g64) <= 5e-6
+    assert rel(npy(lp), lp64) <= 5e-6
+    monkeypatch.setenv("PBNN_NO_TC", "1")
+    lp1, g1 = cuda_ops.logposterior_grad(fs, X, y, th)
+    assert rel(npy(g), npy(g1)) <= 5e-6
+
+
+def test_tc_plan_is_selected_and_can_be_disabled(cuda_ops, monkeypatch):
+    """The engines must actually differ: same inputs, not bit-identical results (else the switch does nothing)."""
+    X, y, sp, fs, th = problem((13, 50, 1), 506, 3)
+    _, g_tc = cuda_ops.logposterior_grad(fs, X, y, th)
+    monkeypatch.setenv("PBNN_NO_TC", "1")
+    _, g_h1 = cuda_ops.logposterior_grad(fs, X, y, th)
+    assert not np.array_equal(npy(g_tc), npy(g_h1))
+    assert rel(npy(g_tc), npy(g_h1)) <= 5e-6
+
+
+@pytest.mark.parametrize("layers,N", [((13, 50, 1), 506), ((8, 50, 1), 300), ((4, 20, 1), 64)])
+def test_tc_hmc_trajectories(cuda_ops, layers, N):
+    """Full HMC through the tensor-core engine: fused half-kicks / drift, L = 1 and L > 1, several iterations."""
+    X, y, sp, fs, th0 = problem(layers, N, 4, scale=0.05)
+    keys = o.split(o.PRNGKey(11), 4)
+    minv = np.linspace(0.8, 1.25, sp.num_params).astype(np.float32)
+    for L, S, eps in ((1, 3, 2e-4), (5, 4, 2e-4), (12, 2, 1e-4)):
+        ref, info = o.hmc(sp, X, y, th0, S, eps, minv, L, keys, return_info=True)
+        out = cuda_ops.hmc(fs, X, y, th0, keys, S, eps, minv, L, info=True)
+        acc = npy(out["accept"]).astype(bool)
+        agree = np.ones(4, bool)
+        for s in range(S):
+            agree &= acc[:, s] == info["accept"][:, s]
+            assert rel(npy(out["trace"])[agree, s], ref[agree, s]) <= 2e-5, (L, s)
+        assert agree.sum() >= 3
+        assert np.allclose(npy(out["delta"])[agree], info["delta"][agree], atol=0.05)
+
+
+def test_tc_hmc_rejections_and_resume(cuda_ops):
+    """Large step: rejected proposals restore (theta, grad); a run split in two calls equals one run (t0 offsets)."""
+    X, y, sp, fs, th0 = problem((6, 16, 1), 200, 6, scale=0.3)
+    keys = o.split(o.PRNGKey(5), 6)
+    minv = np.ones(sp.num_params, np.float32)
+    S, L, eps = 8, 6, 6e-3
+    ref, info = o.hmc(sp, X, y, th0, S, eps, minv, L, keys, return_info=True)
+    assert (~info["accept"]).any() and info["accept"].any()
+    out = cuda_ops.hmc(fs, X, y, th0, keys, S, eps, minv, L, info=True)
+    acc = npy(out["accept"]).astype(bool)
+    near = np.abs(info["u"] - np.minimum(1, np.exp(np.minimum(info["delta"], 0)))) < 1e-3
+    agree = np.ones(6, bool)
+    for s in range(S):
+        same = acc[:, s] == info["accept"][:, s]
+        assert np.all(same[agree] | near[agree, s])
+        agree &= same
+        assert rel(npy(out["trace"])[agree, s], ref[agree, s]) <= 1e-4
+    assert agree.sum() >= 4
+    a = cuda_ops.hmc(fs, X, y, th0, keys, 5, eps, minv, L)
+    b = cuda_ops.hmc(fs, X, y, npy(a["theta"]), keys, 3, eps, minv, L, t0=5)
+    full = npy(out["trace"])
+    got = np.concatenate([npy(a["trace"]), npy(b["trace"])], 1)
+    assert np.array_equal(got, full)
+
+
+def test_tc_many_chains_two_waves(cuda_ops):
+    """More chains than SMs (one CTA per SM: the second wave re-allocates TMEM) -- every chain must be finite and
+    chains with the same key and start must be bit-identical wherever they are scheduled."""
+    X, y, sp, fs, th = problem((13, 50, 1), 506, 1, scale=0.05)
+    C = 333
+    keys = np.repeat(o.split(o.PRNGKey(2), 1), C, 0)
+    th0 = np.repeat(th, C, 0)
+    out = cuda_ops.hmc(fs, X, y, th0, keys, 3, 2e-4, np.ones(sp.num_params, np.float32), 4)
+    tr = npy(out["trace"])
+    assert np.isfinite(tr).all()
+    assert np.array_equal(tr, np.repeat(tr[:1], C, 0))
