@@ -68,13 +68,26 @@ def step_flops(w):
     return per_chain_step * w["C"] * w["T"]
 
 
-def make_inputs(w, rank, world):
-    from oracle import pbnn_oracle as o  # synthetic data + key derivation shared with the tests (checker side)
-    X, y, Xt, _ = o.synthetic_regression(w["N"], w["layers"][0], 0, M=w["M"])
-    sp = o.MlpSpec(tuple(w["layers"]), w["act"], 0.1)
-    keys_all = o.split(o.PRNGKey(0), w["C"] * world)
-    keys = keys_all[rank * w["C"]:(rank + 1) * w["C"]]
-    th0 = o.init_positions(sp, keys)
+def make_data(w):
+    """Synthetic UCI-shaped regression data (seeded numpy; the same arrays feed the GPU arm and the CPU arms)."""
+    N, M, d = w["N"], w["M"], w["layers"][0]
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((N + M, d)).astype(np.float32)
+    X = ((X - X[:N].mean(0)) / X[:N].std(0)).astype(np.float32)
+    wv = rng.standard_normal(d).astype(np.float32)
+    y = (np.tanh(X @ wv / np.sqrt(np.float32(d))) + 0.1 * rng.standard_normal(N + M)).astype(np.float32)[:, None]
+    return X[:N], y[:N], X[N:]
+
+
+def make_inputs(w, rank, world, ops):
+    """Data + per-chain keys and starting points of this rank.  Keys are split(PRNGKey(0), C * world)[rank's slice] and
+    theta0 = 0.01 * normal(key_c, P) (the Flax init law), both produced by the library's own threefry kernels."""
+    X, y, Xt = make_data(w)
+    P = num_params(w["layers"])
+    root = np.array([[0, 0]], np.uint32)  # PRNGKey(0)
+    keys_all = ops.split(root, w["C"] * world)[0]
+    keys = keys_all[rank * w["C"]:(rank + 1) * w["C"]].contiguous()
+    th0 = 0.01 * ops.normal(keys, P)
     return X, y, Xt, keys, th0
 
 
@@ -127,7 +140,7 @@ def cpu_run(w, n_chains, n_iters, seed_rank=0):
     """Run the C restatement on a bounded sample: n_chains chains x n_iters sampler iterations.  Returns seconds."""
     from oracle import c_oracle as co
     from oracle import pbnn_oracle as o
-    X, y, _, _, _ = make_inputs(dict(w, C=1), 0, 1)
+    X, y, _ = make_data(w)
     sp = o.MlpSpec(tuple(w["layers"]), w["act"], 0.1)
     keys = o.split(o.PRNGKey(0), n_chains)
     th0 = o.init_positions(sp, keys)
@@ -242,9 +255,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ops = default_ops()
     fs = FlatSpec(tuple(w["layers"]), w["act"], 0.1)
-    Xh, yh, Xth, keysh, th0h = make_inputs(w, rank, world)
+    Xh, yh, Xth, keys, th0 = make_inputs(w, rank, world, ops)
     X, y, Xt = (ops._as(a, torch.float32) for a in (Xh, yh, Xth))
-    keys, th0 = ops._keys(keysh), ops._as(th0h, torch.float32)
+    keysh, th0h = keys.cpu().numpy(), th0.cpu().numpy()
     step = gpu_step_fn(ops, w, fs, X, y, th0, keys)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
 
@@ -300,10 +313,47 @@ def main():
             src = r["trace"] if (w["algo"] == "hmc" and r.get("trace") is not None) else r["theta"].unsqueeze(1)
             hout.copy_(src, non_blocking=True)
 
-        ms_e2e = timed(e2e_step, args.steps, args.warmup)
+        ms_serial = timed(e2e_step, args.steps, args.warmup)
+
+        # the same calls as a stream pipeline: the D2H of step i (copy stream, double-buffered pinned output) overlaps
+        # the kernel of step i+1; every step still uploads its inputs and downloads its whole result
+        copy_stream = torch.cuda.Stream()
+        houts = [hout, torch.empty(res_shape, dtype=torch.float32).pin_memory()]
+
+        def pipelined(K):
+            cur = torch.cuda.current_stream()
+            for i in range(K):
+                flush.fill_(1)
+                dX, dy = hX.to("cuda", non_blocking=True), hy.to("cuda", non_blocking=True)
+                dk, dt_ = hk.to("cuda", non_blocking=True), ht.to("cuda", non_blocking=True)
+                r = gpu_step_fn(ops, w, fs, dX, dy, dt_, dk)()
+                src = r["trace"] if (w["algo"] == "hmc" and r.get("trace") is not None) else r["theta"].unsqueeze(1)
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                copy_stream.wait_event(ev)
+                with torch.cuda.stream(copy_stream):
+                    houts[i % 2].copy_(src, non_blocking=True)
+                src.record_stream(copy_stream)
+            cur.wait_stream(copy_stream)
+
+        pipelined(args.warmup)
+        barrier()
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record()
+        pipelined(args.steps)
+        eb.record()
+        barrier()
+        ms_e2e = ea.elapsed_time(eb)
+        if world > 1:
+            t = torch.tensor([ms_e2e], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_e2e = float(t.item())
         e2e = {"value": args.steps * chain_steps / (ms_e2e * 1e-3), "unit": "chain-steps/s",
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
-               "api": "pbnn_b200.ops (C ABI) with pinned host buffers; positions returned to the host"}
+               "serial_value": args.steps * chain_steps / (ms_serial * 1e-3),
+               "api": "pbnn_b200.ops (C ABI) with pinned host buffers; positions returned to the host; value = steps "
+                      "issued as a 2-stream pipeline (D2H of step i overlaps the kernel of step i+1), serial_value = "
+                      "one step at a time"}
 
     # the single exchange step: predictive moments of each rank's final states, all_gather'ed (not in the timed region)
     last = step()
@@ -335,15 +385,41 @@ def main():
                 traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
         except (OSError, KeyError, ValueError):
             pass
-        roofline = {"bound": "fma", "achieved": achieved, "peak": peak_nominal, "unit": "TFLOP/s",
-                    "frac": achieved / peak_nominal, "traffic": traffic,
-                    "peak_source": f"FP32 FMA: 148 SM x 128 lanes x 2 x {sm_max:.0f} MHz (the kernel is FP32-FMA bound, "
-                                   f"neither HBM nor tensor; DESIGN.md)",
-                    "kernel": "pb_hmc_kernel" if w["algo"] == "hmc" else "pb_sg_kernel",
-                    "algorithmic_flops_per_launch": flops,
-                    "hbm": {"achieved": trace_bytes / (ms_per_step * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                            "frac": trace_bytes / (ms_per_step * 1e-3) / 1e9 / hbm_peak,
-                            "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback"}}
+        from pbnn_b200 import _lib as plib
+        op = {"hmc": plib.OP_HMC, "sgld": plib.OP_SGLD, "psgld": plib.OP_PSGLD, "sghmc": plib.OP_SGHMC,
+              "adam": plib.OP_ADAM}[w["algo"]]
+        engine = ops.lib.pbnn_plan_engine(fs.c_struct(), op, w["B"], w["C"])
+        hbm = {"achieved": trace_bytes / (ms_per_step * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+               "frac": trace_bytes / (ms_per_step * 1e-3) / 1e9 / hbm_peak,
+               "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback"}
+        if engine == plib.ENGINE_TCGEN05:
+            # the two GEMMs of every gradient run on the tensor cores as split-TF32 products:
+            # achieved = ALGORITHMIC flops / time against the TF32 tensor peak (half the measured dense bf16 rate)
+            tf32_peak = peaks.get("bf16_tflops", 2250.0 * 0.73) / 2
+            ntile = (w["B"] + 127) // 128
+            grads = w["C"] * w["T"] * (w["L"] + 1.0 / w["T"])
+            executed = grads * (ntile * 6 + ((ntile + 1) // 2) * 16) * (128 * 64 * 8 * 2)
+            roofline = {"bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
+                        "frac": achieved / tf32_peak, "traffic": traffic,
+                        "peak_source": "TF32 dense tensor rate = measured cuBLAS bf16 (MEASURED_PEAKS.json burst) / 2"
+                                       if peaks else "fallback: 0.73 x 2250 / 2",
+                        "kernel": "pb_hmc_tc_kernel", "algorithmic_flops_per_launch": flops,
+                        "executed_tensor_flops_per_launch": executed,
+                        "executed_tensor_tflops": executed / (ms_per_step * 1e-3) / 1e12,
+                        "fp32_fma_equivalent": {"achieved": achieved, "peak": peak_nominal, "frac": achieved / peak_nominal,
+                                                "note": "the same algorithmic flops against the FP32-FMA peak the "
+                                                        "scalar engines are bound by (148 SM x 128 lanes x 2 x clock)"},
+                        "note": "latency-bound: per gradient a dependent chain of forward MMA -> epilogue -> backward "
+                                "MMA -> readout on one CTA per SM; see profiles/ and DESIGN.md",
+                        "hbm": hbm}
+        else:
+            roofline = {"bound": "fma", "achieved": achieved, "peak": peak_nominal, "unit": "TFLOP/s",
+                        "frac": achieved / peak_nominal, "traffic": traffic,
+                        "peak_source": f"FP32 FMA: 148 SM x 128 lanes x 2 x {sm_max:.0f} MHz (the kernel is FP32-FMA "
+                                       f"bound, neither HBM nor tensor; DESIGN.md)",
+                        "kernel": "pb_hmc_kernel" if w["algo"] == "hmc" else "pb_sg_kernel",
+                        "algorithmic_flops_per_launch": flops, "hbm": hbm}
+        roofline["engine"] = ["tiled", "fused_h1", "tcgen05", "tiled_global_state"][engine] if 0 <= engine < 4 else engine
         try:  # practical FP32 ceiling measured in the same run (scalar FFMA and packed FFMA2 probes)
             import ctypes
             ops.lib.pbnn_probe_fp32.argtypes = [ctypes.c_int] * 3 + [ctypes.c_void_p] * 2
@@ -358,7 +434,7 @@ def main():
                 torch.cuda.synchronize()
                 best = max(best, 148 * 8 * 256 * 10000 * 64 / (ea.elapsed_time(eb) * 1e-3) / 1e12)
             roofline["peak_measured_fp32_probe"] = best
-            roofline["frac_of_measured"] = achieved / best
+            roofline["frac_of_measured_fp32"] = achieved / best
         except Exception as exc:  # noqa: BLE001
             roofline["peak_measured_fp32_probe"] = None
         out = dict(base, value=value, ms_per_step=ms_per_step, clocks=clocks, roofline=roofline, gpu_launches=args.steps,

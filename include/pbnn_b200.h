@@ -67,6 +67,15 @@ int pbnn_num_params(const pbnn_mlp_spec* spec);
  * out[2]=dynamic shared memory bytes, out[3]=padded parameter count.  `rows` is the minibatch size
  * (or N for full-batch HMC / M for predict), `n_state` the number of resident parameter-sized arrays. */
 int pbnn_plan_query(const pbnn_mlp_spec* spec, int rows, int n_state, int32_t out[4]);
+/* gradient engine sampler `op` (PBNN_OP_*) would run for `C` chains with `rows` rows per gradient evaluation:
+ * PBNN_ENGINE_* below, < 0 on error.  All engines implement the same arithmetic contract (the value_and_grad of
+ * benchmark/pipelines/logprobs.py:6-17); the tcgen05 engine computes the two GEMMs as split-TF32 (hi/lo) tensor-core
+ * products with FP32 accumulation (~1e-6 relative to the FP32 engines). */
+#define PBNN_ENGINE_TILED 0    /* register-tiled FP32 GEMMs, any depth / width                                   */
+#define PBNN_ENGINE_FUSED_H1 1 /* one hidden layer, scalar output: warp-autonomous fused FP32 path                */
+#define PBNN_ENGINE_TCGEN05 2  /* HMC, one hidden relu layer, scalar output: tensor-core engine (pbnn_tc.cuh)     */
+#define PBNN_ENGINE_TILED_GLOBAL_STATE 3 /* as TILED with the parameter-sized arrays in the global workspace      */
+int pbnn_plan_engine(const pbnn_mlp_spec* spec, int op, int rows, int C);
 
 /* Workspace.  Models whose parameter-sized state does not fit shared memory (e.g. 90-256-256-1, P = 89 345) keep it in
  * a caller-provided, 16-byte aligned DEVICE workspace (L2 resident while the chain is advanced).  Returns the bytes the

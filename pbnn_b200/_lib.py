@@ -12,6 +12,7 @@ from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
 PBNN_MAX_LAYERS = 8
 ACT_RELU, ACT_TANH = 0, 1
 OP_SGLD, OP_PSGLD, OP_SGHMC, OP_ADAM, OP_GRAD, OP_HMC = range(6)
+ENGINE_TILED, ENGINE_FUSED_H1, ENGINE_TCGEN05, ENGINE_TILED_GLOBAL_STATE = range(4)
 MB_REFERENCE_FIXED, MB_PER_STEP = 0, 1
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -44,6 +45,7 @@ PROTOTYPES = {
     "pbnn_last_error": (c_char_p, []),
     "pbnn_num_params": (c_int, [_SPEC]),
     "pbnn_plan_query": (c_int, [_SPEC, c_int, c_int, POINTER(c_int32 * 4)]),
+    "pbnn_plan_engine": (c_int, [_SPEC, c_int, c_int, c_int]),
     "pbnn_threefry_split": (c_int, [_P, c_int, c_int, _P, _P]),
     "pbnn_threefry_fold_in": (c_int, [_P, c_int, ctypes.c_uint32, _P, _P]),
     "pbnn_threefry_bits": (c_int, [_P, c_int, c_int, _P, _P]),

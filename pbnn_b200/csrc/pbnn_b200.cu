@@ -38,12 +38,48 @@ pb_hmc_kernel(const __grid_constant__ PbPlan pl, const __grid_constant__ PbHmcAr
   pb_hmc_chain<ACT, GS, ENG>(pl, a, pb_smem, (int)blockIdx.x, (int)blockDim.x);
 }
 
-// tcgen05 engine: 8 epilogue warps + 1 MMA-issue warp, one CTA per SM (the operand buffers need ~200 KB)
+// tcgen05 engine: 8 epilogue warps + 1 MMA-issue warp, one CTA per SM (the operand buffers need ~200 KB).
+// a.sched_done == NULL: CTA c advances chain c.  Else (more chains than SMs) the grid is persistent and balanced:
+// item n = segment * C + chain, CTA b takes items b, b + grid, ...; a chain's next segment starts when the CTA that
+// ran the previous one has published its state (release store / acquire load of sched_done[chain]).  Items are taken
+// in increasing order and all CTAs are co-resident (cooperative launch), so the lowest unfinished item can always run.
 __global__ void __launch_bounds__(288, 1)
 pb_hmc_tc_kernel(const __grid_constant__ PbPlan pl, const __grid_constant__ PbHmcArgs a) {
   extern __shared__ __align__(16) float pb_smem[];
   PB_PROF_START
-  pb_hmc_chain<PBNN_ACT_RELU, false, 2>(pl, a, pb_smem, (int)blockIdx.x, (int)blockDim.x);
+  const int nt = (int)blockDim.x;
+  pb_init_acts(pl, pb_smem, nt);
+  PbTc tc;
+  pb_tc_setup(pl, pb_smem, a.X, a.y, a.N, nt, tc);
+  if (!a.sched_done) {
+    pb_hmc_chain<PBNN_ACT_RELU, false, 2>(pl, a, pb_smem, (int)blockIdx.x, nt, 0, -1, false, &tc);
+  } else {
+    const int nseg = (a.S + a.seg_len - 1) / a.seg_len;
+    const long long nitems = (long long)nseg * a.n_chains;
+    for (long long item = blockIdx.x; item < nitems; item += gridDim.x) {
+      const int seg = (int)(item / a.n_chains), c = (int)(item - (long long)seg * a.n_chains);
+      if (seg > 0) {
+        if (threadIdx.x == 0) {
+          int done = 0;
+          for (unsigned spin = 0; spin < (1u << 24); ++spin) {  // bounded: a scheduling bug must not hang the GPU
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(done) : "l"(a.sched_done + c) : "memory");
+            if (done >= seg) break;
+            __nanosleep(200);
+          }
+          if (done < seg && a.flags) atomicOr(a.flags + c, 2u);
+        }
+        __syncthreads();
+      }
+      const int s0 = seg * a.seg_len, s1 = s0 + a.seg_len < a.S ? s0 + a.seg_len : a.S;
+      pb_hmc_chain<PBNN_ACT_RELU, false, 2>(pl, a, pb_smem, c, nt, s0, s1, seg > 0, &tc);
+      __syncthreads();
+      if (threadIdx.x == 0 && s1 < a.S) {
+        __threadfence();
+        asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.sched_done + c), "r"(seg + 1) : "memory");
+      }
+    }
+  }
+  pb_tc_teardown(pl, pb_smem, tc);
 }
 
 template <int ACT, bool GS>
@@ -359,6 +395,20 @@ static thread_local char g_err[512] = "";
     }                                                                                         \
   } while (0)
 
+// SM count of the current device (148 on a B200; also the answer when no device is visible: host-side queries only)
+static int pb_backend_num_sms() {
+  static int cached = 0;
+  if (cached > 0) return cached;
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+      n < 1) {
+    (void)cudaGetLastError();
+    return 148;
+  }
+  cached = n;
+  return n;
+}
+
 template <class K, class A>
 static int pb_launch(K kern, const PbPlan& pl, const A& a, dim3 grid, void* stream) {
   const size_t smem = (size_t)pl.smem_floats * 4;
@@ -397,7 +447,30 @@ static int pb_backend_hmc(const PbPlan& pl, const PbHmcArgs& a, int C, void* str
     if (pl.act == PBNN_ACT_RELU) return pb_launch(pb_hmc_kernel<PBNN_ACT_RELU, true, 0>, pl, a, dim3(C), stream);
     return pb_launch(pb_hmc_kernel<PBNN_ACT_TANH, true, 0>, pl, a, dim3(C), stream);
   }
-  if (pl.tc) return pb_launch(pb_hmc_tc_kernel, pl, a, dim3(C), stream);
+  if (pl.tc) {
+    if (a.sched_done) {  // balanced persistent grid: needs every CTA co-resident -> cooperative launch
+      const size_t smem = (size_t)pl.smem_floats * 4;
+      PB_CUDA(cudaFuncSetAttribute(pb_hmc_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int dev = 0, nsm = 0, per_sm = 0;
+      PB_CUDA(cudaGetDevice(&dev));
+      PB_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+      PB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pb_hmc_tc_kernel, pl.NT, smem));
+      const int grid = nsm * per_sm < C ? nsm * per_sm : C;
+      if (grid > 0) {
+        PB_CUDA(cudaMemsetAsync(a.sched_done, 0, sizeof(int) * (size_t)C, (cudaStream_t)stream));
+        void* kargs[2] = {(void*)&pl, (void*)&a};
+        if (cudaLaunchCooperativeKernel((const void*)pb_hmc_tc_kernel, dim3(grid), dim3(pl.NT), kargs, smem,
+                                        (cudaStream_t)stream) == cudaSuccess)
+          return PBNN_OK;
+        (void)cudaGetLastError();  // not launchable cooperatively: one CTA per chain instead
+      }
+      PbHmcArgs b = a;
+      b.sched_done = nullptr;
+      b.sched_g0 = nullptr;
+      return pb_launch(pb_hmc_tc_kernel, pl, b, dim3(C), stream);
+    }
+    return pb_launch(pb_hmc_tc_kernel, pl, a, dim3(C), stream);
+  }
   if (pl.h1) {
     if (pl.act == PBNN_ACT_RELU) return pb_launch(pb_hmc_kernel<PBNN_ACT_RELU, false, 1>, pl, a, dim3(C), stream);
     return pb_launch(pb_hmc_kernel<PBNN_ACT_TANH, false, 1>, pl, a, dim3(C), stream);

@@ -412,6 +412,14 @@ struct PbHmcArgs {
   float* ws;
   float* grad_out;  // optional: gradient of the log-posterior at the initial position [C][P]
   int no_store;     // do not write theta back (value_and_grad only)
+  // balanced schedule of the tcgen05 kernel (C > number of SMs): the chains are cut into segments of seg_len
+  // iterations, persistent CTAs take (segment, chain) items round-robin and hand a chain over through global memory
+  int seg_len, n_chains;
+  float* sched_g0;        // [C][P] gradient at the current position
+  float* sched_logp;      // [C]
+  int32_t* sched_acc;     // [C]
+  uint32_t* sched_flags;  // [C]
+  int* sched_done;        // [C] segments completed (release / acquire hand-over)
 };
 
 struct PbPredArgs {

@@ -1153,7 +1153,11 @@ PB_DEV void pb_hmc_logp_reduce(const PbPlan& pl, float* sm, const float* TH, con
 }
 
 template <int ACT, bool GS, int ENG>
-PB_DEV void pb_hmc_chain(const PbPlan& pl, const PbHmcArgs& a, float* sm, int c, int nt) {
+PB_DEV void pb_hmc_chain(const PbPlan& pl, const PbHmcArgs& a, float* sm, int c, int nt, int s_begin = 0,
+                         int s_end = -1, bool resume = false, void* tcx = nullptr) {
+  // iterations [s_begin, s_end) of chain c; resume: continue a chain whose state another CTA left in global memory
+  // (balanced schedule of the tcgen05 kernel); tcx: the CTA's tcgen05 context (ENG == 2: set up by the kernel)
+  if (s_end < 0) s_end = a.S;
   float* ws = a.ws ? a.ws + (size_t)c * pl.nstate * pl.Ps : nullptr;
   float* TH = pb_state<GS>(pl, sm, ws, 0);
   float* G = pb_state<GS>(pl, sm, ws, 1);
@@ -1170,15 +1174,15 @@ PB_DEV void pb_hmc_chain(const PbPlan& pl, const PbHmcArgs& a, float* sm, int c,
   ck.k1 = a.keys ? a.keys[2 * c + 1] : 0u;
   const float eps = a.step_size, heps = a.step_size * 0.5f;
 
-  pb_init_acts(pl, sm, nt);
-  pb_load_state(pl, TH, a.theta + cP, nt);
+  // ENG == 2: tcgen05 engine (pbnn_tc.cuh): buffers, operand staging and TMEM are set up once per CTA by the kernel
+  if (ENG != 2) pb_init_acts(pl, sm, nt);
+  pb_load_state(pl, TH, resume ? nullptr : a.theta + cP, nt);
   pb_load_state(pl, G, nullptr, nt);
   pb_load_state(pl, PM, nullptr, nt);
   pb_load_state(pl, MI, a.inv_mass, nt);
-  // ENG == 2: tcgen05 engine (pbnn_tc.cuh), its own operand staging; else the resident rows of the scalar engines
 #if !defined(PB_EMU)
-  PbTc tc;
-  if constexpr (ENG == 2) pb_tc_setup(pl, sm, a.X, a.y, a.N, nt, tc);
+  PbTc tc_local;
+  PbTc& tc = tcx ? *static_cast<PbTc*>(tcx) : tc_local;
 #define PB_HMC_GRAD()                                                      \
   if constexpr (ENG == 2) pb_grad_tc(pl, sm, TH, G, a.N, pl.inv_s2, nt, tc); \
   else pb_grad<ACT, ENG>(pl, sm, TH, G, a.X, a.y, nullptr, a.N, pl.inv_s2, false, nt);
@@ -1186,30 +1190,50 @@ PB_DEV void pb_hmc_chain(const PbPlan& pl, const PbHmcArgs& a, float* sm, int c,
 #define PB_HMC_GRAD() pb_grad<ACT, ENG>(pl, sm, TH, G, a.X, a.y, nullptr, a.N, pl.inv_s2, false, nt);
 #endif
   if (ENG != 2 && pl.res_rows > 0) pb_load_resident(pl, sm, a.X, a.y, nullptr, a.N, nt);
-  PB_PHASE
-  if (tid == 0) {
-    scu[2] = 0u;
-    scu[15] = 0u;
-  }
-  PB_ENDPHASE
+  if (!resume) {
+    PB_PHASE
+    if (tid == 0) {
+      scu[2] = 0u;
+      scu[15] = 0u;
+    }
+    PB_ENDPHASE
 
-  // init: (logp, grad) at theta0
-  PB_HMC_GRAD()
-  PB_PHASE
-  for (int i = tid; i < pl.Ps; i += nt) {
-    const float g = G[i] - TH[i] * pl.inv_pv;
-    G[i] = g;
-    G0[i] = g;
-    TH0[i] = TH[i];
+    // init: (logp, grad) at theta0
+    PB_HMC_GRAD()
+    PB_PHASE
+    for (int i = tid; i < pl.Ps; i += nt) {
+      const float g = G[i] - TH[i] * pl.inv_pv;
+      G[i] = g;
+      G0[i] = g;
+      TH0[i] = TH[i];
+    }
+    PB_ENDPHASE
+    pb_hmc_logp_reduce(pl, sm, TH, PM, MI, nt);
+    PB_PHASE
+    if (tid == 0) sc[12] = (-0.5f * pl.inv_pv * sc[9] - (float)P * pl.logprior_const) + sc[8];
+    if (a.grad_out) pb_for_each_param(pl, tid, nt, [&](int si, int fi) { a.grad_out[cP + fi] = G0[si]; });
+    PB_ENDPHASE
   }
-  PB_ENDPHASE
-  pb_hmc_logp_reduce(pl, sm, TH, PM, MI, nt);
-  PB_PHASE
-  if (tid == 0) sc[12] = (-0.5f * pl.inv_pv * sc[9] - (float)P * pl.logprior_const) + sc[8];
-  if (a.grad_out) pb_for_each_param(pl, tid, nt, [&](int si, int fi) { a.grad_out[cP + fi] = G0[si]; });
-  PB_ENDPHASE
+#if !defined(PB_EMU)
+  else {
+    // L2 loads (.cg): the previous owner of the chain published these with a release store (pb_hmc_tc_kernel)
+    PB_PHASE
+    pb_for_each_param(pl, tid, nt, [&](int si, int fi) {
+      const float t = __ldcg(a.theta + cP + fi);
+      TH[si] = t;
+      TH0[si] = t;
+      G0[si] = __ldcg(a.sched_g0 + cP + fi);
+    });
+    if (tid == 0) {
+      sc[12] = __ldcg(a.sched_logp + c);
+      scu[15] = (uint32_t)__ldcg(a.sched_acc + c);
+      scu[2] = __ldcg(a.sched_flags + c);
+    }
+    PB_ENDPHASE
+  }
+#endif
 
-  for (int s = 0; s < a.S; ++s) {
+  for (int s = s_begin; s < s_end; ++s) {
     const PbKey ks = pb_split_at(ck, (uint32_t)(a.t0 + s));
     const PbKey km = pb_split_at(ks, 0u), ka = pb_split_at(ks, 1u);
     // momentum ~ sqrt(1/Minv) * N(0, I); proposal starts at the current state
@@ -1299,15 +1323,19 @@ PB_DEV void pb_hmc_chain(const PbPlan& pl, const PbHmcArgs& a, float* sm, int c,
 
   if (!a.no_store) pb_store_state(pl, TH0, a.theta + cP, scu + 2, nt);
   PB_PHASE
-  if (tid == 0) {
+  if (a.sched_g0 && s_end < a.S) {  // hand the chain over: gradient, log-density and counters of the current state
+    pb_for_each_param(pl, tid, nt, [&](int si, int fi) { a.sched_g0[cP + fi] = G0[si]; });
+    if (tid == 0) {
+      a.sched_logp[c] = sc[12];
+      a.sched_acc[c] = (int32_t)scu[15];
+      a.sched_flags[c] = scu[2];
+    }
+  } else if (tid == 0) {
     if (a.logp) a.logp[c] = sc[12];
     if (a.accept_count) a.accept_count[c] = (int32_t)scu[15];
     if (a.flags) a.flags[c] = scu[2];
   }
   PB_ENDPHASE
-#if !defined(PB_EMU)
-  if constexpr (ENG == 2) pb_tc_teardown(pl, sm, tc);
-#endif
 #undef PB_HMC_GRAD
 }
 

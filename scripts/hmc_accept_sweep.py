@@ -3,7 +3,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.ins
 import numpy as np, torch, bench
 from pbnn_b200.ops import FlatSpec, default_ops
 w = dict(bench.WORKLOADS["hmc_cfg2"]); ops = default_ops(); fs = FlatSpec(tuple(w["layers"]), 0, 0.1)
-Xh, yh, Xth, keysh, th0h = bench.make_inputs(w, 0, 1)
+Xh, yh, Xth, keysh, th0h = bench.make_inputs(w, 0, 1, ops)
 minv = torch.ones(fs.num_params, device="cuda")
 for eps in (1e-3, 5e-4, 2.5e-4, 1e-4, 5e-5):
     r = ops.hmc(fs, Xh, yh, th0h, keysh, 200, eps, minv, 20, keep_trace=False, info=True)

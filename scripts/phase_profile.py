@@ -13,9 +13,8 @@ w = dict(bench.WORKLOADS[name], name=name)
 w["T"] = int(sys.argv[2]) if len(sys.argv) > 2 else 4
 ops = default_ops()
 fs = FlatSpec(tuple(w["layers"]), w["act"], 0.1)
-Xh, yh, Xth, keysh, th0h = bench.make_inputs(w, 0, 1)
+Xh, yh, Xth, keys, th0 = bench.make_inputs(w, 0, 1, ops)
 X, y = ops._as(Xh, torch.float32), ops._as(yh, torch.float32)
-keys, th0 = ops._keys(keysh), ops._as(th0h, torch.float32)
 step = bench.gpu_step_fn(ops, w, fs, X, y, th0, keys)
 out = (ctypes.c_ulonglong * 64)()
 step(); ops.lib.pbnn_debug_profile(out)

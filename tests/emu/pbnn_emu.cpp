@@ -10,6 +10,8 @@
 
 #include "../../pbnn_b200/csrc/pbnn_engine.cuh"
 
+static int pb_backend_num_sms() { return 1 << 30; }  // no tcgen05 plans here
+
 static int pb_backend_sg(int algo, const PbPlan& pl, const PbSgArgs& a, int C, void*) {
   const int act = pl.act;
 #pragma omp parallel for schedule(dynamic)

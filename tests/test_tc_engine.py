@@ -106,3 +106,22 @@ def test_tc_many_chains_two_waves(cuda_ops):
     tr = npy(out["trace"])
     assert np.isfinite(tr).all()
     assert np.array_equal(tr, np.repeat(tr[:1], C, 0))
+
+
+@pytest.mark.parametrize("seg_len", [1, 2, 3])
+def test_tc_balanced_schedule_is_bit_identical(cuda_ops, monkeypatch, seg_len):
+    """More chains than SMs: the persistent grid hands chains between CTAs through global memory; the arithmetic is
+    the same, so traces, accept decisions and final states equal the one-CTA-per-chain run bit for bit."""
+    X, y, sp, fs, th = problem((13, 50, 1), 506, 1, scale=0.05)
+    C, S, L = 200, 7, 3
+    keys = o.split(o.PRNGKey(21), C)
+    th0 = (0.05 * np.random.default_rng(4).standard_normal((C, sp.num_params))).astype(np.float32)
+    minv = np.ones(sp.num_params, np.float32)
+    assert cuda_ops.lib.pbnn_workspace_bytes(fs.c_struct(), 5, 506, C) > 0
+    monkeypatch.setenv("PBNN_SEG_LEN", str(seg_len))
+    a = cuda_ops.hmc(fs, X, y, th0, keys, S, 3e-4, minv, L, info=True, thin=2, burnin=1)
+    monkeypatch.setenv("PBNN_NO_SCHED", "1")
+    b = cuda_ops.hmc(fs, X, y, th0, keys, S, 3e-4, minv, L, info=True, thin=2, burnin=1)
+    for k in ("trace", "theta", "logp", "accept_count", "delta", "accept", "flags"):
+        assert np.array_equal(npy(a[k]), npy(b[k])), k
+    assert not npy(a["flags"]).any()
