@@ -53,6 +53,7 @@ struct PbPlan {
   int off_xr, off_yr, off_hpart;
   // tcgen05 path (one hidden relu layer, scalar output): see pbnn_tc.cuh for the operand layouts
   int tc, tc_npad;                // tc_npad = rows rounded up to the 128-row MMA tile
+  int tc_ts;                      // forward A operand (X hi/lo) lives in TMEM (<= 4 tiles); else in shared memory
   int off_xa, off_mk, off_z, off_wb, off_w2s, off_tcm;
   int off_act, off_scr, off_acc, off_idx, off_scal;
   int idx_cap;
@@ -137,8 +138,9 @@ static inline void pb_layout_tc(PbPlan* pl, int rows, int nstate) {
   pl->res_rows = rows;
   pl->xp = 0;
   pl->off_xres = pl->off_yres = pl->off_xr = pl->off_hpart = off;
+  pl->tc_ts = pl->tc_npad <= 512 && !pb_env_int("PBNN_TC_SS", 0);
   pl->off_xa = off;
-  off += 2 * 16 * pl->tc_npad;
+  off += (pl->tc_ts ? 1 : 2) * 16 * pl->tc_npad;  // X raw (epilogue: Z = r x) [+ lo part when the MMA reads X from smem]
   pl->off_yr = off;
   off += pl->tc_npad;
   pl->off_mk = off;

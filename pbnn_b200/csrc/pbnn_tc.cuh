@@ -112,6 +112,26 @@ PB_DEV void pb_tmem_ld16(uint32_t taddr, uint32_t* r) {
       : "r"(taddr));
 }
 
+PB_DEV void pb_tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+
+PB_DEV void pb_tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// A operand in TMEM (lane = row, one tf32 per 32-bit column), B from shared memory
+PB_DEV void pb_umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 PB_DEV void pb_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 PB_DEV uint64_t* pb_tc_mbar(const PbPlan& pl, float* sm, int i) {
@@ -132,7 +152,7 @@ PB_DEV void pb_tc_setup(const PbPlan& pl, float* sm, const float* X, const float
     if (b < nrows) v = k < d ? X[(size_t)b * d + k] : (k == d ? 1.f : 0.f);
     const int o = ((k >> 2) * Npad + b) * 4 + (k & 3);
     Xa[o] = v;
-    Xl[o] = v - pb_trunc_tf32(v);
+    if (!pl.tc_ts) Xl[o] = v - pb_trunc_tf32(v);
   }
   for (int b = tid; b < Npad; b += nt) yr[b] = b < nrows ? y[b] : 0.f;
   if (tid == 0) {
@@ -151,12 +171,36 @@ PB_DEV void pb_tc_setup(const PbPlan& pl, float* sm, const float* X, const float
   PB_ENDPHASE_RAW
   pb_tc_fence_after();
   tc.tmem = *reinterpret_cast<const uint32_t*>(sm + pl.off_tcm + 12);
+  if (pl.tc_ts && tid < 256) {
+    // forward A operand resident in TMEM: tile t, columns 320 + 32 t (raw words = hi) and + 16 (lo); lane = row.
+    // Written once per CTA by the thread that owns the row in the epilogue (warp w -> lanes 32 (w % 4) ..).
+    const int warp = tid >> 5, lane = tid & 31, wg = warp >> 2, q = warp & 3;
+    for (int tile = wg; tile < (Npad >> 7); tile += 2) {
+      const int row = tile * 128 + q * 32 + lane;
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const float v = Xa[((k >> 2) * Npad + row) * 4 + (k & 3)];
+        hi[k] = __float_as_uint(v);
+        lo[k] = __float_as_uint(v - pb_trunc_tf32(v));
+      }
+      const uint32_t taddr = tc.tmem + ((uint32_t)(q * 32) << 16) + 320u + 32u * (uint32_t)tile;
+      pb_tmem_st16(taddr, hi);
+      pb_tmem_st16(taddr + 16u, lo);
+    }
+    pb_tmem_wait_st();
+  }
+  pb_tc_fence_before();
+  PB_ENDPHASE_RAW
+  pb_tc_fence_after();
   tc.ph_f = 0u;
   tc.ph_d = 0u;
   tc.rok = 0u;
   for (int u = 0; u < 4; ++u) {
+    // element e -> (i, j) with i % 4 fastest: 4 consecutive lanes fill one 16-byte slot of the forward B operand
+    // (conflict-free Wb / Wl stores; j fastest was a 4-way bank conflict)
     const int e = pb_min(tid + u * nt, 16 * 64 - 1);
-    const int i = e >> 6, j = e & 63;
+    const int i = (e & 3) + 4 * (e >> 8), j = (e >> 2) & 63;
     const bool ok = tid + u * nt < 16 * 64 && i < pl.L[0].inA && j < pl.L[0].out;
     tc.rok |= ok ? (1u << u) : 0u;
     // missing elements use a pad slot of the output layer (row 0, column 1: always zero and stays zero)
@@ -267,6 +311,17 @@ PB_DEV void pb_tc_grad_core(const PbPlan& pl, float* sm, float* TH, float* G, in
       const bool k2 = pl.h1_dp > 2;
       for (int t = 0; t < ntiles; ++t) {
         const uint32_t dcol = tc.tmem + 64u * (uint32_t)(t + 1);
+        if (pl.tc_ts) {  // A = X tile in TMEM (raw at +0, lo at +16; second k-step = + 8 columns)
+          const uint32_t ta = tc.tmem + 320u + 32u * (uint32_t)t;
+          pb_umma_tf32_ts(dcol, ta, dwb, idesc, 0u);                         // hi * hi
+          if (k2) pb_umma_tf32_ts(dcol, ta + 8u, dwb + w_k, idesc, 1u);
+          pb_umma_tf32_ts(dcol, ta, dwb + w_lo, idesc, 1u);                  // hi * lo
+          if (k2) pb_umma_tf32_ts(dcol, ta + 8u, dwb + w_lo + w_k, idesc, 1u);
+          pb_umma_tf32_ts(dcol, ta + 16u, dwb, idesc, 1u);                   // lo * hi
+          if (k2) pb_umma_tf32_ts(dcol, ta + 24u, dwb + w_k, idesc, 1u);
+          if ((t & 1) || t == ntiles - 1) pb_umma_commit(mb_f0 + 8u * (uint32_t)(t >> 1));
+          continue;
+        }
         const uint64_t da = dxa + (uint64_t)t * 128u;  // + 128 rows x 16 B
         pb_umma_tf32(dcol, da, dwb, idesc, 0u);                              // hi * hi
         if (k2) pb_umma_tf32(dcol, da + x_k, dwb + w_k, idesc, 1u);
