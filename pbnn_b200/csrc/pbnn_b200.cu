@@ -8,6 +8,7 @@
 //   pb_predict_kernel<ACT>   posterior predictive over (test-row tile) x (sample chunk)
 //   pb_rng_kernel / pb_mbidx_kernel / pb_perm_kernel   jax.random primitives
 #include <cuda_runtime.h>
+#include <stdio.h>
 
 #include "pbnn_engine.cuh"
 
@@ -38,12 +39,13 @@ pb_hmc_kernel(const __grid_constant__ PbPlan pl, const __grid_constant__ PbHmcAr
   pb_hmc_chain<ACT, GS, ENG>(pl, a, pb_smem, (int)blockIdx.x, (int)blockDim.x);
 }
 
-// tcgen05 engine: 8 epilogue warps + 1 MMA-issue warp, one CTA per SM (the operand buffers need ~200 KB).
-// a.sched_done == NULL: CTA c advances chain c.  Else (more chains than SMs) the grid is persistent and balanced:
-// item n = segment * C + chain, CTA b takes items b, b + grid, ...; a chain's next segment starts when the CTA that
-// ran the previous one has published its state (release store / acquire load of sched_done[chain]).  Items are taken
-// in increasing order and all CTAs are co-resident (cooperative launch), so the lowest unfinished item can always run.
-__global__ void __launch_bounds__(288, 1)
+// tcgen05 engine: 4 epilogue warps + 1 MMA-issue warp, two CTAs per SM (~93 KB of shared memory, 256 TMEM columns).
+// a.sched_done == NULL: CTA c advances chain c.  Else (more chains than SMs) the CTAs are persistent and balanced:
+// item n = segment * C + chain; a CTA takes the next item from a global counter and starts it when the CTA that ran
+// the chain's previous segment has published its state (release store / acquire load of sched_done[chain]).  Items are
+// handed out in increasing order, so a predecessor (item n - C) is always owned by a CTA that is already running:
+// no co-residency assumption, no deadlock.
+__global__ void __launch_bounds__(160, 2)
 pb_hmc_tc_kernel(const __grid_constant__ PbPlan pl, const __grid_constant__ PbHmcArgs a) {
   extern __shared__ __align__(16) float pb_smem[];
   PB_PROF_START
@@ -55,9 +57,16 @@ pb_hmc_tc_kernel(const __grid_constant__ PbPlan pl, const __grid_constant__ PbHm
     pb_hmc_chain<PBNN_ACT_RELU, false, 2>(pl, a, pb_smem, (int)blockIdx.x, nt, 0, -1, false, &tc);
   } else {
     const int nseg = (a.S + a.seg_len - 1) / a.seg_len;
-    const long long nitems = (long long)nseg * a.n_chains;
-    for (long long item = blockIdx.x; item < nitems; item += gridDim.x) {
-      const int seg = (int)(item / a.n_chains), c = (int)(item - (long long)seg * a.n_chains);
+    const int nitems = nseg * a.n_chains;
+    int* next = a.sched_done + a.n_chains;
+    volatile int* slot = reinterpret_cast<volatile int*>(pb_scu(pl, pb_smem) + 24);
+    for (;;) {
+      if (threadIdx.x == 0) *slot = atomicAdd(next, 1);
+      __syncthreads();
+      const int item = *slot;
+      __syncthreads();
+      if (item >= nitems) break;
+      const int seg = item / a.n_chains, c = item - seg * a.n_chains;
       if (seg > 0) {
         if (threadIdx.x == 0) {
           int done = 0;
@@ -448,26 +457,15 @@ static int pb_backend_hmc(const PbPlan& pl, const PbHmcArgs& a, int C, void* str
     return pb_launch(pb_hmc_kernel<PBNN_ACT_TANH, true, 0>, pl, a, dim3(C), stream);
   }
   if (pl.tc) {
-    if (a.sched_done) {  // balanced persistent grid: needs every CTA co-resident -> cooperative launch
-      const size_t smem = (size_t)pl.smem_floats * 4;
-      PB_CUDA(cudaFuncSetAttribute(pb_hmc_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      int dev = 0, nsm = 0, per_sm = 0;
-      PB_CUDA(cudaGetDevice(&dev));
-      PB_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
-      PB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pb_hmc_tc_kernel, pl.NT, smem));
-      const int grid = nsm * per_sm < C ? nsm * per_sm : C;
-      if (grid > 0) {
-        PB_CUDA(cudaMemsetAsync(a.sched_done, 0, sizeof(int) * (size_t)C, (cudaStream_t)stream));
-        void* kargs[2] = {(void*)&pl, (void*)&a};
-        if (cudaLaunchCooperativeKernel((const void*)pb_hmc_tc_kernel, dim3(grid), dim3(pl.NT), kargs, smem,
-                                        (cudaStream_t)stream) == cudaSuccess)
-          return PBNN_OK;
-        (void)cudaGetLastError();  // not launchable cooperatively: one CTA per chain instead
-      }
-      PbHmcArgs b = a;
-      b.sched_done = nullptr;
-      b.sched_g0 = nullptr;
-      return pb_launch(pb_hmc_tc_kernel, pl, b, dim3(C), stream);
+    if (a.sched_done) {  // balanced persistent CTAs, two per SM (by construction of the plan: <= 113 KB, 160 threads)
+      const long long nitems = (long long)((a.S + a.seg_len - 1) / a.seg_len) * C;
+      const int slots = 2 * pb_backend_num_sms();
+      const int grid = slots < nitems ? slots : (int)nitems;
+      if (pb_env_int("PBNN_DEBUG", 0))
+        fprintf(stderr, "[pbnn] hmc tc sched: grid %d, threads %d, smem %d, seg_len %d, items %lld\n", grid, pl.NT,
+                pl.smem_floats * 4, a.seg_len, nitems);
+      PB_CUDA(cudaMemsetAsync(a.sched_done, 0, sizeof(int) * (size_t)(C + 1), (cudaStream_t)stream));
+      return pb_launch(pb_hmc_tc_kernel, pl, a, dim3(grid), stream);
     }
     return pb_launch(pb_hmc_tc_kernel, pl, a, dim3(C), stream);
   }

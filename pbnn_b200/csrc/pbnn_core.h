@@ -114,13 +114,13 @@ static inline void pb_plan_dw(PbPlan* pl, int nw, int bt, int kcap) {
 #define PB_PLAN_TC 4  // the caller has a tcgen05 kernel for this op (HMC): allow the tensor-core layout
 
 // tcgen05 operand geometry (floats).  K-major, no swizzle: element (row x, k) at (k/4)*LBO + x*16 B + (k%4)*4 B.
-#define PB_TC_MK_LBO 516   // mask^T  [k = batch row / 4][2 tiles x 64 hidden units (+1 pad row: conflict-free stores)][4]
-#define PB_TC_Z_LBO 260    // Z       [k = batch row / 4][2 tiles x (raw, lo) x 16 inputs (+1 pad row)][4]
-#define PB_TC_MK_FLOATS (32 * PB_TC_MK_LBO)
-#define PB_TC_Z_FLOATS (32 * PB_TC_Z_LBO)
-#define PB_TC_MAX_TILES 7
+#define PB_TC_MK_LBO 516   // mask^T  [k = row in half / 4][2 halves x 64 hidden units (+1 pad row: conflict-free stores)][4]
+#define PB_TC_Z_LBO 260    // Z       [k = row in half / 4][2 halves x (raw, lo) x 16 inputs (+1 pad row)][4]
+#define PB_TC_MK_FLOATS (16 * PB_TC_MK_LBO)  // one 128-row tile = 2 halves x 64 rows = 16 k-groups
+#define PB_TC_Z_FLOATS (16 * PB_TC_Z_LBO)
+#define PB_TC_MAX_TILES 4  // X (hi, lo) of all tiles lives in 128 of the CTA's 256 TMEM columns
 
-// shared-memory layout of the tcgen05 plan: state | X (raw, lo) | y | mask | Z | W1 (raw, lo) | w2 | ...
+// shared-memory layout of the tcgen05 plan: state | y | mask | Z | W1 (raw, lo) | w2 | ... (X lives in TMEM)
 static inline void pb_layout_tc(PbPlan* pl, int rows, int nstate) {
   pl->BT = 128;
   pl->ap = 132;
@@ -128,19 +128,17 @@ static inline void pb_layout_tc(PbPlan* pl, int rows, int nstate) {
   pl->tc = 1;
   pl->ksmax = 1;
   pl->gstate = 0;
-  pl->NT = 288;  // 8 epilogue warps + 1 MMA-issue warp
+  pl->NT = 160;  // 4 epilogue warps + 1 MMA-issue warp; two CTAs per SM
   pl->h1_dp = pb_r4(pl->d + 1) / 4;
   pl->tc_npad = ((rows + 127) / 128) * 128;
+  pl->tc_ts = 1;
   int off = nstate * pl->Ps;
   pl->off_gpart = off;
   pl->off_act = off;
   for (int l = 0; l <= pl->nl + 1; ++l) pl->aoff[l] = off;
   pl->res_rows = rows;
   pl->xp = 0;
-  pl->off_xres = pl->off_yres = pl->off_xr = pl->off_hpart = off;
-  pl->tc_ts = pl->tc_npad <= 512 && !pb_env_int("PBNN_TC_SS", 0);
-  pl->off_xa = off;
-  off += (pl->tc_ts ? 1 : 2) * 16 * pl->tc_npad;  // X raw (epilogue: Z = r x) [+ lo part when the MMA reads X from smem]
+  pl->off_xres = pl->off_yres = pl->off_xr = pl->off_hpart = pl->off_xa = off;
   pl->off_yr = off;
   off += pl->tc_npad;
   pl->off_mk = off;
@@ -421,7 +419,7 @@ struct PbHmcArgs {
   float* sched_logp;      // [C]
   int32_t* sched_acc;     // [C]
   uint32_t* sched_flags;  // [C]
-  int* sched_done;        // [C] segments completed (release / acquire hand-over)
+  int* sched_done;        // [C] segments completed (release / acquire hand-over); [C] = next item to hand out
 };
 
 struct PbPredArgs {

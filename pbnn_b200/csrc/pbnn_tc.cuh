@@ -6,41 +6,36 @@
 // FP32 accuracy on TF32 tensor cores.  tcgen05.mma.kind::tf32 reads the top 19 bits of every fp32 operand word, so an
 // operand a is fed as a = hi + lo with hi = the raw word (truncated by the hardware) and lo = a - trunc19(a) (exact in
 // fp32); hi*hi + hi*lo + lo*hi accumulated in the fp32 TMEM accumulator reproduces the fp32 product to ~1e-6 relative
-// (measured by tests/test_umma_experimental.py).  Both GEMMs of the gradient are arranged so that one operand is
-// (nearly) free:
+// (measured by tests/test_umma_experimental.py and tests/test_tc_engine.py).  Both GEMMs of the gradient are arranged so
+// that one operand is (nearly) free:
 //
-//   forward   Hpre[b][j]  = sum_i Xaug[b][i] W1aug[i][j]        A = X tile   [128 rows][K=16]   (hi, lo: staged ONCE)
+//   forward   Hpre[b][j]  = sum_i Xaug[b][i] W1aug[i][j]        A = X tile   [128 rows][K=16]   (hi, lo: in TMEM, ONCE)
 //                                                               B = W1aug^T  [64 units][K=16]   (hi, lo: per gradient)
-//             3 passes x 2 k-steps per 128-row tile, D = TMEM columns 64(t+1)..64(t+1)+63 of tile t
+//             3 passes x 2 k-steps per 128-row tile, D = TMEM columns 64..127 (one tile in flight)
 //   epilogue  one thread per row (= TMEM lane): h = relu(Hpre), f = w2.h + b2, r = (y - f)/sigma^2, and the relu
 //             MASK m[b][j] = [Hpre > 0] plus Z[b][i] = r_b Xaug[b][i] go back to shared memory as MMA operands
 //   backward  Gm[j][i]    = sum_b m[b][j] Z[b][i]               mask is 0/1: EXACT in tf32, no lo part; Z = hi + lo.
-//             Two 128-row tiles (even tile = warps 0-3, odd tile = warps 4-7) share one MMA per k-step:
-//               A = [mask_even^T ; mask_odd^T]               [2 x 64 units][K = row within the tile]
-//               B = [Z_even hi ; Z_even lo ; Z_odd hi ; Z_odd lo]   [4 x 16 inputs][K]
-//             D (TMEM columns 0..63): lanes 0..63 x columns 0..31 = even tiles (hi | lo), lanes 64..127 x columns
-//             32..63 = odd tiles; the two off-diagonal blocks are cross terms nobody reads.  16 k-steps per round, every
-//             operand byte read from shared memory once (the MMAs of this shape are shared-memory-bandwidth bound).
+//             The two 64-row halves of a tile share one MMA per k-step (M = 128 fully used, K = 64 rows):
+//               A = [mask^T of rows 0..63 ; mask^T of rows 64..127]            [2 x 64 units][K = row within the half]
+//               B = [Z hi ; Z lo of rows 0..63 ; Z hi ; Z lo of rows 64..127]  [4 x 16 inputs][K]
+//             D (TMEM columns 0..63): lanes 0..63 x columns 0..31 = first halves (hi | lo), lanes 64..127 x columns
+//             32..63 = second halves; the two off-diagonal blocks are cross terms nobody reads.  8 k-steps per tile, every
+//             operand byte read from shared memory once (MMAs of this shape are shared-memory-bandwidth bound).
 //             dW1[i][j] = w2_j Gm[j][i]       dw2_j = sum_b r_b relu(Hpre)[b][j] = sum_i W1aug[i][j] Gm[j][i]
 //             (the second identity: relu(Hpre) = m * (Xaug W1aug), so the output-layer gradient needs no extra GEMM)
+//
+// Occupancy.  One gradient is a dependent chain (forward MMA -> epilogue -> backward MMA -> readout -> update); a single
+// chain keeps an SM ~30 % busy.  The CTA is therefore kept small -- 4 epilogue warps + 1 MMA-issue warp, ~93 KB of
+// shared memory, 256 TMEM columns -- so that TWO chains are co-resident per SM and fill each other's bubbles.
 //
 // Operand storage (K-major, SWIZZLE_NONE "interleaved" core matrices of 8 rows x 16 B):
 //   element (row x, k) at (k/4)*LBO + x*16 B + (k%4)*4 B,   SBO (next 8 rows) = 128 B.
 // The mask and Z k-groups are padded by one 16-byte row (LBO = 129 / 65 rows) so that the 32 lanes of a warp (32
 // consecutive batch rows) store to 32 different banks.
+// TMEM columns: 0..63 backward accumulator, 64..127 forward accumulator, 128 + 32 t .. : X tile t (16 raw | 16 lo).
 #pragma once
 #if !defined(PB_EMU)
 
-struct PbTc {
-  uint32_t tmem;  // TMEM base address (512 columns allocated)
-  uint32_t ph_f;  // parity of the forward-MMA mbarrier
-  uint32_t ph_d;  // parity of the backward-MMA mbarrier
-  // readout B: this thread's (up to) 4 first-layer weights -- constant over the chain, kept in registers
-  int ridx[4];    // index in the padded resident arrays (a pad slot when the element does not exist)
-  int rwo[4];     // index in the forward B operand Wb / Wl
-  int rgx[4];     // i * 64 + j in the readout scratch
-  uint32_t rok;   // bit u: element u exists
-};
 
 PB_DEV uint32_t pb_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -134,57 +129,62 @@ PB_DEV void pb_umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint3
 
 PB_DEV void pb_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+#define PB_TC_RU 7  // first-layer weights per thread in the update phase: ceil(16 * 64 / 160)
+
+struct PbTc {
+  uint32_t tmem;  // TMEM base address (256 columns allocated)
+  uint32_t ph_f;  // parity of the forward-MMA mbarrier   (epilogue warps)
+  uint32_t ph_d;  // parity of the backward-MMA mbarrier  (epilogue warps)
+  uint32_t ph_h;  // parity of the "forward accumulator has been read" mbarrier (issue warp)
+  uint32_t wsel;  // which half of the double-buffered output-weight vector the next evaluation reads
+  // update phase: this thread's first-layer weights -- constant over the chain, kept in registers
+  int ridx[PB_TC_RU];  // index in the padded resident arrays (a pad slot when the element does not exist)
+  int rwo[PB_TC_RU];   // index in the forward B operand Wb / Wl
+  int rgx[PB_TC_RU];   // i * 64 + j in the readout scratch
+  uint32_t rok;        // bit u: element u exists
+};
+
 PB_DEV uint64_t* pb_tc_mbar(const PbPlan& pl, float* sm, int i) {
   return reinterpret_cast<uint64_t*>(sm + pl.off_tcm) + i;
 }
 
-// once per chain: X (raw + lo) in the forward A-operand layout, y, mbarriers, TMEM
+// once per CTA: y, mbarriers, TMEM, X (raw + lo) into TMEM as the forward A operand
 PB_DEV void pb_tc_setup(const PbPlan& pl, float* sm, const float* X, const float* y, int nrows, int nt, PbTc& tc) {
   PB_TAG(10)
   const int tid = threadIdx.x;
   const int Npad = pl.tc_npad, d = pl.d;
-  float* Xa = sm + pl.off_xa;
-  float* Xl = Xa + 16 * Npad;
   float* yr = sm + pl.off_yr;
-  for (int item = tid; item < Npad * 16; item += nt) {
-    const int b = item >> 4, k = item & 15;
-    float v = 0.f;
-    if (b < nrows) v = k < d ? X[(size_t)b * d + k] : (k == d ? 1.f : 0.f);
-    const int o = ((k >> 2) * Npad + b) * 4 + (k & 3);
-    Xa[o] = v;
-    if (!pl.tc_ts) Xl[o] = v - pb_trunc_tf32(v);
-  }
   for (int b = tid; b < Npad; b += nt) yr[b] = b < nrows ? y[b] : 0.f;
   if (tid == 0) {
-    for (int i = 0; i < 5; ++i)  // 0..3: forward MMAs of epilogue round i; 4: backward MMAs
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(pb_smem_u32(pb_tc_mbar(pl, sm, i))));
+    // 0: forward MMAs done; 1: forward accumulator read by all 128 epilogue threads; 4: backward MMAs done
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(pb_smem_u32(pb_tc_mbar(pl, sm, 0))));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 128;" ::"r"(pb_smem_u32(pb_tc_mbar(pl, sm, 1))));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(pb_smem_u32(pb_tc_mbar(pl, sm, 4))));
     asm volatile("fence.mbarrier_init.release.cluster;");
   }
-  if (tid < 32) {  // TMEM allocation by one full warp: all 512 columns (one CTA per SM: the plan needs > 113 KB)
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                     pb_smem_u32(sm + pl.off_tcm + 12)),
-                 "r"(512));
+  if (tid < 32) {  // TMEM allocation by one full warp: half of the SM's columns (two CTAs per SM)
+    // (immediate column count: with a register operand the occupancy calculator assumes the whole TMEM -> 1 CTA/SM)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(
+        pb_smem_u32(sm + pl.off_tcm + 12)));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  pb_fence_async_smem();
   pb_tc_fence_before();
   PB_ENDPHASE_RAW
   pb_tc_fence_after();
   tc.tmem = *reinterpret_cast<const uint32_t*>(sm + pl.off_tcm + 12);
-  if (pl.tc_ts && tid < 256) {
-    // forward A operand resident in TMEM: tile t, columns 320 + 32 t (raw words = hi) and + 16 (lo); lane = row.
-    // Written once per CTA by the thread that owns the row in the epilogue (warp w -> lanes 32 (w % 4) ..).
-    const int warp = tid >> 5, lane = tid & 31, wg = warp >> 2, q = warp & 3;
-    for (int tile = wg; tile < (Npad >> 7); tile += 2) {
-      const int row = tile * 128 + q * 32 + lane;
+  if (tid < 128) {
+    // lane = row of the tile; written by the thread that owns the row in the epilogue (warp w -> lanes 32 w ..)
+    for (int tile = 0; tile < (Npad >> 7); ++tile) {
+      const int row = tile * 128 + tid;
       uint32_t hi[16], lo[16];
 #pragma unroll
       for (int k = 0; k < 16; ++k) {
-        const float v = Xa[((k >> 2) * Npad + row) * 4 + (k & 3)];
+        float v = 0.f;
+        if (row < nrows) v = k < d ? X[(size_t)row * d + k] : (k == d ? 1.f : 0.f);
         hi[k] = __float_as_uint(v);
         lo[k] = __float_as_uint(v - pb_trunc_tf32(v));
       }
-      const uint32_t taddr = tc.tmem + ((uint32_t)(q * 32) << 16) + 320u + 32u * (uint32_t)tile;
+      const uint32_t taddr = tc.tmem + ((uint32_t)(tid & ~31) << 16) + 128u + 32u * (uint32_t)tile;
       pb_tmem_st16(taddr, hi);
       pb_tmem_st16(taddr + 16u, lo);
     }
@@ -193,12 +193,11 @@ PB_DEV void pb_tc_setup(const PbPlan& pl, float* sm, const float* X, const float
   pb_tc_fence_before();
   PB_ENDPHASE_RAW
   pb_tc_fence_after();
-  tc.ph_f = 0u;
-  tc.ph_d = 0u;
+  tc.ph_f = tc.ph_d = tc.ph_h = tc.wsel = 0u;
   tc.rok = 0u;
-  for (int u = 0; u < 4; ++u) {
+  for (int u = 0; u < PB_TC_RU; ++u) {
     // element e -> (i, j) with i % 4 fastest: 4 consecutive lanes fill one 16-byte slot of the forward B operand
-    // (conflict-free Wb / Wl stores; j fastest was a 4-way bank conflict)
+    // (conflict-free Wb / Wl stores)
     const int e = pb_min(tid + u * nt, 16 * 64 - 1);
     const int i = (e & 3) + 4 * (e >> 8), j = (e >> 2) & 63;
     const bool ok = tid + u * nt < 16 * 64 && i < pl.L[0].inA && j < pl.L[0].out;
@@ -215,7 +214,7 @@ PB_DEV void pb_tc_teardown(const PbPlan& pl, float* sm, const PbTc& tc) {
   PB_ENDPHASE_RAW
   if (threadIdx.x < 32) {
     pb_tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tc.tmem), "r"(512));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tc.tmem));
   }
 }
 
@@ -238,7 +237,7 @@ PB_DEV void pb_tc_stage_w(const PbPlan& pl, float* sm, float* TH, const float* G
   const int H = L0.out, wp = L0.wp, inA = L0.inA;
   float* Wb = sm + pl.off_wb;
   float* Wl = Wb + 16 * 64;
-  float* w2s = sm + pl.off_w2s + 64 * (int)tc.ph_f;
+  float* w2s = sm + pl.off_w2s + 64 * (int)tc.wsel;
   auto upd = [&](int idx) -> float {
     float th = TH[idx];
     if (FIRST_PRE) {
@@ -251,7 +250,7 @@ PB_DEV void pb_tc_stage_w(const PbPlan& pl, float* sm, float* TH, const float* G
   };
 #pragma unroll 4
   for (int e = tid; e < 16 * 64; e += nt) {
-    const int i = e >> 6, j = e & 63;
+    const int i = (e & 3) + 4 * (e >> 8), j = (e >> 2) & 63;
     const float v = (i < inA && j < H) ? upd(L0.soff + i * wp + j) : 0.f;
     const int o = (i >> 2) * 256 + j * 4 + (i & 3);
     Wb[o] = v;
@@ -264,9 +263,23 @@ PB_DEV void pb_tc_stage_w(const PbPlan& pl, float* sm, float* TH, const float* G
   PB_ENDPHASE_RAW
 }
 
+// 6 forward MMAs of one tile (3xTF32 x 2 k-steps): A = X tile in TMEM (raw at +0, lo at +16; second k-step + 8
+// columns), B = W1aug^T in shared memory (raw, lo at + 16*64 floats; second k-step + 2 k-groups)
+PB_DEV void pb_tc_issue_fwd(const PbTc& tc, uint64_t dwb, uint32_t idesc, int tile, bool k2, uint32_t mb_f) {
+  const uint32_t dcol = tc.tmem + 64u, ta = tc.tmem + 128u + 32u * (uint32_t)tile;
+  const uint64_t w_lo = 256u, w_k = 128u;
+  pb_umma_tf32_ts(dcol, ta, dwb, idesc, 0u);  // hi * hi
+  if (k2) pb_umma_tf32_ts(dcol, ta + 8u, dwb + w_k, idesc, 1u);
+  pb_umma_tf32_ts(dcol, ta, dwb + w_lo, idesc, 1u);  // hi * lo
+  if (k2) pb_umma_tf32_ts(dcol, ta + 8u, dwb + w_lo + w_k, idesc, 1u);
+  pb_umma_tf32_ts(dcol, ta + 16u, dwb, idesc, 1u);  // lo * hi
+  if (k2) pb_umma_tf32_ts(dcol, ta + 24u, dwb + w_k, idesc, 1u);
+  pb_umma_commit(mb_f);
+}
+
 // The gradient proper; the forward B operand (Wb, Wl), w2s and TH must be current (pb_tc_stage_w or a MODE 1 call).
-// 288 threads: warps 0-3 own the even 128-row tiles, warps 4-7 the odd ones (warp w reads TMEM lanes 32*(w%4)..+31),
-// warp 8 issues the MMAs.
+// 160 threads: warps 0-3 are the epilogue / readout warps (warp w owns TMEM lanes 32 w .. = rows of the tile), warp 4
+// issues the MMAs.  One 128-row tile per round.
 //   MODE 0: G <- d loglik / d theta (padded resident layout, pads untouched = 0)
 //   MODE 1: leapfrog interior, fused into the readout: G <- grad log posterior, p += eps/2 G (end of this step),
 //           p += eps/2 G, theta += eps Minv p (start of the next step), next W operands staged
@@ -276,83 +289,52 @@ template <int MODE>
 PB_DEV void pb_tc_grad_core(const PbPlan& pl, float* sm, float* TH, float* G, int nrows, float scale, int nt,
                             PbTc& tc, const PbTcLeap& lf) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int wg = warp >> 2, q = warp & 3;
   const PbLayer& L0 = pl.L[0];
   const PbLayer& L1 = pl.L[1];
-  const int H = L0.out, wp = L0.wp, inA = L0.inA, Npad = pl.tc_npad;
-  const int ntiles = Npad >> 7, nrounds = (ntiles + 1) >> 1, nj8 = (H + 7) >> 3;
-  const float* Xa = sm + pl.off_xa;
+  const int H = L0.out, wp = L0.wp, inA = L0.inA;
+  const int ntiles = pl.tc_npad >> 7, nj8 = (H + 7) >> 3;
   const float* yr = sm + pl.off_yr;
   float* Wb = sm + pl.off_wb;
   float* Wl = Wb + 16 * 64;
-  const float* w2s = sm + pl.off_w2s + 64 * (int)tc.ph_f;  // output weights of this evaluation (double-buffered)
-  float* w2nxt = sm + pl.off_w2s + 64 * (int)(tc.ph_f ^ 1u);
+  const float* w2s = sm + pl.off_w2s + 64 * (int)tc.wsel;  // output weights of this evaluation (double-buffered)
+  float* w2nxt = sm + pl.off_w2s + 64 * (int)(tc.wsel ^ 1u);
   float* rs = sm + pl.off_tcm + 16;
-  float* gx = sm + pl.off_z;  // readout scratch (even | odd partial sums [2][16][64], dots [2][64]): the Z buffer is
-                              // free once the last backward MMAs are done
+  float* gx = sm + pl.off_z;  // readout scratch (half 0 | half 1 partial sums [2][16][64], dots [2][64]): the Z buffer
+                              // is free once the last backward MMAs are done
   float* llbuf = pb_llbuf(pl, sm);
-  const uint32_t mb_f0 = pb_smem_u32(pb_tc_mbar(pl, sm, 0)), mb_d = pb_smem_u32(pb_tc_mbar(pl, sm, 4));
+  const uint32_t mb_f = pb_smem_u32(pb_tc_mbar(pl, sm, 0)), mb_h = pb_smem_u32(pb_tc_mbar(pl, sm, 1));
+  const uint32_t mb_d = pb_smem_u32(pb_tc_mbar(pl, sm, 4));
   const float b2 = TH[L1.soff + H * L1.wp];
   PB_TAG(2)
-  // warp 8 only issues MMAs (one elected lane); warps 0-7 are the epilogue / readout warps
   const int warp_u = __shfl_sync(0xffffffffu, warp, 0);  // warp-uniform for the compiler
-  if (warp_u == 8) {
+  const uint32_t idesc = pb_umma_idesc_tf32(128, 64);
+  const uint64_t dwb = pb_umma_desc(pb_smem_u32(Wb), 1024u, 128u);
+  const bool k2 = pl.h1_dp > 2;
+  if (warp_u == 4) {
     pb_tc_fence_after();
-    if (pb_elect_one()) {
-      const uint32_t idesc = pb_umma_idesc_tf32(128, 64);
-      const uint32_t lbo_x = (uint32_t)Npad * 16u;
-      const uint32_t xa = pb_smem_u32(Xa), wb = pb_smem_u32(Wb);
-      // descriptors of k-step 0; the other operands are constant offsets in the 14-bit address field (16-byte units)
-      const uint64_t dxa = pb_umma_desc(xa, lbo_x, 128u), dwb = pb_umma_desc(wb, 1024u, 128u);
-      const uint64_t x_lo = (uint64_t)Npad * 4u;  // + 16 * Npad floats
-      const uint64_t w_lo = 256u;                 // + 16 * 64 floats
-      const uint64_t x_k = (uint64_t)Npad * 2u;   // + 2 k-groups of Npad rows x 16 B
-      const uint64_t w_k = 128u;                  // + 2 k-groups of 64 rows x 16 B
-      const bool k2 = pl.h1_dp > 2;
-      for (int t = 0; t < ntiles; ++t) {
-        const uint32_t dcol = tc.tmem + 64u * (uint32_t)(t + 1);
-        if (pl.tc_ts) {  // A = X tile in TMEM (raw at +0, lo at +16; second k-step = + 8 columns)
-          const uint32_t ta = tc.tmem + 320u + 32u * (uint32_t)t;
-          pb_umma_tf32_ts(dcol, ta, dwb, idesc, 0u);                         // hi * hi
-          if (k2) pb_umma_tf32_ts(dcol, ta + 8u, dwb + w_k, idesc, 1u);
-          pb_umma_tf32_ts(dcol, ta, dwb + w_lo, idesc, 1u);                  // hi * lo
-          if (k2) pb_umma_tf32_ts(dcol, ta + 8u, dwb + w_lo + w_k, idesc, 1u);
-          pb_umma_tf32_ts(dcol, ta + 16u, dwb, idesc, 1u);                   // lo * hi
-          if (k2) pb_umma_tf32_ts(dcol, ta + 24u, dwb + w_k, idesc, 1u);
-          if ((t & 1) || t == ntiles - 1) pb_umma_commit(mb_f0 + 8u * (uint32_t)(t >> 1));
-          continue;
-        }
-        const uint64_t da = dxa + (uint64_t)t * 128u;  // + 128 rows x 16 B
-        pb_umma_tf32(dcol, da, dwb, idesc, 0u);                              // hi * hi
-        if (k2) pb_umma_tf32(dcol, da + x_k, dwb + w_k, idesc, 1u);
-        pb_umma_tf32(dcol, da, dwb + w_lo, idesc, 1u);                       // hi * lo
-        if (k2) pb_umma_tf32(dcol, da + x_k, dwb + w_lo + w_k, idesc, 1u);
-        pb_umma_tf32(dcol, da + x_lo, dwb, idesc, 1u);                       // lo * hi
-        if (k2) pb_umma_tf32(dcol, da + x_lo + x_k, dwb + w_k, idesc, 1u);
-        if ((t & 1) || t == ntiles - 1) pb_umma_commit(mb_f0 + 8u * (uint32_t)(t >> 1));  // one barrier per round
-      }
-    }
+    if (pb_elect_one()) pb_tc_issue_fwd(tc, dwb, idesc, 0, k2, mb_f);
     __syncwarp();
-    PB_MARK(20)
   }
 
-  // ---- epilogue rounds: two tiles at a time ---------------------------------------------------------------
-  const int bl = q * 32 + lane;
+  // ---- one tile per round ------------------------------------------------------------------------------------
+  const int half = tid >> 6, kk = tid & 63;  // backward operands: row kk of half `half` (epilogue threads)
   float ll = 0.f, rsum = 0.f;
-  for (int round = 0; round < nrounds; ++round) {
-    const int tile = 2 * round + wg;
+  for (int round = 0; round < ntiles; ++round) {
     PB_TAG(round == 0 ? 2 : 4)
-    if (warp_u < 8) {
-    pb_mbar_wait(mb_f0 + 8u * (uint32_t)round, tc.ph_f);
-    PB_MARK(21)
-    pb_tc_fence_after();
-    float* zr = sm + pl.off_z + (bl >> 2) * PB_TC_Z_LBO + (wg * 32) * 4 + (bl & 3);
-    if (tile < ntiles) {
-      uint32_t h[64];
-      const uint32_t taddr = tc.tmem + ((uint32_t)(q * 32) << 16) + 64u * (uint32_t)(tile + 1);
-      pb_tmem_ld32(taddr, h);
-      pb_tmem_ld32(taddr + 32u, h + 32);
+    if (warp_u < 4) {
+      pb_mbar_wait(mb_f, tc.ph_f);
+      tc.ph_f ^= 1u;
+      PB_MARK(21)
+      pb_tc_fence_after();
+      uint32_t h[64], xr[16];
+      const uint32_t lane_base = tc.tmem + ((uint32_t)(warp * 32) << 16);
+      pb_tmem_ld32(lane_base + 64u, h);
+      pb_tmem_ld32(lane_base + 96u, h + 32);
+      pb_tmem_ld16(lane_base + 128u + 32u * (uint32_t)round, xr);
       pb_tmem_wait_ld();
+      pb_tc_fence_before();
+      if (round + 1 < ntiles)  // the accumulator is free: the issue warp may start the next tile's forward MMAs
+        asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(mb_h) : "memory");
       float f0 = 0.f, f1 = 0.f;
       // blocks of 8 hidden units behind a (uniform) branch: units >= H are skipped at that granularity
 #pragma unroll
@@ -367,91 +349,84 @@ PB_DEV void pb_tc_grad_core(const PbPlan& pl, float* sm, float* TH, float* G, in
             f1 = fmaf(fmaxf(__uint_as_float(h[4 * j4 + 3]), 0.f), w.w, f1);
           }
         }
-      const int row = tile * 128 + bl;
+      const int row = round * 128 + tid;
       const bool valid = row < nrows;
       const float res = yr[row] - ((f0 + f1) + b2);
       const float r = valid ? res * scale : 0.f;
       ll += valid ? -0.5f * res * res * pl.inv_s2 : 0.f;
       rsum += r;
-      float4 x[4];
-#pragma unroll
-      for (int kg = 0; kg < 4; ++kg) x[kg] = pb_ld4(Xa + ((size_t)kg * Npad + row) * 4);
-      if (round > 0) {  // the previous round's backward MMAs have finished reading the mask / Z buffers
+      if (round > 0) {  // the previous tile's backward MMAs have finished reading the mask / Z buffers
         pb_mbar_wait(mb_d, tc.ph_d);
+        tc.ph_d ^= 1u;
         PB_MARK(24)
       }
-      float* mk = sm + pl.off_mk + (bl >> 2) * PB_TC_MK_LBO + (wg * 64) * 4 + (bl & 3);
+      float* mk = sm + pl.off_mk + (kk >> 2) * PB_TC_MK_LBO + (half * 64) * 4 + (kk & 3);
 #pragma unroll
       for (int c8 = 0; c8 < 8; ++c8)
         if (c8 < nj8) {
 #pragma unroll
           for (int j = 8 * c8; j < 8 * c8 + 8; ++j) mk[j * 4] = __uint_as_float(h[j]) > 0.f ? 1.f : 0.f;
         }
+      float* zr = sm + pl.off_z + (kk >> 2) * PB_TC_Z_LBO + (half * 32) * 4 + (kk & 3);
 #pragma unroll
-      for (int kg = 0; kg < 4; ++kg) {
-        const float z0 = r * x[kg].x, z1 = r * x[kg].y, z2 = r * x[kg].z, z3 = r * x[kg].w;
-        zr[(4 * kg) * 4] = z0;
-        zr[(4 * kg + 1) * 4] = z1;
-        zr[(4 * kg + 2) * 4] = z2;
-        zr[(4 * kg + 3) * 4] = z3;
-        zr[(16 + 4 * kg) * 4] = z0 - pb_trunc_tf32(z0);
-        zr[(16 + 4 * kg + 1) * 4] = z1 - pb_trunc_tf32(z1);
-        zr[(16 + 4 * kg + 2) * 4] = z2 - pb_trunc_tf32(z2);
-        zr[(16 + 4 * kg + 3) * 4] = z3 - pb_trunc_tf32(z3);
+      for (int i = 0; i < 16; ++i) {
+        const float z = r * __uint_as_float(xr[i]);
+        zr[i * 4] = z;
+        zr[(16 + i) * 4] = z - pb_trunc_tf32(z);
       }
-    } else {  // odd number of tiles: the odd half of the last round contributes nothing
-      if (round > 0) pb_mbar_wait(mb_d, tc.ph_d);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) zr[i * 4] = 0.f;
-    }
-    PB_MARK(22)
-    pb_fence_async_smem();
-    PB_MARK(25)
-    if (round == nrounds - 1) {
-      ll = pb_warp_sum(ll);
-      rsum = pb_warp_sum(rsum);
-      if (lane == 0) {
-        llbuf[warp] = ll;
-        rs[warp] = rsum;
+      PB_MARK(22)
+      pb_fence_async_smem();
+      PB_MARK(25)
+      if (round == ntiles - 1) {
+        ll = pb_warp_sum(ll);
+        rsum = pb_warp_sum(rsum);
+        if (lane == 0) {
+          llbuf[warp] = ll;
+          rs[warp] = rsum;
+        }
+        if (tid >= 4) llbuf[tid] = 0.f;
       }
-      if (tid >= 8 && tid < 128) llbuf[tid] = 0.f;
+    } else if (round + 1 < ntiles) {
+      // issue warp: the next tile's forward MMAs start as soon as the accumulator has been read
+      pb_mbar_wait(mb_h, tc.ph_h);
+      tc.ph_h ^= 1u;
+      pb_tc_fence_after();
+      if (pb_elect_one()) pb_tc_issue_fwd(tc, dwb, idesc, round + 1, k2, mb_f);
+      __syncwarp();
     }
-    }
-    if (round > 0) tc.ph_d ^= 1u;
     pb_tc_fence_before();
     PB_ENDPHASE_RAW
     PB_TAG(5)
-    if (warp_u == 8) {
+    if (warp_u == 4) {
       pb_tc_fence_after();
       if (pb_elect_one()) {
-        const uint32_t idesc = pb_umma_idesc_tf32(128, 64);
         const uint64_t dm = pb_umma_desc(pb_smem_u32(sm + pl.off_mk), PB_TC_MK_LBO * 4u, 128u);
         const uint64_t dz = pb_umma_desc(pb_smem_u32(sm + pl.off_z), PB_TC_Z_LBO * 4u, 128u);
         pb_umma_tf32(tc.tmem, dm, dz, idesc, round == 0 ? 0u : 1u);
 #pragma unroll
-        for (int kb = 1; kb < 16; ++kb)
+        for (int kb = 1; kb < 8; ++kb)
           pb_umma_tf32(tc.tmem, dm + (uint64_t)(kb * (2 * PB_TC_MK_LBO * 4 / 16)),
                        dz + (uint64_t)(kb * (2 * PB_TC_Z_LBO * 4 / 16)), idesc, 1u);
         pb_umma_commit(mb_d);
       }
       __syncwarp();
-      PB_MARK(23)
     }
   }
-  tc.ph_f ^= 1u;
+  if (MODE == 1) tc.wsel ^= 1u;  // the update phase below writes the next evaluation's output weights to w2nxt
   PB_TAG(3)
-  // ---- readout A (warps 0-3): TMEM lane = hidden unit (lanes 64..127: the odd tiles' partial sums), 16 columns hi +
-  //      16 columns lo -> gx[half][i][j]; partial dot products for the output-layer weights -> gx[2][half][j]
+  // ---- readout A (warps 0-3): TMEM lane = hidden unit (lanes 64..127: the second halves' partial sums), 16 columns
+  //      hi + 16 columns lo -> gx[half][i][j]; partial dot products for the output-layer weights -> gx[2][half][j]
   if (warp < 4) {
     pb_mbar_wait(mb_d, tc.ph_d);
+    tc.ph_d ^= 1u;
     PB_MARK(24)
     pb_tc_fence_after();
     uint32_t g[32];
     pb_tmem_ld32(tc.tmem + ((uint32_t)(warp * 32) << 16) + (warp >= 2 ? 32u : 0u), g);
     pb_tmem_wait_ld();
     pb_tc_fence_before();
-    const int j = tid & 63, half = warp >> 1;
-    float* gh = gx + half * 1024;
+    const int j = tid & 63, hf = warp >> 1;
+    float* gh = gx + hf * 1024;
     float dot = 0.f;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
@@ -459,9 +434,8 @@ PB_DEV void pb_tc_grad_core(const PbPlan& pl, float* sm, float* TH, float* G, in
       gh[i * 64 + j] = gm;
       if (i < inA && j < H) dot = fmaf(TH[L0.soff + i * wp + j], gm, dot);
     }
-    gx[2048 + half * 64 + j] = dot;
+    gx[2048 + hf * 64 + j] = dot;
   }
-  tc.ph_d ^= 1u;
   PB_ENDPHASE_RAW
   // ---- readout B (all threads): gradient of the log posterior and, fused, the leapfrog updates + next W operands
   PB_TAG(6)
@@ -483,11 +457,11 @@ PB_DEV void pb_tc_grad_core(const PbPlan& pl, float* sm, float* TH, float* G, in
     lf.PM[idx] = p;
   };
   {
-    // up to 4 first-layer weights per thread, branch-free: a missing element works on a zero pad slot with a zero
-    // gradient (every update of it is 0 -> 0); all loads first (the stores may alias for the compiler)
-    float gl[4], th[4], pm[4], mi[4];
+    // first-layer weights, branch-free: a missing element works on a zero pad slot with a zero gradient (every
+    // update of it is 0 -> 0); all loads first (the stores may alias for the compiler)
+    float gl[PB_TC_RU], th[PB_TC_RU], pm[PB_TC_RU], mi[PB_TC_RU];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < PB_TC_RU; ++u) {
       const float gsum = gx[tc.rgx[u]] + gx[1024 + tc.rgx[u]];
       gl[u] = (tc.rok >> u) & 1u ? w2s[tc.rgx[u] & 63] * gsum : 0.f;
       th[u] = pm[u] = mi[u] = 0.f;
@@ -498,7 +472,7 @@ PB_DEV void pb_tc_grad_core(const PbPlan& pl, float* sm, float* TH, float* G, in
       if (MODE == 1) mi[u] = lf.MI[tc.ridx[u]];
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < PB_TC_RU; ++u) {
       if (MODE == 0) {
         G[tc.ridx[u]] = gl[u];
       } else {
@@ -523,7 +497,7 @@ PB_DEV void pb_tc_grad_core(const PbPlan& pl, float* sm, float* TH, float* G, in
   }
   if (tid == 64) {
     float a = 0.f, bn = 0.f;
-    for (int w = 0; w < 8; ++w) a += rs[w];
+    for (int w = 0; w < 4; ++w) a += rs[w];
     upd(L1.soff + H * L1.wp, a, bn);
   }
   if (MODE == 1) pb_fence_async_smem();

@@ -48,7 +48,7 @@ def test_host_side_calls_without_gpu(cuda_lib_path):
     assert lib.pbnn_workspace_bytes(big, _lib.OP_SGLD, 128, 10) == 10 * 2 * out[3] * 4 > 0
     # resident plans need no workspace; the tcgen05 HMC plan asks for hand-over buffers once chains outnumber the SMs
     assert lib.pbnn_workspace_bytes(spec, _lib.OP_HMC, 506, 100) == 0
-    assert lib.pbnn_workspace_bytes(spec, _lib.OP_HMC, 506, 256) == 256 * (751 + 4) * 4
+    assert lib.pbnn_workspace_bytes(spec, _lib.OP_HMC, 506, 256) == 256 * (751 + 4) * 4 + 16
     assert lib.pbnn_workspace_bytes(spec, _lib.OP_SGLD, 32, 256) == 0
     assert lib.pbnn_plan_engine(spec, _lib.OP_HMC, 506, 256) == _lib.ENGINE_TCGEN05
     assert lib.pbnn_plan_engine(spec, _lib.OP_SGLD, 32, 256) == _lib.ENGINE_FUSED_H1
