@@ -398,7 +398,7 @@ def main():
             tf32_peak = peaks.get("bf16_tflops", 2250.0 * 0.73) / 2
             ntile = (w["B"] + 127) // 128
             grads = w["C"] * w["T"] * (w["L"] + 1.0 / w["T"])
-            executed = grads * (ntile * 6 + ((ntile + 1) // 2) * 16) * (128 * 64 * 8 * 2)
+            executed = grads * ntile * (6 + 8) * (128 * 64 * 8 * 2)  # 6 forward + 8 backward MMAs 128x64x8 per tile
             roofline = {"bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
                         "frac": achieved / tf32_peak, "traffic": traffic,
                         "peak_source": "TF32 dense tensor rate = measured cuBLAS bf16 (MEASURED_PEAKS.json burst) / 2"
@@ -410,7 +410,7 @@ def main():
                                                 "note": "the same algorithmic flops against the FP32-FMA peak the "
                                                         "scalar engines are bound by (148 SM x 128 lanes x 2 x clock)"},
                         "note": "latency-bound: per gradient a dependent chain of forward MMA -> epilogue -> backward "
-                                "MMA -> readout on one CTA per SM; see profiles/ and DESIGN.md",
+                                "MMA -> readout; two CTAs per SM overlap each other's waits; see profiles/ and DESIGN.md",
                         "hbm": hbm}
         else:
             roofline = {"bound": "fma", "achieved": achieved, "peak": peak_nominal, "unit": "TFLOP/s",

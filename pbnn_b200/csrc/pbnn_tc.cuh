@@ -140,7 +140,8 @@ struct PbTc {
   // update phase: this thread's first-layer weights -- constant over the chain, kept in registers
   int ridx[PB_TC_RU];  // index in the padded resident arrays (a pad slot when the element does not exist)
   int rwo[PB_TC_RU];   // index in the forward B operand Wb / Wl
-  int rgx[PB_TC_RU];   // i * 64 + j in the readout scratch
+  int rgx[PB_TC_RU];   // i * 72 + j in the readout scratch
+  int rw2[PB_TC_RU];   // j (index of the output weight)
   uint32_t rok;        // bit u: element u exists
 };
 
@@ -205,7 +206,8 @@ PB_DEV void pb_tc_setup(const PbPlan& pl, float* sm, const float* X, const float
     // missing elements use a pad slot of the output layer (row 0, column 1: always zero and stays zero)
     tc.ridx[u] = ok ? pl.L[0].soff + i * pl.L[0].wp + j : pl.L[1].soff + 1;
     tc.rwo[u] = (i >> 2) * 256 + j * 4 + (i & 3);
-    tc.rgx[u] = i * 64 + j;
+    tc.rw2[u] = j;
+    tc.rgx[u] = i * 72 + j;  // pitch 72: the 4 x 8 (i, j) pairs of a warp hit 32 different banks
   }
 }
 
@@ -299,7 +301,7 @@ PB_DEV void pb_tc_grad_core(const PbPlan& pl, float* sm, float* TH, float* G, in
   const float* w2s = sm + pl.off_w2s + 64 * (int)tc.wsel;  // output weights of this evaluation (double-buffered)
   float* w2nxt = sm + pl.off_w2s + 64 * (int)(tc.wsel ^ 1u);
   float* rs = sm + pl.off_tcm + 16;
-  float* gx = sm + pl.off_z;  // readout scratch (half 0 | half 1 partial sums [2][16][64], dots [2][64]): the Z buffer
+  float* gx = sm + pl.off_z;  // readout scratch (half 0 | half 1 partial sums [2][16][72], dots [2][64]): the Z buffer
                               // is free once the last backward MMAs are done
   float* llbuf = pb_llbuf(pl, sm);
   const uint32_t mb_f = pb_smem_u32(pb_tc_mbar(pl, sm, 0)), mb_h = pb_smem_u32(pb_tc_mbar(pl, sm, 1));
@@ -426,15 +428,15 @@ PB_DEV void pb_tc_grad_core(const PbPlan& pl, float* sm, float* TH, float* G, in
     pb_tmem_wait_ld();
     pb_tc_fence_before();
     const int j = tid & 63, hf = warp >> 1;
-    float* gh = gx + hf * 1024;
+    float* gh = gx + hf * 1152;
     float dot = 0.f;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       const float gm = __uint_as_float(g[i]) + __uint_as_float(g[16 + i]);
-      gh[i * 64 + j] = gm;
+      gh[i * 72 + j] = gm;
       if (i < inA && j < H) dot = fmaf(TH[L0.soff + i * wp + j], gm, dot);
     }
-    gx[2048 + hf * 64 + j] = dot;
+    gx[2304 + hf * 64 + j] = dot;
   }
   PB_ENDPHASE_RAW
   // ---- readout B (all threads): gradient of the log posterior and, fused, the leapfrog updates + next W operands
@@ -462,8 +464,8 @@ PB_DEV void pb_tc_grad_core(const PbPlan& pl, float* sm, float* TH, float* G, in
     float gl[PB_TC_RU], th[PB_TC_RU], pm[PB_TC_RU], mi[PB_TC_RU];
 #pragma unroll
     for (int u = 0; u < PB_TC_RU; ++u) {
-      const float gsum = gx[tc.rgx[u]] + gx[1024 + tc.rgx[u]];
-      gl[u] = (tc.rok >> u) & 1u ? w2s[tc.rgx[u] & 63] * gsum : 0.f;
+      const float gsum = gx[tc.rgx[u]] + gx[1152 + tc.rgx[u]];
+      gl[u] = (tc.rok >> u) & 1u ? w2s[tc.rw2[u]] * gsum : 0.f;
       th[u] = pm[u] = mi[u] = 0.f;
       if (MODE != 0) {
         th[u] = TH[tc.ridx[u]];
@@ -492,7 +494,7 @@ PB_DEV void pb_tc_grad_core(const PbPlan& pl, float* sm, float* TH, float* G, in
   }
   if (tid < H) {  // the output weights are double-buffered: the loop above (other threads) still reads the current ones
     float w2n = 0.f;
-    upd(L1.soff + tid * L1.wp, gx[2048 + tid] + gx[2048 + 64 + tid], w2n);
+    upd(L1.soff + tid * L1.wp, gx[2304 + tid] + gx[2304 + 64 + tid], w2n);
     if (MODE == 1) w2nxt[tid] = w2n;
   }
   if (tid == 64) {
