@@ -79,7 +79,10 @@ int pbnn_plan_engine(const pbnn_mlp_spec* spec, int op, int rows, int C);
 
 /* Workspace.  Models whose parameter-sized state does not fit shared memory (e.g. 90-256-256-1, P = 89 345) keep it in
  * a caller-provided, 16-byte aligned DEVICE workspace (L2 resident while the chain is advanced).  Returns the bytes the
- * sampler `op` needs for C chains (0 when everything is resident on chip; pass NULL then), < 0 on error. */
+ * sampler `op` needs for C chains (0 when everything is resident on chip; pass NULL then), < 0 on error.
+ * PBNN_OP_HMC on the tcgen05 engine with more chains than SMs also returns > 0: hand-over buffers of the balanced
+ * persistent schedule (C * (P + 4) * 4 + 16 bytes).  That workspace is OPTIONAL -- without it pbnn_hmc_run runs one
+ * CTA per chain (same results bit for bit, whole waves instead of balanced SMs). */
 #define PBNN_OP_SGLD 0
 #define PBNN_OP_PSGLD 1
 #define PBNN_OP_SGHMC 2
