@@ -449,7 +449,7 @@ PB_DEV void pb_tc_grad_core(const PbPlan& pl, float* sm, float* TH, float* G, in
     }
     const float th = TH[idx];
     const float gp = gll - th * lf.inv_pv;
-    G[idx] = gp;
+    if (MODE == 2) G[idx] = gp;
     float p = lf.PM[idx] + lf.heps * gp;
     if (MODE == 1) {
       p = p + lf.heps * gp;
@@ -479,7 +479,7 @@ PB_DEV void pb_tc_grad_core(const PbPlan& pl, float* sm, float* TH, float* G, in
         G[tc.ridx[u]] = gl[u];
       } else {
         const float gp = gl[u] - th[u] * lf.inv_pv;
-        G[tc.ridx[u]] = gp;
+        if (MODE == 2) G[tc.ridx[u]] = gp;  // (interior steps: nobody reads G before the next evaluation)
         float p = pm[u] + lf.heps * gp;
         if (MODE == 1) {
           p = p + lf.heps * gp;
