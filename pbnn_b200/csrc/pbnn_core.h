@@ -53,8 +53,7 @@ struct PbPlan {
   int off_xr, off_yr, off_hpart;
   // tcgen05 path (one hidden relu layer, scalar output): see pbnn_tc.cuh for the operand layouts
   int tc, tc_npad;                // tc_npad = rows rounded up to the 128-row MMA tile
-  int tc_ts;                      // forward A operand (X hi/lo) lives in TMEM (<= 4 tiles); else in shared memory
-  int off_xa, off_mk, off_z, off_wb, off_w2s, off_tcm;
+  int off_mk, off_z, off_wb, off_w2s, off_tcm;
   int off_act, off_scr, off_acc, off_idx, off_scal;
   int idx_cap;
   int smem_floats;
@@ -131,14 +130,13 @@ static inline void pb_layout_tc(PbPlan* pl, int rows, int nstate) {
   pl->NT = 160;  // 4 epilogue warps + 1 MMA-issue warp; two CTAs per SM
   pl->h1_dp = pb_r4(pl->d + 1) / 4;
   pl->tc_npad = ((rows + 127) / 128) * 128;
-  pl->tc_ts = 1;
   int off = nstate * pl->Ps;
   pl->off_gpart = off;
   pl->off_act = off;
   for (int l = 0; l <= pl->nl + 1; ++l) pl->aoff[l] = off;
   pl->res_rows = rows;
   pl->xp = 0;
-  pl->off_xres = pl->off_yres = pl->off_xr = pl->off_hpart = pl->off_xa = off;
+  pl->off_xres = pl->off_yres = pl->off_xr = pl->off_hpart = off;
   pl->off_yr = off;
   off += pl->tc_npad;
   pl->off_mk = off;
