@@ -117,7 +117,7 @@ static inline void pb_plan_dw(PbPlan* pl, int nw, int bt, int kcap) {
 #define PB_TC_Z_LBO 260    // Z       [k = row in half / 4][2 halves x (raw, lo) x 16 inputs (+1 pad row)][4]
 #define PB_TC_MK_FLOATS (16 * PB_TC_MK_LBO)  // one 128-row tile = 2 halves x 64 rows = 16 k-groups
 #define PB_TC_Z_FLOATS (16 * PB_TC_Z_LBO)
-#define PB_TC_MAX_TILES 4  // X (hi, lo) of all tiles lives in 128 of the CTA's 256 TMEM columns
+#define PB_TC_MAX_TILES 32  // y stays in shared memory (N <= 4096); X (hi, lo) lives in TMEM, 4 tiles at a time
 
 // shared-memory layout of the tcgen05 plan: state | y | mask | Z | W1 (raw, lo) | w2 | ... (X lives in TMEM)
 static inline void pb_layout_tc(PbPlan* pl, int rows, int nstate) {

@@ -32,7 +32,8 @@
 //   element (row x, k) at (k/4)*LBO + x*16 B + (k%4)*4 B,   SBO (next 8 rows) = 128 B.
 // The mask and Z k-groups are padded by one 16-byte row (LBO = 129 / 65 rows) so that the 32 lanes of a warp (32
 // consecutive batch rows) store to 32 different banks.
-// TMEM columns: 0..63 backward accumulator, 64..127 forward accumulator, 128 + 32 t .. : X tile t (16 raw | 16 lo).
+// TMEM columns: 0..63 backward accumulator, 64..127 forward accumulator, 128 + 32 t .. : X tile t (16 raw | 16 lo) of
+// the current group of 4 tiles (N <= 512: staged once per CTA; larger N: re-staged from L2 per group and evaluation).
 #pragma once
 #if !defined(PB_EMU)
 
@@ -137,6 +138,8 @@ struct PbTc {
   uint32_t ph_d;  // parity of the backward-MMA mbarrier  (epilogue warps)
   uint32_t ph_h;  // parity of the "forward accumulator has been read" mbarrier (issue warp)
   uint32_t wsel;  // which half of the double-buffered output-weight vector the next evaluation reads
+  const float* X;  // data rows (global): re-staged into TMEM per group of 4 tiles when N > 512
+  int xd, xn;      // columns / rows of X
   // update phase: this thread's first-layer weights -- constant over the chain, kept in registers
   int ridx[PB_TC_RU];  // index in the padded resident arrays (a pad slot when the element does not exist)
   int rwo[PB_TC_RU];   // index in the forward B operand Wb / Wl
@@ -147,6 +150,27 @@ struct PbTc {
 
 PB_DEV uint64_t* pb_tc_mbar(const PbPlan& pl, float* sm, int i) {
   return reinterpret_cast<uint64_t*>(sm + pl.off_tcm) + i;
+}
+
+// X rows of tiles 4 g .. 4 g + 3 (raw + lo) -> TMEM slots 0..3 as the forward A operand.  Lane = row of the tile; written
+// by the thread that owns the row in the epilogue (warp w -> lanes 32 w ..).  Threads 0..127.
+PB_DEV void pb_tc_stage_x(const PbTc& tc, int group, int ntiles) {
+  const int tid = threadIdx.x, d = tc.xd;
+  for (int t = 0; t < 4 && 4 * group + t < ntiles; ++t) {
+    const int row = (4 * group + t) * 128 + tid;
+    uint32_t hi[16], lo[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      float v = 0.f;
+      if (row < tc.xn) v = k < d ? tc.X[(size_t)row * d + k] : (k == d ? 1.f : 0.f);
+      hi[k] = __float_as_uint(v);
+      lo[k] = __float_as_uint(v - pb_trunc_tf32(v));
+    }
+    const uint32_t taddr = tc.tmem + ((uint32_t)(tid & ~31) << 16) + 128u + 32u * (uint32_t)t;
+    pb_tmem_st16(taddr, hi);
+    pb_tmem_st16(taddr + 16u, lo);
+  }
+  pb_tmem_wait_st();
 }
 
 // once per CTA: y, mbarriers, TMEM, X (raw + lo) into TMEM as the forward A operand
@@ -173,24 +197,10 @@ PB_DEV void pb_tc_setup(const PbPlan& pl, float* sm, const float* X, const float
   PB_ENDPHASE_RAW
   pb_tc_fence_after();
   tc.tmem = *reinterpret_cast<const uint32_t*>(sm + pl.off_tcm + 12);
-  if (tid < 128) {
-    // lane = row of the tile; written by the thread that owns the row in the epilogue (warp w -> lanes 32 w ..)
-    for (int tile = 0; tile < (Npad >> 7); ++tile) {
-      const int row = tile * 128 + tid;
-      uint32_t hi[16], lo[16];
-#pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        float v = 0.f;
-        if (row < nrows) v = k < d ? X[(size_t)row * d + k] : (k == d ? 1.f : 0.f);
-        hi[k] = __float_as_uint(v);
-        lo[k] = __float_as_uint(v - pb_trunc_tf32(v));
-      }
-      const uint32_t taddr = tc.tmem + ((uint32_t)(tid & ~31) << 16) + 128u + 32u * (uint32_t)tile;
-      pb_tmem_st16(taddr, hi);
-      pb_tmem_st16(taddr + 16u, lo);
-    }
-    pb_tmem_wait_st();
-  }
+  tc.X = X;
+  tc.xd = d;
+  tc.xn = nrows;
+  if (tid < 128) pb_tc_stage_x(tc, 0, Npad >> 7);
   pb_tc_fence_before();
   PB_ENDPHASE_RAW
   pb_tc_fence_after();
@@ -268,7 +278,7 @@ PB_DEV void pb_tc_stage_w(const PbPlan& pl, float* sm, float* TH, const float* G
 // 6 forward MMAs of one tile (3xTF32 x 2 k-steps): A = X tile in TMEM (raw at +0, lo at +16; second k-step + 8
 // columns), B = W1aug^T in shared memory (raw, lo at + 16*64 floats; second k-step + 2 k-groups)
 PB_DEV void pb_tc_issue_fwd(const PbTc& tc, uint64_t dwb, uint32_t idesc, int tile, bool k2, uint32_t mb_f) {
-  const uint32_t dcol = tc.tmem + 64u, ta = tc.tmem + 128u + 32u * (uint32_t)tile;
+  const uint32_t dcol = tc.tmem + 64u, ta = tc.tmem + 128u + 32u * (uint32_t)(tile & 3);
   const uint64_t w_lo = 256u, w_k = 128u;
   pb_umma_tf32_ts(dcol, ta, dwb, idesc, 0u);  // hi * hi
   if (k2) pb_umma_tf32_ts(dcol, ta + 8u, dwb + w_k, idesc, 1u);
@@ -312,6 +322,11 @@ PB_DEV void pb_tc_grad_core(const PbPlan& pl, float* sm, float* TH, float* G, in
   const uint32_t idesc = pb_umma_idesc_tf32(128, 64);
   const uint64_t dwb = pb_umma_desc(pb_smem_u32(Wb), 1024u, 128u);
   const bool k2 = pl.h1_dp > 2;
+  if (ntiles > 4) {  // more than one group of 4 tiles: the previous evaluation left the last group in TMEM
+    if (warp_u < 4) pb_tc_stage_x(tc, 0, ntiles);
+    pb_tc_fence_before();
+    PB_ENDPHASE_RAW
+  }
   if (warp_u == 4) {
     pb_tc_fence_after();
     if (pb_elect_one()) pb_tc_issue_fwd(tc, dwb, idesc, 0, k2, mb_f);
@@ -332,8 +347,10 @@ PB_DEV void pb_tc_grad_core(const PbPlan& pl, float* sm, float* TH, float* G, in
       const uint32_t lane_base = tc.tmem + ((uint32_t)(warp * 32) << 16);
       pb_tmem_ld32(lane_base + 64u, h);
       pb_tmem_ld32(lane_base + 96u, h + 32);
-      pb_tmem_ld16(lane_base + 128u + 32u * (uint32_t)round, xr);
+      pb_tmem_ld16(lane_base + 128u + 32u * (uint32_t)(round & 3), xr);
       pb_tmem_wait_ld();
+      // group boundary: every forward MMA of this group is done, bring the next 4 tiles of X into TMEM
+      if ((round & 3) == 3 && round + 1 < ntiles) pb_tc_stage_x(tc, (round + 1) >> 2, ntiles);
       pb_tc_fence_before();
       if (round + 1 < ntiles)  // the accumulator is free: the issue warp may start the next tile's forward MMAs
         asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(mb_h) : "memory");

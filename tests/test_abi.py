@@ -52,8 +52,8 @@ def test_host_side_calls_without_gpu(cuda_lib_path):
     assert lib.pbnn_workspace_bytes(spec, _lib.OP_SGLD, 32, 256) == 0
     assert lib.pbnn_plan_engine(spec, _lib.OP_HMC, 506, 256) == _lib.ENGINE_TCGEN05
     assert lib.pbnn_plan_engine(spec, _lib.OP_SGLD, 32, 256) == _lib.ENGINE_FUSED_H1
-    assert lib.pbnn_plan_engine(spec, _lib.OP_HMC, 512, 4) == _lib.ENGINE_TCGEN05      # 4 tiles: X fits the TMEM columns
-    assert lib.pbnn_plan_engine(spec, _lib.OP_HMC, 513, 4) == _lib.ENGINE_FUSED_H1     # larger data sets: FP32 path
+    assert lib.pbnn_plan_engine(spec, _lib.OP_HMC, 4096, 4) == _lib.ENGINE_TCGEN05     # X streams through TMEM, 4 tiles at a time
+    assert lib.pbnn_plan_engine(spec, _lib.OP_HMC, 4097, 4) != _lib.ENGINE_TCGEN05     # larger data sets: FP32 engines
     assert lib.pbnn_plan_engine(_lib.make_spec((13, 65, 1), 0, 0.1), _lib.OP_HMC, 506, 4) != _lib.ENGINE_TCGEN05
     assert lib.pbnn_plan_engine(_lib.make_spec((16, 50, 1), 0, 0.1), _lib.OP_HMC, 506, 4) != _lib.ENGINE_TCGEN05
     assert lib.pbnn_plan_engine(big, _lib.OP_SGLD, 128, 10) == _lib.ENGINE_TILED_GLOBAL_STATE

@@ -25,7 +25,7 @@ def problem(layers, N, C, seed=3, scale=0.2):
 
 # one tile, an odd number of tiles, a full last tile, the widest / narrowest shapes of the engine, N = 2
 SHAPES = [((13, 50, 1), 506), ((8, 50, 1), 300), ((5, 64, 1), 100), ((15, 33, 1), 640), ((3, 7, 1), 129),
-          ((1, 1, 1), 2), ((2, 64, 1), 256), ((15, 64, 1), 768)]
+          ((1, 1, 1), 2), ((2, 64, 1), 256), ((15, 64, 1), 768), ((8, 50, 1), 1030), ((6, 20, 1), 2500)]
 
 
 @pytest.mark.parametrize("layers,N", SHAPES)
@@ -52,7 +52,7 @@ def test_tc_plan_is_selected_and_can_be_disabled(cuda_ops, monkeypatch):
     assert rel(npy(g_tc), npy(g_h1)) <= 5e-6
 
 
-@pytest.mark.parametrize("layers,N", [((13, 50, 1), 506), ((8, 50, 1), 300), ((4, 20, 1), 64)])
+@pytest.mark.parametrize("layers,N", [((13, 50, 1), 506), ((8, 50, 1), 300), ((4, 20, 1), 64), ((8, 50, 1), 1030)])
 def test_tc_hmc_trajectories(cuda_ops, layers, N):
     """Full HMC through the tensor-core engine: fused half-kicks / drift, L = 1 and L > 1, several iterations."""
     X, y, sp, fs, th0 = problem(layers, N, 4, scale=0.05)
