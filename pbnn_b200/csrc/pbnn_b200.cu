@@ -45,6 +45,7 @@ pb_hmc_kernel(const __grid_constant__ PbPlan pl, const __grid_constant__ PbHmcAr
 // the chain's previous segment has published its state (release store / acquire load of sched_done[chain]).  Items are
 // handed out in increasing order, so a predecessor (item n - C) is always owned by a CTA that is already running:
 // no co-residency assumption, no deadlock.
+template <int ENG>  // 2: N <= 512 (X resident in TMEM); 3: larger N (X re-staged per group of 4 tiles)
 __global__ void __launch_bounds__(160, 2)
 pb_hmc_tc_kernel(const __grid_constant__ PbPlan pl, const __grid_constant__ PbHmcArgs a) {
   extern __shared__ __align__(16) float pb_smem[];
@@ -54,7 +55,7 @@ pb_hmc_tc_kernel(const __grid_constant__ PbPlan pl, const __grid_constant__ PbHm
   PbTc tc;
   pb_tc_setup(pl, pb_smem, a.X, a.y, a.N, nt, tc);
   if (!a.sched_done) {
-    pb_hmc_chain<PBNN_ACT_RELU, false, 2>(pl, a, pb_smem, (int)blockIdx.x, nt, 0, -1, false, &tc);
+    pb_hmc_chain<PBNN_ACT_RELU, false, ENG>(pl, a, pb_smem, (int)blockIdx.x, nt, 0, -1, false, &tc);
   } else {
     const int nseg = (a.S + a.seg_len - 1) / a.seg_len;
     const int nitems = nseg * a.n_chains;
@@ -80,7 +81,7 @@ pb_hmc_tc_kernel(const __grid_constant__ PbPlan pl, const __grid_constant__ PbHm
         __syncthreads();
       }
       const int s0 = seg * a.seg_len, s1 = s0 + a.seg_len < a.S ? s0 + a.seg_len : a.S;
-      pb_hmc_chain<PBNN_ACT_RELU, false, 2>(pl, a, pb_smem, c, nt, s0, s1, seg > 0, &tc);
+      pb_hmc_chain<PBNN_ACT_RELU, false, ENG>(pl, a, pb_smem, c, nt, s0, s1, seg > 0, &tc);
       __syncthreads();
       if (threadIdx.x == 0 && s1 < a.S) {
         __threadfence();
@@ -465,9 +466,11 @@ static int pb_backend_hmc(const PbPlan& pl, const PbHmcArgs& a, int C, void* str
         fprintf(stderr, "[pbnn] hmc tc sched: grid %d, threads %d, smem %d, seg_len %d, items %lld\n", grid, pl.NT,
                 pl.smem_floats * 4, a.seg_len, nitems);
       PB_CUDA(cudaMemsetAsync(a.sched_done, 0, sizeof(int) * (size_t)(C + 1), (cudaStream_t)stream));
-      return pb_launch(pb_hmc_tc_kernel, pl, a, dim3(grid), stream);
+      return pl.tc_npad > 512 ? pb_launch(pb_hmc_tc_kernel<3>, pl, a, dim3(grid), stream)
+                              : pb_launch(pb_hmc_tc_kernel<2>, pl, a, dim3(grid), stream);
     }
-    return pb_launch(pb_hmc_tc_kernel, pl, a, dim3(C), stream);
+    return pl.tc_npad > 512 ? pb_launch(pb_hmc_tc_kernel<3>, pl, a, dim3(C), stream)
+                            : pb_launch(pb_hmc_tc_kernel<2>, pl, a, dim3(C), stream);
   }
   if (pl.h1) {
     if (pl.act == PBNN_ACT_RELU) return pb_launch(pb_hmc_kernel<PBNN_ACT_RELU, false, 1>, pl, a, dim3(C), stream);

@@ -1156,7 +1156,7 @@ template <int ACT, bool GS, int ENG>
 PB_DEV void pb_hmc_chain(const PbPlan& pl, const PbHmcArgs& a, float* sm, int c, int nt, int s_begin = 0,
                          int s_end = -1, bool resume = false, void* tcx = nullptr) {
   // iterations [s_begin, s_end) of chain c; resume: continue a chain whose state another CTA left in global memory
-  // (balanced schedule of the tcgen05 kernel); tcx: the CTA's tcgen05 context (ENG == 2: set up by the kernel)
+  // (balanced schedule of the tcgen05 kernel); tcx: the CTA's tcgen05 context (ENG >= 2: set up by the kernel)
   if (s_end < 0) s_end = a.S;
   float* ws = a.ws ? a.ws + (size_t)c * pl.nstate * pl.Ps : nullptr;
   float* TH = pb_state<GS>(pl, sm, ws, 0);
@@ -1174,8 +1174,8 @@ PB_DEV void pb_hmc_chain(const PbPlan& pl, const PbHmcArgs& a, float* sm, int c,
   ck.k1 = a.keys ? a.keys[2 * c + 1] : 0u;
   const float eps = a.step_size, heps = a.step_size * 0.5f;
 
-  // ENG == 2: tcgen05 engine (pbnn_tc.cuh): buffers, operand staging and TMEM are set up once per CTA by the kernel
-  if (ENG != 2) pb_init_acts(pl, sm, nt);
+  // ENG >= 2: tcgen05 engine (pbnn_tc.cuh): buffers, operand staging and TMEM are set up once per CTA by the kernel
+  if (ENG < 2) pb_init_acts(pl, sm, nt);
   pb_load_state(pl, TH, resume ? nullptr : a.theta + cP, nt);
   pb_load_state(pl, G, nullptr, nt);
   pb_load_state(pl, PM, nullptr, nt);
@@ -1184,12 +1184,12 @@ PB_DEV void pb_hmc_chain(const PbPlan& pl, const PbHmcArgs& a, float* sm, int c,
   PbTc tc_local;
   PbTc& tc = tcx ? *static_cast<PbTc*>(tcx) : tc_local;
 #define PB_HMC_GRAD()                                                      \
-  if constexpr (ENG == 2) pb_grad_tc(pl, sm, TH, G, a.N, pl.inv_s2, nt, tc); \
+  if constexpr (ENG >= 2) pb_grad_tc<ENG == 3>(pl, sm, TH, G, a.N, pl.inv_s2, nt, tc); \
   else pb_grad<ACT, ENG>(pl, sm, TH, G, a.X, a.y, nullptr, a.N, pl.inv_s2, false, nt);
 #else
 #define PB_HMC_GRAD() pb_grad<ACT, ENG>(pl, sm, TH, G, a.X, a.y, nullptr, a.N, pl.inv_s2, false, nt);
 #endif
-  if (ENG != 2 && pl.res_rows > 0) pb_load_resident(pl, sm, a.X, a.y, nullptr, a.N, nt);
+  if (ENG < 2 && pl.res_rows > 0) pb_load_resident(pl, sm, a.X, a.y, nullptr, a.N, nt);
   if (!resume) {
     PB_PHASE
     if (tid == 0) {
@@ -1256,13 +1256,13 @@ PB_DEV void pb_hmc_chain(const PbPlan& pl, const PbHmcArgs& a, float* sm, int c,
     pb_block_sums(pl, sm, 1, sc + 13, nt);
 
 #if !defined(PB_EMU)
-    if constexpr (ENG == 2) {
-      // tcgen05 engine: half-kicks, drift and operand staging are fused into the gradient's readout (pbnn_tc.cuh)
+    if constexpr (ENG >= 2) {
+      // tcgen05 engine (ENG 2: N <= 512, ENG 3: larger N): half-kicks, drift and operand staging are fused into the gradient's readout (pbnn_tc.cuh)
       const PbTcLeap lf = {PM, MI, eps, heps, pl.inv_pv};
       if (a.L > 0) {
         pb_tc_stage_w<true>(pl, sm, TH, G, lf, nt, tc);
-        for (int l = 0; l < a.L - 1; ++l) pb_tc_grad_core<1>(pl, sm, TH, G, a.N, pl.inv_s2, nt, tc, lf);
-        pb_tc_grad_core<2>(pl, sm, TH, G, a.N, pl.inv_s2, nt, tc, lf);
+        for (int l = 0; l < a.L - 1; ++l) pb_tc_grad_core<1, ENG == 3>(pl, sm, TH, G, a.N, pl.inv_s2, nt, tc, lf);
+        pb_tc_grad_core<2, ENG == 3>(pl, sm, TH, G, a.N, pl.inv_s2, nt, tc, lf);
       }
     } else
 #endif

@@ -296,8 +296,9 @@ PB_DEV void pb_tc_issue_fwd(const PbTc& tc, uint64_t dwb, uint32_t idesc, int ti
 //   MODE 1: leapfrog interior, fused into the readout: G <- grad log posterior, p += eps/2 G (end of this step),
 //           p += eps/2 G, theta += eps Minv p (start of the next step), next W operands staged
 //   MODE 2: last step of a trajectory: G <- grad log posterior, p += eps/2 G
+// BIG: N > 512 (a separate kernel, so that the X re-staging code stays out of the headline configuration's round loop).
 // always: llbuf[0..127] <- per-warp log-likelihood partials.
-template <int MODE>
+template <int MODE, bool BIG>
 PB_DEV void pb_tc_grad_core(const PbPlan& pl, float* sm, float* TH, float* G, int nrows, float scale, int nt,
                             PbTc& tc, const PbTcLeap& lf) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -322,7 +323,7 @@ PB_DEV void pb_tc_grad_core(const PbPlan& pl, float* sm, float* TH, float* G, in
   const uint32_t idesc = pb_umma_idesc_tf32(128, 64);
   const uint64_t dwb = pb_umma_desc(pb_smem_u32(Wb), 1024u, 128u);
   const bool k2 = pl.h1_dp > 2;
-  if (ntiles > 4) {  // more than one group of 4 tiles: the previous evaluation left the last group in TMEM
+  if (BIG) {  // more than one group of 4 tiles (N > 512): the previous evaluation left the last group in TMEM
     if (warp_u < 4) pb_tc_stage_x(tc, 0, ntiles);
     pb_tc_fence_before();
     PB_ENDPHASE_RAW
@@ -347,10 +348,10 @@ PB_DEV void pb_tc_grad_core(const PbPlan& pl, float* sm, float* TH, float* G, in
       const uint32_t lane_base = tc.tmem + ((uint32_t)(warp * 32) << 16);
       pb_tmem_ld32(lane_base + 64u, h);
       pb_tmem_ld32(lane_base + 96u, h + 32);
-      pb_tmem_ld16(lane_base + 128u + 32u * (uint32_t)(round & 3), xr);
+      pb_tmem_ld16(lane_base + 128u + 32u * (uint32_t)(BIG ? (round & 3) : round), xr);
       pb_tmem_wait_ld();
       // group boundary: every forward MMA of this group is done, bring the next 4 tiles of X into TMEM
-      if ((round & 3) == 3 && round + 1 < ntiles) pb_tc_stage_x(tc, (round + 1) >> 2, ntiles);
+      if (BIG && (round & 3) == 3 && round + 1 < ntiles) pb_tc_stage_x(tc, (round + 1) >> 2, ntiles);
       pb_tc_fence_before();
       if (round + 1 < ntiles)  // the accumulator is free: the issue warp may start the next tile's forward MMAs
         asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(mb_h) : "memory");
@@ -526,9 +527,10 @@ PB_DEV void pb_tc_grad_core(const PbPlan& pl, float* sm, float* TH, float* G, in
 }
 
 // plain gradient (initial point of a chain; pbnn_logposterior_grad)
+template <bool BIG>
 PB_DEV void pb_grad_tc(const PbPlan& pl, float* sm, float* TH, float* G, int nrows, float scale, int nt, PbTc& tc) {
   PbTcLeap lf = {nullptr, nullptr, 0.f, 0.f, 0.f};
   pb_tc_stage_w<false>(pl, sm, TH, G, lf, nt, tc);
-  pb_tc_grad_core<0>(pl, sm, TH, G, nrows, scale, nt, tc, lf);
+  pb_tc_grad_core<0, BIG>(pl, sm, TH, G, nrows, scale, nt, tc, lf);
 }
 #endif
