@@ -125,3 +125,23 @@ def test_tc_balanced_schedule_is_bit_identical(cuda_ops, monkeypatch, seg_len):
     for k in ("trace", "theta", "logp", "accept_count", "delta", "accept", "flags"):
         assert np.array_equal(npy(a[k]), npy(b[k])), k
     assert not npy(a["flags"]).any()
+
+
+def test_tc_repeated_runs_are_bit_identical(cuda_ops):
+    """Dynamic item scheduling, two CTAs per SM, mbarrier hand-shakes: none of it may change a single bit between
+    runs (a missed fence or barrier shows up here as run-to-run differences)."""
+    X, y, sp, fs, th = problem((13, 50, 1), 506, 1, scale=0.05)
+    C, S, L = 300, 6, 7
+    keys = o.split(o.PRNGKey(33), C)
+    th0 = (0.05 * np.random.default_rng(8).standard_normal((C, sp.num_params))).astype(np.float32)
+    minv = np.ones(sp.num_params, np.float32)
+    ref = None
+    for rep in range(4):
+        out = cuda_ops.hmc(fs, X, y, th0, keys, S, 3e-4, minv, L, info=True)
+        got = {k: npy(out[k]).copy() for k in ("trace", "theta", "logp", "accept", "delta")}
+        assert np.isfinite(got["trace"]).all()
+        if ref is None:
+            ref = got
+        else:
+            for k in ref:
+                assert np.array_equal(got[k], ref[k]), (rep, k)
