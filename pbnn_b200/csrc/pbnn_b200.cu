@@ -4,7 +4,9 @@
 //   pb_sg_kernel<ALGO,ACT>   fused chain-step kernel: one CTA per chain / ensemble member, persistent over
 //                            all T steps (forward, backward, drift, threefry noise, trace) -- SGLD, pSGLD,
 //                            SGHMC, Adam, and the grad_estimator test hook
-//   pb_hmc_kernel<ACT>       full-batch leapfrog + Metropolis accept, one CTA per chain
+//   pb_hmc_kernel<ACT>       full-batch leapfrog + Metropolis accept, one CTA per chain (FP32 engines)
+//   pb_hmc_tc_kernel<ENG>    the same chain on the tcgen05 engine (pbnn_tc.cuh): split-TF32 GEMMs with TMEM
+//                            accumulators, two small CTAs per SM, balanced persistent schedule for C > #SM
 //   pb_predict_kernel<ACT>   posterior predictive over (test-row tile) x (sample chunk)
 //   pb_rng_kernel / pb_mbidx_kernel / pb_perm_kernel   jax.random primitives
 #include <cuda_runtime.h>
