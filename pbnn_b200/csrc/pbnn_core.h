@@ -50,6 +50,7 @@ struct PbPlan {
   int ksmax, off_gpart;           // (ksmax - 1) partial gradient arrays for split-K
   int gstate;                     // resident arrays live in a global-memory workspace (model too large for smem)
   int h1, h1_dp;                  // fused one-hidden-layer path: X row-major [rows][4*h1_dp], per-warp partial grads
+  int h1_nw;                      // warps per CTA the fused path should use (0: the caller's default)
   int off_xr, off_yr, off_hpart;
   // tcgen05 path (one hidden relu layer, scalar output): see pbnn_tc.cuh for the operand layouts
   int tc, tc_npad;                // tc_npad = rows rounded up to the 128-row MMA tile
@@ -175,7 +176,8 @@ static inline void pb_layout(PbPlan* pl, const pbnn_mlp_spec* sp, int rows, int 
   pl->off_act = off;
   if (h1) {
     // fused path: no activation buffers; X row-major with the ones column, y, one partial gradient per warp
-    if (pl->NT > 256) pl->NT = 256;
+    if (pl->h1_nw > 0) pl->NT = 32 * pl->h1_nw;
+    else if (pl->NT > 256) pl->NT = 256;
     for (int l = 0; l <= pl->nl + 1; ++l) pl->aoff[l] = off;
     pl->res_rows = rows;
     pl->h1_dp = pb_r4(pl->d + 1) / 4;
@@ -304,12 +306,21 @@ static inline int pb_build_plan(const pbnn_mlp_spec* sp, int rows, int nstate, i
 #if defined(PB_EMU)
   h1_ok = 0;
 #endif
+  const int nw_env = pb_env_int("PBNN_NW", 0);
   // tcgen05 path: the same nets, relu only (the weight gradient uses the 0/1 activation mask as an exact operand)
   if (h1_ok && (flags & PB_PLAN_TC) && sp->activation == PBNN_ACT_RELU && !hetero && !pb_env_int("PBNN_NO_TC", 0) &&
       rows <= 128 * PB_TC_MAX_TILES) {
     pb_layout_tc(pl, rows, nstate);
     if ((size_t)pl->smem_floats * 4 <= (size_t)PB_SMEM_LIMIT_BYTES) return PBNN_OK;
     pl->tc = 0;
+  }
+  // Fused path, many chains: the warp-autonomous gradient wants >= 16 rows per warp (fewer partial-gradient arrays to
+  // reduce, cheaper barriers) and the SM is filled by co-resident chains instead (measured, 8-50-1 B=32 x 4096 chains:
+  // 2 warps per CTA 98 M steps/s, 4 warps 83 M, 8 warps 65 M).  Few chains: 8 warps for the latency of each one.
+  pl->h1_nw = 0;
+  if (h1_ok && nw_env == 0 && chains_hint >= 4 * 148) {
+    const int w = rows / 16;
+    pl->h1_nw = w >= 8 ? 8 : w >= 4 ? 4 : 2;
   }
   const int forced = pb_env_int("PBNN_BT", 0);
   if (forced > 0) maxbt = pb_r32(forced) > 128 ? 128 : pb_r32(forced);
@@ -319,7 +330,6 @@ static inline int pb_build_plan(const pbnn_mlp_spec* sp, int rows, int nstate, i
   const int two = (chains_hint > 148 || pb_env_int("PBNN_TWO_CTA", 0)) && !pb_env_int("PBNN_ONE_CTA", 0);
   // Plans that end up with one CTA per SM anyway (large resident state) run 16 warps instead of 8: the phases are
   // short dependent sequences, 4 warps per scheduler hide their latency much better than 2.
-  const int nw_env = pb_env_int("PBNN_NW", 0);
   for (int pass = pb_env_int("PBNN_FORCE_GSTATE", 0) ? 2 : (two ? 0 : 1); pass < 2; ++pass) {
     pl->NT = nw_env > 0 ? 32 * nw_env : (pass == 0 ? 256 : 512);
     const size_t limit = pass == 0 ? lim2 : lim1;
