@@ -146,6 +146,9 @@ struct PbTc {
   int rgx[PB_TC_RU];   // i * 72 + j in the readout scratch
   int rw2[PB_TC_RU];   // j (index of the output weight)
   uint32_t rok;        // bit u: element u exists
+  // ... and, during a trajectory, their position / momentum / inverse mass (registers: no shared-memory round trip
+  // per leapfrog step; written back by the last step)
+  float rth[PB_TC_RU], rpm[PB_TC_RU], rmi[PB_TC_RU];
 };
 
 PB_DEV uint64_t* pb_tc_mbar(const PbPlan& pl, float* sm, int i) {
@@ -241,7 +244,7 @@ struct PbTcLeap {
 // trajectory (p += eps/2 g; theta += eps Minv p) is applied on the way (same arithmetic as the scalar engines).
 template <bool FIRST_PRE>
 PB_DEV void pb_tc_stage_w(const PbPlan& pl, float* sm, float* TH, const float* G, const PbTcLeap& lf, int nt,
-                          const PbTc& tc) {
+                          PbTc& tc) {
   PB_TAG(1)
   const int tid = threadIdx.x;
   const PbLayer& L0 = pl.L[0];
@@ -260,13 +263,31 @@ PB_DEV void pb_tc_stage_w(const PbPlan& pl, float* sm, float* TH, const float* G
     }
     return th;
   };
+  if (FIRST_PRE) {
+    // start of a trajectory: this thread's first-layer weights move into registers (same enumeration as the update
+    // phase of pb_tc_grad_core); the shared-memory copies of theta / p are stale until the last step writes them back
+#pragma unroll
+    for (int u = 0; u < PB_TC_RU; ++u) {
+      const int idx = tc.ridx[u];
+      const float mi = lf.MI[idx];
+      const float p = lf.PM[idx] + lf.heps * G[idx];
+      const float th = TH[idx] + lf.eps * (mi * p);
+      tc.rth[u] = th;
+      tc.rpm[u] = p;
+      tc.rmi[u] = mi;
+      const float v = (tc.rok >> u) & 1u ? th : 0.f;
+      Wb[tc.rwo[u]] = v;
+      Wl[tc.rwo[u]] = v - pb_trunc_tf32(v);
+    }
+  } else {
 #pragma unroll 4
-  for (int e = tid; e < 16 * 64; e += nt) {
-    const int i = (e & 3) + 4 * (e >> 8), j = (e >> 2) & 63;
-    const float v = (i < inA && j < H) ? upd(L0.soff + i * wp + j) : 0.f;
-    const int o = (i >> 2) * 256 + j * 4 + (i & 3);
-    Wb[o] = v;
-    Wl[o] = v - pb_trunc_tf32(v);
+    for (int e = tid; e < 16 * 64; e += nt) {
+      const int i = (e & 3) + 4 * (e >> 8), j = (e >> 2) & 63;
+      const float v = (i < inA && j < H) ? upd(L0.soff + i * wp + j) : 0.f;
+      const int o = (i >> 2) * 256 + j * 4 + (i & 3);
+      Wb[o] = v;
+      Wl[o] = v - pb_trunc_tf32(v);
+    }
   }
   if (tid < 64) w2s[tid] = tid < H ? upd(L1.soff + tid * L1.wp) : 0.f;
   if (FIRST_PRE && tid == 64) upd(L1.soff + H * L1.wp);
@@ -304,7 +325,7 @@ PB_DEV void pb_tc_grad_core(const PbPlan& pl, float* sm, float* TH, float* G, in
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const PbLayer& L0 = pl.L[0];
   const PbLayer& L1 = pl.L[1];
-  const int H = L0.out, wp = L0.wp, inA = L0.inA;
+  const int H = L0.out, inA = L0.inA;
   const int ntiles = pl.tc_npad >> 7, nj8 = (H + 7) >> 3;
   const float* yr = sm + pl.off_yr;
   float* Wb = sm + pl.off_wb;
@@ -452,7 +473,7 @@ PB_DEV void pb_tc_grad_core(const PbPlan& pl, float* sm, float* TH, float* G, in
     for (int i = 0; i < 16; ++i) {
       const float gm = __uint_as_float(g[i]) + __uint_as_float(g[16 + i]);
       gh[i * 72 + j] = gm;
-      if (i < inA && j < H) dot = fmaf(TH[L0.soff + i * wp + j], gm, dot);
+      if (i < inA && j < H) dot = fmaf(Wb[(i >> 2) * 256 + j * 4 + (i & 3)], gm, dot);  // Wb raw = current W1
     }
     gx[2304 + hf * 64 + j] = dot;
   }
@@ -479,34 +500,32 @@ PB_DEV void pb_tc_grad_core(const PbPlan& pl, float* sm, float* TH, float* G, in
   {
     // first-layer weights, branch-free: a missing element works on a zero pad slot with a zero gradient (every
     // update of it is 0 -> 0); all loads first (the stores may alias for the compiler)
-    float gl[PB_TC_RU], th[PB_TC_RU], pm[PB_TC_RU], mi[PB_TC_RU];
+    float gl[PB_TC_RU];
 #pragma unroll
     for (int u = 0; u < PB_TC_RU; ++u) {
       const float gsum = gx[tc.rgx[u]] + gx[1152 + tc.rgx[u]];
       gl[u] = (tc.rok >> u) & 1u ? w2s[tc.rw2[u]] * gsum : 0.f;
-      th[u] = pm[u] = mi[u] = 0.f;
-      if (MODE != 0) {
-        th[u] = TH[tc.ridx[u]];
-        pm[u] = lf.PM[tc.ridx[u]];
-      }
-      if (MODE == 1) mi[u] = lf.MI[tc.ridx[u]];
     }
 #pragma unroll
     for (int u = 0; u < PB_TC_RU; ++u) {
       if (MODE == 0) {
         G[tc.ridx[u]] = gl[u];
       } else {
-        const float gp = gl[u] - th[u] * lf.inv_pv;
-        if (MODE == 2) G[tc.ridx[u]] = gp;  // (interior steps: nobody reads G before the next evaluation)
-        float p = pm[u] + lf.heps * gp;
+        // theta, p, Minv of these weights live in registers for the whole trajectory (pb_tc_stage_w<true>)
+        const float gp = gl[u] - tc.rth[u] * lf.inv_pv;
+        float p = tc.rpm[u] + lf.heps * gp;
         if (MODE == 1) {
           p = p + lf.heps * gp;
-          const float tn = th[u] + lf.eps * (mi[u] * p);
-          TH[tc.ridx[u]] = tn;
+          const float tn = tc.rth[u] + lf.eps * (tc.rmi[u] * p);
+          tc.rth[u] = tn;
           Wb[tc.rwo[u]] = tn;
           Wl[tc.rwo[u]] = tn - pb_trunc_tf32(tn);
+        } else {  // last step: everything back to the resident arrays
+          G[tc.ridx[u]] = gp;
+          TH[tc.ridx[u]] = tc.rth[u];
+          lf.PM[tc.ridx[u]] = p;
         }
-        lf.PM[tc.ridx[u]] = p;
+        tc.rpm[u] = p;
       }
     }
   }
