@@ -366,6 +366,23 @@ def main():
     torch.cuda.synchronize()
     exchange_ms = 1e3 * (time.perf_counter() - t0)
 
+    # posterior predictive over stored samples (north_star subsystem 4), timed on its own: every stored position of the
+    # HMC workload (C x T samples), else the final states, on the M test points
+    psmp = last["trace"].reshape(-1, fs.num_params) if (w["algo"] == "hmc" and last.get("trace") is not None) else final
+    ops.predict(fs, psmp, Xt, want_preds=False, want_moments=True)
+    pa, pb_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pa.record()
+    for _ in range(3):
+        ops.predict(fs, psmp, Xt, want_preds=False, want_moments=True)
+    pb_.record()
+    torch.cuda.synchronize()
+    pred_ms = pa.elapsed_time(pb_) / 3
+    predictive = {"samples": int(psmp.shape[0]), "test_points": int(Xt.shape[0]), "ms": pred_ms,
+                  "evals_per_s": psmp.shape[0] * Xt.shape[0] / (pred_ms * 1e-3),
+                  "engine": "tcgen05" if (len(w["layers"]) == 3 and w["act"] == 0 and w["layers"][1] <= 64
+                                          and w["layers"][0] + 1 <= 16 and not os.environ.get("PBNN_NO_TC")) else "fp32",
+                  "note": "mean / variance over the samples for every test point; not part of `value`"}
+
     if rank == 0:
         peaks = {}
         try:
@@ -438,6 +455,7 @@ def main():
         except Exception as exc:  # noqa: BLE001
             roofline["peak_measured_fp32_probe"] = None
         out = dict(base, value=value, ms_per_step=ms_per_step, clocks=clocks, roofline=roofline, gpu_launches=args.steps,
+                   predictive=predictive,
                    exchange={"what": "predictive moments (sum, sumsq over chains) all_gather", "ms": exchange_ms,
                              "pred_mean_abs": float(pm.abs().mean()), "pred_var_mean": float(pv.mean())},
                    chains_finite=bool(torch.isfinite(final).all().item()))

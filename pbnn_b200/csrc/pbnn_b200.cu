@@ -94,6 +94,201 @@ pb_hmc_tc_kernel(const __grid_constant__ PbPlan pl, const __grid_constant__ PbHm
   pb_tc_teardown(pl, pb_smem, tc);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Posterior predictive on the tcgen05 engine (one-hidden-layer relu nets, scalar output): CTA (g, ch) evaluates the
+// samples of chunk ch on `tpc` 128-row tiles of test rows.  X_test (hi, lo) of the CTA's tiles is resident in TMEM
+// (forward A operand, as in pb_hmc_tc_kernel); per sample the first-layer weights are staged as the B operand (hi, lo)
+// and 6 MMAs per tile put Hpre into one of two TMEM accumulators; one thread per row forms f = w2 . relu(Hpre) + b2,
+// writes it and accumulates sum f, sum f^2 in registers (predict_fn, langevin.py:75-76; moments:
+// benchmark/pipelines/metrics_prediction_intervals.py:188).
+// ------------------------------------------------------------------------------------------------
+struct PbPredTcArgs {
+  const float* samples;
+  int S;
+  const float* Xtest;
+  int M;
+  float* preds;
+  float* part;
+  int nchunk, chunk, tpc;
+  int d, H, P, fb0, fw0, fb1, fw1;
+};
+
+__global__ void __launch_bounds__(160, 2) pb_predict_tc_kernel(const __grid_constant__ PbPredTcArgs a) {
+  __shared__ __align__(16) float Wb[2 * 16 * 64];  // forward B operand: raw | lo
+  __shared__ __align__(16) float w2s[64];
+  __shared__ __align__(8) uint64_t mbar[4];        // 0,1: forward MMAs into accumulator 0/1 done; 2,3: accumulator read
+  __shared__ uint32_t tmem_s;
+  __shared__ float b2s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+  const int row0 = (int)blockIdx.x * a.tpc * 128, ch = (int)blockIdx.y;
+  const int left = (a.M - row0 + 127) >> 7;
+  const int ntl = left < a.tpc ? left : a.tpc;
+  const int d = a.d, H = a.H, nj8 = (H + 7) >> 3;
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(pb_smem_u32(mbar + i)));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 128;" ::"r"(pb_smem_u32(mbar + 2 + i)));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;");
+  }
+  if (tid < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(pb_smem_u32(&tmem_s)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  pb_tc_fence_before();
+  __syncthreads();
+  pb_tc_fence_after();
+  const uint32_t tmem = tmem_s;
+  if (tid < 128) {  // X_test tiles -> TMEM columns 128 + 32 t (raw | lo), lane = row of the tile
+    for (int t = 0; t < ntl; ++t) {
+      const int row = row0 + t * 128 + tid;
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        float v = 0.f;
+        if (row < a.M) v = k < d ? a.Xtest[(size_t)row * d + k] : (k == d ? 1.f : 0.f);
+        hi[k] = __float_as_uint(v);
+        lo[k] = __float_as_uint(v - pb_trunc_tf32(v));
+      }
+      const uint32_t taddr = tmem + ((uint32_t)(tid & ~31) << 16) + 128u + 32u * (uint32_t)t;
+      pb_tmem_st16(taddr, hi);
+      pb_tmem_st16(taddr + 16u, lo);
+    }
+    pb_tmem_wait_st();
+  }
+  pb_tc_fence_before();
+  __syncthreads();
+  pb_tc_fence_after();
+
+  const uint32_t idesc = pb_umma_idesc_tf32(128, 64);
+  const uint64_t dwb = pb_umma_desc(pb_smem_u32(Wb), 1024u, 128u);
+  const bool k2 = d + 1 > 8;
+  uint32_t pf0 = 0u, pf1 = 0u, ph0 = 0u, ph1 = 0u;  // mbarrier parities (epilogue: pf, issue warp: ph)
+  float sum[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
+  const int s0 = ch * a.chunk, s1 = s0 + a.chunk < a.S ? s0 + a.chunk : a.S;
+  // this thread's 7 first-layer slots (constant over the samples) and a register prefetch of the next sample's
+  // parameters: the global-memory latency of a sample is hidden behind the MMAs + epilogue of the previous one
+  int wsrc[7], wdst[7];
+#pragma unroll
+  for (int u = 0; u < 7; ++u) {
+    const int e = tid + u * 160;
+    const int i = (e & 3) + 4 * (e >> 8), j = (e >> 2) & 63;
+    wdst[u] = e < 16 * 64 ? (i >> 2) * 256 + j * 4 + (i & 3) : -1;
+    wsrc[u] = (e < 16 * 64 && j < H) ? (i < d ? a.fw0 + i * H + j : (i == d ? a.fb0 + j : -1)) : -1;
+  }
+  const int w2src = tid < 64 ? (tid < H ? a.fw1 + tid : -1) : (tid == 64 ? a.fb1 : -2);
+  float wv[7], w2v = 0.f;
+  auto fetch = [&](int smp) {
+    const float* th = a.samples + (size_t)smp * a.P;
+#pragma unroll
+    for (int u = 0; u < 7; ++u) wv[u] = wsrc[u] >= 0 ? __ldg(th + wsrc[u]) : 0.f;
+    w2v = w2src >= 0 ? __ldg(th + w2src) : 0.f;
+  };
+  if (s0 < s1) fetch(s0);
+  for (int smp = s0; smp < s1; ++smp) {
+    // first-layer weights -> B operand (raw + lo); kernel [d][H] at fw0, bias [H] at fb0 (ravel_pytree order)
+#pragma unroll
+    for (int u = 0; u < 7; ++u)
+      if (wdst[u] >= 0) {
+        Wb[wdst[u]] = wv[u];
+        Wb[1024 + wdst[u]] = wv[u] - pb_trunc_tf32(wv[u]);
+      }
+    if (tid < 64) w2s[tid] = w2v;
+    if (tid == 64) b2s = w2v;
+    if (smp + 1 < s1) fetch(smp + 1);
+    pb_fence_async_smem();
+    pb_tc_fence_before();
+    __syncthreads();
+    if (warp_u == 4) {
+      pb_tc_fence_after();
+      for (int t = 0; t < ntl; ++t) {
+        const int hb = t & 1;
+        if (t >= 2) {  // the accumulator's previous tile has been read
+          if (hb) { pb_mbar_wait(pb_smem_u32(mbar + 3), ph1); ph1 ^= 1u; }
+          else { pb_mbar_wait(pb_smem_u32(mbar + 2), ph0); ph0 ^= 1u; }
+          pb_tc_fence_after();
+        }
+        if (pb_elect_one()) {
+          const uint32_t dcol = tmem + 64u * (uint32_t)hb, ta = tmem + 128u + 32u * (uint32_t)t;
+          const uint64_t w_lo = 256u, w_k = 128u;
+          pb_umma_tf32_ts(dcol, ta, dwb, idesc, 0u);
+          if (k2) pb_umma_tf32_ts(dcol, ta + 8u, dwb + w_k, idesc, 1u);
+          pb_umma_tf32_ts(dcol, ta, dwb + w_lo, idesc, 1u);
+          if (k2) pb_umma_tf32_ts(dcol, ta + 8u, dwb + w_lo + w_k, idesc, 1u);
+          pb_umma_tf32_ts(dcol, ta + 16u, dwb, idesc, 1u);
+          if (k2) pb_umma_tf32_ts(dcol, ta + 24u, dwb + w_k, idesc, 1u);
+          pb_umma_commit(pb_smem_u32(mbar + hb));
+        }
+        __syncwarp();
+      }
+      // every "accumulator read" phase is waited for exactly once (the parities stay in step)
+      for (int t = ntl >= 2 ? ntl - 2 : 0; t < ntl; ++t) {
+        if (t & 1) { pb_mbar_wait(pb_smem_u32(mbar + 3), ph1); ph1 ^= 1u; }
+        else { pb_mbar_wait(pb_smem_u32(mbar + 2), ph0); ph0 ^= 1u; }
+      }
+    } else {
+      const float b2 = b2s;
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        if (t < ntl) {
+          const int hb = t & 1;
+          if (hb) { pb_mbar_wait(pb_smem_u32(mbar + 1), pf1); pf1 ^= 1u; }
+          else { pb_mbar_wait(pb_smem_u32(mbar + 0), pf0); pf0 ^= 1u; }
+          pb_tc_fence_after();
+          uint32_t h[64];
+          const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16) + 64u * (uint32_t)hb;
+          pb_tmem_ld32(lane_base, h);
+          pb_tmem_ld32(lane_base + 32u, h + 32);
+          pb_tmem_wait_ld();
+          pb_tc_fence_before();
+          asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(
+                           pb_smem_u32(mbar + 2 + hb))
+                       : "memory");
+          float f0 = 0.f, f1 = 0.f;
+#pragma unroll
+          for (int c8 = 0; c8 < 8; ++c8)
+            if (c8 < nj8) {
+#pragma unroll
+              for (int j4 = 2 * c8; j4 < 2 * c8 + 2; ++j4) {
+                const float4 w = pb_ld4(w2s + 4 * j4);
+                f0 = fmaf(fmaxf(__uint_as_float(h[4 * j4]), 0.f), w.x, f0);
+                f1 = fmaf(fmaxf(__uint_as_float(h[4 * j4 + 1]), 0.f), w.y, f1);
+                f0 = fmaf(fmaxf(__uint_as_float(h[4 * j4 + 2]), 0.f), w.z, f0);
+                f1 = fmaf(fmaxf(__uint_as_float(h[4 * j4 + 3]), 0.f), w.w, f1);
+              }
+            }
+          const float f = (f0 + f1) + b2;
+          const int row = row0 + t * 128 + tid;
+          if (row < a.M) {
+            sum[t] += f;
+            sq[t] += f * f;
+            if (a.preds) a.preds[(size_t)smp * a.M + row] = f;
+          }
+        }
+    }
+    pb_tc_fence_before();
+    __syncthreads();  // every MMA of this sample has completed (each tile was waited for): Wb may be rewritten
+  }
+  if (a.part && tid < 128) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+      if (t < ntl) {
+        const int row = row0 + t * 128 + tid;
+        if (row < a.M) {
+          a.part[((size_t)ch * 2) * a.M + row] = sum[t];
+          a.part[((size_t)ch * 2 + 1) * a.M + row] = sq[t];
+        }
+      }
+  }
+  pb_tc_fence_before();
+  __syncthreads();
+  if (tid < 32) {
+    pb_tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem));
+  }
+}
+
 template <int ACT, bool GS>
 __global__ void __launch_bounds__(PB_MAX_NT)
 pb_predict_kernel(const __grid_constant__ PbPlan pl, const __grid_constant__ PbPredArgs a) {
@@ -484,6 +679,27 @@ static int pb_backend_hmc(const PbPlan& pl, const PbHmcArgs& a, int C, void* str
 
 static int pb_backend_predict(const PbPlan& pl, const PbPredArgs& a, int mtiles, float* sum, float* sumsq,
                               void* stream) {
+  const PbLayer& L0 = pl.L[0];
+  if (pl.nl == 2 && pl.s == 1 && pl.act == PBNN_ACT_RELU && L0.out <= 64 && pl.d + 1 <= 16 && !pl.gstate &&
+      !pb_env_int("PBNN_NO_TC", 0)) {
+    // tcgen05 path; tiles per CTA: as many as still leave every CTA slot (2 per SM) with work
+    PbPredTcArgs t;
+    t.samples = a.samples; t.S = a.S; t.Xtest = a.Xtest; t.M = a.M; t.preds = a.preds; t.part = a.part;
+    t.nchunk = a.nchunk; t.chunk = a.chunk;
+    t.d = pl.d; t.H = L0.out; t.P = pl.P; t.fb0 = L0.fb; t.fw0 = L0.fw; t.fb1 = pl.L[1].fb; t.fw1 = pl.L[1].fw;
+    const int tiles = (a.M + 127) / 128, slots = 2 * pb_backend_num_sms();
+    t.tpc = 4;
+    while (t.tpc > 1 && (long long)((tiles + t.tpc - 1) / t.tpc) * a.nchunk < slots) t.tpc >>= 1;
+    const dim3 g((tiles + t.tpc - 1) / t.tpc, a.nchunk);
+    pb_predict_tc_kernel<<<g, 160, 0, (cudaStream_t)stream>>>(t);
+    PB_CUDA(cudaGetLastError());
+    if (sum) {
+      const int n = a.M;
+      pb_predict_reduce_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(a.part, a.nchunk, n, sum, sumsq);
+      PB_CUDA(cudaGetLastError());
+    }
+    return PBNN_OK;
+  }
   const dim3 grid(mtiles, a.nchunk);
   int rc;
   if (pl.gstate) {

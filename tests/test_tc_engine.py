@@ -145,3 +145,25 @@ def test_tc_repeated_runs_are_bit_identical(cuda_ops):
         else:
             for k in ref:
                 assert np.array_equal(got[k], ref[k]), (rep, k)
+
+
+@pytest.mark.parametrize("layers,S,M", [((13, 50, 1), 37, 150), ((8, 50, 1), 70, 1024), ((3, 7, 1), 5, 129),
+                                         ((15, 64, 1), 33, 700), ((1, 1, 1), 3, 1), ((6, 20, 1), 1, 2500)])
+def test_tc_predict(cuda_ops, monkeypatch, layers, S, M):
+    """Posterior predictive on the tcgen05 engine (pb_predict_tc_kernel): predictions and moments vs the float64
+    oracle, and vs the FP32 kernel (PBNN_NO_TC=1) -- ragged tile counts, more / fewer samples than chunks."""
+    sp, fs = o.MlpSpec(tuple(layers), o.RELU, 0.1), FlatSpec(tuple(layers), o.RELU, 0.1)
+    rng = np.random.default_rng(5)
+    th = (0.3 * rng.standard_normal((S, sp.num_params))).astype(np.float32)
+    Xt = rng.standard_normal((M, layers[0])).astype(np.float32)
+    F = o.predict(sp, th.astype(np.float64), Xt.astype(np.float64), dtype=np.float64)
+    res = cuda_ops.predict(fs, th, Xt, want_preds=True, want_moments=True)
+    assert rel(npy(res["preds"]), F) <= 5e-6
+    assert rel(npy(res["mean"]), F.mean(0)) <= 5e-6
+    assert np.abs(npy(res["var"]) - F.var(0)).max() <= 1e-5 * max(1.0, float((F ** 2).mean(0).max()))
+    only_m = cuda_ops.predict(fs, th, Xt, want_preds=False, want_moments=True)
+    assert np.array_equal(npy(only_m["mean"]), npy(res["mean"]))
+    monkeypatch.setenv("PBNN_NO_TC", "1")
+    ref = cuda_ops.predict(fs, th, Xt, want_preds=True, want_moments=True)
+    assert rel(npy(res["preds"]), npy(ref["preds"])) <= 5e-6
+    assert not np.array_equal(npy(res["preds"]), npy(ref["preds"])) or S * M < 8  # the two kernels really differ
