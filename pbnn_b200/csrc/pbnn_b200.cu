@@ -688,7 +688,7 @@ static int pb_backend_predict(const PbPlan& pl, const PbPredArgs& a, int mtiles,
     t.nchunk = a.nchunk; t.chunk = a.chunk;
     t.d = pl.d; t.H = L0.out; t.P = pl.P; t.fb0 = L0.fb; t.fw0 = L0.fw; t.fb1 = pl.L[1].fb; t.fw1 = pl.L[1].fw;
     const int tiles = (a.M + 127) / 128, slots = 2 * pb_backend_num_sms();
-    t.tpc = 4;
+    t.tpc = pb_env_int("PBNN_PRED_TPC", 4);
     while (t.tpc > 1 && (long long)((tiles + t.tpc - 1) / t.tpc) * a.nchunk < slots) t.tpc >>= 1;
     const dim3 g((tiles + t.tpc - 1) / t.tpc, a.nchunk);
     pb_predict_tc_kernel<<<g, 160, 0, (cudaStream_t)stream>>>(t);
