@@ -33,6 +33,23 @@ pb_sg_kernel(const __grid_constant__ PbPlan pl, const __grid_constant__ PbSgArgs
   pb_sg_chain<ALGO, ACT, GS, ENG>(pl, a, pb_smem, (int)blockIdx.x, (int)blockDim.x);
 }
 
+// two-hidden-layer tcgen05 engine (pbnn_tc2.cuh): 8 worker warps + TMA producer warp + MMA-issue warp, one persistent
+// CTA per SM looping over its chains; state arrays in the global workspace, operand images in the CTA's image block
+template <int ALGO>
+__global__ void __launch_bounds__(PB_T2_NT, 1)
+pb_sg_tc2_kernel(const __grid_constant__ PbPlan pl, const __grid_constant__ PbSgArgs a) {
+  extern __shared__ __align__(16) float pb_smem[];
+  PB_PROF_START
+  const int nt = (int)blockDim.x;
+  PbTc2 tc;
+  pb_tc2_setup(pl, pb_smem, a.ws_img + (size_t)blockIdx.x * (size_t)pl.t2_img_bytes, nt, tc);
+  for (int c = (int)blockIdx.x; c < a.n_chains; c += (int)gridDim.x) {
+    pb_sg_chain<ALGO, PBNN_ACT_RELU, true, 2>(pl, a, pb_smem, c, nt, &tc);
+    __syncthreads();
+  }
+  pb_tc2_teardown(tc);
+}
+
 template <int ACT, bool GS, int ENG>
 __global__ void __launch_bounds__(PB_MAX_NT)
 pb_hmc_kernel(const __grid_constant__ PbPlan pl, const __grid_constant__ PbHmcArgs a) {
@@ -627,6 +644,10 @@ static int pb_launch(K kern, const PbPlan& pl, const A& a, dim3 grid, void* stre
 
 template <int ALGO>
 static int pb_sg_dispatch(const PbPlan& pl, const PbSgArgs& a, int C, void* stream) {
+  if (pl.tc2) {
+    const int nsm = pb_backend_num_sms();
+    return pb_launch(pb_sg_tc2_kernel<ALGO>, pl, a, dim3(C < nsm ? C : nsm), stream);
+  }
   if (pl.gstate) {
     if (pl.act == PBNN_ACT_RELU) return pb_launch(pb_sg_kernel<ALGO, PBNN_ACT_RELU, true, 0>, pl, a, dim3(C), stream);
     return pb_launch(pb_sg_kernel<ALGO, PBNN_ACT_TANH, true, 0>, pl, a, dim3(C), stream);

@@ -55,6 +55,13 @@ struct PbPlan {
   // tcgen05 path (one hidden relu layer, scalar output): see pbnn_tc.cuh for the operand layouts
   int tc, tc_npad;                // tc_npad = rows rounded up to the 128-row MMA tile
   int off_mk, off_z, off_wb, off_w2s, off_tcm;
+  // tcgen05 engine for two equal hidden relu layers and a scalar output (pbnn_tc2.cuh): bf16x3 operands, weights
+  // streamed from a per-CTA global image block with cp.async.bulk, state arrays in the global workspace
+  int tc2, t2_H, t2_Hp, t2_Hy, t2_Kx;      // hidden width, padded to 16, (H + 1) padded to 16, (d + 1) padded to 16
+  int t2_nch, t2_nchy, t2_ncbx, t2_nmt;    // 64-wide chunks of Hp / Hy / Kx; 128-row tiles of Hp
+  int t2_wstage, t2_ring;                  // bytes of one weight-ring stage / of the whole ring
+  int off_t2_vec, off_t2_bar, off_t2_big;  // float offsets: small vectors, mbarriers, 1024-byte aligned operand area
+  int t2_img_w1, t2_img_w2, t2_img_w2s, t2_img_bytes;  // byte offsets inside the image block (X image at 0)
   int off_act, off_scr, off_acc, off_idx, off_scal;
   int idx_cap;
   int smem_floats;
@@ -112,6 +119,64 @@ static inline void pb_plan_dw(PbPlan* pl, int nw, int bt, int kcap) {
 #define PB_PLAN_RES 1
 #define PB_PLAN_ACC 2
 #define PB_PLAN_TC 4  // the caller has a tcgen05 kernel for this op (HMC): allow the tensor-core layout
+#define PB_PLAN_TC2 8  // the caller can run the two-hidden-layer tcgen05 engine (SG samplers, Adam, grad hook)
+
+#define PB_T2_NT 320       // 8 worker warps + 1 TMA warp + 1 MMA-issue warp
+#define PB_T2_NS 3         // weight-ring stages
+#define PB_T2_TILE 16384   // bytes of one [128 rows][64 bf16] operand tile (SWIZZLE_128B)
+#define PB_T2_VEC_FLOATS 1536
+static inline int pb_r16(int x) { return (x + 15) & ~15; }
+
+// two-hidden-layer tcgen05 plan: shared memory = scratch | small vectors | mbarriers | aligned operand area
+// (activation chunk x 3 terms | relu mask of layer 2 | weight ring); everything parameter-sized lives in global memory
+static inline void pb_layout_tc2(PbPlan* pl, const pbnn_mlp_spec* sp, int rows) {
+  const int H = sp->dims[1];
+  pl->tc2 = 1;
+  pl->t2_H = H;
+  pl->t2_Hp = pb_r16(H);
+  pl->t2_Hy = pb_r16(H + 1);
+  pl->t2_Kx = pb_r16(pl->d + 1);
+  pl->t2_nch = (pl->t2_Hp + 63) / 64;
+  pl->t2_nchy = (pl->t2_Hy + 63) / 64;
+  pl->t2_ncbx = (pl->t2_Kx + 63) / 64;
+  pl->t2_nmt = (pl->t2_Hp + 127) / 128;
+  const int st_a = pl->t2_nch * 64 * 128, st_b = pl->t2_Hp * 128;
+  pl->t2_wstage = st_a > st_b ? st_a : st_b;
+  const int xi = 3 * pl->t2_ncbx * PB_T2_TILE;
+  pl->t2_ring = PB_T2_NS * pl->t2_wstage > xi ? PB_T2_NS * pl->t2_wstage : xi;
+  pl->BT = 128;
+  pl->ap = 132;
+  pl->h1 = 0;
+  pl->tc = 0;
+  pl->ksmax = 1;
+  pl->gstate = 1;
+  pl->NT = PB_T2_NT;
+  pl->res_rows = rows;
+  pl->xp = 0;
+  int off = 0;
+  pl->off_gpart = pl->off_act = off;
+  for (int l = 0; l <= pl->nl + 1; ++l) pl->aoff[l] = off;
+  pl->off_xres = pl->off_yres = pl->off_xr = pl->off_yr = pl->off_hpart = off;
+  pl->off_scr = off;
+  off += PB_SCR_FLOATS;
+  pl->off_acc = off;
+  pl->off_idx = off;
+  off += pl->idx_cap;
+  pl->off_scal = off;
+  off += 32;
+  pl->off_t2_vec = off;
+  off += PB_T2_VEC_FLOATS;
+  pl->off_t2_bar = off;
+  off += 64;
+  pl->off_t2_big = off;
+  off += 256;  // slack for the run-time 1024-byte alignment
+  off += (3 * PB_T2_TILE + pl->t2_nch * PB_T2_TILE + pl->t2_ring) / 4;
+  pl->smem_floats = off;
+  pl->t2_img_w1 = xi;
+  pl->t2_img_w2 = pl->t2_img_w1 + 3 * pl->t2_nch * pl->t2_Kx * 128;
+  pl->t2_img_w2s = pl->t2_img_w2 + 3 * pl->t2_nch * pl->t2_Hp * 128;
+  pl->t2_img_bytes = pl->t2_img_w2s + 3 * pl->t2_nch * pl->t2_Hp * 128;
+}
 
 // tcgen05 operand geometry (floats).  K-major, no swizzle: element (row x, k) at (k/4)*LBO + x*16 B + (k%4)*4 B.
 #define PB_TC_MK_LBO 516   // mask^T  [k = row in half / 4][2 halves x 64 hidden units (+1 pad row: conflict-free stores)][4]
@@ -307,6 +372,18 @@ static inline int pb_build_plan(const pbnn_mlp_spec* sp, int rows, int nstate, i
   h1_ok = 0;
 #endif
   const int nw_env = pb_env_int("PBNN_NW", 0);
+#if !defined(PB_EMU)
+  // two-hidden-layer tcgen05 engine: d-H-H-1 relu, one 128-row tile per gradient evaluation
+  if ((flags & PB_PLAN_TC2) && pl->nl == 3 && pl->s == 1 && !hetero && sp->activation == PBNN_ACT_RELU &&
+      sp->dims[1] == sp->dims[2] && sp->dims[1] <= 256 && sp->dims[1] >= pb_env_int("PBNN_TC2_MIN_H", 48) &&
+      pl->d + 1 <= 128 && rows <= 128 && rows >= pb_env_int("PBNN_TC2_MIN_ROWS", 32) && !(flags & PB_PLAN_ACC) &&
+      !pb_env_int("PBNN_NO_TC", 0) && !pb_env_int("PBNN_NO_TC2", 0)) {
+    pb_layout_tc2(pl, sp, rows);
+    if ((size_t)pl->smem_floats * 4 <= (size_t)PB_SMEM_LIMIT_BYTES) return PBNN_OK;
+    pl->tc2 = 0;
+    pl->gstate = 0;
+  }
+#endif
   // tcgen05 path: the same nets, relu only (the weight gradient uses the 0/1 activation mask as an exact operand)
   if (h1_ok && (flags & PB_PLAN_TC) && sp->activation == PBNN_ACT_RELU && !hetero && !pb_env_int("PBNN_NO_TC", 0) &&
       rows <= 128 * PB_TC_MAX_TILES) {
@@ -398,6 +475,8 @@ struct PbSgArgs {
   const float* cv_center_est;  //                   minibatch estimate at the centring point [C][P]
   float temperature;           // SGLD / SGHMC temperature (1 in pbnn; 0 = plain gradient step)
   float* ws;    // global workspace [C][nstate][Ps] when plan.gstate
+  unsigned char* ws_img;  // plan.tc2: one operand-image block of plan.t2_img_bytes per CTA (1024-byte aligned)
+  int n_chains;           // plan.tc2: the CTAs are persistent and loop over the chains
 };
 
 struct PbHmcArgs {

@@ -178,32 +178,43 @@ PB_DEV int pb_flat_to_resident(const PbPlan& pl, int fi) {
   return Ly.soff + r * Ly.wp + (q - r * Ly.out);
 }
 
-// One jax.random.normal(key, (P,))[flat] per parameter handed to f(resident_index, flat_index, z), iterating over the
-// FLAT index (no pad slots, coalesced trace order).  The threefry2x32 + erf_inv chains of ILP parameters are
-// evaluated together: a single chain is ~250 cycles of dependent integer ops, so instruction-level parallelism
-// (not more warps) is what hides its latency.
-template <int ILP, class F>
-PB_DEV void pb_flat_normal_ilp(const PbPlan& pl, int tid, int nt, PbKey key, F f) {
+// values an update needs from the state arrays, loaded BEFORE the threefry + erf_inv chains of a group are evaluated:
+// with the state arrays in global memory (L2) the loads of a whole group are in flight while the integer work runs,
+// instead of one dependent load -> compute -> store round trip per element
+struct PbPre {
+  float a, b, c, d, e;
+};
+
+// One jax.random.normal(key, (P,))[flat] per parameter: pre = pf(resident_index, flat_index) is loaded first, then
+// f(resident_index, flat_index, z, pre) is called, iterating over the FLAT index (no pad slots, coalesced trace order).
+// The threefry2x32 + erf_inv chains of ILP parameters are evaluated together: a single chain is ~250 cycles of
+// dependent integer ops, so instruction-level parallelism (not more warps) is what hides its latency.
+template <int ILP, class PF, class F>
+PB_DEV void pb_flat_normal_ilp(const PbPlan& pl, int tid, int nt, PbKey key, PF pf, F f) {
   for (int p0 = tid; p0 < pl.P; p0 += ILP * nt) {
     int si[ILP];
     float z[ILP];
+    PbPre pre[ILP];
 #pragma unroll
     for (int j = 0; j < ILP; ++j) {
       const int fi = p0 + j * nt;
       si[j] = fi < pl.P ? pb_flat_to_resident(pl, fi) : -1;
     }
 #pragma unroll
+    for (int j = 0; j < ILP; ++j)
+      if (si[j] >= 0) pre[j] = pf(si[j], p0 + j * nt);
+#pragma unroll
     for (int j = 0; j < ILP; ++j) z[j] = pb_normal_at(key, (uint32_t)(p0 + j * nt));
 #pragma unroll
     for (int j = 0; j < ILP; ++j)
-      if (si[j] >= 0) f(si[j], p0 + j * nt, z[j]);
+      if (si[j] >= 0) f(si[j], p0 + j * nt, z[j], pre[j]);
   }
 }
 
 // Large nets: iterate over the padded resident index instead (pad slots are a few % there, and the flat -> resident
 // mapping per element costs more than they do); 4 chains in flight as above.
-template <class F>
-PB_DEV void pb_padded_normal_ilp4(const PbPlan& pl, int tid, int nt, PbKey key, F f) {
+template <class PF, class F>
+PB_DEV void pb_padded_normal_ilp4(const PbPlan& pl, int tid, int nt, PbKey key, PF pf, F f) {
   for (int l = 0; l < pl.nl; ++l) {
     const PbLayer& Ly = pl.L[l];
     const int total = Ly.inA * Ly.wp;
@@ -211,6 +222,7 @@ PB_DEV void pb_padded_normal_ilp4(const PbPlan& pl, int tid, int nt, PbKey key, 
     for (int e0 = tid; e0 < total; e0 += 4 * nt) {
       int si[4], fi[4];
       float z[4];
+      PbPre pre[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int e = e0 + j * nt;
@@ -221,20 +233,38 @@ PB_DEV void pb_padded_normal_ilp4(const PbPlan& pl, int tid, int nt, PbKey key, 
         fi[j] = (r < Ly.in) ? (Ly.fw + r * Ly.out + c) : (Ly.fb + c);
       }
 #pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (si[j] >= 0) pre[j] = pf(si[j], fi[j]);
+#pragma unroll
       for (int j = 0; j < 4; ++j) z[j] = pb_normal_at(key, (uint32_t)fi[j]);
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        if (si[j] >= 0) f(si[j], fi[j], z[j]);
+        if (si[j] >= 0) f(si[j], fi[j], z[j], pre[j]);
     }
   }
 }
 
-template <class F>
-PB_DEV void pb_for_each_param_normal(const PbPlan& pl, int tid, int nt, PbKey key, F f) {
-  if (pl.P > 16 * nt) pb_padded_normal_ilp4(pl, tid, nt, key, f);
-  else if (pl.P > 3 * nt) pb_flat_normal_ilp<4>(pl, tid, nt, key, f);
-  else if (pl.P > nt) pb_flat_normal_ilp<2>(pl, tid, nt, key, f);
-  else pb_flat_normal_ilp<1>(pl, tid, nt, key, f);
+template <class PF, class F>
+PB_DEV void pb_for_each_param_normal(const PbPlan& pl, int tid, int nt, PbKey key, PF pf, F f) {
+  if (pl.P > 16 * nt) pb_padded_normal_ilp4(pl, tid, nt, key, pf, f);
+  else if (pl.P > 3 * nt) pb_flat_normal_ilp<4>(pl, tid, nt, key, pf, f);
+  else if (pl.P > nt) pb_flat_normal_ilp<2>(pl, tid, nt, key, pf, f);
+  else pb_flat_normal_ilp<1>(pl, tid, nt, key, pf, f);
+}
+
+// element-wise pass over the padded resident arrays, 4 elements per thread in flight: all loads (ld -> PbPre) of a
+// group are issued before the first store (the arrays may alias for the compiler)
+template <class LD, class ST>
+PB_DEV void pb_elementwise4(int n, int tid, int nt, LD ld, ST st) {
+  for (int i0 = tid; i0 < n; i0 += 4 * nt) {
+    PbPre v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (i0 + j * nt < n) v[j] = ld(i0 + j * nt);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (i0 + j * nt < n) st(i0 + j * nt, v[j]);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -419,7 +449,7 @@ PB_DEV void pb_init_acts(const PbPlan& pl, float* sm, int nt) {
   PB_PHASE
   for (int i = pl.off_gpart + tid; i < pl.off_idx; i += nt) sm[i] = 0.f;
   PB_ENDPHASE
-  if (pl.h1) return;  // fused path: no activation buffers, the loader writes the ones column
+  if (pl.h1 || pl.tc2) return;  // fused / tcgen05 paths: no activation buffers, the loaders write the ones column
   PB_PHASE
   for (int l = 1; l < pl.nl; ++l) {
     float* row = pb_A(pl, sm, l) + pl.L[l].in * pl.ap;
@@ -817,6 +847,7 @@ PB_DEV void pb_grad_h1(const PbPlan& pl, float* sm, const float* TH, float* G, i
 #endif
 
 #include "pbnn_tc.cuh"
+#include "pbnn_tc2.cuh"
 
 // likelihood gradient over the rows of one evaluation: fused one-hidden-layer path or the tiled GEMM engine
 // ENG selects the gradient engine at COMPILE time (0 = tiled GEMM engine, 1 = fused one-hidden-layer path): separate
@@ -925,7 +956,8 @@ PB_DEV void pb_copy_indices(const PbPlan& pl, float* sm, const int32_t* src, int
 // resident arrays: st[0]=theta, st[1]=g, st[2]=aux (p | V | m), st[3]=aux2 (v)
 // ------------------------------------------------------------------------------------------------
 template <int ALGO, int ACT, bool GS, int ENG>
-PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, int nt) {
+PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, int nt, void* ctx = nullptr) {
+  // ENG: 0 tiled GEMM engine, 1 fused one-hidden-layer path, 2 two-hidden-layer tcgen05 engine (ctx = the CTA's PbTc2)
   float* ws = a.ws ? a.ws + (size_t)c * pl.nstate * pl.Ps : nullptr;
   float* TH = pb_state<GS>(pl, sm, ws, 0);
   float* G = pb_state<GS>(pl, sm, ws, 1);
@@ -939,6 +971,25 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
   PbKey ck;
   ck.k0 = a.keys ? a.keys[2 * c] : 0u;
   ck.k1 = a.keys ? a.keys[2 * c + 1] : 0u;
+
+  auto load_res = [&]() {
+#if !defined(PB_EMU)
+    if constexpr (ENG == 2) {
+      pb_tc2_stage_x(pl, sm, *static_cast<PbTc2*>(ctx), a.X, a.y, sidx, B, nt);
+      return;
+    }
+#endif
+    pb_load_resident(pl, sm, a.X, a.y, sidx, B, nt);
+  };
+  auto grad = [&](bool tile_loaded_) {
+#if !defined(PB_EMU)
+    if constexpr (ENG == 2) {
+      pb_grad_tc2(pl, sm, TH, G, B, a.scale, nt, *static_cast<PbTc2*>(ctx));
+      return;
+    }
+#endif
+    pb_grad<ACT, (ENG == 2 ? 0 : ENG)>(pl, sm, TH, G, a.X, a.y, sidx, B, a.scale, tile_loaded_, nt);
+  };
 
   pb_init_acts(pl, sm, nt);
   pb_load_state(pl, TH, a.theta + cP, nt);
@@ -970,8 +1021,8 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
 
   if (ALGO == PB_ALGO_GRAD) {
     pb_copy_indices(pl, sm, cidx, B, nt);
-    if (res) pb_load_resident(pl, sm, a.X, a.y, sidx, B, nt);
-    pb_grad<ACT, ENG>(pl, sm, TH, G, a.X, a.y, sidx, B, a.scale, false, nt);
+    if (res) load_res();
+    grad(false);
     PB_PHASE
     pb_for_each_param(pl, tid, nt, [&](int si, int fi) { a.aux1[cP + fi] = G[si] - TH[si] * pl.inv_pv; });
     float* scr = pb_scr(pl, sm);
@@ -996,8 +1047,8 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
       gen_pos = a.init_draw;
       pb_gen_indices(pl, sm, B, a.N, a.randint_mult, nt);
     }
-    if (res) pb_load_resident(pl, sm, a.X, a.y, sidx, B, nt);
-    pb_grad<ACT, ENG>(pl, sm, TH, G, a.X, a.y, sidx, B, a.scale, false, nt);
+    if (res) load_res();
+    grad(false);
     PB_PHASE
     for (int i = tid; i < pl.Ps; i += nt) {
       const float g = G[i] - TH[i] * pl.inv_pv;
@@ -1018,7 +1069,7 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
       pb_gen_indices(pl, sm, B, a.N, a.randint_mult, nt);
     }
     if (res) {
-      pb_load_resident(pl, sm, a.X, a.y, sidx, B, nt);
+      load_res();
     } else if (single_tile) {
       pb_gather_rows(pl, pb_A(pl, sm, 0), pb_A(pl, sm, pl.nl + 1), pl.ap, pl.BT, a.X, a.y, sidx, 0, B, nt);
       tile_loaded = true;
@@ -1040,40 +1091,70 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
         pb_gen_advance(pl, sm, 1, nt);
         pb_gen_indices(pl, sm, B, a.N, a.randint_mult, nt);
       }
-      if (res) pb_load_resident(pl, sm, a.X, a.y, sidx, B, nt);
+      if (res) load_res();
     }
 
     if (ALGO == PB_ALGO_SGLD) {
-      pb_grad<ACT, ENG>(pl, sm, TH, G, a.X, a.y, sidx, B, a.scale, tile_loaded, nt);
+      grad(tile_loaded);
       const float ns = sqrtf(2.0f * a.temperature * eps);
       const float* cvc = a.cv_center ? a.cv_center + cP : nullptr;
       const float* cve = a.cv_center ? a.cv_center_est + cP : nullptr;
       PB_PHASE
-      pb_for_each_param_normal(pl, tid, nt, kt, [&](int si, int fi, float z) {
-        const float th = TH[si];
-        float g = G[si] - th * pl.inv_pv;
-        if (cvc) g = (cvc[fi] + g) - cve[fi];  // blackjax control_variates: grad_center + grad_est - grad_center_est
-        TH[si] = th + eps * g + ns * z;
-      });
+      pb_for_each_param_normal(
+          pl, tid, nt, kt,
+          [&](int si, int fi) {
+            PbPre v;
+            v.a = TH[si];
+            v.b = G[si];
+            v.c = cvc ? cvc[fi] : 0.f;
+            v.d = cvc ? cve[fi] : 0.f;
+            return v;
+          },
+          [&](int si, int fi, float z, const PbPre& v) {
+            const float th = v.a;
+            float g = v.b - th * pl.inv_pv;
+            if (cvc) g = (v.c + g) - v.d;  // blackjax control_variates: grad_center + grad_est - grad_center_est
+            TH[si] = th + eps * g + ns * z;
+          });
       PB_ENDPHASE
     } else if (ALGO == PB_ALGO_PSGLD) {
       PB_PHASE
-      pb_for_each_param_normal(pl, tid, nt, kt, [&](int si, int fi, float z) {
-        const float pre = 1.0f / (sqrtf(A1[si]) + 1e-6f);
-        TH[si] = TH[si] + eps * pre * G[si] + sqrtf(2.0f * pre * eps) * z;
-      });
+      pb_for_each_param_normal(
+          pl, tid, nt, kt,
+          [&](int si, int fi) {
+            PbPre v;
+            v.a = A1[si];
+            v.b = TH[si];
+            v.c = G[si];
+            return v;
+          },
+          [&](int si, int fi, float z, const PbPre& v) {
+            const float pre = 1.0f / (sqrtf(v.a) + 1e-6f);
+            TH[si] = v.b + eps * pre * v.c + sqrtf(2.0f * pre * eps) * z;
+          });
       PB_ENDPHASE
-      pb_grad<ACT, ENG>(pl, sm, TH, G, a.X, a.y, sidx, B, a.scale, tile_loaded, nt);
+      grad(tile_loaded);
       PB_PHASE
-      for (int i = tid; i < pl.Ps; i += nt) {
-        const float g = G[i] - TH[i] * pl.inv_pv;
-        G[i] = g;
-        A1[i] = a.alpha * A1[i] + (1.0f - a.alpha) * (g * g);
-      }
+      pb_elementwise4(
+          pl.Ps, tid, nt,
+          [&](int i) {
+            PbPre v;
+            v.a = G[i];
+            v.b = TH[i];
+            v.c = A1[i];
+            return v;
+          },
+          [&](int i, const PbPre& v) {
+            const float g = v.a - v.b * pl.inv_pv;
+            G[i] = g;
+            A1[i] = a.alpha * v.c + (1.0f - a.alpha) * (g * g);
+          });
       PB_ENDPHASE
     } else if (ALGO == PB_ALGO_SGHMC) {
       PB_PHASE
-      pb_for_each_param_normal(pl, tid, nt, kt, [&](int si, int fi, float z) { A1[si] = z; });
+      pb_for_each_param_normal(
+          pl, tid, nt, kt, [&](int si, int fi) { return PbPre(); },
+          [&](int si, int fi, float z, const PbPre& v) { A1[si] = z; });
       PB_ENDPHASE
       const float ns = sqrtf(2.0f * eps * (a.alpha - a.beta) * a.temperature);
       const float* cvc = a.cv_center ? a.cv_center + cP : nullptr;
@@ -1081,31 +1162,52 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
       const float fric = 1.0f - a.alpha;
       for (int l = 0; l < a.L; ++l) {
         const PbKey kl = pb_split_at(kt, (uint32_t)l);  // split(keys[t], L)[l]
-        pb_grad<ACT, ENG>(pl, sm, TH, G, a.X, a.y, sidx, B, a.scale, tile_loaded, nt);
+        grad(tile_loaded);
         PB_PHASE
-        pb_for_each_param_normal(pl, tid, nt, kl, [&](int si, int fi, float z) {
-          const float th = TH[si], p = A1[si];
-          float g = G[si] - th * pl.inv_pv;
-          if (cvc) g = (cvc[fi] + g) - cve[fi];
-          TH[si] = th + p;
-          A1[si] = fric * p + eps * g + ns * z;
-        });
+        pb_for_each_param_normal(
+            pl, tid, nt, kl,
+            [&](int si, int fi) {
+              PbPre v;
+              v.a = TH[si];
+              v.b = A1[si];
+              v.c = G[si];
+              v.d = cvc ? cvc[fi] : 0.f;
+              v.e = cvc ? cve[fi] : 0.f;
+              return v;
+            },
+            [&](int si, int fi, float z, const PbPre& v) {
+              const float th = v.a, p = v.b;
+              float g = v.c - th * pl.inv_pv;
+              if (cvc) g = (v.d + g) - v.e;
+              TH[si] = th + p;
+              A1[si] = fric * p + eps * g + ns * z;
+            });
         PB_ENDPHASE
       }
     } else if (ALGO == PB_ALGO_ADAM) {
-      pb_grad<ACT, ENG>(pl, sm, TH, G, a.X, a.y, sidx, B, a.scale, false, nt);
+      grad(false);
       const float cnt = (float)(a.count0 + t + 1);
       const float ibc1 = 1.0f / (1.0f - powf(a.b1, cnt)), ibc2 = 1.0f / (1.0f - powf(a.b2, cnt));
       PB_PHASE
-      for (int i = tid; i < pl.Ps; i += nt) {
-        const float th = TH[i];
-        const float g = -(G[i] - th * pl.inv_pv);  // gradient of the loss -logposterior
-        const float m = (1.0f - a.b1) * g + a.b1 * A1[i];
-        const float v = (1.0f - a.b2) * (g * g) + a.b2 * A2[i];
-        A1[i] = m;
-        A2[i] = v;
-        TH[i] = th + (-a.lr) * __fdividef(m * ibc1, sqrtf(v * ibc2) + a.eps);
-      }
+      pb_elementwise4(
+          pl.Ps, tid, nt,
+          [&](int i) {
+            PbPre p;
+            p.a = TH[i];
+            p.b = G[i];
+            p.c = A1[i];
+            p.d = A2[i];
+            return p;
+          },
+          [&](int i, const PbPre& p) {
+            const float th = p.a;
+            const float g = -(p.b - th * pl.inv_pv);  // gradient of the loss -logposterior
+            const float m = (1.0f - a.b1) * g + a.b1 * p.c;
+            const float v = (1.0f - a.b2) * (g * g) + a.b2 * p.d;
+            A1[i] = m;
+            A2[i] = v;
+            TH[i] = th + (-a.lr) * __fdividef(m * ibc1, sqrtf(v * ibc2) + a.eps);
+          });
       PB_ENDPHASE
     }
 

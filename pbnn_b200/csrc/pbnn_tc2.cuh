@@ -1,0 +1,681 @@
+// pbnn_b200: tcgen05 gradient engine for nets d-H-H-1 (two equal hidden relu layers, scalar output) -- the minibatch
+// log-likelihood gradient behind blackjax's grad_estimator (src/pbnn/utils/misc.py:34-55 with
+// src/pbnn/models.py:19-35 and benchmark/pipelines/logprobs.py:12-17) for BASELINE configs 3-5 (9-100-100-1,
+// 8-50-50-1, 90-256-256-1; B <= 128 rows = ONE 128-row MMA tile).
+//
+// FP32 accuracy on bf16 tensor cores.  Every fp32 operand a is fed as a = a1 + a2 + a3 (three bf16 terms, exact to 24
+// bits); a product keeps the term pairs with i + j <= 4 (6 MMA passes, fp32 accumulation in TMEM; measured 7e-7 relative
+// to the exact product, pbnn_b200/csrc/experimental/umma_bf16.cu).  A 0/1 relu mask is exact in ONE term, so the two
+// backward GEMMs that can be written against the mask take 3 passes:
+//
+//   G1 fwd1   Z1 = Xaug W1aug                      A = X tile   (K-major)   B = W1aug (MN-major)            6 passes
+//   G2 fwd2   Z2 = relu(Z1) W2                     A = H1 chunk (K-major)   B = W2     (MN-major)            6 passes
+//   G3        f = w3 . relu(Z2 + b2) + b3,  r = (y - f) scale,  M2 = [Z2 + b2 > 0]           (CUDA cores)
+//   G4 dW2    D2[n][i] = sum_b M2[b][n] Y[b][i],   Y = r * [relu(Z1) | 1]   A = M2^T (MN-major)  B = Y chunk (MN-major)   3 passes
+//             dW2[i][n] = w3[n] D2[n][i],  db2[n] = w3[n] D2[n][H],
+//             dw3[n] = sum_i W2[i][n] D2[n][i] + b2[n] D2[n][H]      (relu(Z2 + b2) = M2 * (H1 W2 + b2): no extra GEMM)
+//   G5 dH1    E[b][i]  = sum_n M2[b][n] (w3[n] W2[i][n])                  A = M2 (K-major)  B = W2s (K-major)             3 passes
+//   G6 dW1    D1[k][i] = sum_b Xaug[b][k] dZ1[b][i],  dZ1 = r * E * [Z1 > 0]   A = X^T (MN-major)  B = dZ1 chunk (MN-major) 6 passes
+//
+// Operand images are SWIZZLE_128B tiles: 64 bf16 (128 B) per storage row, 16-byte chunk j of row r at chunk j ^ (r & 7),
+// column blocks of 64 elements one after the other.  The SAME image is read K-major (storage row = M/N index) or
+// MN-major (storage row = K index): X, M2 and the activation chunks are written once and used both ways.
+//
+// Where things live.  Parameter-sized state (theta, g, ...) in the global workspace (L2).  Per CTA a global IMAGE block
+// holds the bf16x3 operand images of X (fixed minibatch), W1aug, W2 and W2s = W2 diag(w3), rewritten by
+// pb_tc2_restage after every parameter update and streamed back through a 3-stage shared-memory ring with
+// cp.async.bulk (TMA engine) + mbarriers by a dedicated producer warp.  Shared memory: one activation chunk
+// [128 rows][64] x 3 terms (48 KB), the layer-2 mask [128][Hp] bf16, the weight ring.  TMEM (512 columns):
+// S0 = columns 0..255: Z1 -> E -> D1;  S1 = columns 256..511: Z2 -> D2 chunk slots.
+//
+// Roles (320 threads): warps 0-7 workers (TMEM -> registers -> operand chunks / drains; warp w owns TMEM lanes
+// 32 (w % 4) .., column half w / 4), warp 8 producer (bulk copies), warp 9 MMA issue.  All mbarriers are re-initialised
+// at the start of every gradient evaluation (the evaluation is bracketed by CTA barriers), so every parity starts at 0.
+#pragma once
+#if !defined(PB_EMU)
+
+#define PB_T2_WORKERS 256
+
+PB_DEV uint64_t pb_t2_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {  // SWIZZLE_128B
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+
+// instruction descriptor: D = f32, A = B = bf16, dense; a_mn / b_mn: operand is MN-major
+PB_DEV uint32_t pb_t2_idesc(int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+PB_DEV void pb_t2_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// (a0, a1) -> three packed bf16x2 words (terms 1..3); element 0 in the low half
+PB_DEV void pb_t2_split3(float a0, float a1, uint32_t& t1, uint32_t& t2, uint32_t& t3) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(t1) : "f"(a1), "f"(a0));
+  float r0 = a0 - __uint_as_float(t1 << 16);
+  float r1 = a1 - __uint_as_float(t1 & 0xFFFF0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(t2) : "f"(r1), "f"(r0));
+  r0 -= __uint_as_float(t2 << 16);
+  r1 -= __uint_as_float(t2 & 0xFFFF0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(t3) : "f"(r1), "f"(r0));
+}
+
+PB_DEV void pb_t2_arrive(uint32_t mbar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(mbar) : "memory");
+}
+PB_DEV void pb_t2_expect(uint32_t mbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+PB_DEV void pb_t2_bulk(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(mbar)
+               : "memory");
+}
+PB_DEV void pb_t2_fence_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+PB_DEV void pb_t2_st4(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// mbarrier slots (8 bytes each) at off_t2_bar
+enum {
+  PB_T2_B_WFULL = 0,                    // [NS] ring stage filled (tx bytes)
+  PB_T2_B_WEMPTY = PB_T2_B_WFULL + 3,   // [NS] ring stage consumed (tcgen05.commit)
+  PB_T2_B_AXFULL = PB_T2_B_WEMPTY + 3,  // activation area filled by bulk copies (X chunk of fwd1)
+  PB_T2_B_AFULL,                        // activation chunk written by the 256 workers
+  PB_T2_B_AEMPTY,                       // activation chunk consumed (commit)
+  PB_T2_B_ACC,                          // accumulator complete: Z1, Z2, E, D1 in this order (commit)
+  PB_T2_B_D2FULL,                       // [2] D2 chunk slot complete (commit)
+  PB_T2_B_D2EMPTY = PB_T2_B_D2FULL + 2, // [2] D2 chunk slot drained by the 256 workers
+  PB_T2_B_XFULL = PB_T2_B_D2EMPTY + 2,  // X image resident in the ring area (dW1)
+  PB_T2_NBAR
+};
+
+struct PbTc2 {
+  uint32_t tmem;   // TMEM base (512 columns)
+  uint32_t big;    // shared address of the 1024-byte aligned operand area: activation | mask | ring
+  uint8_t* img;    // this CTA's global image block
+};
+
+PB_DEV uint32_t pb_t2_bar(const PbPlan& pl, float* sm, int i) {
+  return pb_smem_u32(reinterpret_cast<uint64_t*>(sm + pl.off_t2_bar) + i);
+}
+
+// byte offset of element (row r, column c) inside an image whose column blocks hold `rows` rows
+PB_DEV uint32_t pb_t2_off(int rows, int r, int c) {
+  return (uint32_t)((c >> 6) * rows * 128 + r * 128 + ((((c & 63) >> 3) ^ (r & 7)) << 4) + ((c & 7) << 1));
+}
+
+// once per CTA: TMEM, image block zeroed (pad rows / columns of the images must read as zeros)
+PB_DEV void pb_tc2_setup(const PbPlan& pl, float* sm, uint8_t* img, int nt, PbTc2& tc) {
+  const int tid = threadIdx.x;
+  uint32_t* slot = reinterpret_cast<uint32_t*>(sm + pl.off_t2_bar) + 2 * PB_T2_NBAR;
+  if (tid < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(pb_smem_u32(slot)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  uint4* z = reinterpret_cast<uint4*>(img);
+  for (int i = tid; i < pl.t2_img_bytes / 16; i += nt) z[i] = make_uint4(0u, 0u, 0u, 0u);
+  pb_tc_fence_before();
+  __syncthreads();
+  pb_tc_fence_after();
+  tc.tmem = *slot;
+  tc.img = img;
+  const uint32_t raw = pb_smem_u32(sm + pl.off_t2_big);
+  tc.big = (raw + 1023u) & ~1023u;
+  __syncthreads();
+}
+
+PB_DEV void pb_tc2_teardown(const PbTc2& tc) {
+  pb_tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    pb_tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tc.tmem));
+  }
+}
+
+// minibatch rows -> bf16x3 image of Xaug = (x, 1, 0..) [128 rows][Kx] (rows >= nrows are zero) + y in shared memory
+PB_DEV void pb_tc2_stage_x(const PbPlan& pl, float* sm, const PbTc2& tc, const float* X, const float* y,
+                           const int* idxs, int nrows, int nt) {
+  const int tid = threadIdx.x, d = pl.d, Kx = pl.t2_Kx;
+  const int tbytes = pl.t2_ncbx * PB_T2_TILE;
+  float* yv = sm + pl.off_t2_vec + 512;
+  for (int e = tid; e < 128 * (Kx >> 1); e += nt) {
+    const int b = e / (Kx >> 1), k0 = 2 * (e - b * (Kx >> 1));
+    float v0 = 0.f, v1 = 0.f;
+    if (b < nrows) {
+      const size_t row = (size_t)(idxs ? idxs[b] : b);
+      v0 = k0 < d ? X[row * d + k0] : (k0 == d ? 1.f : 0.f);
+      v1 = k0 + 1 < d ? X[row * d + k0 + 1] : (k0 + 1 == d ? 1.f : 0.f);
+    }
+    uint32_t t1, t2, t3;
+    pb_t2_split3(v0, v1, t1, t2, t3);
+    uint8_t* p = tc.img + pb_t2_off(128, b, k0);
+    *reinterpret_cast<uint32_t*>(p) = t1;
+    *reinterpret_cast<uint32_t*>(p + tbytes) = t2;
+    *reinterpret_cast<uint32_t*>(p + 2 * tbytes) = t3;
+  }
+  for (int b = tid; b < 128; b += nt) yv[b] = b < nrows ? y[(size_t)(idxs ? idxs[b] : b)] : 0.f;
+  pb_t2_fence_async_global();
+  PB_TAG(10)
+  PB_ENDPHASE_RAW
+}
+
+// theta (padded resident layout, global) -> operand images of W1aug, W2, W2s = W2 diag(w3); b2, w3, b3 -> shared memory
+PB_DEV void pb_tc2_restage(const PbPlan& pl, float* sm, const PbTc2& tc, const float* __restrict__ TH, int nt) {
+  const int tid = threadIdx.x;
+  const PbLayer& L0 = pl.L[0];
+  const PbLayer& L1 = pl.L[1];
+  const PbLayer& L2 = pl.L[2];
+  const int H = pl.t2_H, Hp = pl.t2_Hp, Kx = pl.t2_Kx, d = pl.d;
+  float* b2v = sm + pl.off_t2_vec;
+  float* w3v = b2v + 256;
+  for (int n = tid; n < 256; n += nt) {
+    b2v[n] = n < H ? TH[L1.soff + H * L1.wp + n] : 0.f;
+    w3v[n] = n < H ? TH[L2.soff + n * L2.wp] : 0.f;
+  }
+  if (tid == 0) sm[pl.off_t2_vec + 1408] = TH[L2.soff + H * L2.wp];  // b3
+  PB_TAG(1)
+  PB_ENDPHASE_RAW
+  {  // W1aug: rows k (bias = row d), columns n
+    const int tb = pl.t2_nch * Kx * 128, hp2 = Hp >> 1;
+    uint8_t* base = tc.img + pl.t2_img_w1;
+    const int total = (d + 1) * hp2;
+    for (int e0 = tid; e0 < total; e0 += 4 * nt) {
+      float v0[4], v1[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + u * nt;
+        const int k = e / hp2, n0 = 2 * (e - k * hp2);
+        v0[u] = (e < total && n0 < H) ? TH[L0.soff + k * L0.wp + n0] : 0.f;
+        v1[u] = (e < total && n0 + 1 < H) ? TH[L0.soff + k * L0.wp + n0 + 1] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + u * nt;
+        if (e < total) {
+          const int k = e / hp2, n0 = 2 * (e - k * hp2);
+          uint32_t t1, t2, t3;
+          pb_t2_split3(v0[u], v1[u], t1, t2, t3);
+          uint8_t* p = base + pb_t2_off(Kx, k, n0);
+          *reinterpret_cast<uint32_t*>(p) = t1;
+          *reinterpret_cast<uint32_t*>(p + tb) = t2;
+          *reinterpret_cast<uint32_t*>(p + 2 * tb) = t3;
+        }
+      }
+    }
+  }
+  {  // W2 and W2s: rows i, columns n
+    const int tb = pl.t2_nch * Hp * 128, hp2 = Hp >> 1;
+    uint8_t* b1 = tc.img + pl.t2_img_w2;
+    uint8_t* bs = tc.img + pl.t2_img_w2s;
+    const int total = H * hp2;
+    for (int e0 = tid; e0 < total; e0 += 4 * nt) {
+      float v0[4], v1[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + u * nt;
+        const int i = e / hp2, n0 = 2 * (e - i * hp2);
+        v0[u] = (e < total && n0 < H) ? TH[L1.soff + i * L1.wp + n0] : 0.f;
+        v1[u] = (e < total && n0 + 1 < H) ? TH[L1.soff + i * L1.wp + n0 + 1] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + u * nt;
+        if (e < total) {
+          const int i = e / hp2, n0 = 2 * (e - i * hp2);
+          uint32_t t1, t2, t3;
+          pb_t2_split3(v0[u], v1[u], t1, t2, t3);
+          const uint32_t o = pb_t2_off(Hp, i, n0);
+          *reinterpret_cast<uint32_t*>(b1 + o) = t1;
+          *reinterpret_cast<uint32_t*>(b1 + o + tb) = t2;
+          *reinterpret_cast<uint32_t*>(b1 + o + 2 * tb) = t3;
+          pb_t2_split3(v0[u] * w3v[n0], v1[u] * w3v[n0 + 1], t1, t2, t3);
+          *reinterpret_cast<uint32_t*>(bs + o) = t1;
+          *reinterpret_cast<uint32_t*>(bs + o + tb) = t2;
+          *reinterpret_cast<uint32_t*>(bs + o + 2 * tb) = t3;
+        }
+      }
+    }
+  }
+  pb_t2_fence_async_global();
+  PB_ENDPHASE_RAW
+}
+
+// ---- the gradient: G <- d loglik / d theta (padded resident layout), llbuf[0..127] <- per-row log-likelihood terms ----
+PB_DEV void pb_grad_tc2(const PbPlan& pl, float* sm, const float* __restrict__ TH, float* __restrict__ G, int nrows,
+                        float scale, int nt,
+                        const PbTc2& tc) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+  const PbLayer& L0 = pl.L[0];
+  const PbLayer& L1 = pl.L[1];
+  const PbLayer& L2 = pl.L[2];
+  const int H = pl.t2_H, Hp = pl.t2_Hp, Hy = pl.t2_Hy, Kx = pl.t2_Kx;
+  const int nch = pl.t2_nch, nchy = pl.t2_nchy, ncbx = pl.t2_ncbx, nmt = pl.t2_nmt;
+  const uint32_t acta = tc.big, m2 = tc.big + 3u * PB_T2_TILE, ring = m2 + (uint32_t)nch * PB_T2_TILE;
+  const uint32_t wstage = (uint32_t)pl.t2_wstage;
+  const uint32_t S0 = tc.tmem, S1 = tc.tmem + 256u;
+  float* b2v = sm + pl.off_t2_vec;
+  float* w3v = b2v + 256;
+  float* yv = b2v + 512;
+  float* fp = b2v + 640;    // [2][128] partial outputs of the two column halves
+  float* dw3p = b2v + 896;  // [2][256] partial output-weight gradients
+  float* llbuf = pb_llbuf(pl, sm);
+
+  pb_tc2_restage(pl, sm, tc, TH, nt);
+  if (tid == 0) {
+    for (int i = 0; i < PB_T2_NBAR; ++i) {
+      const uint32_t b = pb_t2_bar(pl, sm, i);
+      const uint32_t cnt = (i == PB_T2_B_AFULL || i == PB_T2_B_D2EMPTY || i == PB_T2_B_D2EMPTY + 1) ? PB_T2_WORKERS : 1u;
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(b), "r"(cnt));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;");
+  }
+  pb_tc_fence_before();
+  PB_TAG(2)
+  PB_ENDPHASE_RAW
+  pb_tc_fence_after();
+  const uint32_t bar0 = pb_t2_bar(pl, sm, 0);
+#define PB_T2_BAR(i) (bar0 + 8u * (uint32_t)(i))
+
+  if (warp_u == 8) {
+    // =============================== producer: bulk copies ===============================
+    if (pb_elect_one()) {
+      int fill = 0, ause = 0;  // ring fills / activation-area uses so far
+      auto stage_begin = [&](uint32_t bytes) -> uint32_t {
+        const int s = fill % PB_T2_NS;
+        if (fill >= PB_T2_NS) pb_mbar_wait(PB_T2_BAR(PB_T2_B_WEMPTY + s), (uint32_t)((fill / PB_T2_NS - 1) & 1));
+        pb_t2_expect(PB_T2_BAR(PB_T2_B_WFULL + s), bytes);
+        return ring + (uint32_t)s * wstage;
+      };
+      // G1: X chunk kc (3 terms) -> activation area; W1aug rows of chunk kc, one term per stage
+      for (int kc = 0; kc < ncbx; ++kc) {
+        const int rows = (Kx - 64 * kc) < 64 ? (Kx - 64 * kc) : 64;
+        if (ause > 0) pb_mbar_wait(PB_T2_BAR(PB_T2_B_AEMPTY), (uint32_t)((ause - 1) & 1));
+        pb_t2_expect(PB_T2_BAR(PB_T2_B_AXFULL), 3u * PB_T2_TILE);
+        for (int t = 0; t < 3; ++t)
+          pb_t2_bulk(acta + (uint32_t)t * PB_T2_TILE, tc.img + ((size_t)t * ncbx + kc) * PB_T2_TILE, PB_T2_TILE,
+                     PB_T2_BAR(PB_T2_B_AXFULL));
+        ++ause;
+        for (int t = 0; t < 3; ++t) {
+          const uint32_t dst = stage_begin((uint32_t)(nch * rows * 128));
+          const int s = fill % PB_T2_NS;
+          for (int cb = 0; cb < nch; ++cb)
+            pb_t2_bulk(dst + (uint32_t)cb * 8192u,
+                       tc.img + pl.t2_img_w1 + ((size_t)(t * nch + cb) * Kx + 64 * kc) * 128, (uint32_t)(rows * 128),
+                       PB_T2_BAR(PB_T2_B_WFULL + s));
+          ++fill;
+        }
+      }
+      // G2: W2 rows of chunk ic
+      for (int ic = 0; ic < nch; ++ic) {
+        const int rows = (Hp - 64 * ic) < 64 ? (Hp - 64 * ic) : 64;
+        for (int t = 0; t < 3; ++t) {
+          const uint32_t dst = stage_begin((uint32_t)(nch * rows * 128));
+          const int s = fill % PB_T2_NS;
+          for (int cb = 0; cb < nch; ++cb)
+            pb_t2_bulk(dst + (uint32_t)cb * 8192u,
+                       tc.img + pl.t2_img_w2 + ((size_t)(t * nch + cb) * Hp + 64 * ic) * 128, (uint32_t)(rows * 128),
+                       PB_T2_BAR(PB_T2_B_WFULL + s));
+          ++fill;
+        }
+      }
+      // G5: W2s column block kc (all Hp rows)
+      for (int kc = 0; kc < nch; ++kc)
+        for (int t = 0; t < 3; ++t) {
+          const uint32_t bytes = (uint32_t)(Hp * 128);
+          const uint32_t dst = stage_begin(bytes);
+          const int s = fill % PB_T2_NS;
+          const uint8_t* src = tc.img + pl.t2_img_w2s + ((size_t)(t * nch + kc) * Hp) * 128;
+          for (uint32_t o = 0; o < bytes; o += 16384u)
+            pb_t2_bulk(dst + o, src + o, bytes - o < 16384u ? bytes - o : 16384u, PB_T2_BAR(PB_T2_B_WFULL + s));
+          ++fill;
+        }
+      // G6: the whole X image into the ring area once every stage has been consumed
+      for (int j = fill > PB_T2_NS ? fill - PB_T2_NS : 0; j < fill; ++j)
+        pb_mbar_wait(PB_T2_BAR(PB_T2_B_WEMPTY + j % PB_T2_NS), (uint32_t)((j / PB_T2_NS) & 1));
+      const uint32_t xbytes = 3u * (uint32_t)ncbx * PB_T2_TILE;
+      pb_t2_expect(PB_T2_BAR(PB_T2_B_XFULL), xbytes);
+      for (uint32_t o = 0; o < xbytes; o += PB_T2_TILE)
+        pb_t2_bulk(ring + o, tc.img + o, PB_T2_TILE, PB_T2_BAR(PB_T2_B_XFULL));
+    }
+    __syncwarp();
+  } else if (warp_u == 9) {
+    // =============================== MMA issue ===============================
+    int fill = 0, ause = 0;
+    uint32_t axph = 0u, afph = 0u;
+    auto stage_wait = [&]() -> uint32_t {
+      const int s = fill % PB_T2_NS;
+      pb_mbar_wait(PB_T2_BAR(PB_T2_B_WFULL + s), (uint32_t)((fill / PB_T2_NS) & 1));
+      pb_tc_fence_after();
+      return ring + (uint32_t)s * wstage;
+    };
+    auto stage_done = [&]() {
+      if (pb_elect_one()) pb_umma_commit(PB_T2_BAR(PB_T2_B_WEMPTY + fill % PB_T2_NS));
+      __syncwarp();
+      ++fill;
+    };
+    auto commit = [&](int b) {
+      if (pb_elect_one()) pb_umma_commit(PB_T2_BAR(b));
+      __syncwarp();
+    };
+    // forward GEMM over 64-wide K chunks: A chunk (3 terms, K-major) in the activation area, B row chunk per stage
+    auto fwd = [&](uint32_t dcol, int nchunks, int ktotal, bool a_from_tma) {
+      const uint32_t idesc = pb_t2_idesc(128, Hp, 0, 1);
+      for (int c = 0; c < nchunks; ++c) {
+        const int ksteps = ((ktotal - 64 * c) < 64 ? (ktotal - 64 * c) : 64) >> 4;
+        if (a_from_tma) {
+          pb_mbar_wait(PB_T2_BAR(PB_T2_B_AXFULL), axph);
+          axph ^= 1u;
+        } else {
+          pb_mbar_wait(PB_T2_BAR(PB_T2_B_AFULL), afph);
+          afph ^= 1u;
+        }
+        pb_tc_fence_after();
+        for (int wt = 0; wt < 3; ++wt) {
+          const uint32_t st = stage_wait();
+          if (pb_elect_one()) {
+            for (int xa = 0; xa + wt < 3; ++xa)
+              for (int ks = 0; ks < ksteps; ++ks)
+                pb_t2_mma(dcol, pb_t2_desc(acta + (uint32_t)xa * PB_T2_TILE + (uint32_t)ks * 32u, 16u, 1024u),
+                          pb_t2_desc(st + (uint32_t)ks * 2048u, 8192u, 1024u), idesc, (c | wt | xa | ks) ? 1u : 0u);
+          }
+          __syncwarp();
+          stage_done();
+        }
+        commit(PB_T2_B_AEMPTY);
+        ++ause;
+      }
+      commit(PB_T2_B_ACC);
+    };
+    fwd(S0, ncbx, Kx, true);    // G1: Z1
+    fwd(S1, nch, Hp, false);    // G2: Z2
+    // G4: D2 chunks.  A = M2^T tile (MN-major, 128 n), B = Y chunk (MN-major), K = 128 batch rows
+    for (int ic = 0; ic < nchy; ++ic) {
+      const int ncols = (Hy - 64 * ic) < 64 ? (Hy - 64 * ic) : 64;
+      const int slot = ic & 1;
+      pb_mbar_wait(PB_T2_BAR(PB_T2_B_AFULL), afph);
+      afph ^= 1u;
+      if (ic >= 2) pb_mbar_wait(PB_T2_BAR(PB_T2_B_D2EMPTY + slot), (uint32_t)(((ic >> 1) - 1) & 1));
+      pb_tc_fence_after();
+      if (pb_elect_one()) {
+        const uint32_t idesc = pb_t2_idesc(128, ncols, 1, 1);
+        for (int mt = 0; mt < nmt; ++mt)
+          for (int t = 0; t < 3; ++t)
+            for (int ks = 0; ks < 8; ++ks)
+              pb_t2_mma(S1 + (uint32_t)slot * 128u + (uint32_t)mt * 64u,
+                        pb_t2_desc(m2 + (uint32_t)(2 * mt) * PB_T2_TILE + (uint32_t)ks * 2048u,
+                                   nch > 2 * mt + 1 ? PB_T2_TILE : 0u, 1024u),
+                        pb_t2_desc(acta + (uint32_t)t * PB_T2_TILE + (uint32_t)ks * 2048u, 0u, 1024u), idesc,
+                        (t | ks) ? 1u : 0u);
+      }
+      __syncwarp();
+      commit(PB_T2_B_AEMPTY);
+      ++ause;
+      commit(PB_T2_B_D2FULL + slot);
+    }
+    // G5: E = M2 W2s^T.  A = M2 column block kc (K-major), B = W2s column block kc (K-major, Hp rows)
+    {
+      const uint32_t idesc = pb_t2_idesc(128, Hp, 0, 0);
+      for (int kc = 0; kc < nch; ++kc) {
+        const int ksteps = ((Hp - 64 * kc) < 64 ? (Hp - 64 * kc) : 64) >> 4;
+        for (int t = 0; t < 3; ++t) {
+          const uint32_t st = stage_wait();
+          if (pb_elect_one()) {
+            for (int ks = 0; ks < ksteps; ++ks)
+              pb_t2_mma(S0, pb_t2_desc(m2 + (uint32_t)kc * PB_T2_TILE + (uint32_t)ks * 32u, 16u, 1024u),
+                        pb_t2_desc(st + (uint32_t)ks * 32u, 16u, 1024u), idesc, (kc | t | ks) ? 1u : 0u);
+          }
+          __syncwarp();
+          stage_done();
+        }
+      }
+      commit(PB_T2_B_ACC);
+    }
+    // G6: D1 chunks.  A = X^T (MN-major, lanes = input index k), B = dZ1 chunk (MN-major), K = 128 batch rows
+    pb_mbar_wait(PB_T2_BAR(PB_T2_B_XFULL), 0u);
+    pb_tc_fence_after();
+    for (int ic = 0; ic < nch; ++ic) {
+      const int ncols = (Hp - 64 * ic) < 64 ? (Hp - 64 * ic) : 64;
+      pb_mbar_wait(PB_T2_BAR(PB_T2_B_AFULL), afph);
+      afph ^= 1u;
+      pb_tc_fence_after();
+      if (pb_elect_one()) {
+        const uint32_t idesc = pb_t2_idesc(128, ncols, 1, 1);
+        for (int zt = 0; zt < 3; ++zt)
+          for (int xa = 0; xa + zt < 3; ++xa)
+            for (int ks = 0; ks < 8; ++ks)
+              pb_t2_mma(S0 + (uint32_t)ic * 64u,
+                        pb_t2_desc(ring + (uint32_t)(xa * ncbx) * PB_T2_TILE + (uint32_t)ks * 2048u,
+                                   ncbx > 1 ? PB_T2_TILE : 0u, 1024u),
+                        pb_t2_desc(acta + (uint32_t)zt * PB_T2_TILE + (uint32_t)ks * 2048u, 0u, 1024u), idesc,
+                        (zt | xa | ks) ? 1u : 0u);
+      }
+      __syncwarp();
+      commit(PB_T2_B_AEMPTY);
+      ++ause;
+    }
+    commit(PB_T2_B_ACC);
+  } else {
+    // =============================== workers ===============================
+    const int q = warp & 3, g = warp >> 2;
+    const int b = 32 * q + lane;                       // batch row == TMEM lane in the forward accumulators
+    const uint32_t lane_off = (uint32_t)(32 * q) << 16;
+    const uint32_t rowaddr = (uint32_t)b * 128u;
+    const uint32_t bx = (uint32_t)(b & 7);
+    int ause = ncbx;                                   // activation-area uses before the first worker chunk
+    uint32_t accph = 0u;
+    uint32_t m1[4] = {0u, 0u, 0u, 0u};                 // relu mask of layer 1: this thread's 32 columns of each chunk
+    // three packed terms of 32 values -> this thread's 4 chunks (16 B each) of the activation rows
+    auto store_chunk = [&](const float* v) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        uint32_t t1[4], t2[4], t3[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pb_t2_split3(v[8 * u + 2 * j], v[8 * u + 2 * j + 1], t1[j], t2[j], t3[j]);
+        const uint32_t a = acta + rowaddr + ((((uint32_t)(4 * g + u)) ^ bx) << 4);
+        pb_t2_st4(a, t1[0], t1[1], t1[2], t1[3]);
+        pb_t2_st4(a + PB_T2_TILE, t2[0], t2[1], t2[2], t2[3]);
+        pb_t2_st4(a + 2u * PB_T2_TILE, t3[0], t3[1], t3[2], t3[3]);
+      }
+    };
+    auto chunk_begin = [&]() {  // the previous user of the activation area has been consumed by the tensor core
+      pb_mbar_wait(PB_T2_BAR(PB_T2_B_AEMPTY), (uint32_t)((ause - 1) & 1));
+    };
+    auto chunk_end = [&]() {
+      pb_fence_async_smem();
+      pb_tc_fence_before();
+      pb_t2_arrive(PB_T2_BAR(PB_T2_B_AFULL));
+      ++ause;
+    };
+    auto acc_wait = [&]() {
+      pb_mbar_wait(PB_T2_BAR(PB_T2_B_ACC), accph);
+      accph ^= 1u;
+      pb_tc_fence_after();
+    };
+
+    // ---- G2: H1 chunks = relu(Z1) ----
+    acc_wait();  // Z1
+    PB_MARK(2)
+    for (int ic = 0; ic < nch; ++ic) {
+      uint32_t z[32];
+      float v[32];
+      pb_tmem_ld32(S0 + lane_off + (uint32_t)(64 * ic + 32 * g), z);
+      pb_tmem_wait_ld();
+      uint32_t mb = 0u;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float zz = __uint_as_float(z[j]);
+        mb |= zz > 0.f ? (1u << j) : 0u;
+        v[j] = fmaxf(zz, 0.f);
+      }
+      if (ic == 0) m1[0] = mb; else if (ic == 1) m1[1] = mb; else if (ic == 2) m1[2] = mb; else m1[3] = mb;
+      chunk_begin();
+      store_chunk(v);
+      chunk_end();
+    }
+    PB_MARK(3)
+    // ---- G3: output, residual, layer-2 mask ----
+    acc_wait();  // Z2
+    PB_MARK(4)
+    float fpart = 0.f;
+    for (int ic = 0; ic < nch; ++ic) {
+      uint32_t z[32];
+      pb_tmem_ld32(S1 + lane_off + (uint32_t)(64 * ic + 32 * g), z);
+      pb_tmem_wait_ld();
+      const int c0 = 64 * ic + 32 * g;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        uint32_t mk[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = 8 * u + 2 * j;
+          const float h0 = __uint_as_float(z[c]) + b2v[c0 + c], h1 = __uint_as_float(z[c + 1]) + b2v[c0 + c + 1];
+          fpart = fmaf(fmaxf(h0, 0.f), w3v[c0 + c], fpart);
+          fpart = fmaf(fmaxf(h1, 0.f), w3v[c0 + c + 1], fpart);
+          mk[j] = (h0 > 0.f ? 0x3F80u : 0u) | (h1 > 0.f ? 0x3F800000u : 0u);
+        }
+        pb_t2_st4(m2 + (uint32_t)ic * PB_T2_TILE + rowaddr + ((((uint32_t)(4 * g + u)) ^ bx) << 4), mk[0], mk[1], mk[2],
+                  mk[3]);
+      }
+    }
+    pb_tc_fence_before();
+    fp[g * 128 + b] = fpart;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    float r;
+    {
+      const float f = (fp[b] + fp[128 + b]) + sm[pl.off_t2_vec + 1408];
+      const bool valid = b < nrows;
+      const float res = yv[b] - f;
+      r = valid ? res * scale : 0.f;
+      if (g == 0) llbuf[b] = valid ? -0.5f * res * res * pl.inv_s2 : 0.f;
+    }
+    PB_MARK(5)
+    // ---- G4: Y chunks = r * [relu(Z1) | 1 | 0..], D2 drains one chunk behind ----
+    const bool two_tiles = nmt > 1;
+    const int n_own = two_tiles ? 128 * g + b : b;  // output unit (TMEM lane of D2) this thread drains
+    const float w3n = n_own < H ? w3v[n_own] : 0.f;
+    float dw3 = 0.f;
+    auto drain_d2 = [&](int ic) {
+      const int slot = ic & 1;
+      const int ncols = (Hy - 64 * ic) < 64 ? (Hy - 64 * ic) : 64;
+      pb_mbar_wait(PB_T2_BAR(PB_T2_B_D2FULL + slot), (uint32_t)((ic >> 1) & 1));
+      pb_tc_fence_after();
+      // two tiles: group g drains tile g, all columns; one tile: group g drains columns [32 g, 32 g + 32)
+      const int cbeg = two_tiles ? 0 : 32 * g;
+      const int cend = two_tiles ? ncols : (ncols < 32 * g + 32 ? ncols : 32 * g + 32);
+      for (int c0 = cbeg; c0 < cend; c0 += 16) {
+        uint32_t dv[16];
+        pb_tmem_ld16(S1 + lane_off + (uint32_t)(slot * 128 + (two_tiles ? 64 * g : 0) + c0), dv);
+        pb_tmem_wait_ld();
+        if (n_own < H) {
+          // i = input index of W2 (i == H: the bias row); all loads of the group before the first store
+          const int sbase = L1.soff + (64 * ic + c0) * L1.wp + n_own;
+          float thv[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) thv[j] = 64 * ic + c0 + j <= H ? TH[sbase + j * L1.wp] : 0.f;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (64 * ic + c0 + j <= H) {
+              const float dd = __uint_as_float(dv[j]);
+              G[sbase + j * L1.wp] = w3n * dd;
+              dw3 = fmaf(thv[j], dd, dw3);
+            }
+          }
+        }
+      }
+      pb_tc_fence_before();
+      pb_t2_arrive(PB_T2_BAR(PB_T2_B_D2EMPTY + slot));
+    };
+    for (int ic = 0; ic < nchy; ++ic) {
+      float v[32];
+      const int c0 = 64 * ic + 32 * g;
+      if (c0 < Hp) {
+        uint32_t z[32];
+        pb_tmem_ld32(S0 + lane_off + (uint32_t)c0, z);
+        pb_tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = r * fmaxf(__uint_as_float(z[j]), 0.f);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
+      if (H >= c0 && H < c0 + 32) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = (c0 + j == H) ? r : v[j];
+      }
+      chunk_begin();
+      store_chunk(v);
+      chunk_end();
+      if (ic >= 1) drain_d2(ic - 1);
+    }
+    drain_d2(nchy - 1);
+    // output-layer gradient: dw3[n] (one tile: the two column halves are summed), db3 = sum_b r_b
+    dw3p[g * 256 + n_own % 256] = dw3;
+    fp[g * 128 + b] = r;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (two_tiles) {
+      if (n_own < H) G[L2.soff + n_own * L2.wp] = dw3;
+    } else if (g == 0 && n_own < H) {
+      G[L2.soff + n_own * L2.wp] = dw3p[n_own] + dw3p[256 + n_own];
+    }
+    if (warp == 0) {
+      float a = fp[lane] + fp[32 + lane] + fp[64 + lane] + fp[96 + lane];
+      a = pb_warp_sum(a);
+      if (lane == 0) G[L2.soff + H * L2.wp] = a;
+    }
+    PB_MARK(6)
+    // ---- G6: dZ1 chunks = r * E * [Z1 > 0] ----
+    acc_wait();  // E
+    PB_MARK(7)
+    for (int ic = 0; ic < nch; ++ic) {
+      uint32_t z[32];
+      float v[32];
+      pb_tmem_ld32(S0 + lane_off + (uint32_t)(64 * ic + 32 * g), z);
+      pb_tmem_wait_ld();
+      const uint32_t mb = ic == 0 ? m1[0] : ic == 1 ? m1[1] : ic == 2 ? m1[2] : m1[3];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = (mb >> j) & 1u ? r * __uint_as_float(z[j]) : 0.f;
+      chunk_begin();
+      store_chunk(v);
+      chunk_end();
+    }
+    PB_MARK(8)
+    // ---- G7: D1 drain: TMEM lane = input index k (k == d: bias row), group g takes its half of every chunk ----
+    acc_wait();  // D1
+    PB_MARK(9)
+    {
+      const int k = b;
+      for (int ic = 0; ic < nch; ++ic) {
+        const int ncols = (Hp - 64 * ic) < 64 ? (Hp - 64 * ic) : 64;
+        for (int c0 = 32 * g; c0 < ncols && c0 < 32 * g + 32; c0 += 16) {
+          uint32_t dv[16];
+          pb_tmem_ld16(S0 + lane_off + (uint32_t)(64 * ic + c0), dv);
+          pb_tmem_wait_ld();
+          if (k <= pl.d) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int i = 64 * ic + c0 + j;
+              if (i < H) G[L0.soff + k * L0.wp + i] = __uint_as_float(dv[j]);
+            }
+          }
+        }
+      }
+    }
+    pb_tc_fence_before();
+  }
+#undef PB_T2_BAR
+  pb_tc_fence_before();
+  PB_TAG(11)
+  PB_ENDPHASE_RAW
+  pb_tc_fence_after();
+  PB_TAG(0)
+}
+#endif

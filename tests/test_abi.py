@@ -45,7 +45,10 @@ def test_host_side_calls_without_gpu(cuda_lib_path):
     assert out[0] % 32 == 0 and out[1] % 32 == 0 and out[2] <= 227 * 1024
     big = _lib.make_spec((90, 256, 256, 1), 0, 0.1)  # state goes to a global workspace, activations stay on chip
     assert lib.pbnn_plan_query(big, 128, 2, out) == 0
-    assert lib.pbnn_workspace_bytes(big, _lib.OP_SGLD, 128, 10) == 10 * 2 * out[3] * 4 > 0
+    # (relu, B <= 128: the two-hidden-layer tcgen05 engine adds one operand-image block per CTA; tanh: state only)
+    assert lib.pbnn_workspace_bytes(big, _lib.OP_SGLD, 128, 10) > 10 * 2 * out[3] * 4 > 0
+    big_tanh = _lib.make_spec((90, 256, 256, 1), 1, 0.1)
+    assert lib.pbnn_workspace_bytes(big_tanh, _lib.OP_SGLD, 128, 10) == 10 * 2 * out[3] * 4
     # resident plans need no workspace; the tcgen05 HMC plan asks for hand-over buffers once chains outnumber the SMs
     assert lib.pbnn_workspace_bytes(spec, _lib.OP_HMC, 506, 100) == 0
     assert lib.pbnn_workspace_bytes(spec, _lib.OP_HMC, 506, 256) == 256 * (751 + 4) * 4 + 16
@@ -56,8 +59,12 @@ def test_host_side_calls_without_gpu(cuda_lib_path):
     assert lib.pbnn_plan_engine(spec, _lib.OP_HMC, 4097, 4) != _lib.ENGINE_TCGEN05     # larger data sets: FP32 engines
     assert lib.pbnn_plan_engine(_lib.make_spec((13, 65, 1), 0, 0.1), _lib.OP_HMC, 506, 4) != _lib.ENGINE_TCGEN05
     assert lib.pbnn_plan_engine(_lib.make_spec((16, 50, 1), 0, 0.1), _lib.OP_HMC, 506, 4) != _lib.ENGINE_TCGEN05
-    assert lib.pbnn_plan_engine(big, _lib.OP_SGLD, 128, 10) == _lib.ENGINE_TILED_GLOBAL_STATE
-    assert lib.pbnn_plan_engine(_lib.make_spec((9, 100, 100, 1), 0, 0.1), _lib.OP_SGLD, 128, 1024) == _lib.ENGINE_TILED
+    assert lib.pbnn_plan_engine(big, _lib.OP_SGLD, 128, 10) == _lib.ENGINE_TCGEN05_MLP2
+    assert lib.pbnn_plan_engine(big_tanh, _lib.OP_SGLD, 128, 10) == _lib.ENGINE_TILED_GLOBAL_STATE
+    assert lib.pbnn_plan_engine(big, _lib.OP_SGLD, 129, 10) == _lib.ENGINE_TILED_GLOBAL_STATE  # more than one 128-row tile
+    assert lib.pbnn_plan_engine(_lib.make_spec((9, 100, 100, 1), 0, 0.1), _lib.OP_SGLD, 128, 1024) == _lib.ENGINE_TCGEN05_MLP2
+    assert lib.pbnn_plan_engine(_lib.make_spec((9, 100, 100, 1), 1, 0.1), _lib.OP_SGLD, 128, 1024) == _lib.ENGINE_TILED
+    assert lib.pbnn_plan_engine(_lib.make_spec((9, 100, 90, 1), 0, 0.1), _lib.OP_SGLD, 128, 1024) == _lib.ENGINE_TILED
     assert lib.pbnn_plan_engine(_lib.make_spec((13, 50, 1), 1, 0.1), _lib.OP_HMC, 506, 256) == _lib.ENGINE_FUSED_H1  # tanh
     huge = _lib.make_spec((3000, 4000, 1), 0, 0.1)
     assert lib.pbnn_plan_query(huge, 128, 2, out) == -2
