@@ -124,7 +124,7 @@ static inline void pb_plan_dw(PbPlan* pl, int nw, int bt, int kcap) {
 #define PB_T2_NT 320       // 8 worker warps + 1 TMA warp + 1 MMA-issue warp
 #define PB_T2_NS 3         // weight-ring stages
 #define PB_T2_TILE 16384   // bytes of one [128 rows][64 bf16] operand tile (SWIZZLE_128B)
-#define PB_T2_VEC_FLOATS 1536
+#define PB_T2_VEC_FLOATS 1856
 static inline int pb_r16(int x) { return (x + 15) & ~15; }
 
 // two-hidden-layer tcgen05 plan: shared memory = scratch | small vectors | mbarriers | aligned operand area
@@ -144,6 +144,8 @@ static inline void pb_layout_tc2(PbPlan* pl, const pbnn_mlp_spec* sp, int rows) 
   pl->t2_wstage = st_a > st_b ? st_a : st_b;
   const int xi = 3 * pl->t2_ncbx * PB_T2_TILE;
   pl->t2_ring = PB_T2_NS * pl->t2_wstage > xi ? PB_T2_NS * pl->t2_wstage : xi;
+  const int d1 = (((pl->d + 1) * (pl->t2_Hp + 4) * 4) + 1023) & ~1023;  // first-layer gradient dump [d + 1][Hp + 4]
+  if (d1 > pl->t2_ring) pl->t2_ring = d1;
   pl->BT = 128;
   pl->ap = 132;
   pl->h1 = 0;
@@ -174,8 +176,8 @@ static inline void pb_layout_tc2(PbPlan* pl, const pbnn_mlp_spec* sp, int rows) 
   pl->smem_floats = off;
   pl->t2_img_w1 = xi;
   pl->t2_img_w2 = pl->t2_img_w1 + 3 * pl->t2_nch * pl->t2_Kx * 128;
-  pl->t2_img_w2s = pl->t2_img_w2 + 3 * pl->t2_nch * pl->t2_Hp * 128;
-  pl->t2_img_bytes = pl->t2_img_w2s + 3 * pl->t2_nch * pl->t2_Hp * 128;
+  pl->t2_img_w2s = 0;
+  pl->t2_img_bytes = pl->t2_img_w2 + 3 * pl->t2_nch * pl->t2_Hp * 128;
 }
 
 // tcgen05 operand geometry (floats).  K-major, no swizzle: element (row x, k) at (k/4)*LBO + x*16 B + (k%4)*4 B.

@@ -982,14 +982,19 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
     pb_load_resident(pl, sm, a.X, a.y, sidx, B, nt);
   };
   auto grad = [&](bool tile_loaded_) {
-#if !defined(PB_EMU)
-    if constexpr (ENG == 2) {
-      pb_grad_tc2(pl, sm, TH, G, B, a.scale, nt, *static_cast<PbTc2*>(ctx));
-      return;
-    }
-#endif
     pb_grad<ACT, (ENG == 2 ? 0 : ENG)>(pl, sm, TH, G, a.X, a.y, sidx, B, a.scale, tile_loaded_, nt);
   };
+#if !defined(PB_EMU)
+  // ENG 2: gradient + parameter update in one pass (pbnn_tc2.cuh); the functors own the sampler arithmetic
+  auto t2grad = [&](PbKey nkey_, bool noise_, auto pf_, auto uf_) {
+    pb_grad_tc2(pl, sm, TH, B, a.scale, nt, *static_cast<PbTc2*>(ctx), nkey_, noise_, pf_, uf_);
+  };
+  auto pf_theta = [&](int si, int fi) {
+    PbPre v;
+    v.a = TH[si];
+    return v;
+  };
+#endif
 
   pb_init_acts(pl, sm, nt);
   pb_load_state(pl, TH, a.theta + cP, nt);
@@ -1010,6 +1015,9 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
     scu[2] = 0u;
   }
   PB_ENDPHASE
+#if !defined(PB_EMU)
+  if constexpr (ENG == 2) pb_tc2_restage(pl, sm, *static_cast<PbTc2*>(ctx), TH, nt);  // operand images of theta0
+#endif
 
   const bool res = pl.res_rows > 0;
   const bool single_tile = B <= pl.BT;
@@ -1022,9 +1030,17 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
   if (ALGO == PB_ALGO_GRAD) {
     pb_copy_indices(pl, sm, cidx, B, nt);
     if (res) load_res();
-    grad(false);
+#if !defined(PB_EMU)
+    if constexpr (ENG == 2) {
+      t2grad(ck, false, pf_theta, [&](int si, int fi, const PbPre& v, float gll, float z) {
+        a.aux1[cP + fi] = gll - v.a * pl.inv_pv;
+        return v.a;
+      });
+    } else
+#endif
+      grad(false);
     PB_PHASE
-    pb_for_each_param(pl, tid, nt, [&](int si, int fi) { a.aux1[cP + fi] = G[si] - TH[si] * pl.inv_pv; });
+    if (ENG != 2) pb_for_each_param(pl, tid, nt, [&](int si, int fi) { a.aux1[cP + fi] = G[si] - TH[si] * pl.inv_pv; });
     float* scr = pb_scr(pl, sm);
     const float* llbuf = pb_llbuf(pl, sm);
     float v = 0.f;
@@ -1048,14 +1064,26 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
       pb_gen_indices(pl, sm, B, a.N, a.randint_mult, nt);
     }
     if (res) load_res();
-    grad(false);
-    PB_PHASE
-    for (int i = tid; i < pl.Ps; i += nt) {
-      const float g = G[i] - TH[i] * pl.inv_pv;
-      G[i] = g;
-      A1[i] = g * g;
+#if !defined(PB_EMU)
+    if constexpr (ENG == 2) {
+      t2grad(ck, false, pf_theta, [&](int si, int fi, const PbPre& v, float gll, float z) {
+        const float g = gll - v.a * pl.inv_pv;
+        G[si] = g;
+        A1[si] = g * g;
+        return v.a;
+      });
+    } else
+#endif
+    {
+      grad(false);
+      PB_PHASE
+      for (int i = tid; i < pl.Ps; i += nt) {
+        const float g = G[i] - TH[i] * pl.inv_pv;
+        G[i] = g;
+        A1[i] = g * g;
+      }
+      PB_ENDPHASE
     }
-    PB_ENDPHASE
   }
 
   // the minibatch the traced loop re-uses (quirk Q1), or the state before the first per-step draw
@@ -1094,7 +1122,30 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
       if (res) load_res();
     }
 
-    if (ALGO == PB_ALGO_SGLD) {
+    if (ALGO == PB_ALGO_SGLD && ENG == 2) {
+#if !defined(PB_EMU)
+      if constexpr (ENG == 2) {
+        const float ns = sqrtf(2.0f * a.temperature * eps);
+        const float* cvc = a.cv_center ? a.cv_center + cP : nullptr;
+        const float* cve = a.cv_center ? a.cv_center_est + cP : nullptr;
+        t2grad(
+            kt, true,
+            [&](int si, int fi) {
+              PbPre v;
+              v.a = TH[si];
+              v.c = cvc ? cvc[fi] : 0.f;
+              v.d = cvc ? cve[fi] : 0.f;
+              return v;
+            },
+            [&](int si, int fi, const PbPre& v, float gll, float z) {
+              const float th = v.a;
+              float g = gll - th * pl.inv_pv;
+              if (cvc) g = (v.c + g) - v.d;
+              return th + eps * g + ns * z;
+            });
+      }
+#endif
+    } else if (ALGO == PB_ALGO_SGLD) {
       grad(tile_loaded);
       const float ns = sqrtf(2.0f * a.temperature * eps);
       const float* cvc = a.cv_center ? a.cv_center + cP : nullptr;
@@ -1117,6 +1168,59 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
             TH[si] = th + eps * g + ns * z;
           });
       PB_ENDPHASE
+    } else if (ALGO == PB_ALGO_PSGLD && ENG == 2) {
+#if !defined(PB_EMU)
+      if constexpr (ENG == 2) {
+        // fused order: [theta update of step 0 by the generic pass] then per step: trace of theta_t, gradient at
+        // theta_t with (g, V) update AND the theta update of step t + 1 in the drains (diffusions.py:42-59 unrolled)
+        if (t == 0) {
+          PB_PHASE
+          pb_for_each_param_normal(
+              pl, tid, nt, kt,
+              [&](int si, int fi) {
+                PbPre v;
+                v.a = A1[si];
+                v.b = TH[si];
+                v.c = G[si];
+                return v;
+              },
+              [&](int si, int fi, float z, const PbPre& v) {
+                const float pre = 1.0f / (sqrtf(v.a) + 1e-6f);
+                TH[si] = v.b + eps * pre * v.c + sqrtf(2.0f * pre * eps) * z;
+              });
+          PB_ENDPHASE
+          pb_tc2_restage(pl, sm, *static_cast<PbTc2*>(ctx), TH, nt);
+        }
+        if (a.trace && t >= a.burnin && ((t - a.burnin) % a.thin) == 0) {
+          float* dst = a.trace + ((size_t)c * a.T_out + (size_t)((t - a.burnin) / a.thin)) * P;
+          PB_PHASE
+          pb_for_each_param(pl, tid, nt, [&](int si, int fi) { dst[fi] = TH[si]; });
+          PB_ENDPHASE
+        }
+        const bool more = t + 1 < a.T;
+        const PbKey kn = a.direct_key ? ck : pb_split_at(ck, (uint32_t)(tg + 1));
+        const float epsn =
+            a.step_sizes ? a.step_sizes[t + 1 < a.n_step_sizes ? t + 1 : a.n_step_sizes - 1] : a.const_step;
+        t2grad(
+            kn, more,
+            [&](int si, int fi) {
+              PbPre v;
+              v.a = TH[si];
+              v.b = A1[si];
+              return v;
+            },
+            [&](int si, int fi, const PbPre& v, float gll, float z) {
+              const float g = gll - v.a * pl.inv_pv;
+              const float V = a.alpha * v.b + (1.0f - a.alpha) * (g * g);
+              G[si] = g;
+              A1[si] = V;
+              if (!more) return v.a;
+              const float pre = 1.0f / (sqrtf(V) + 1e-6f);
+              return v.a + epsn * pre * g + sqrtf(2.0f * pre * epsn) * z;
+            });
+        continue;  // (the trace of this step has been written above)
+      }
+#endif
     } else if (ALGO == PB_ALGO_PSGLD) {
       PB_PHASE
       pb_for_each_param_normal(
@@ -1162,6 +1266,28 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
       const float fric = 1.0f - a.alpha;
       for (int l = 0; l < a.L; ++l) {
         const PbKey kl = pb_split_at(kt, (uint32_t)l);  // split(keys[t], L)[l]
+#if !defined(PB_EMU)
+        if constexpr (ENG == 2) {
+          t2grad(
+              kl, true,
+              [&](int si, int fi) {
+                PbPre v;
+                v.a = TH[si];
+                v.b = A1[si];
+                v.d = cvc ? cvc[fi] : 0.f;
+                v.e = cvc ? cve[fi] : 0.f;
+                return v;
+              },
+              [&](int si, int fi, const PbPre& v, float gll, float z) {
+                const float th = v.a, p = v.b;
+                float g = gll - th * pl.inv_pv;
+                if (cvc) g = (v.d + g) - v.e;
+                A1[si] = fric * p + eps * g + ns * z;
+                return th + p;
+              });
+          continue;
+        }
+#endif
         grad(tile_loaded);
         PB_PHASE
         pb_for_each_param_normal(
@@ -1184,6 +1310,31 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
             });
         PB_ENDPHASE
       }
+    } else if (ALGO == PB_ALGO_ADAM && ENG == 2) {
+#if !defined(PB_EMU)
+      if constexpr (ENG == 2) {
+        const float cnt = (float)(a.count0 + t + 1);
+        const float ibc1 = 1.0f / (1.0f - powf(a.b1, cnt)), ibc2 = 1.0f / (1.0f - powf(a.b2, cnt));
+        t2grad(
+            ck, false,
+            [&](int si, int fi) {
+              PbPre p;
+              p.a = TH[si];
+              p.c = A1[si];
+              p.d = A2[si];
+              return p;
+            },
+            [&](int si, int fi, const PbPre& p, float gll, float z) {
+              const float th = p.a;
+              const float g = -(gll - th * pl.inv_pv);  // gradient of the loss -logposterior
+              const float m = (1.0f - a.b1) * g + a.b1 * p.c;
+              const float v = (1.0f - a.b2) * (g * g) + a.b2 * p.d;
+              A1[si] = m;
+              A2[si] = v;
+              return th + (-a.lr) * __fdividef(m * ibc1, sqrtf(v * ibc2) + a.eps);
+            });
+      }
+#endif
     } else if (ALGO == PB_ALGO_ADAM) {
       grad(false);
       const float cnt = (float)(a.count0 + t + 1);

@@ -78,33 +78,50 @@ PB_DEV float pb_u32_as_float(uint32_t u) {
 PB_DEV float pb_bits_to_uniform(uint32_t bits) { return pb_u32_as_float((bits >> 9) | 0x3F800000u) - 1.0f; }
 
 // XLA ErfInv for float32 (Giles 2010 single-precision polynomial)
+PB_DEV float pb_erfinv_poly_bulk(float w) {  // w < 5 (after w -= 2.5)
+  float p = 2.81022636e-08f;
+  p = 3.43273939e-07f + p * w;
+  p = -3.5233877e-06f + p * w;
+  p = -4.39150654e-06f + p * w;
+  p = 0.00021858087f + p * w;
+  p = -0.00125372503f + p * w;
+  p = -0.00417768164f + p * w;
+  p = 0.246640727f + p * w;
+  p = 1.50140941f + p * w;
+  return p;
+}
+PB_DEV float pb_erfinv_poly_tail(float w) {  // w >= 5 (after w = sqrt(w) - 3)
+  float p = -0.000200214257f;
+  p = 0.000100950558f + p * w;
+  p = 0.00134934322f + p * w;
+  p = -0.00367342844f + p * w;
+  p = 0.00573950773f + p * w;
+  p = -0.0076224613f + p * w;
+  p = 0.00943887047f + p * w;
+  p = 1.00167406f + p * w;
+  p = 2.83297682f + p * w;
+  return p;
+}
+
 PB_DEV float pb_erfinv(float x) {
+#if defined(__CUDA_ARCH__)
+  // Branch-free (the chains of several parameters are interleaved by the compiler; a branch would serialise them).
+  // w = -log1p(-x^2) as -log(1 + t), t = -(x*x): 1 + t is exact for |t| >= 0.5 and off by <= 6e-8 (absolute) below, and
+  // lg2.approx (MUFU.LG2) * ln 2 is within 2^-21.4 absolute on [0.5, 2] / 3 ulp elsewhere; the result enters z only through
+  // x * p(w) with |p'| <= 0.25, so z moves by < 3e-7 in the bulk -- inside the 1e-6 contract on normals (tests).  The
+  // tail (w >= 5, 0.3 % of the draws) uses w * rsqrt(w): relative 2^-22, inside the 5e-6 relative contract there.
+  float l2, rs;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(1.0f + (-(x * x))));  // argument in [2^-23, 1]: never denormal
+  const float w = l2 * -0.693147180559945f;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(w));  // w == 0 -> inf -> NaN below: discarded by the select
+  const float pb = pb_erfinv_poly_bulk(w - 2.5f);
+  const float pt = pb_erfinv_poly_tail(w * rs - 3.0f);
+  return (w < 5.0f ? pb : pt) * x;
+#else
   float w = -log1pf(-(x * x));
-  float p;
-  if (w < 5.0f) {
-    w = w - 2.5f;
-    p = 2.81022636e-08f;
-    p = 3.43273939e-07f + p * w;
-    p = -3.5233877e-06f + p * w;
-    p = -4.39150654e-06f + p * w;
-    p = 0.00021858087f + p * w;
-    p = -0.00125372503f + p * w;
-    p = -0.00417768164f + p * w;
-    p = 0.246640727f + p * w;
-    p = 1.50140941f + p * w;
-  } else {
-    w = sqrtf(w) - 3.0f;
-    p = -0.000200214257f;
-    p = 0.000100950558f + p * w;
-    p = 0.00134934322f + p * w;
-    p = -0.00367342844f + p * w;
-    p = 0.00573950773f + p * w;
-    p = -0.0076224613f + p * w;
-    p = 0.00943887047f + p * w;
-    p = 1.00167406f + p * w;
-    p = 2.83297682f + p * w;
-  }
+  const float p = w < 5.0f ? pb_erfinv_poly_bulk(w - 2.5f) : pb_erfinv_poly_tail(sqrtf(w) - 3.0f);
   return p * x;
+#endif
 }
 
 // jax.random.normal float32: sqrt(2) * erf_inv(u in (-1, 1))
@@ -116,6 +133,42 @@ PB_DEV float pb_bits_to_normal(uint32_t bits) {
 }
 
 PB_DEV float pb_normal_at(PbKey k, uint32_t i) { return pb_bits_to_normal(pb_bits_at(k, i)); }
+
+// N draws normal(k, .)[idx[j]] with the N threefry chains interleaved IN SOURCE ORDER, round by round: one chain is
+// ~70 dependent integer instructions, so a thread needs several in flight; left to itself the compiler serialises the
+// chains as soon as the surrounding code is short of registers (measured: 3x slower drains in pbnn_tc2.cuh).
+template <int N>
+PB_DEV void pb_normal_n(PbKey k, const uint32_t* idx, float* z) {
+  const uint32_t ks0 = k.k0, ks1 = k.k1, ks2 = k.k0 ^ k.k1 ^ 0x1BD11BDAu;
+  uint32_t x0[N], x1[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    x0[j] = ks0;
+    x1[j] = idx[j] + ks1;
+  }
+#define PB_TF_ROUND_N(r)                   \
+  _Pragma("unroll") for (int j = 0; j < N; ++j) x0[j] += x1[j];                  \
+  _Pragma("unroll") for (int j = 0; j < N; ++j) x1[j] = pb_rotl(x1[j], r) ^ x0[j];
+#define PB_TF_INJECT_N(a, b, c)            \
+  _Pragma("unroll") for (int j = 0; j < N; ++j) {                                \
+    x0[j] += a;                            \
+    x1[j] += b + c;                        \
+  }
+  PB_TF_ROUND_N(13) PB_TF_ROUND_N(15) PB_TF_ROUND_N(26) PB_TF_ROUND_N(6)
+  PB_TF_INJECT_N(ks1, ks2, 1u)
+  PB_TF_ROUND_N(17) PB_TF_ROUND_N(29) PB_TF_ROUND_N(16) PB_TF_ROUND_N(24)
+  PB_TF_INJECT_N(ks2, ks0, 2u)
+  PB_TF_ROUND_N(13) PB_TF_ROUND_N(15) PB_TF_ROUND_N(26) PB_TF_ROUND_N(6)
+  PB_TF_INJECT_N(ks0, ks1, 3u)
+  PB_TF_ROUND_N(17) PB_TF_ROUND_N(29) PB_TF_ROUND_N(16) PB_TF_ROUND_N(24)
+  PB_TF_INJECT_N(ks1, ks2, 4u)
+  PB_TF_ROUND_N(13) PB_TF_ROUND_N(15) PB_TF_ROUND_N(26) PB_TF_ROUND_N(6)
+  PB_TF_INJECT_N(ks2, ks0, 5u)
+#undef PB_TF_ROUND_N
+#undef PB_TF_INJECT_N
+#pragma unroll
+  for (int j = 0; j < N; ++j) z[j] = pb_bits_to_normal(x0[j] ^ x1[j]);
+}
 
 // jax.random.randint(key, (B,), 0, span)[b]; k1,k2 = split(key); mult = (2^16 % span)^2 % span
 PB_DEV int pb_randint_at(PbKey k1, PbKey k2, uint32_t b, uint32_t span, uint32_t mult) {

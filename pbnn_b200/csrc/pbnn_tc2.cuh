@@ -14,17 +14,22 @@
 //   G4 dW2    D2[n][i] = sum_b M2[b][n] Y[b][i],   Y = r * [relu(Z1) | 1]   A = M2^T (MN-major)  B = Y chunk (MN-major)   3 passes
 //             dW2[i][n] = w3[n] D2[n][i],  db2[n] = w3[n] D2[n][H],
 //             dw3[n] = sum_i W2[i][n] D2[n][i] + b2[n] D2[n][H]      (relu(Z2 + b2) = M2 * (H1 W2 + b2): no extra GEMM)
-//   G5 dH1    E[b][i]  = sum_n M2[b][n] (w3[n] W2[i][n])                  A = M2 (K-major)  B = W2s (K-major)             3 passes
+//   G5 dH1    E[b][i]  = sum_n (w3[n] M2[b][n]) W2[i][n]                  A = w3 * M2 chunk (K-major)  B = W2 (K-major)     6 passes
+//             (the chunk terms are SELECTED from a per-step 3-term split of w3: no arithmetic per element)
 //   G6 dW1    D1[k][i] = sum_b Xaug[b][k] dZ1[b][i],  dZ1 = r * E * [Z1 > 0]   A = X^T (MN-major)  B = dZ1 chunk (MN-major) 6 passes
 //
 // Operand images are SWIZZLE_128B tiles: 64 bf16 (128 B) per storage row, 16-byte chunk j of row r at chunk j ^ (r & 7),
 // column blocks of 64 elements one after the other.  The SAME image is read K-major (storage row = M/N index) or
 // MN-major (storage row = K index): X, M2 and the activation chunks are written once and used both ways.
 //
-// Where things live.  Parameter-sized state (theta, g, ...) in the global workspace (L2).  Per CTA a global IMAGE block
-// holds the bf16x3 operand images of X (fixed minibatch), W1aug, W2 and W2s = W2 diag(w3), rewritten by
-// pb_tc2_restage after every parameter update and streamed back through a 3-stage shared-memory ring with
-// cp.async.bulk (TMA engine) + mbarriers by a dedicated producer warp.  Shared memory: one activation chunk
+// Where things live.  Parameter-sized state (theta, momentum, ...) in the global workspace (L2 / HBM).  Per CTA a
+// global IMAGE block holds the bf16x3 operand images of X (fixed minibatch), W1aug and W2; they are streamed through
+// a 3-stage shared-memory ring with cp.async.bulk (TMA engine) + mbarriers by a dedicated producer warp.
+//
+// Fused drains.  The weight-gradient accumulators are never written out: the thread that reads dW[i][n] from TMEM
+// also loads theta[i][n] (+ the sampler's state), draws the threefry normal, applies the caller's update functor
+// (SGLD / SGHMC / Adam / pSGLD step), stores the new theta and its three bf16 terms into the operand image.  One
+// pass over the parameters per step: no gradient array, no separate update or re-staging pass.  Shared memory: one activation chunk
 // [128 rows][64] x 3 terms (48 KB), the layer-2 mask [128][Hp] bf16, the weight ring.  TMEM (512 columns):
 // S0 = columns 0..255: Z1 -> E -> D1;  S1 = columns 256..511: Z2 -> D2 chunk slots.
 //
@@ -35,6 +40,20 @@
 #if !defined(PB_EMU)
 
 #define PB_T2_WORKERS 256
+
+// 4 normals behind a call boundary: inside the drains the register allocator otherwise re-serialises the four
+// threefry chains (measured: LG2 instructions ~100 apart in the SASS, 2-3x slower drains); as a separate function the
+// chains are scheduled on their own, interleaved, and cost the caller one call + a float4 return
+__device__ __noinline__ float4 pb_t2_normal4(uint32_t k0, uint32_t k1, uint32_t i0, uint32_t i1, uint32_t i2,
+                                             uint32_t i3) {
+  PbKey k;
+  k.k0 = k0;
+  k.k1 = k1;
+  const uint32_t ix[4] = {i0, i1, i2, i3};
+  float z[4];
+  pb_normal_n<4>(k, ix, z);
+  return make_float4(z[0], z[1], z[2], z[3]);
+}
 
 PB_DEV uint64_t pb_t2_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {  // SWIZZLE_128B
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
@@ -93,6 +112,7 @@ enum {
   PB_T2_B_D2FULL,                       // [2] D2 chunk slot complete (commit)
   PB_T2_B_D2EMPTY = PB_T2_B_D2FULL + 2, // [2] D2 chunk slot drained by the 256 workers
   PB_T2_B_XFULL = PB_T2_B_D2EMPTY + 2,  // X image resident in the ring area (dW1)
+  PB_T2_B_S1FREE,                       // D1 drained by the 256 workers: TMEM S1 may take the D2 chunk slots
   PB_T2_NBAR
 };
 
@@ -167,34 +187,53 @@ PB_DEV void pb_tc2_stage_x(const PbPlan& pl, float* sm, const PbTc2& tc, const f
   PB_ENDPHASE_RAW
 }
 
-// theta (padded resident layout, global) -> operand images of W1aug, W2, W2s = W2 diag(w3); b2, w3, b3 -> shared memory
-PB_DEV void pb_tc2_restage(const PbPlan& pl, float* sm, const PbTc2& tc, const float* __restrict__ TH, int nt) {
+// small vectors of one evaluation: b2, w3 (fp32) and the packed 3-term split of w3 (pairs), b3 -> shared memory
+PB_DEV void pb_tc2_vectors(const PbPlan& pl, float* sm, const float* __restrict__ TH, int nt) {
   const int tid = threadIdx.x;
-  const PbLayer& L0 = pl.L[0];
   const PbLayer& L1 = pl.L[1];
   const PbLayer& L2 = pl.L[2];
-  const int H = pl.t2_H, Hp = pl.t2_Hp, Kx = pl.t2_Kx, d = pl.d;
+  const int H = pl.t2_H;
   float* b2v = sm + pl.off_t2_vec;
   float* w3v = b2v + 256;
+  uint32_t* w3t = reinterpret_cast<uint32_t*>(b2v + 1412);  // [3][128] packed pairs
   for (int n = tid; n < 256; n += nt) {
     b2v[n] = n < H ? TH[L1.soff + H * L1.wp + n] : 0.f;
     w3v[n] = n < H ? TH[L2.soff + n * L2.wp] : 0.f;
   }
+  for (int p = tid; p < 128; p += nt) {
+    const float a0 = 2 * p < H ? TH[L2.soff + (2 * p) * L2.wp] : 0.f;
+    const float a1 = 2 * p + 1 < H ? TH[L2.soff + (2 * p + 1) * L2.wp] : 0.f;
+    uint32_t t1, t2, t3;
+    pb_t2_split3(a0, a1, t1, t2, t3);
+    w3t[p] = t1;
+    w3t[128 + p] = t2;
+    w3t[256 + p] = t3;
+  }
   if (tid == 0) sm[pl.off_t2_vec + 1408] = TH[L2.soff + H * L2.wp];  // b3
+}
+
+// theta (padded resident layout, global) -> operand images of W1aug and W2 (start of a chain; afterwards the fused
+// drains keep the images current)
+PB_DEV void pb_tc2_restage(const PbPlan& pl, float* sm, const PbTc2& tc, const float* __restrict__ TH, int nt) {
+  const int tid = threadIdx.x;
+  const PbLayer& L0 = pl.L[0];
+  const PbLayer& L1 = pl.L[1];
+  const int H = pl.t2_H, Hp = pl.t2_Hp, Kx = pl.t2_Kx, d = pl.d;
   PB_TAG(1)
-  PB_ENDPHASE_RAW
-  {  // W1aug: rows k (bias = row d), columns n
-    const int tb = pl.t2_nch * Kx * 128, hp2 = Hp >> 1;
-    uint8_t* base = tc.img + pl.t2_img_w1;
-    const int total = (d + 1) * hp2;
+  for (int which = 0; which < 2; ++which) {
+    const PbLayer& Ly = which ? L1 : L0;
+    const int rows = which ? Hp : Kx, nrow = which ? H : d + 1;
+    const int tb = pl.t2_nch * rows * 128, hp2 = Hp >> 1;
+    uint8_t* base = tc.img + (which ? pl.t2_img_w2 : pl.t2_img_w1);
+    const int total = nrow * hp2;
     for (int e0 = tid; e0 < total; e0 += 4 * nt) {
       float v0[4], v1[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int e = e0 + u * nt;
         const int k = e / hp2, n0 = 2 * (e - k * hp2);
-        v0[u] = (e < total && n0 < H) ? TH[L0.soff + k * L0.wp + n0] : 0.f;
-        v1[u] = (e < total && n0 + 1 < H) ? TH[L0.soff + k * L0.wp + n0 + 1] : 0.f;
+        v0[u] = (e < total && n0 < H) ? TH[Ly.soff + k * Ly.wp + n0] : 0.f;
+        v1[u] = (e < total && n0 + 1 < H) ? TH[Ly.soff + k * Ly.wp + n0 + 1] : 0.f;
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -203,43 +242,10 @@ PB_DEV void pb_tc2_restage(const PbPlan& pl, float* sm, const PbTc2& tc, const f
           const int k = e / hp2, n0 = 2 * (e - k * hp2);
           uint32_t t1, t2, t3;
           pb_t2_split3(v0[u], v1[u], t1, t2, t3);
-          uint8_t* p = base + pb_t2_off(Kx, k, n0);
+          uint8_t* p = base + pb_t2_off(rows, k, n0);
           *reinterpret_cast<uint32_t*>(p) = t1;
           *reinterpret_cast<uint32_t*>(p + tb) = t2;
           *reinterpret_cast<uint32_t*>(p + 2 * tb) = t3;
-        }
-      }
-    }
-  }
-  {  // W2 and W2s: rows i, columns n
-    const int tb = pl.t2_nch * Hp * 128, hp2 = Hp >> 1;
-    uint8_t* b1 = tc.img + pl.t2_img_w2;
-    uint8_t* bs = tc.img + pl.t2_img_w2s;
-    const int total = H * hp2;
-    for (int e0 = tid; e0 < total; e0 += 4 * nt) {
-      float v0[4], v1[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int e = e0 + u * nt;
-        const int i = e / hp2, n0 = 2 * (e - i * hp2);
-        v0[u] = (e < total && n0 < H) ? TH[L1.soff + i * L1.wp + n0] : 0.f;
-        v1[u] = (e < total && n0 + 1 < H) ? TH[L1.soff + i * L1.wp + n0 + 1] : 0.f;
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int e = e0 + u * nt;
-        if (e < total) {
-          const int i = e / hp2, n0 = 2 * (e - i * hp2);
-          uint32_t t1, t2, t3;
-          pb_t2_split3(v0[u], v1[u], t1, t2, t3);
-          const uint32_t o = pb_t2_off(Hp, i, n0);
-          *reinterpret_cast<uint32_t*>(b1 + o) = t1;
-          *reinterpret_cast<uint32_t*>(b1 + o + tb) = t2;
-          *reinterpret_cast<uint32_t*>(b1 + o + 2 * tb) = t3;
-          pb_t2_split3(v0[u] * w3v[n0], v1[u] * w3v[n0 + 1], t1, t2, t3);
-          *reinterpret_cast<uint32_t*>(bs + o) = t1;
-          *reinterpret_cast<uint32_t*>(bs + o + tb) = t2;
-          *reinterpret_cast<uint32_t*>(bs + o + 2 * tb) = t3;
         }
       }
     }
@@ -248,10 +254,27 @@ PB_DEV void pb_tc2_restage(const PbPlan& pl, float* sm, const PbTc2& tc, const f
   PB_ENDPHASE_RAW
 }
 
-// ---- the gradient: G <- d loglik / d theta (padded resident layout), llbuf[0..127] <- per-row log-likelihood terms ----
-PB_DEV void pb_grad_tc2(const PbPlan& pl, float* sm, const float* __restrict__ TH, float* __restrict__ G, int nrows,
-                        float scale, int nt,
-                        const PbTc2& tc) {
+// new value of one weight -> its three bf16 terms in an operand image (term images `tb` bytes apart)
+PB_DEV void pb_t2_put(uint8_t* p, int tb, float v) {
+  uint32_t t1, t2, t3;
+  pb_t2_split3(v, 0.f, t1, t2, t3);
+  *reinterpret_cast<uint16_t*>(p) = (uint16_t)t1;
+  *reinterpret_cast<uint16_t*>(p + tb) = (uint16_t)t2;
+  *reinterpret_cast<uint16_t*>(p + 2 * tb) = (uint16_t)t3;
+}
+
+// ---- one gradient evaluation with the parameter update fused into the drains ------------------------------------
+//   pre = pf(resident_index, flat_index)          loads everything the update needs (pre.a MUST be theta); issued for a
+//                                                 group of elements before any of them is stored
+//   theta_new = uf(resident_index, flat_index, pre, gll, z)   gll = d loglik / d theta of the element, z =
+//                                                 jax.random.normal(nkey, (P,))[flat_index] when `noise` (else 0); the
+//                                                 functor owns the sampler arithmetic (prior term, state arrays) and
+//                                                 returns the value theta is set to (pre.a leaves it unchanged)
+// The drains work on groups of 8 elements: 8 x pf, then the 8 threefry + erf_inv chains (branch-free, interleaved by the
+// compiler), then 8 x uf, then the stores.  llbuf[0..127] <- per-row log-likelihood terms.  TH is updated in place.
+template <class PF, class UF>
+PB_DEV void pb_grad_tc2(const PbPlan& pl, float* sm, float* TH, int nrows, float scale, int nt, const PbTc2& tc,
+                        PbKey nkey, bool noise, PF pf, UF uf) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
   const PbLayer& L0 = pl.L[0];
@@ -267,19 +290,23 @@ PB_DEV void pb_grad_tc2(const PbPlan& pl, float* sm, const float* __restrict__ T
   float* yv = b2v + 512;
   float* fp = b2v + 640;    // [2][128] partial outputs of the two column halves
   float* dw3p = b2v + 896;  // [2][256] partial output-weight gradients
+  const uint32_t* w3t = reinterpret_cast<const uint32_t*>(b2v + 1412);
   float* llbuf = pb_llbuf(pl, sm);
 
-  pb_tc2_restage(pl, sm, tc, TH, nt);
+  PB_TAG(1)
+  pb_tc2_vectors(pl, sm, TH, nt);
   if (tid == 0) {
     for (int i = 0; i < PB_T2_NBAR; ++i) {
       const uint32_t b = pb_t2_bar(pl, sm, i);
-      const uint32_t cnt = (i == PB_T2_B_AFULL || i == PB_T2_B_D2EMPTY || i == PB_T2_B_D2EMPTY + 1) ? PB_T2_WORKERS : 1u;
+      const uint32_t cnt = (i == PB_T2_B_AFULL || i == PB_T2_B_D2EMPTY || i == PB_T2_B_D2EMPTY + 1 || i == PB_T2_B_S1FREE)
+                               ? PB_T2_WORKERS
+                               : 1u;
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(b), "r"(cnt));
     }
     asm volatile("fence.mbarrier_init.release.cluster;");
   }
+  pb_t2_fence_async_global();  // image stores of the previous evaluation's drains -> visible to the bulk copies
   pb_tc_fence_before();
-  PB_TAG(2)
   PB_ENDPHASE_RAW
   pb_tc_fence_after();
   const uint32_t bar0 = pb_t2_bar(pl, sm, 0);
@@ -295,7 +322,18 @@ PB_DEV void pb_grad_tc2(const PbPlan& pl, float* sm, const float* __restrict__ T
         pb_t2_expect(PB_T2_BAR(PB_T2_B_WFULL + s), bytes);
         return ring + (uint32_t)s * wstage;
       };
-      // G1: X chunk kc (3 terms) -> activation area; W1aug rows of chunk kc, one term per stage
+      // row chunks of an MN-major B image: rows [64 c, 64 c + rows) of every column block, one term per stage
+      auto row_chunk = [&](const uint8_t* img, int img_rows, int c, int rows) {
+        for (int t = 0; t < 3; ++t) {
+          const uint32_t dst = stage_begin((uint32_t)(nch * rows * 128));
+          const int s = fill % PB_T2_NS;
+          for (int cb = 0; cb < nch; ++cb)
+            pb_t2_bulk(dst + (uint32_t)cb * 8192u, img + ((size_t)(t * nch + cb) * img_rows + 64 * c) * 128,
+                       (uint32_t)(rows * 128), PB_T2_BAR(PB_T2_B_WFULL + s));
+          ++fill;
+        }
+      };
+      // G1: X chunk kc (3 terms) -> activation area; W1aug rows of chunk kc
       for (int kc = 0; kc < ncbx; ++kc) {
         const int rows = (Kx - 64 * kc) < 64 ? (Kx - 64 * kc) : 64;
         if (ause > 0) pb_mbar_wait(PB_T2_BAR(PB_T2_B_AEMPTY), (uint32_t)((ause - 1) & 1));
@@ -304,36 +342,17 @@ PB_DEV void pb_grad_tc2(const PbPlan& pl, float* sm, const float* __restrict__ T
           pb_t2_bulk(acta + (uint32_t)t * PB_T2_TILE, tc.img + ((size_t)t * ncbx + kc) * PB_T2_TILE, PB_T2_TILE,
                      PB_T2_BAR(PB_T2_B_AXFULL));
         ++ause;
-        for (int t = 0; t < 3; ++t) {
-          const uint32_t dst = stage_begin((uint32_t)(nch * rows * 128));
-          const int s = fill % PB_T2_NS;
-          for (int cb = 0; cb < nch; ++cb)
-            pb_t2_bulk(dst + (uint32_t)cb * 8192u,
-                       tc.img + pl.t2_img_w1 + ((size_t)(t * nch + cb) * Kx + 64 * kc) * 128, (uint32_t)(rows * 128),
-                       PB_T2_BAR(PB_T2_B_WFULL + s));
-          ++fill;
-        }
+        row_chunk(tc.img + pl.t2_img_w1, Kx, kc, rows);
       }
-      // G2: W2 rows of chunk ic
-      for (int ic = 0; ic < nch; ++ic) {
-        const int rows = (Hp - 64 * ic) < 64 ? (Hp - 64 * ic) : 64;
-        for (int t = 0; t < 3; ++t) {
-          const uint32_t dst = stage_begin((uint32_t)(nch * rows * 128));
-          const int s = fill % PB_T2_NS;
-          for (int cb = 0; cb < nch; ++cb)
-            pb_t2_bulk(dst + (uint32_t)cb * 8192u,
-                       tc.img + pl.t2_img_w2 + ((size_t)(t * nch + cb) * Hp + 64 * ic) * 128, (uint32_t)(rows * 128),
-                       PB_T2_BAR(PB_T2_B_WFULL + s));
-          ++fill;
-        }
-      }
-      // G5: W2s column block kc (all Hp rows)
+      // G2: W2 rows of chunk ic (MN-major B)
+      for (int ic = 0; ic < nch; ++ic) row_chunk(tc.img + pl.t2_img_w2, Hp, ic, (Hp - 64 * ic) < 64 ? (Hp - 64 * ic) : 64);
+      // G5: W2 column block kc, all Hp rows (K-major B)
       for (int kc = 0; kc < nch; ++kc)
         for (int t = 0; t < 3; ++t) {
           const uint32_t bytes = (uint32_t)(Hp * 128);
           const uint32_t dst = stage_begin(bytes);
           const int s = fill % PB_T2_NS;
-          const uint8_t* src = tc.img + pl.t2_img_w2s + ((size_t)(t * nch + kc) * Hp) * 128;
+          const uint8_t* src = tc.img + pl.t2_img_w2 + ((size_t)(t * nch + kc) * Hp) * 128;
           for (uint32_t o = 0; o < bytes; o += 16384u)
             pb_t2_bulk(dst + o, src + o, bytes - o < 16384u ? bytes - o : 16384u, PB_T2_BAR(PB_T2_B_WFULL + s));
           ++fill;
@@ -349,7 +368,7 @@ PB_DEV void pb_grad_tc2(const PbPlan& pl, float* sm, const float* __restrict__ T
     __syncwarp();
   } else if (warp_u == 9) {
     // =============================== MMA issue ===============================
-    int fill = 0, ause = 0;
+    int fill = 0;
     uint32_t axph = 0u, afph = 0u;
     auto stage_wait = [&]() -> uint32_t {
       const int s = fill % PB_T2_NS;
@@ -366,9 +385,10 @@ PB_DEV void pb_grad_tc2(const PbPlan& pl, float* sm, const float* __restrict__ T
       if (pb_elect_one()) pb_umma_commit(PB_T2_BAR(b));
       __syncwarp();
     };
-    // forward GEMM over 64-wide K chunks: A chunk (3 terms, K-major) in the activation area, B row chunk per stage
-    auto fwd = [&](uint32_t dcol, int nchunks, int ktotal, bool a_from_tma) {
-      const uint32_t idesc = pb_t2_idesc(128, Hp, 0, 1);
+    // GEMM over 64-wide K chunks: A chunk (3 terms, K-major) in the activation area, one term of B per ring stage
+    // (b_kmajor: B rows = output index, else B rows = K index of the chunk); 6 passes (term pairs i + j <= 4)
+    auto kgemm = [&](uint32_t dcol, int nchunks, int ktotal, bool a_from_tma, bool b_kmajor) {
+      const uint32_t idesc = pb_t2_idesc(128, Hp, 0, b_kmajor ? 0 : 1);
       for (int c = 0; c < nchunks; ++c) {
         const int ksteps = ((ktotal - 64 * c) < 64 ? (ktotal - 64 * c) : 64) >> 4;
         if (a_from_tma) {
@@ -385,19 +405,46 @@ PB_DEV void pb_grad_tc2(const PbPlan& pl, float* sm, const float* __restrict__ T
             for (int xa = 0; xa + wt < 3; ++xa)
               for (int ks = 0; ks < ksteps; ++ks)
                 pb_t2_mma(dcol, pb_t2_desc(acta + (uint32_t)xa * PB_T2_TILE + (uint32_t)ks * 32u, 16u, 1024u),
-                          pb_t2_desc(st + (uint32_t)ks * 2048u, 8192u, 1024u), idesc, (c | wt | xa | ks) ? 1u : 0u);
+                          b_kmajor ? pb_t2_desc(st + (uint32_t)ks * 32u, 16u, 1024u)
+                                   : pb_t2_desc(st + (uint32_t)ks * 2048u, 8192u, 1024u),
+                          idesc, (c | wt | xa | ks) ? 1u : 0u);
           }
           __syncwarp();
           stage_done();
         }
         commit(PB_T2_B_AEMPTY);
-        ++ause;
       }
       commit(PB_T2_B_ACC);
     };
-    fwd(S0, ncbx, Kx, true);    // G1: Z1
-    fwd(S1, nch, Hp, false);    // G2: Z2
-    // G4: D2 chunks.  A = M2^T tile (MN-major, 128 n), B = Y chunk (MN-major), K = 128 batch rows
+    kgemm(S0, ncbx, Kx, true, false);   // G1: Z1
+    kgemm(S1, nch, Hp, false, false);   // G2: Z2
+    kgemm(S1, nch, Hp, false, true);    // G5: E = (w3 * M2) W2^T  (S1: Z2 has been consumed; Z1 stays in S0 for G4)
+    // G6: D1 chunks.  A = X^T (MN-major, lanes = input index k), B = dZ1 chunk (MN-major), K = 128 batch rows
+    pb_mbar_wait(PB_T2_BAR(PB_T2_B_XFULL), 0u);
+    pb_tc_fence_after();
+    for (int ic = 0; ic < nch; ++ic) {
+      const int ncols = (Hp - 64 * ic) < 64 ? (Hp - 64 * ic) : 64;
+      pb_mbar_wait(PB_T2_BAR(PB_T2_B_AFULL), afph);
+      afph ^= 1u;
+      pb_tc_fence_after();
+      if (pb_elect_one()) {
+        const uint32_t idesc = pb_t2_idesc(128, ncols, 1, 1);
+        for (int zt = 0; zt < 3; ++zt)
+          for (int xa = 0; xa + zt < 3; ++xa)
+            for (int ks = 0; ks < 8; ++ks)
+              pb_t2_mma(S1 + (uint32_t)ic * 64u,
+                        pb_t2_desc(ring + (uint32_t)(xa * ncbx) * PB_T2_TILE + (uint32_t)ks * 2048u,
+                                   ncbx > 1 ? PB_T2_TILE : 0u, 1024u),
+                        pb_t2_desc(acta + (uint32_t)zt * PB_T2_TILE + (uint32_t)ks * 2048u, 0u, 1024u), idesc,
+                        (zt | xa | ks) ? 1u : 0u);
+      }
+      __syncwarp();
+      commit(PB_T2_B_AEMPTY);
+    }
+    commit(PB_T2_B_ACC);
+    // G4 (last: the fused drains overwrite the W2 image, which fwd2 and dH1 must have read): D2 chunks.  A = M2^T tile (MN-major, 128 n), B = Y chunk (MN-major), K = 128 batch rows
+    pb_mbar_wait(PB_T2_BAR(PB_T2_B_S1FREE), 0u);
+    pb_tc_fence_after();
     for (int ic = 0; ic < nchy; ++ic) {
       const int ncols = (Hy - 64 * ic) < 64 ? (Hy - 64 * ic) : 64;
       const int slot = ic & 1;
@@ -418,51 +465,8 @@ PB_DEV void pb_grad_tc2(const PbPlan& pl, float* sm, const float* __restrict__ T
       }
       __syncwarp();
       commit(PB_T2_B_AEMPTY);
-      ++ause;
       commit(PB_T2_B_D2FULL + slot);
     }
-    // G5: E = M2 W2s^T.  A = M2 column block kc (K-major), B = W2s column block kc (K-major, Hp rows)
-    {
-      const uint32_t idesc = pb_t2_idesc(128, Hp, 0, 0);
-      for (int kc = 0; kc < nch; ++kc) {
-        const int ksteps = ((Hp - 64 * kc) < 64 ? (Hp - 64 * kc) : 64) >> 4;
-        for (int t = 0; t < 3; ++t) {
-          const uint32_t st = stage_wait();
-          if (pb_elect_one()) {
-            for (int ks = 0; ks < ksteps; ++ks)
-              pb_t2_mma(S0, pb_t2_desc(m2 + (uint32_t)kc * PB_T2_TILE + (uint32_t)ks * 32u, 16u, 1024u),
-                        pb_t2_desc(st + (uint32_t)ks * 32u, 16u, 1024u), idesc, (kc | t | ks) ? 1u : 0u);
-          }
-          __syncwarp();
-          stage_done();
-        }
-      }
-      commit(PB_T2_B_ACC);
-    }
-    // G6: D1 chunks.  A = X^T (MN-major, lanes = input index k), B = dZ1 chunk (MN-major), K = 128 batch rows
-    pb_mbar_wait(PB_T2_BAR(PB_T2_B_XFULL), 0u);
-    pb_tc_fence_after();
-    for (int ic = 0; ic < nch; ++ic) {
-      const int ncols = (Hp - 64 * ic) < 64 ? (Hp - 64 * ic) : 64;
-      pb_mbar_wait(PB_T2_BAR(PB_T2_B_AFULL), afph);
-      afph ^= 1u;
-      pb_tc_fence_after();
-      if (pb_elect_one()) {
-        const uint32_t idesc = pb_t2_idesc(128, ncols, 1, 1);
-        for (int zt = 0; zt < 3; ++zt)
-          for (int xa = 0; xa + zt < 3; ++xa)
-            for (int ks = 0; ks < 8; ++ks)
-              pb_t2_mma(S0 + (uint32_t)ic * 64u,
-                        pb_t2_desc(ring + (uint32_t)(xa * ncbx) * PB_T2_TILE + (uint32_t)ks * 2048u,
-                                   ncbx > 1 ? PB_T2_TILE : 0u, 1024u),
-                        pb_t2_desc(acta + (uint32_t)zt * PB_T2_TILE + (uint32_t)ks * 2048u, 0u, 1024u), idesc,
-                        (zt | xa | ks) ? 1u : 0u);
-      }
-      __syncwarp();
-      commit(PB_T2_B_AEMPTY);
-      ++ause;
-    }
-    commit(PB_T2_B_ACC);
   } else {
     // =============================== workers ===============================
     const int q = warp & 3, g = warp >> 2;
@@ -472,7 +476,8 @@ PB_DEV void pb_grad_tc2(const PbPlan& pl, float* sm, const float* __restrict__ T
     const uint32_t bx = (uint32_t)(b & 7);
     int ause = ncbx;                                   // activation-area uses before the first worker chunk
     uint32_t accph = 0u;
-    uint32_t m1[4] = {0u, 0u, 0u, 0u};                 // relu mask of layer 1: this thread's 32 columns of each chunk
+    uint32_t m1[4] = {0u, 0u, 0u, 0u};                 // relu masks: this thread's 32 columns of each chunk
+    uint32_t m2b[4] = {0u, 0u, 0u, 0u};
     // three packed terms of 32 values -> this thread's 4 chunks (16 B each) of the activation rows
     auto store_chunk = [&](const float* v) {
 #pragma unroll
@@ -531,6 +536,7 @@ PB_DEV void pb_grad_tc2(const PbPlan& pl, float* sm, const float* __restrict__ T
       pb_tmem_ld32(S1 + lane_off + (uint32_t)(64 * ic + 32 * g), z);
       pb_tmem_wait_ld();
       const int c0 = 64 * ic + 32 * g;
+      uint32_t mb = 0u;
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         uint32_t mk[4];
@@ -541,10 +547,12 @@ PB_DEV void pb_grad_tc2(const PbPlan& pl, float* sm, const float* __restrict__ T
           fpart = fmaf(fmaxf(h0, 0.f), w3v[c0 + c], fpart);
           fpart = fmaf(fmaxf(h1, 0.f), w3v[c0 + c + 1], fpart);
           mk[j] = (h0 > 0.f ? 0x3F80u : 0u) | (h1 > 0.f ? 0x3F800000u : 0u);
+          mb |= (h0 > 0.f ? (1u << c) : 0u) | (h1 > 0.f ? (2u << c) : 0u);
         }
         pb_t2_st4(m2 + (uint32_t)ic * PB_T2_TILE + rowaddr + ((((uint32_t)(4 * g + u)) ^ bx) << 4), mk[0], mk[1], mk[2],
                   mk[3]);
       }
+      if (ic == 0) m2b[0] = mb; else if (ic == 1) m2b[1] = mb; else if (ic == 2) m2b[2] = mb; else m2b[3] = mb;
     }
     pb_tc_fence_before();
     fp[g * 128 + b] = fpart;
@@ -558,10 +566,123 @@ PB_DEV void pb_grad_tc2(const PbPlan& pl, float* sm, const float* __restrict__ T
       if (g == 0) llbuf[b] = valid ? -0.5f * res * res * pl.inv_s2 : 0.f;
     }
     PB_MARK(5)
-    // ---- G4: Y chunks = r * [relu(Z1) | 1 | 0..], D2 drains one chunk behind ----
+    // ---- G5: chunks of w3 * M2 (terms selected from the split of w3) ----
+    for (int kc = 0; kc < nch; ++kc) {
+      const uint32_t mb = kc == 0 ? m2b[0] : kc == 1 ? m2b[1] : kc == 2 ? m2b[2] : m2b[3];
+      const int p0 = (64 * kc + 32 * g) >> 1;
+      chunk_begin();
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        uint32_t t1[4], t2[4], t3[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = 8 * u + 2 * j;
+          const uint32_t mw = ((mb >> c) & 1u ? 0xFFFFu : 0u) | ((mb >> (c + 1)) & 1u ? 0xFFFF0000u : 0u);
+          t1[j] = w3t[p0 + 4 * u + j] & mw;
+          t2[j] = w3t[128 + p0 + 4 * u + j] & mw;
+          t3[j] = w3t[256 + p0 + 4 * u + j] & mw;
+        }
+        const uint32_t a = acta + rowaddr + ((((uint32_t)(4 * g + u)) ^ bx) << 4);
+        pb_t2_st4(a, t1[0], t1[1], t1[2], t1[3]);
+        pb_t2_st4(a + PB_T2_TILE, t2[0], t2[1], t2[2], t2[3]);
+        pb_t2_st4(a + 2u * PB_T2_TILE, t3[0], t3[1], t3[2], t3[3]);
+      }
+      chunk_end();
+    }
+    // ---- G6: dZ1 chunks = r * E * [Z1 > 0] ----
+    acc_wait();  // E
+    PB_MARK(6)
+    for (int ic = 0; ic < nch; ++ic) {
+      uint32_t z[32];
+      float v[32];
+      pb_tmem_ld32(S1 + lane_off + (uint32_t)(64 * ic + 32 * g), z);
+      pb_tmem_wait_ld();
+      const uint32_t mb = ic == 0 ? m1[0] : ic == 1 ? m1[1] : ic == 2 ? m1[2] : m1[3];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = (mb >> j) & 1u ? r * __uint_as_float(z[j]) : 0.f;
+      chunk_begin();
+      store_chunk(v);
+      chunk_end();
+    }
+    PB_MARK(7)
+    // ---- G7: D1 drain with the fused update of W1, b1: TMEM lane = input index k (k == d: bias row), group g takes
+    //      its half of every chunk ----
+    acc_wait();  // D1
+    PB_MARK(8)
+    // D1 (TMEM lane = input index k, k == d: bias row) -> shared memory [k][Hp + 4] in the ring area (the X image
+    // there has been consumed): the update below then runs with one COLUMN per thread, coalesced and balanced
+    float* d1buf = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sm + pl.off_t2_big) +
+                                            ((ring - pb_smem_u32(sm + pl.off_t2_big))));
+    const int dp = Hp + 4;
+    {
+      const int k = b;
+      for (int ic = 0; ic < nch; ++ic) {
+        const int ncols = (Hp - 64 * ic) < 64 ? (Hp - 64 * ic) : 64;
+        for (int c0 = 32 * g; c0 < ncols && c0 < 32 * g + 32; c0 += 8) {
+          uint32_t dv[8];
+          pb_tmem_ld8(S1 + lane_off + (uint32_t)(64 * ic + c0), dv);
+          pb_tmem_wait_ld();
+          if (k <= pl.d) {
+            float4* dst = reinterpret_cast<float4*>(d1buf + k * dp + 64 * ic + c0);
+            dst[0] = make_float4(__uint_as_float(dv[0]), __uint_as_float(dv[1]), __uint_as_float(dv[2]),
+                                 __uint_as_float(dv[3]));
+            dst[1] = make_float4(__uint_as_float(dv[4]), __uint_as_float(dv[5]), __uint_as_float(dv[6]),
+                                 __uint_as_float(dv[7]));
+          }
+        }
+      }
+    }
+    pb_tc_fence_before();
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    auto update_w1 = [&]() {
+      const int d = pl.d;
+      const int tb1 = nch * Kx * 128;
+      uint8_t* img1 = tc.img + pl.t2_img_w1;
+      const int wt = warp * 32 + lane;                       // worker thread 0..255
+      const int i = Hp > 128 ? wt : (wt & 127);              // this thread's column (hidden unit)
+      const int kg = Hp > 128 ? 0 : (wt >> 7), nkg = Hp > 128 ? 1 : 2;
+      for (int k0 = kg; k0 <= d; k0 += 4 * nkg) {
+        PbPre pre[4];
+        float nv[4], zz[4];
+        uint32_t ix[4];
+        const bool own = i < H;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int k = k0 + j * nkg;
+          ix[j] = (uint32_t)((k < d ? L0.fw + k * H : L0.fb) + i);
+          if (own && k <= d) pre[j] = pf(L0.soff + k * L0.wp + i, (int)ix[j]);
+        }
+        if (noise) {
+          const float4 z4 = pb_t2_normal4(nkey.k0, nkey.k1, ix[0], ix[1], ix[2], ix[3]);
+          zz[0] = z4.x; zz[1] = z4.y; zz[2] = z4.z; zz[3] = z4.w;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) zz[j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int k = k0 + j * nkg;
+          if (own && k <= d) nv[j] = uf(L0.soff + k * L0.wp + i, (int)ix[j], pre[j], d1buf[k * dp + i], zz[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int k = k0 + j * nkg;
+          if (own && k <= d) {
+            TH[L0.soff + k * L0.wp + i] = nv[j];
+            pb_t2_put(img1 + pb_t2_off(Kx, k, i), tb1, nv[j]);
+          }
+        }
+      }
+    };
+    pb_tc_fence_before();
+    pb_t2_arrive(PB_T2_BAR(PB_T2_B_S1FREE));
+    PB_MARK(9)
+    // ---- G4: Y chunks = r * [relu(Z1) | 1 | 0..]; the D2 drains (fused update of W2, b2) run one chunk behind ----
     const bool two_tiles = nmt > 1;
     const int n_own = two_tiles ? 128 * g + b : b;  // output unit (TMEM lane of D2) this thread drains
     const float w3n = n_own < H ? w3v[n_own] : 0.f;
+    const int tb2 = nch * Hp * 128;
+    uint8_t* img2 = tc.img + pl.t2_img_w2;
     float dw3 = 0.f;
     auto drain_d2 = [&](int ic) {
       const int slot = ic & 1;
@@ -571,22 +692,84 @@ PB_DEV void pb_grad_tc2(const PbPlan& pl, float* sm, const float* __restrict__ T
       // two tiles: group g drains tile g, all columns; one tile: group g drains columns [32 g, 32 g + 32)
       const int cbeg = two_tiles ? 0 : 32 * g;
       const int cend = two_tiles ? ncols : (ncols < 32 * g + 32 ? ncols : 32 * g + 32);
-      for (int c0 = cbeg; c0 < cend; c0 += 16) {
-        uint32_t dv[16];
-        pb_tmem_ld16(S1 + lane_off + (uint32_t)(slot * 128 + (two_tiles ? 64 * g : 0) + c0), dv);
+      for (int c0 = cbeg; c0 < cend; c0 += 8) {
+        uint32_t dv[8];
+        pb_tmem_ld8(S1 + lane_off + (uint32_t)(slot * 128 + (two_tiles ? 64 * g : 0) + c0), dv);
         pb_tmem_wait_ld();
-        if (n_own < H) {
-          // i = input index of W2 (i == H: the bias row); all loads of the group before the first store
-          const int sbase = L1.soff + (64 * ic + c0) * L1.wp + n_own;
-          float thv[16];
+        const int i0 = 64 * ic + c0;  // input index of W2 (i == H: the bias row b2)
+        const bool own = n_own < H;
+        if (i0 + 8 <= H) {
+          // fast path: 8 kernel rows i0 .. i0 + 7 in two groups of 4 (i0 is a multiple of 8: (i & 7) == j in the swizzle)
+          const int sb = L1.soff + i0 * L1.wp + n_own, fb = L1.fw + i0 * H + n_own;
+          uint8_t* ib = img2 + (n_own >> 6) * (Hp * 128) + i0 * 128 + ((n_own & 7) << 1);
+          const uint32_t cn = (uint32_t)((n_own & 63) >> 3);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) thv[j] = 64 * ic + c0 + j <= H ? TH[sbase + j * L1.wp] : 0.f;
+          for (int j0 = 0; j0 < 8; j0 += 4) {
+            PbPre pre[4];
+            float nv[4], zz[4];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            if (64 * ic + c0 + j <= H) {
-              const float dd = __uint_as_float(dv[j]);
-              G[sbase + j * L1.wp] = w3n * dd;
-              dw3 = fmaf(thv[j], dd, dw3);
+            for (int j = 0; j < 4; ++j)
+              if (own) pre[j] = pf(sb + (j0 + j) * L1.wp, fb + (j0 + j) * H);
+            if (noise) {
+              uint32_t ix[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) ix[j] = (uint32_t)(fb + (j0 + j) * H);
+              const float4 z4 = pb_t2_normal4(nkey.k0, nkey.k1, ix[0], ix[1], ix[2], ix[3]);
+              zz[0] = z4.x; zz[1] = z4.y; zz[2] = z4.z; zz[3] = z4.w;
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) zz[j] = 0.f;
+            }
+            if (own) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float dd = __uint_as_float(dv[j0 + j]);
+                dw3 = fmaf(pre[j].a, dd, dw3);
+                nv[j] = uf(sb + (j0 + j) * L1.wp, fb + (j0 + j) * H, pre[j], w3n * dd, zz[j]);
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                TH[sb + (j0 + j) * L1.wp] = nv[j];
+                pb_t2_put(ib + (j0 + j) * 128 + ((cn ^ (uint32_t)(j0 + j)) << 4), tb2, nv[j]);
+              }
+            }
+          }
+        } else if (i0 <= H) {
+          // ragged tail: the last kernel rows and the bias row (i == H)
+#pragma unroll
+          for (int j0 = 0; j0 < 8; j0 += 4) {
+            PbPre pre[4];
+            float nv[4], zz[4];
+            uint32_t ix[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int i = i0 + j0 + j;
+              ix[j] = (uint32_t)(i < H ? L1.fw + i * H + n_own : L1.fb + n_own);
+              if (own && i <= H) pre[j] = pf(L1.soff + i * L1.wp + n_own, (int)ix[j]);
+            }
+            if (noise) {
+              const float4 z4 = pb_t2_normal4(nkey.k0, nkey.k1, ix[0], ix[1], ix[2], ix[3]);
+              zz[0] = z4.x; zz[1] = z4.y; zz[2] = z4.z; zz[3] = z4.w;
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) zz[j] = 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int i = i0 + j0 + j;
+              if (own && i <= H) {
+                const float dd = __uint_as_float(dv[j0 + j]);
+                dw3 = fmaf(pre[j].a, dd, dw3);
+                nv[j] = uf(L1.soff + i * L1.wp + n_own, (int)ix[j], pre[j], w3n * dd, zz[j]);
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int i = i0 + j0 + j;
+              if (own && i <= H) {
+                TH[L1.soff + i * L1.wp + n_own] = nv[j];
+                if (i < H) pb_t2_put(img2 + pb_t2_off(Hp, i, n_own), tb2, nv[j]);
+              }
             }
           }
         }
@@ -615,58 +798,27 @@ PB_DEV void pb_grad_tc2(const PbPlan& pl, float* sm, const float* __restrict__ T
       store_chunk(v);
       chunk_end();
       if (ic >= 1) drain_d2(ic - 1);
+      else update_w1();  // the tensor core works on the first D2 chunk meanwhile
     }
     drain_d2(nchy - 1);
-    // output-layer gradient: dw3[n] (one tile: the two column halves are summed), db3 = sum_b r_b
-    dw3p[g * 256 + n_own % 256] = dw3;
+    PB_MARK(10)
+    // output layer: dw3[n] (one tile: the two column halves are summed), db3 = sum_b r_b; fused update of w3, b3
+    dw3p[g * 256 + (n_own & 255)] = dw3;
     fp[g * 128 + b] = r;
     asm volatile("bar.sync 1, 256;" ::: "memory");
-    if (two_tiles) {
-      if (n_own < H) G[L2.soff + n_own * L2.wp] = dw3;
-    } else if (g == 0 && n_own < H) {
-      G[L2.soff + n_own * L2.wp] = dw3p[n_own] + dw3p[256 + n_own];
+    if ((two_tiles || g == 0) && n_own < H) {
+      const float gl = two_tiles ? dw3 : dw3p[n_own] + dw3p[256 + n_own];
+      const int si = L2.soff + n_own * L2.wp, fi = L2.fw + n_own;
+      const PbPre pre = pf(si, fi);
+      TH[si] = uf(si, fi, pre, gl, noise ? pb_normal_at(nkey, (uint32_t)fi) : 0.f);
     }
     if (warp == 0) {
       float a = fp[lane] + fp[32 + lane] + fp[64 + lane] + fp[96 + lane];
       a = pb_warp_sum(a);
-      if (lane == 0) G[L2.soff + H * L2.wp] = a;
-    }
-    PB_MARK(6)
-    // ---- G6: dZ1 chunks = r * E * [Z1 > 0] ----
-    acc_wait();  // E
-    PB_MARK(7)
-    for (int ic = 0; ic < nch; ++ic) {
-      uint32_t z[32];
-      float v[32];
-      pb_tmem_ld32(S0 + lane_off + (uint32_t)(64 * ic + 32 * g), z);
-      pb_tmem_wait_ld();
-      const uint32_t mb = ic == 0 ? m1[0] : ic == 1 ? m1[1] : ic == 2 ? m1[2] : m1[3];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = (mb >> j) & 1u ? r * __uint_as_float(z[j]) : 0.f;
-      chunk_begin();
-      store_chunk(v);
-      chunk_end();
-    }
-    PB_MARK(8)
-    // ---- G7: D1 drain: TMEM lane = input index k (k == d: bias row), group g takes its half of every chunk ----
-    acc_wait();  // D1
-    PB_MARK(9)
-    {
-      const int k = b;
-      for (int ic = 0; ic < nch; ++ic) {
-        const int ncols = (Hp - 64 * ic) < 64 ? (Hp - 64 * ic) : 64;
-        for (int c0 = 32 * g; c0 < ncols && c0 < 32 * g + 32; c0 += 16) {
-          uint32_t dv[16];
-          pb_tmem_ld16(S0 + lane_off + (uint32_t)(64 * ic + c0), dv);
-          pb_tmem_wait_ld();
-          if (k <= pl.d) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int i = 64 * ic + c0 + j;
-              if (i < H) G[L0.soff + k * L0.wp + i] = __uint_as_float(dv[j]);
-            }
-          }
-        }
+      if (lane == 0) {
+        const int si = L2.soff + H * L2.wp, fi = L2.fb;
+        const PbPre pre = pf(si, fi);
+        TH[si] = uf(si, fi, pre, a, noise ? pb_normal_at(nkey, (uint32_t)fi) : 0.f);
       }
     }
     pb_tc_fence_before();

@@ -31,9 +31,10 @@ names = {11: "hmc momentum", 12: "leapfrog pre", 13: "leapfrog post", 14: "logp 
          6: "dW gemm", 7: "dH gemm", 8: "gpart reduce", 9: "post", 10: "gather rows"}
 names.update(tcn)
 if len(w["layers"]) == 4 and os.environ.get("PBNN_NO_TC2") is None and os.environ.get("PBNN_NO_TC") is None:
-    names.update({1: "tc2: restage", 2: "tc2: Z1 wait (fwd1)", 3: "tc2: H1 chunks (fwd2)", 4: "tc2: Z2 wait", 5: "tc2: f, r, mask",
-                  6: "tc2: Y chunks + D2 drain", 7: "tc2: E wait (dH1)", 8: "tc2: dZ1 chunks", 9: "tc2: D1 wait + drain",
-                  10: "tc2: stage X", 11: "tc2: end barrier", 0: "update / other"})
+    names.update({1: "tc2: vectors/restage", 2: "tc2: Z1 wait (fwd1)", 3: "tc2: H1 chunks (fwd2)", 4: "tc2: Z2 wait",
+                  5: "tc2: f, r, mask", 6: "tc2: w3*M2 chunks + E wait", 7: "tc2: dZ1 chunks", 8: "tc2: D1 wait",
+                  9: "tc2: D1 drain+update", 10: "tc2: Y chunks + D2 drain+update (stage X at chain start)",
+                  11: "tc2: w3/b3 + end barrier", 0: "other"})
 tot = sum(out[i] for i in range(32))
 print(f"{name}: T={w['T']}  kernel {a.elapsed_time(b):.3f} ms; CTA0 accounted {tot} cycles; plan {ops.plan(fs, w['B'], 6 if w['algo']=='hmc' else 3)}")
 for i in range(32):

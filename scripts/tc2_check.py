@@ -40,8 +40,8 @@ def check_grad(layers, B, C=3, N=300, scale=0.2):
     return eg
 
 
-def check_samplers(layers, B, C=3, N=300):
-    X, y, sp, fs, keys, th0 = problem(layers, C, N)
+def check_samplers(layers, B, C=3, N=300, scale=0.2):
+    X, y, sp, fs, keys, th0 = problem(layers, C, N, scale=scale)
     T = 5
     ref = o.sgld(sp, X, y, th0, B, 1e-5, T, keys)
     out = ops.sgld(fs, X, y, th0, keys, B, 1e-5, T)
@@ -49,9 +49,17 @@ def check_samplers(layers, B, C=3, N=300):
     ref, (gref, Vref) = o.psgld(sp, X, y, th0, B, 1e-6, T, 0.95, keys, return_state=True)
     out = ops.psgld(fs, X, y, th0, keys, B, 1e-6, T, 0.95)
     print(f"  psgld {layers} B={B}: trace rel {rel(npy(out['trace']), ref):.2e} V rel {rel(npy(out['square_avg']), Vref):.2e}", flush=True)
-    ref = o.sghmc(sp, X, y, th0, B, 1e-9, 3, 4, keys)
-    out = ops.sghmc(fs, X, y, th0, keys, B, 1e-9, 3, 4)
+    ref = o.sghmc(sp, X, y, th0, B, 1e-9, 1, 2, keys)
+    out = ops.sghmc(fs, X, y, th0, keys, B, 1e-9, 1, 2)
     print(f"  sghmc {layers} B={B}: trace rel {rel(npy(out['trace']), ref):.2e}", flush=True)
+    # Adam: 4 steps on explicit minibatches
+    idx = np.random.default_rng(5).integers(0, N, (C, 4, B)).astype(np.int32)
+    th, m, v, cnt = th0.copy(), np.zeros_like(th0), np.zeros_like(th0), 0
+    for s_ in range(4):
+        g = -o.grad_estimator(sp, th, X[idx[:, s_]], y[idx[:, s_]], N)
+        th, m, v, cnt = o.adam_step(th, g.astype(np.float32), m, v, cnt, 1e-3)
+    out = ops.adam_ensemble(fs, X, y, th0, idx, 1e-3)
+    print(f"  adam  {layers} B={B}: theta rel {rel(npy(out['theta']), th):.2e} m rel {rel(npy(out['m']), m):.2e}", flush=True)
 
 
 if __name__ == "__main__":
@@ -67,4 +75,9 @@ if __name__ == "__main__":
         check_grad((70, 160, 160, 1), 128, C=2, N=400, scale=0.05)
     if which in ("samplers", "all"):
         check_samplers((9, 100, 100, 1), 128)
-        check_samplers((90, 256, 256, 1), 128, C=2, N=400)
+        check_samplers((8, 50, 50, 1), 32)
+        check_samplers((90, 256, 256, 1), 128, C=2, N=400, scale=0.03)
+        os.environ["PBNN_NO_TC2"] = "1"
+        print("  (FP32 engine on the same problem:)")
+        check_samplers((90, 256, 256, 1), 128, C=2, N=400, scale=0.03)
+        os.environ.pop("PBNN_NO_TC2")
