@@ -380,7 +380,7 @@ def main():
     predictive = {"samples": int(psmp.shape[0]), "test_points": int(Xt.shape[0]), "ms": pred_ms,
                   "evals_per_s": psmp.shape[0] * Xt.shape[0] / (pred_ms * 1e-3),
                   "engine": "tcgen05" if (len(w["layers"]) == 3 and w["act"] == 0 and w["layers"][1] <= 64
-                                          and w["layers"][0] + 1 <= 16 and not os.environ.get("PBNN_NO_TC")) else "fp32",
+                                          and w["layers"][0] + 1 <= 16 and not ops.get_option("no_tc")) else "fp32",
                   "note": "mean / variance over the samples for every test point; not part of `value`"}
 
     if rank == 0:

@@ -10,7 +10,10 @@
  * Conventions
  *  - all data pointers are DEVICE pointers (cudaMalloc'd / torch CUDA tensors), float32 / uint32 /
  *    int32, C-contiguous; `stream` is a cudaStream_t passed as void* (NULL = default stream);
- *  - no allocation, no hidden global state, re-entrant across streams;
+ *  - no allocation, re-entrant across streams, nothing read from the environment; the only process-wide state is
+ *    the option table written EXPLICITLY through pbnn_set_option() (engine selection for tests / experiments;
+ *    with no option set the library picks engines from the arguments alone) plus per-device caches of immutable
+ *    device properties (SM count, kernel shared-memory attribute);
  *  - return 0 on success, a negative PBNN_E* code otherwise; pbnn_last_error() gives the text
  *    (thread-local);
  *  - parameters are FLAT vectors in jax.flatten_util.ravel_pytree order of the Flax tree
@@ -61,6 +64,15 @@ typedef struct pbnn_mlp_spec {
 
 int pbnn_version(void);
 const char* pbnn_last_error(void);
+/* Engine-selection / tuning options (process-wide, explicit).  Names: "no_tc" (no tensor-core engines), "no_tc2"
+ * (no two-hidden-layer tcgen05 engine), "no_h1" (no fused one-hidden-layer path), "no_resident", "force_gstate",
+ * "no_sched" / "seg_len" (balanced HMC schedule), "nw", "bt", "dw_ks", "two_cta", "one_cta", "pred_tpc" (1, 2 or 4),
+ * "pred_chunks", "tc2_min_h", "tc2_min_rows", "debug".  pbnn_get_option returns 1 (and the sentinel INT_MIN in
+ * *value) when the option is unset.  Every engine computes the same arithmetic contract; options never change
+ * results beyond the stated tolerances. */
+int pbnn_set_option(const char* name, int value);
+int pbnn_get_option(const char* name, int* value);
+void pbnn_reset_options(void);
 /* number of parameters P of the flat vector; <0 on invalid spec */
 int pbnn_num_params(const pbnn_mlp_spec* spec);
 /* launch plan the library would use: out[0]=threads per CTA, out[1]=batch-tile rows,
@@ -121,7 +133,9 @@ int pbnn_permutation(const uint32_t* keys, int C, int N, int32_t* out, void* wor
  *   t0                           index of the first step (keys[t0+t] are used) -- exact resume
  *   thin, burnin                 trace keeps steps t>=burnin with (t-burnin)%thin==0
  *   trace [C][T_out][P]          optional (NULL = keep only the final state)
- *   flags [C]                    optional; bit0 set if the chain became non-finite
+ *   flags [C]                    optional; bit 0: the chain became non-finite; bit 1 (HMC): a segment of the balanced
+ *                                schedule timed out and was skipped (an error: the host API raises); bit 2: a
+ *                                caller-supplied minibatch index was outside [0, N) and has been clamped
  *   cv_grad_center, cv_grad_center_est [C][P]  (sgld, sghmc) optional control variates of blackjax.sgmcmc.gradients
  *                                control_variates, as used by sgld_cv / sghmc_cv / *_svrg (langevin.py:207-354,
  *                                hamiltonian.py:207-359): gradient of the full-data log-posterior at the centring
@@ -158,11 +172,18 @@ int pbnn_psgld_step(const pbnn_mlp_spec* spec, const float* Xb, const float* yb,
                     const uint32_t* keys, float* theta, float* g, float* V, float alpha, float step_size, int C,
                     void* stream);
 
-/* pbnn.mcmc.sghmc (src/pbnn/mcmc/hamiltonian.py:80-140) over blackjax.sghmc(grad_fn, L, alpha=0.01, beta=0) */
+/* pbnn.mcmc.sghmc (src/pbnn/mcmc/hamiltonian.py:80-140) over blackjax.sghmc(grad_fn, L, alpha=0.01, beta=0).
+ * Momentum resampling at the start of every iteration (upstream: `generate_gaussian_noise(rng_key, position, ...)` in
+ * blackjax/sgmcmc/sghmc.py, not vendored -- SURVEY.md 2b):
+ *     p = (momentum_mu + momentum_mu_sqrt_step * sqrt(step)) + (momentum_sigma + momentum_sigma_sqrt_step * sqrt(step)) z
+ * (0, 0, 1, 0): p ~ N(0, 1) ("unit", a call without a scale argument); (0, 0, 0, 1): p ~ N(0, step), the SGHMC paper's
+ * parameterisation and the only one of the three that yields a usable sampler at the reference's settings;
+ * (0, 1, 1, 0): p ~ N(sqrt(step), 1), sqrt(step) passed positionally into the `mu` slot. */
 int pbnn_sghmc_run(const pbnn_mlp_spec* spec, const float* X, const float* y, int N, const int32_t* idx,
                    int idx_steps, int mb_mode, int B, const uint32_t* keys, float* theta, int L, float alpha,
-                   float beta, const float* step_sizes, int n_step_sizes, int64_t t0, int T, int C, int thin,
-                   int burnin, float* trace, uint32_t* flags, const float* cv_grad_center,
+                   float beta, float momentum_mu, float momentum_mu_sqrt_step, float momentum_sigma,
+                   float momentum_sigma_sqrt_step, const float* step_sizes, int n_step_sizes, int64_t t0, int T, int C,
+                   int thin, int burnin, float* trace, uint32_t* flags, const float* cv_grad_center,
                    const float* cv_grad_center_est, float temperature, void* workspace, int64_t workspace_bytes,
                    void* stream);
 

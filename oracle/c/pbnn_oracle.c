@@ -259,9 +259,15 @@ void pbo_reference_draw(const uint32_t* keys, int C, int draw, int B, int N, int
   for (int c = 0; c < C; ++c) reference_draw(keys + 2 * c, draw, B, N, out + (size_t)c * B);
 }
 
-/* algo: 0 sgld, 1 psgld, 2 sghmc.  trace [C][T][P] or NULL.  Fixed minibatch = draw #2. */
+/* algo: 0 sgld, 1 psgld, 2 sghmc.  trace [C][T][P] or NULL.  Fixed minibatch = draw #2.
+ * mom[4]: SGHMC momentum resampling p = (mom[0] + mom[1] sqrt(step)) + (mom[2] + mom[3] sqrt(step)) z -- the upstream
+ * blackjax.sghmc body is not vendored (src/pbnn/mcmc/hamiltonian.py:118-128 is only the call site), so the variant is
+ * a parameter; NULL = unit variance, zero mean. */
 void pbo_sg_run(const Spec* s, int algo, const float* X, const float* y, int N, int B, const uint32_t* keys,
-                float* theta, float step, int T, int C, int L, float alpha, float beta, float* trace) {
+                float* theta, float step, int T, int C, int L, float alpha, float beta, const float* mom,
+                float* trace) {
+  const float mom_mu = mom ? mom[0] + mom[1] * sqrtf(step) : 0.0f;
+  const float mom_sig = mom ? mom[2] + mom[3] * sqrtf(step) : 1.0f;
   const int P = num_params(s);
 #pragma omp parallel for schedule(dynamic)
   for (int c = 0; c < C; ++c) {
@@ -293,7 +299,7 @@ void pbo_sg_run(const Spec* s, int algo, const float* X, const float* y, int N, 
         grad_estimator(s, &w, th, X, y, idx, B, N, g);
         for (int j = 0; j < P; ++j) a1[j] = alpha * a1[j] + (1.0f - alpha) * (g[j] * g[j]);
       } else {
-        for (int j = 0; j < P; ++j) a1[j] = normal_at(kt, (uint32_t)j);
+        for (int j = 0; j < P; ++j) a1[j] = mom_mu + mom_sig * normal_at(kt, (uint32_t)j);
         const float ns = sqrtf(2.0f * step * (alpha - beta)), fr = 1.0f - alpha;
         for (int l = 0; l < L; ++l) {
           uint32_t kl[2];

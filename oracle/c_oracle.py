@@ -83,8 +83,10 @@ def reference_draw(keys, draw, B, N):
     return out
 
 
-def sg_run(layers, act, sigma, algo, X, y, theta0, B, step, T, keys, L=1, alpha=0.01, beta=0.0, trace=True):
-    """algo: 'sgld' | 'psgld' | 'sghmc'; for psgld alpha is the preconditioning factor."""
+def sg_run(layers, act, sigma, algo, X, y, theta0, B, step, T, keys, L=1, alpha=0.01, beta=0.0, trace=True,
+           momentum=(0.0, 0.0, 1.0, 0.0)):
+    """algo: 'sgld' | 'psgld' | 'sghmc'; for psgld alpha is the preconditioning factor; momentum = SGHMC resampling
+    coefficients (mu, mu_sqrt_step, sigma, sigma_sqrt_step)."""
     s = _spec(layers, act, sigma)
     X, y = _f32(X), _f32(y)
     th = _f32(theta0).copy()
@@ -93,7 +95,7 @@ def sg_run(layers, act, sigma, algo, X, y, theta0, B, step, T, keys, L=1, alpha=
     tr = np.empty((C, T, P), np.float32) if trace else None
     lib().pbo_sg_run(ctypes.byref(s), c_int({"sgld": 0, "psgld": 1, "sghmc": 2}[algo]), _p(X), _p(y), c_int(len(X)),
                      c_int(B), _p(keys), _p(th), c_float(step), c_int(T), c_int(C), c_int(L), c_float(alpha),
-                     c_float(beta), _p(tr))
+                     c_float(beta), _p(np.asarray(momentum, np.float32)), _p(tr))
     return th, tr
 
 

@@ -8,7 +8,7 @@ PARITY STATUS: **parity unpinned by the reference** -- the reference's own test-
 ``assert True`` (``/root/reference/tests/test_dummpy.py:1-2``) and JAX / BlackJAX / Flax / Optax
 cannot be installed in this environment, so the reference cannot be executed.  The RNG layer
 is pinned against the Random123 threefry2x32 known-answer vectors and against outputs printed
-in the public JAX documentation (``tests/test_oracle_rng.py``); everything above the RNG is a
+in the public JAX documentation (``tests/test_oracle.py``); everything above the RNG is a
 restatement of the formulas in the files cited per function.
 
 Conventions
@@ -445,11 +445,27 @@ def psgld(spec, X, y, theta0, B, step_size, T, alpha, keys, *, dtype=np.float32,
     return (out, (g, V)) if return_state else out
 
 
+MOMENTUM_UNIT = (0.0, 0.0, 1.0, 0.0)             # p ~ N(0, 1): generate_gaussian_noise(rng_key, position)
+MOMENTUM_SIGMA_SQRT_STEP = (0.0, 0.0, 0.0, 1.0)  # p ~ N(0, step): sigma = sqrt(step_size) (Chen et al. 2014)
+MOMENTUM_MU_SQRT_STEP = (0.0, 1.0, 1.0, 0.0)     # p ~ N(sqrt(step), 1): sqrt(step_size) in the positional `mu` slot
+
+
+def _momentum(momentum, step_size, dt):
+    mu0, mu1, s0, s1 = (np.float32(v) for v in momentum)
+    se = np.sqrt(np.float32(step_size))
+    return dt.type(mu0 + mu1 * se), dt.type(s0 + s1 * se)
+
+
 def sghmc(spec, X, y, theta0, B, step_size, T, L, keys, *, alpha=0.01, beta=0.0, dtype=np.float32,
-          which_draw=2, t0=0):
+          which_draw=2, t0=0, momentum=MOMENTUM_UNIT, _drop_drift=False):
     """src/pbnn/mcmc/hamiltonian.py:80-140 + blackjax.sghmc (1.2.5): fresh momentum from
     ``keys[t]``, ``split(keys[t], L)`` for the L inner noise draws; gradient at the position
-    *before* the position update."""
+    *before* the position update.
+
+    ``momentum`` = (mu, mu_sqrt_step, sigma, sigma_sqrt_step): the resampled momentum is
+    ``(mu + mu_sqrt_step sqrt(eps)) + (sigma + sigma_sqrt_step sqrt(eps)) z``.  The upstream body
+    (blackjax/sgmcmc/sghmc.py, ``generate_gaussian_noise(rng_key, position, ...)``) is not vendored with the reference
+    and cannot be read here, so -- like ``which_draw`` -- the variant is a parameter of the oracle, not a constant."""
     keys = _as_keys(keys)
     dt = np.dtype(dtype)
     theta = np.array(theta0, dtype=dt).reshape(len(keys), -1)
@@ -459,16 +475,17 @@ def sghmc(spec, X, y, theta0, B, step_size, T, L, keys, *, alpha=0.01, beta=0.0,
     eps = dt.type(np.float32(step_size))
     fric = dt.type(1.0) - dt.type(np.float32(alpha))
     ns = dt.type(np.sqrt(np.float32(2.0) * np.float32(step_size) * (np.float32(alpha) - np.float32(beta))))
+    mom_mu, mom_sig = _momentum(momentum, step_size, dt)
     out = np.empty((C, T, P), dtype=dt)
     for t in range(T):
         kt = _step_keys(keys, t0 + t)
-        p = _normals(kt, P, dt)
+        p = mom_mu + mom_sig * _normals(kt, P, dt)
         for l in range(L):
             sub = _step_keys(kt, l)
             g = grad_estimator(spec, theta, Xb, yb, N)
             xi = _normals(sub, P, dt)
             theta = theta + p
-            p = fric * p + eps * g + ns * xi
+            p = fric * p + (dt.type(0) if _drop_drift else eps * g) + ns * xi  # _drop_drift: test-sensitivity probe
         out[:, t] = theta
     return out
 
@@ -555,7 +572,7 @@ def sgld_cv(spec, X, y, theta0, B, step_size, T, centering, keys, *, batch_keys=
 
 
 def sghmc_cv(spec, X, y, theta0, B, step_size, T, centering, L, keys, *, batch_keys=None, alpha=0.01, beta=0.0,
-             dtype=np.float32, which_draw=2):
+             dtype=np.float32, which_draw=2, momentum=MOMENTUM_UNIT):
     """src/pbnn/mcmc/hamiltonian.py:207-273."""
     keys = _as_keys(keys)
     dt = np.dtype(dtype)
@@ -568,10 +585,11 @@ def sghmc_cv(spec, X, y, theta0, B, step_size, T, centering, L, keys, *, batch_k
     eps = dt.type(np.float32(step_size))
     fric = dt.type(1.0) - dt.type(np.float32(alpha))
     ns = dt.type(np.sqrt(np.float32(2.0) * np.float32(step_size) * (np.float32(alpha) - np.float32(beta))))
+    mom_mu, mom_sig = _momentum(momentum, step_size, dt)
     out = np.empty((C, T, P), dtype=dt)
     for t in range(T):
         kt = _step_keys(keys, t)
-        p = _normals(kt, P, dt)
+        p = mom_mu + mom_sig * _normals(kt, P, dt)
         for l in range(L):
             g = (g_c + grad_estimator(spec, theta, Xb, yb, N)) - g_ce
             xi = _normals(_step_keys(kt, l), P, dt)

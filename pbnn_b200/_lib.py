@@ -43,6 +43,9 @@ _SPEC = POINTER(MlpSpecC)
 PROTOTYPES = {
     "pbnn_version": (c_int, []),
     "pbnn_last_error": (c_char_p, []),
+    "pbnn_set_option": (c_int, [c_char_p, c_int]),
+    "pbnn_get_option": (c_int, [c_char_p, POINTER(c_int)]),
+    "pbnn_reset_options": (None, []),
     "pbnn_num_params": (c_int, [_SPEC]),
     "pbnn_plan_query": (c_int, [_SPEC, c_int, c_int, POINTER(c_int32 * 4)]),
     "pbnn_plan_engine": (c_int, [_SPEC, c_int, c_int, c_int]),
@@ -62,7 +65,8 @@ PROTOTYPES = {
                                c_int64, c_int, c_int, c_int, c_int, _P, _P, _P, c_int64, _P]),
     "pbnn_psgld_init": (c_int, [_SPEC, _P, _P, c_int, c_int, _P, _P, _P, c_int, _P]),
     "pbnn_psgld_step": (c_int, [_SPEC, _P, _P, c_int, c_int, _P, _P, _P, _P, c_float, c_float, c_int, _P]),
-    "pbnn_sghmc_run": (c_int, [_SPEC, _P, _P, c_int, _P, c_int, c_int, c_int, _P, _P, c_int, c_float, c_float, _P, c_int,
+    "pbnn_sghmc_run": (c_int, [_SPEC, _P, _P, c_int, _P, c_int, c_int, c_int, _P, _P, c_int, c_float, c_float, c_float,
+                               c_float, c_float, c_float, _P, c_int,
                                c_int64, c_int, c_int, c_int, c_int, _P, _P, _P, _P, c_float, _P, c_int64, _P]),
     "pbnn_hmc_run": (c_int, [_SPEC, _P, _P, c_int, _P, _P, _P, c_float, c_int, c_int64, c_int, c_int, c_int, c_int, _P,
                              _P, _P, _P, _P, _P, _P, c_int64, _P]),

@@ -12,6 +12,11 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 
+#include <atomic>
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "pbnn_engine.cuh"
 
 #if defined(PB_PROFILE)
@@ -87,24 +92,39 @@ pb_hmc_tc_kernel(const __grid_constant__ PbPlan pl, const __grid_constant__ PbHm
       __syncthreads();
       if (item >= nitems) break;
       const int seg = item / a.n_chains, c = item - seg * a.n_chains;
-      if (seg > 0) {
-        if (threadIdx.x == 0) {
-          int done = 0;
-          for (unsigned spin = 0; spin < (1u << 24); ++spin) {  // bounded: a scheduling bug must not hang the GPU
+      const int s0 = seg * a.seg_len, s1 = s0 + a.seg_len < a.S ? s0 + a.seg_len : a.S;
+      volatile int* ok = slot + 1;
+      if (threadIdx.x == 0) {
+        int done = seg;  // segment 0 has no predecessor
+        if (seg > 0) {
+          // bounded in TIME (30 s): a scheduling bug must not hang the GPU.  On time-out the segment is SKIPPED (the
+          // chain keeps the last published state), bit 1 of the chain's flag word is set and carried to the end --
+          // the host turns it into an error -- and the hand-over is still published so later segments do not stall.
+          unsigned long long t_start, t_now;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+          for (;;) {
             asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(done) : "l"(a.sched_done + c) : "memory");
             if (done >= seg) break;
             __nanosleep(200);
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_now));
+            if (t_now - t_start > 30000000000ull) break;
           }
-          if (done < seg && a.flags) atomicOr(a.flags + c, 2u);
         }
-        __syncthreads();
+        *ok = done >= seg ? 1 : 0;
       }
-      const int s0 = seg * a.seg_len, s1 = s0 + a.seg_len < a.S ? s0 + a.seg_len : a.S;
-      pb_hmc_chain<PBNN_ACT_RELU, false, ENG>(pl, a, pb_smem, c, nt, s0, s1, seg > 0, &tc);
       __syncthreads();
-      if (threadIdx.x == 0 && s1 < a.S) {
-        __threadfence();
-        asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.sched_done + c), "r"(seg + 1) : "memory");
+      const bool run = *ok != 0;
+      if (run) pb_hmc_chain<PBNN_ACT_RELU, false, ENG>(pl, a, pb_smem, c, nt, s0, s1, seg > 0, &tc);
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        if (!run) {
+          atomicOr(a.sched_flags + c, 2u);
+          if (s1 >= a.S && a.flags) a.flags[c] = a.sched_flags[c];
+        }
+        if (s1 < a.S) {
+          __threadfence();
+          asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.sched_done + c), "r"(seg + 1) : "memory");
+        }
       }
     }
   }
@@ -620,23 +640,43 @@ static thread_local char g_err[512] = "";
   } while (0)
 
 // SM count of the current device (148 on a B200; also the answer when no device is visible: host-side queries only)
+// (per-device caches of immutable device / kernel properties -- not behavioural state)
 static int pb_backend_num_sms() {
-  static int cached = 0;
-  if (cached > 0) return cached;
+  static std::atomic<int> cached[64];
   int dev = 0, n = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
-      n < 1) {
+  if (cudaGetDevice(&dev) != cudaSuccess) {
     (void)cudaGetLastError();
     return 148;
   }
-  cached = n;
+  if (dev >= 0 && dev < 64 && cached[dev].load(std::memory_order_relaxed) > 0) return cached[dev].load();
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) {
+    (void)cudaGetLastError();
+    return 148;
+  }
+  if (dev >= 0 && dev < 64) cached[dev].store(n);
   return n;
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is raised once per (kernel, device), not on every launch
+static int pb_ensure_smem(const void* kern, size_t smem) {
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, size_t> have;
+  int dev = 0;
+  PB_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  size_t& cur = have[std::make_pair(kern, dev)];
+  if (smem > cur) {
+    PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cur = smem;
+  }
+  return PBNN_OK;
 }
 
 template <class K, class A>
 static int pb_launch(K kern, const PbPlan& pl, const A& a, dim3 grid, void* stream) {
   const size_t smem = (size_t)pl.smem_floats * 4;
-  PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int rc = pb_ensure_smem(reinterpret_cast<const void*>(kern), smem);
+  if (rc) return rc;
   kern<<<grid, pl.NT, smem, (cudaStream_t)stream>>>(pl, a);
   PB_CUDA(cudaGetLastError());
   return PBNN_OK;
@@ -680,7 +720,7 @@ static int pb_backend_hmc(const PbPlan& pl, const PbHmcArgs& a, int C, void* str
       const long long nitems = (long long)((a.S + a.seg_len - 1) / a.seg_len) * C;
       const int slots = 2 * pb_backend_num_sms();
       const int grid = slots < nitems ? slots : (int)nitems;
-      if (pb_env_int("PBNN_DEBUG", 0))
+      if (pb_opt(PB_OPT_DEBUG, 0))
         fprintf(stderr, "[pbnn] hmc tc sched: grid %d, threads %d, smem %d, seg_len %d, items %lld\n", grid, pl.NT,
                 pl.smem_floats * 4, a.seg_len, nitems);
       PB_CUDA(cudaMemsetAsync(a.sched_done, 0, sizeof(int) * (size_t)(C + 1), (cudaStream_t)stream));
@@ -702,14 +742,15 @@ static int pb_backend_predict(const PbPlan& pl, const PbPredArgs& a, int mtiles,
                               void* stream) {
   const PbLayer& L0 = pl.L[0];
   if (pl.nl == 2 && pl.s == 1 && pl.act == PBNN_ACT_RELU && L0.out <= 64 && pl.d + 1 <= 16 && !pl.gstate &&
-      !pb_env_int("PBNN_NO_TC", 0)) {
+      !pb_opt(PB_OPT_NO_TC, 0)) {
     // tcgen05 path; tiles per CTA: as many as still leave every CTA slot (2 per SM) with work
     PbPredTcArgs t;
     t.samples = a.samples; t.S = a.S; t.Xtest = a.Xtest; t.M = a.M; t.preds = a.preds; t.part = a.part;
     t.nchunk = a.nchunk; t.chunk = a.chunk;
     t.d = pl.d; t.H = L0.out; t.P = pl.P; t.fb0 = L0.fb; t.fw0 = L0.fw; t.fb1 = pl.L[1].fb; t.fw1 = pl.L[1].fw;
     const int tiles = (a.M + 127) / 128, slots = 2 * pb_backend_num_sms();
-    t.tpc = pb_env_int("PBNN_PRED_TPC", 4);
+    t.tpc = pb_opt(PB_OPT_PRED_TPC, 4);
+    t.tpc = t.tpc >= 4 ? 4 : (t.tpc >= 2 ? 2 : 1);  // the kernel holds 4 X tiles in its 256 TMEM columns
     while (t.tpc > 1 && (long long)((tiles + t.tpc - 1) / t.tpc) * a.nchunk < slots) t.tpc >>= 1;
     const dim3 g((tiles + t.tpc - 1) / t.tpc, a.nchunk);
     pb_predict_tc_kernel<<<g, 160, 0, (cudaStream_t)stream>>>(t);
@@ -764,7 +805,10 @@ static int pb_backend_perm(const uint32_t* keys, int C, int N, int32_t* out, voi
   while (Np2 < N) Np2 <<= 1;
   const size_t bytes = (size_t)Np2 * 8;
   const int use_smem = bytes <= 200 * 1024;
-  if (use_smem) PB_CUDA(cudaFuncSetAttribute(pb_perm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  if (use_smem) {
+    const int rc = pb_ensure_smem(reinterpret_cast<const void*>(pb_perm_kernel), bytes);
+    if (rc) return rc;
+  }
   pb_perm_kernel<<<C, 1024, use_smem ? bytes : 0, (cudaStream_t)stream>>>(keys, N, Np2, pb_perm_rounds(N), use_smem,
                                                                           out, (unsigned long long*)ws);
   PB_CUDA(cudaGetLastError());

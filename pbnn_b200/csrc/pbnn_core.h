@@ -72,9 +72,34 @@ struct PbPlan {
 static inline int pb_r4(int x) { return (x + 3) & ~3; }
 static inline int pb_r32(int x) { return (x + 31) & ~31; }
 
-static inline int pb_env_int(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return (v && *v) ? atoi(v) : dflt;
+// Engine-selection / tuning options.  The ONLY process-wide state of the library: an explicit table written through
+// pbnn_set_option() (tests and experiments select engines with it); nothing is read from the environment.
+enum {
+  PB_OPT_DW_KS = 0, PB_OPT_NW, PB_OPT_NO_RESIDENT, PB_OPT_NO_H1, PB_OPT_NO_TC, PB_OPT_BT, PB_OPT_TWO_CTA,
+  PB_OPT_ONE_CTA, PB_OPT_FORCE_GSTATE, PB_OPT_NO_SCHED, PB_OPT_SEG_LEN, PB_OPT_DEBUG, PB_OPT_PRED_TPC,
+  PB_OPT_PRED_CHUNKS, PB_OPT_TC2_MIN_H, PB_OPT_TC2_MIN_ROWS, PB_OPT_NO_TC2, PB_OPT_COUNT
+};
+static const char* const pb_opt_names[PB_OPT_COUNT] = {
+    "dw_ks", "nw", "no_resident", "no_h1", "no_tc", "bt", "two_cta", "one_cta", "force_gstate", "no_sched", "seg_len",
+    "debug", "pred_tpc", "pred_chunks", "tc2_min_h", "tc2_min_rows", "no_tc2"};
+#define PB_OPT_UNSET (-2147483647 - 1)
+inline int* pb_opt_table() {
+  static int t[PB_OPT_COUNT];
+  static bool init = false;
+  if (!init) {
+    for (int i = 0; i < PB_OPT_COUNT; ++i) t[i] = PB_OPT_UNSET;
+    init = true;
+  }
+  return t;
+}
+static inline int pb_opt(int id, int dflt) {
+  const int v = pb_opt_table()[id];
+  return v == PB_OPT_UNSET ? dflt : v;
+}
+static inline int pb_opt_find(const char* name) {
+  for (int i = 0; i < PB_OPT_COUNT; ++i)
+    if (name && !strcmp(name, pb_opt_names[i])) return i;
+  return -1;
 }
 
 static inline int pb_num_params(const pbnn_mlp_spec* sp) {
@@ -89,7 +114,7 @@ static inline int pb_num_params(const pbnn_mlp_spec* sp) {
 // choose the lane layout / split-K of every weight-gradient GEMM for `nw` warps and batch tile `bt`
 static inline void pb_plan_dw(PbPlan* pl, int nw, int bt, int kcap) {
   pl->ksmax = 1;
-  const int ks_env = pb_env_int("PBNN_DW_KS", 0);
+  const int ks_env = pb_opt(PB_OPT_DW_KS, 0);
   for (int l = 0; l < pl->nl; ++l) {
     PbLayer& Ly = pl->L[l];
     int best_ni = 8, best_ks = 1;
@@ -359,27 +384,27 @@ static inline int pb_build_plan(const pbnn_mlp_spec* sp, int rows, int nstate, i
   pl->Ps = soff;
   pl->nstate = nstate;
   pl->idx_cap = pb_r4(idx_cap);
-  pl->NT = 32 * pb_env_int("PBNN_NW", 8);
+  pl->NT = 32 * pb_opt(PB_OPT_NW, 8);
   if (pl->NT < 32 || pl->NT > PB_MAX_NT || (pl->NT & (pl->NT - 1))) {
     snprintf(err, errn, "PBNN_NW out of range");
     return PBNN_EINVAL;
   }
-  const int want_res = (flags & PB_PLAN_RES) && !pb_env_int("PBNN_NO_RESIDENT", 0);
+  const int want_res = (flags & PB_PLAN_RES) && !pb_opt(PB_OPT_NO_RESIDENT, 0);
   int maxbt = pb_r32(rows);
   if (maxbt > 128) maxbt = 128;
   // fused one-hidden-layer path (scalar output, H <= 64, d+1 <= 16, all rows resident); CUDA only (warp shuffles)
   int h1_ok = want_res && pl->nl == 2 && pl->s == 1 && sp->dims[1] <= 64 && pl->d + 1 <= 16 &&
-              !(flags & PB_PLAN_ACC) && !pb_env_int("PBNN_NO_H1", 0);
+              !(flags & PB_PLAN_ACC) && !pb_opt(PB_OPT_NO_H1, 0);
 #if defined(PB_EMU)
   h1_ok = 0;
 #endif
-  const int nw_env = pb_env_int("PBNN_NW", 0);
+  const int nw_env = pb_opt(PB_OPT_NW, 0);
 #if !defined(PB_EMU)
   // two-hidden-layer tcgen05 engine: d-H-H-1 relu, one 128-row tile per gradient evaluation
   if ((flags & PB_PLAN_TC2) && pl->nl == 3 && pl->s == 1 && !hetero && sp->activation == PBNN_ACT_RELU &&
-      sp->dims[1] == sp->dims[2] && sp->dims[1] <= 256 && sp->dims[1] >= pb_env_int("PBNN_TC2_MIN_H", 48) &&
-      pl->d + 1 <= 128 && rows <= 128 && rows >= pb_env_int("PBNN_TC2_MIN_ROWS", 32) && !(flags & PB_PLAN_ACC) &&
-      !pb_env_int("PBNN_NO_TC", 0) && !pb_env_int("PBNN_NO_TC2", 0)) {
+      sp->dims[1] == sp->dims[2] && sp->dims[1] <= 256 && sp->dims[1] >= pb_opt(PB_OPT_TC2_MIN_H, 64) &&
+      pl->d + 1 <= 128 && rows <= 128 && rows >= pb_opt(PB_OPT_TC2_MIN_ROWS, 64) && !(flags & PB_PLAN_ACC) &&
+      !pb_opt(PB_OPT_NO_TC, 0) && !pb_opt(PB_OPT_NO_TC2, 0)) {
     pb_layout_tc2(pl, sp, rows);
     if ((size_t)pl->smem_floats * 4 <= (size_t)PB_SMEM_LIMIT_BYTES) return PBNN_OK;
     pl->tc2 = 0;
@@ -387,7 +412,7 @@ static inline int pb_build_plan(const pbnn_mlp_spec* sp, int rows, int nstate, i
   }
 #endif
   // tcgen05 path: the same nets, relu only (the weight gradient uses the 0/1 activation mask as an exact operand)
-  if (h1_ok && (flags & PB_PLAN_TC) && sp->activation == PBNN_ACT_RELU && !hetero && !pb_env_int("PBNN_NO_TC", 0) &&
+  if (h1_ok && (flags & PB_PLAN_TC) && sp->activation == PBNN_ACT_RELU && !hetero && !pb_opt(PB_OPT_NO_TC, 0) &&
       rows <= 128 * PB_TC_MAX_TILES) {
     pb_layout_tc(pl, rows, nstate);
     if ((size_t)pl->smem_floats * 4 <= (size_t)PB_SMEM_LIMIT_BYTES) return PBNN_OK;
@@ -401,15 +426,15 @@ static inline int pb_build_plan(const pbnn_mlp_spec* sp, int rows, int nstate, i
     const int w = rows / 16;
     pl->h1_nw = w >= 8 ? 8 : w >= 4 ? 4 : 2;
   }
-  const int forced = pb_env_int("PBNN_BT", 0);
+  const int forced = pb_opt(PB_OPT_BT, 0);
   if (forced > 0) maxbt = pb_r32(forced) > 128 ? 128 : pb_r32(forced);
   // Two passes: first try to stay under half an SM's shared memory so that two CTAs are co-resident (more warps to
   // hide the latency of the short dependent phases) when there are more chains than SMs; then the full SM.
   const size_t lim2 = (size_t)(228 * 1024) / 2 - 1024, lim1 = PB_SMEM_LIMIT_BYTES;
-  const int two = (chains_hint > 148 || pb_env_int("PBNN_TWO_CTA", 0)) && !pb_env_int("PBNN_ONE_CTA", 0);
+  const int two = (chains_hint > 148 || pb_opt(PB_OPT_TWO_CTA, 0)) && !pb_opt(PB_OPT_ONE_CTA, 0);
   // Plans that end up with one CTA per SM anyway (large resident state) run 16 warps instead of 8: the phases are
   // short dependent sequences, 4 warps per scheduler hide their latency much better than 2.
-  for (int pass = pb_env_int("PBNN_FORCE_GSTATE", 0) ? 2 : (two ? 0 : 1); pass < 2; ++pass) {
+  for (int pass = pb_opt(PB_OPT_FORCE_GSTATE, 0) ? 2 : (two ? 0 : 1); pass < 2; ++pass) {
     pl->NT = nw_env > 0 ? 32 * nw_env : (pass == 0 ? 256 : 512);
     const size_t limit = pass == 0 ? lim2 : lim1;
     for (int bt = maxbt; bt >= 32; bt -= 32) {
@@ -469,6 +494,7 @@ struct PbSgArgs {
   float* trace;
   uint32_t* flags;
   float alpha, beta;
+  float mom_mu0, mom_mu1, mom_sig0, mom_sig1;  // SGHMC momentum resampling: p = (mu0 + mu1 sqrt(eps)) + (sig0 + sig1 sqrt(eps)) z
   int L;
   float lr, b1, b2, eps;
   int count0;

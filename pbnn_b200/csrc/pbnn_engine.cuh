@@ -939,10 +939,21 @@ PB_DEV void pb_gen_indices(const PbPlan& pl, float* sm, int B, int N, uint32_t m
   PB_ENDPHASE
 }
 
-PB_DEV void pb_copy_indices(const PbPlan& pl, float* sm, const int32_t* src, int B, int nt) {
+// caller-supplied indices are clamped to [0, N) like a JAX gather (an out-of-range index must not become an
+// out-of-bounds read); bit 2 of the chain's flag word records that it happened
+PB_DEV void pb_copy_indices(const PbPlan& pl, float* sm, const int32_t* src, int B, int N, int nt) {
   PB_PHASE
   int* idx = pb_idx(pl, sm);
-  for (int b = tid; b < B; b += nt) idx[b] = src ? src[b] : b;  // nullptr: rows 0..B-1
+  bool clamped = false;
+  for (int b = tid; b < B; b += nt) {
+    int v = src ? src[b] : b;  // nullptr: rows 0..B-1
+    if (v < 0 || v >= N) {
+      v = v < 0 ? 0 : N - 1;
+      clamped = true;
+    }
+    idx[b] = v;
+  }
+  if (clamped) PB_ATOMIC_OR(pb_scu(pl, sm) + 2, 4u);
   PB_ENDPHASE
 }
 
@@ -998,7 +1009,7 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
 
   pb_init_acts(pl, sm, nt);
   pb_load_state(pl, TH, a.theta + cP, nt);
-  pb_load_state(pl, G, nullptr, nt);
+  if (ENG != 2 || ALGO == PB_ALGO_PSGLD) pb_load_state(pl, G, nullptr, nt);
   if (ALGO == PB_ALGO_PSGLD) {
     pb_load_state(pl, G, a.has_state ? a.aux1 + cP : nullptr, nt);
     pb_load_state(pl, A1, a.has_state ? a.aux2 + cP : nullptr, nt);
@@ -1028,7 +1039,7 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
   int gen_pos = 0;  // how many draws of the generator have been consumed (uniform across threads)
 
   if (ALGO == PB_ALGO_GRAD) {
-    pb_copy_indices(pl, sm, cidx, B, nt);
+    pb_copy_indices(pl, sm, cidx, B, a.N, nt);
     if (res) load_res();
 #if !defined(PB_EMU)
     if constexpr (ENG == 2) {
@@ -1057,7 +1068,7 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
   // pSGLD init (psgld.py:25-29): g0 = grad(theta0, draw #init_draw), V0 = g0^2
   if (ALGO == PB_ALGO_PSGLD && !a.has_state) {
     if (explicit_idx) {
-      pb_copy_indices(pl, sm, cidx, B, nt);
+      pb_copy_indices(pl, sm, cidx, B, a.N, nt);
     } else {
       pb_gen_advance(pl, sm, a.init_draw - gen_pos, nt);
       gen_pos = a.init_draw;
@@ -1090,7 +1101,7 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
   bool tile_loaded = false;
   if (!per_step) {
     if (explicit_idx) {
-      pb_copy_indices(pl, sm, cidx, B, nt);
+      pb_copy_indices(pl, sm, cidx, B, a.N, nt);
     } else {
       pb_gen_advance(pl, sm, a.which_draw - gen_pos, nt);
       gen_pos = a.which_draw;
@@ -1114,7 +1125,7 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
     const float eps = a.step_sizes ? a.step_sizes[t < a.n_step_sizes ? t : a.n_step_sizes - 1] : a.const_step;
     if (per_step) {
       if (explicit_idx) {
-        pb_copy_indices(pl, sm, cidx ? cidx + (size_t)t * B : nullptr, B, nt);
+        pb_copy_indices(pl, sm, cidx ? cidx + (size_t)t * B : nullptr, B, a.N, nt);
       } else {
         pb_gen_advance(pl, sm, 1, nt);
         pb_gen_indices(pl, sm, B, a.N, a.randint_mult, nt);
@@ -1128,21 +1139,27 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
         const float ns = sqrtf(2.0f * a.temperature * eps);
         const float* cvc = a.cv_center ? a.cv_center + cP : nullptr;
         const float* cve = a.cv_center ? a.cv_center_est + cP : nullptr;
-        t2grad(
-            kt, true,
-            [&](int si, int fi) {
-              PbPre v;
-              v.a = TH[si];
-              v.c = cvc ? cvc[fi] : 0.f;
-              v.d = cvc ? cve[fi] : 0.f;
-              return v;
-            },
-            [&](int si, int fi, const PbPre& v, float gll, float z) {
-              const float th = v.a;
-              float g = gll - th * pl.inv_pv;
-              if (cvc) g = (v.c + g) - v.d;
-              return th + eps * g + ns * z;
-            });
+        if (cvc) {
+          t2grad(
+              kt, true,
+              [&](int si, int fi) {
+                PbPre v;
+                v.a = TH[si];
+                v.c = cvc[fi];
+                v.d = cve[fi];
+                return v;
+              },
+              [&](int si, int fi, const PbPre& v, float gll, float z) {
+                const float th = v.a;
+                const float g = (v.c + (gll - th * pl.inv_pv)) - v.d;
+                return th + eps * g + ns * z;
+              });
+        } else {
+          t2grad(kt, true, pf_theta, [&](int si, int fi, const PbPre& v, float gll, float z) {
+            const float th = v.a;
+            return th + eps * (gll - th * pl.inv_pv) + ns * z;
+          });
+        }
       }
 #endif
     } else if (ALGO == PB_ALGO_SGLD) {
@@ -1256,9 +1273,13 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
       PB_ENDPHASE
     } else if (ALGO == PB_ALGO_SGHMC) {
       PB_PHASE
+      // momentum resampling p = mu + sigma z (blackjax.sghmc: generate_gaussian_noise(rng_key, position, ...); which
+      // of (mu, sigma) carries sqrt(step_size) is a parameter -- see DESIGN.md and include/pbnn_b200.h)
+      const float seps = sqrtf(eps);
+      const float mom_mu = a.mom_mu0 + a.mom_mu1 * seps, mom_sig = a.mom_sig0 + a.mom_sig1 * seps;
       pb_for_each_param_normal(
           pl, tid, nt, kt, [&](int si, int fi) { return PbPre(); },
-          [&](int si, int fi, float z, const PbPre& v) { A1[si] = z; });
+          [&](int si, int fi, float z, const PbPre& v) { A1[si] = mom_mu + mom_sig * z; });
       PB_ENDPHASE
       const float ns = sqrtf(2.0f * eps * (a.alpha - a.beta) * a.temperature);
       const float* cvc = a.cv_center ? a.cv_center + cP : nullptr;
@@ -1268,23 +1289,38 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
         const PbKey kl = pb_split_at(kt, (uint32_t)l);  // split(keys[t], L)[l]
 #if !defined(PB_EMU)
         if constexpr (ENG == 2) {
-          t2grad(
-              kl, true,
-              [&](int si, int fi) {
-                PbPre v;
-                v.a = TH[si];
-                v.b = A1[si];
-                v.d = cvc ? cvc[fi] : 0.f;
-                v.e = cvc ? cve[fi] : 0.f;
-                return v;
-              },
-              [&](int si, int fi, const PbPre& v, float gll, float z) {
-                const float th = v.a, p = v.b;
-                float g = gll - th * pl.inv_pv;
-                if (cvc) g = (v.d + g) - v.e;
-                A1[si] = fric * p + eps * g + ns * z;
-                return th + p;
-              });
+          if (cvc) {
+            t2grad(
+                kl, true,
+                [&](int si, int fi) {
+                  PbPre v;
+                  v.a = TH[si];
+                  v.b = A1[si];
+                  v.d = cvc[fi];
+                  v.e = cve[fi];
+                  return v;
+                },
+                [&](int si, int fi, const PbPre& v, float gll, float z) {
+                  const float th = v.a, p = v.b;
+                  const float g = (v.d + (gll - th * pl.inv_pv)) - v.e;
+                  A1[si] = fric * p + eps * g + ns * z;
+                  return th + p;
+                });
+          } else {
+            t2grad(
+                kl, true,
+                [&](int si, int fi) {
+                  PbPre v;
+                  v.a = TH[si];
+                  v.b = A1[si];
+                  return v;
+                },
+                [&](int si, int fi, const PbPre& v, float gll, float z) {
+                  const float th = v.a, p = v.b;
+                  A1[si] = fric * p + eps * (gll - th * pl.inv_pv) + ns * z;
+                  return th + p;
+                });
+          }
           continue;
         }
 #endif

@@ -111,7 +111,10 @@ PB_DEV float pb_erfinv(float x) {
   // x * p(w) with |p'| <= 0.25, so z moves by < 3e-7 in the bulk -- inside the 1e-6 contract on normals (tests).  The
   // tail (w >= 5, 0.3 % of the draws) uses w * rsqrt(w): relative 2^-22, inside the 5e-6 relative contract there.
   float l2, rs;
-  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(1.0f + (-(x * x))));  // argument in [2^-23, 1]: never denormal
+  // x * x must be ROUNDED before the subtraction, as XLA's log1p(-(x * x)) sees it: contracted into an FMA the argument
+  // is the exact 1 - x^2, which differs from the reference's by up to 2e-4 relative when |x| -> 1 (2e-5 on z at |z| ~ 4)
+  const float xx = __fmul_rn(x, x);
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(__fadd_rn(1.0f, -xx)));  // argument in [2^-23, 1]: never denormal
   const float w = l2 * -0.693147180559945f;
   asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(w));  // w == 0 -> inf -> NaN below: discarded by the select
   const float pb = pb_erfinv_poly_bulk(w - 2.5f);

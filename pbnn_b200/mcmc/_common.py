@@ -24,6 +24,33 @@ def chain_layout(init_positions, rng_key):
     return flat, layers, keys, batched
 
 
+def setup(loglikelihood_fn, logprior_fn, init_positions, rng_key):
+    """Common front end of the SG wrappers: spec objects checked, chains laid out, network widths verified."""
+    from ..logprobs import require_specs
+    require_specs(loglikelihood_fn, logprior_fn)
+    flat, layers, keys, batched = chain_layout(init_positions, rng_key)
+    spec = loglikelihood_fn.flat_spec(layers[0], logprior_fn)
+    if tuple(spec.layers) != tuple(layers):
+        raise ValueError(f"init_positions widths {layers} do not match the network {spec.layers}")
+    return default_ops(), spec, flat, layers, keys, batched
+
+
+def check_flags(res, who: str):
+    """The kernels report per-chain conditions in ``flags`` (include/pbnn_b200.h): bit 0 non-finite state (the
+    reference's pipelines detect NaNs after the fact, benchmark/pipelines/sgmcmc.py:207-209), bit 2 clamped minibatch
+    index.  A warning, not an error: a diverged chain is a legitimate sampler outcome.  (One small D2H read.)"""
+    import warnings
+    flags = res.get("flags")
+    if flags is None:
+        return
+    f = flags.detach().cpu().numpy()
+    if (f & 1).any():
+        warnings.warn(f"{who}: {int((f & 1).sum())} of {f.size} chains became non-finite (flags bit 0)", RuntimeWarning,
+                      stacklevel=3)
+    if (f & 4).any():
+        warnings.warn(f"{who}: minibatch indices outside [0, N) were clamped (flags bit 2)", RuntimeWarning, stacklevel=3)
+
+
 def positions_tree(trace: torch.Tensor, layers, batched: bool):
     """(C, T, P) trace -> pytree with leading (T, ...) (single chain) or (C, T, ...)."""
     t = trace if batched else trace[0]

@@ -8,20 +8,16 @@ from __future__ import annotations
 
 from ..logprobs import require_specs
 from ..ops import default_ops
-from ._common import chain_layout, make_predict_fn, make_ravel_fn, positions_tree
+from ._common import chain_layout, check_flags, make_predict_fn, make_ravel_fn, positions_tree, setup
 
 
 def _run(algo, X, y, loglikelihood_fn, logprior_fn, init_positions, batch_size, step_size, num_iterations, rng_key,
          thin, burnin, minibatch_mode, **extra):
-    require_specs(loglikelihood_fn, logprior_fn)
-    ops = default_ops()
-    flat, layers, keys, batched = chain_layout(init_positions, rng_key)
-    spec = loglikelihood_fn.flat_spec(layers[0], logprior_fn)
-    if tuple(spec.layers) != tuple(layers):
-        raise ValueError(f"init_positions widths {layers} do not match the network {spec.layers}")
+    ops, spec, flat, layers, keys, batched = setup(loglikelihood_fn, logprior_fn, init_positions, rng_key)
     fn = getattr(ops, algo)
     res = fn(spec, X, y, flat, keys, int(batch_size), step_size, int(num_iterations), minibatch_mode=minibatch_mode,
              thin=thin, burnin=burnin, **extra)
+    check_flags(res, algo)
     return positions_tree(res["trace"], layers, batched), make_ravel_fn(layers), make_predict_fn(layers)
 
 
@@ -35,12 +31,10 @@ def sgld(X, y, loglikelihood_fn, logprior_fn, init_positions, batch_size, step_s
 def pSGLD(X, y, loglikelihood_fn, logprior_fn, init_positions, batch_size, step_size, num_iterations,
           preconditioning_factor, rng_key, *, thin=1, burnin=0, minibatch_mode="reference_fixed"):
     """pbnn.mcmc.pSGLD (langevin.py:81-140)."""
-    require_specs(loglikelihood_fn, logprior_fn)
-    ops = default_ops()
-    flat, layers, keys, batched = chain_layout(init_positions, rng_key)
-    spec = loglikelihood_fn.flat_spec(layers[0], logprior_fn)
+    ops, spec, flat, layers, keys, batched = setup(loglikelihood_fn, logprior_fn, init_positions, rng_key)
     res = ops.psgld(spec, X, y, flat, keys, int(batch_size), step_size, int(num_iterations),
                     float(preconditioning_factor), minibatch_mode=minibatch_mode, thin=thin, burnin=burnin)
+    check_flags(res, "pSGLD")
     return positions_tree(res["trace"], layers, batched), make_ravel_fn(layers), make_predict_fn(layers)
 
 
@@ -66,14 +60,12 @@ def _cv_terms(ops, spec, X, y, centering_flat, batch_keys, batch_size):
 def sgld_cv(X, y, loglikelihood_fn, logprior_fn, init_positions, batch_size, step_size, num_iterations,
             centering_positions, rng_key, *, thin=1, burnin=0):
     """pbnn.mcmc.sgld_cv (langevin.py:207-270): SGLD with blackjax's control-variates gradient estimator."""
-    require_specs(loglikelihood_fn, logprior_fn)
-    ops = default_ops()
-    flat, layers, keys, batched = chain_layout(init_positions, rng_key)
+    ops, spec, flat, layers, keys, batched = setup(loglikelihood_fn, logprior_fn, init_positions, rng_key)
     cflat, _, _, _ = chain_layout(centering_positions, rng_key)
-    spec = loglikelihood_fn.flat_spec(layers[0], logprior_fn)
     g_full, g_est, idx = _cv_terms(ops, spec, X, y, cflat, keys, batch_size)
     res = ops.sgld(spec, X, y, flat, keys, int(batch_size), step_size, int(num_iterations), idx=idx,
                    cv=(g_full, g_est), thin=thin, burnin=burnin)
+    check_flags(res, "sgld_cv")
     return positions_tree(res["trace"], layers, batched), make_ravel_fn(layers), make_predict_fn(layers)
 
 
@@ -82,11 +74,8 @@ def sgld_svrg(X, y, loglikelihood_fn, logprior_fn, init_positions, batch_size, s
     """pbnn.mcmc.sgld_svrg (langevin.py:273-354): ``num_svrg_iterations`` re-centred blocks of ``num_cv_iterations``
     control-variate SGLD steps; positions of all blocks concatenated."""
     import torch
-    require_specs(loglikelihood_fn, logprior_fn)
-    ops = default_ops()
-    flat, layers, keys, batched = chain_layout(init_positions, rng_key)
+    ops, spec, flat, layers, keys, batched = setup(loglikelihood_fn, logprior_fn, init_positions, rng_key)
     cflat, _, _, _ = chain_layout(centering_positions, rng_key)
-    spec = loglikelihood_fn.flat_spec(layers[0], logprior_fn)
     outer = ops.split(keys, int(num_svrg_iterations))  # (C, n_svrg, 2)
     traces, theta, centre = [], flat, cflat
     for i in range(int(num_svrg_iterations)):
@@ -95,6 +84,7 @@ def sgld_svrg(X, y, loglikelihood_fn, logprior_fn, init_positions, batch_size, s
                        int(num_cv_iterations), idx=idx, cv=(g_full, g_est))
         traces.append(res["trace"])
         theta = centre = res["theta"]
+    check_flags(res, "sgld_svrg")
     trace = torch.cat(traces, dim=1)
     return positions_tree(trace, layers, batched), make_ravel_fn(layers), make_predict_fn(layers)
 
@@ -109,10 +99,7 @@ def cyclical_sgld(X, y, loglikelihood_fn, logprior_fn, init_positions, batch_siz
     import math
 
     import torch
-    require_specs(loglikelihood_fn, logprior_fn)
-    ops = default_ops()
-    flat, layers, keys, batched = chain_layout(init_positions, rng_key)
-    spec = loglikelihood_fn.flat_spec(layers[0], logprior_fn)
+    ops, spec, flat, layers, keys, batched = setup(loglikelihood_fn, logprior_fn, init_positions, rng_key)
     N = int(X.shape[0]) if hasattr(X, "shape") else len(X)
     cycle_length = int(num_sgd_steps) + int(num_sgld_steps)
 
@@ -132,5 +119,6 @@ def cyclical_sgld(X, y, loglikelihood_fn, logprior_fn, init_positions, batch_siz
         res = ops.sgld(spec, X, y, res["theta"], key, int(batch_size), schedule(int(num_sgld_steps)),
                        int(num_sgld_steps), idx=idx, burnin=int(burnin_sgld))
         kept.append(res["trace"])
+    check_flags(res, "cyclical_sgld")
     trace = torch.cat(kept, dim=1)
     return positions_tree(trace, layers, batched), make_ravel_fn(layers), make_predict_fn(layers)

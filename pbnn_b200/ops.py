@@ -17,6 +17,26 @@ from ._lib import ACT_RELU, ACT_TANH, MB_PER_STEP, MB_REFERENCE_FIXED, check, ma
 
 _MB_MODES = {"reference_fixed": MB_REFERENCE_FIXED, "per_step": MB_PER_STEP}
 
+# SGHMC momentum resampling p = (mu0 + mu1 sqrt(step)) + (sig0 + sig1 sqrt(step)) z  (include/pbnn_b200.h):
+# blackjax.sghmc is not vendored with the reference, so which of the three the pinned 1.2.5 implements cannot be read
+# here; the default is the restatement of SURVEY.md 2b.
+MOMENTUM_RESAMPLING = {
+    "unit": (0.0, 0.0, 1.0, 0.0),             # p ~ N(0, 1): generate_gaussian_noise(rng_key, position)
+    "sigma_sqrt_step": (0.0, 0.0, 0.0, 1.0),  # p ~ N(0, step): sigma=sqrt(step_size) (Chen et al. 2014)
+    "mu_sqrt_step": (0.0, 1.0, 1.0, 0.0),     # p ~ N(sqrt(step), 1): sqrt(step_size) landing in the `mu` slot
+}
+
+
+def momentum_coefficients(momentum):
+    if isinstance(momentum, str):
+        if momentum not in MOMENTUM_RESAMPLING:
+            raise ValueError(f"momentum_resampling must be one of {sorted(MOMENTUM_RESAMPLING)} or 4 coefficients")
+        return MOMENTUM_RESAMPLING[momentum]
+    coef = tuple(float(v) for v in momentum)
+    if len(coef) != 4:
+        raise ValueError("momentum_resampling: expected (mu, mu_sqrt_step, sigma, sigma_sqrt_step)")
+    return coef
+
 
 @dataclass(frozen=True)
 class FlatSpec:
@@ -53,6 +73,20 @@ class Ops:
 
     def __init__(self, lib=None):
         self.lib = lib if lib is not None else _lib.load_library()
+
+    # ---- explicit engine-selection options (the library reads nothing from the environment) ------------
+    def set_option(self, name: str, value: int) -> None:
+        check(self.lib, self.lib.pbnn_set_option(name.encode(), int(value)), "set_option")
+
+    def get_option(self, name: str):
+        v = _lib.c_int(0)
+        rc = self.lib.pbnn_get_option(name.encode(), v)
+        if rc < 0:
+            check(self.lib, rc, "get_option")
+        return None if rc == 1 else int(v.value)
+
+    def reset_options(self) -> None:
+        self.lib.pbnn_reset_options()
 
     # ---- array handling (CUDA) -----------------------------------------------------------------
     def _device(self):
@@ -248,7 +282,8 @@ class Ops:
 
     def sghmc(self, spec: FlatSpec, X, y, theta, keys, B: int, step_size, T: int, L: int, *, alpha=0.01, beta=0.0,
               idx=None, minibatch_mode="reference_fixed", t0=0, thin=1, burnin=0, keep_trace=True, cv=None,
-              temperature=1.0):
+              temperature=1.0, momentum_resampling="unit"):
+        mom = momentum_coefficients(momentum_resampling)
         keys, C, X, y, th, ix, idx_steps, steps, nsteps, trace, flags = self._sg_common(
             spec, X, y, theta, keys, B, step_size, T, idx, thin, burnin, keep_trace)
         cs = spec.c_struct()
@@ -256,7 +291,8 @@ class Ops:
         cvc, cve = self._cv(cv, spec, C)
         rc = self.lib.pbnn_sghmc_run(cs, self._ptr(X), self._ptr(y), X.shape[0], self._ptr(ix), idx_steps,
                                      _MB_MODES[minibatch_mode], B, self._ptr(keys), self._ptr(th), int(L), float(alpha),
-                                     float(beta), self._ptr(steps), nsteps, t0, T, C, thin, burnin, self._ptr(trace),
+                                     float(beta), mom[0], mom[1], mom[2], mom[3], self._ptr(steps), nsteps, t0, T, C,
+                                     thin, burnin, self._ptr(trace),
                                      self._ptr(flags), self._ptr(cvc), self._ptr(cve), float(temperature),
                                      self._ptr(ws), wsb, self._stream())
         check(self.lib, rc, "sghmc")
@@ -285,6 +321,9 @@ class Ops:
                                    self._ptr(trace), self._ptr(logp), self._ptr(acc), self._ptr(idelta), self._ptr(iacc),
                                    self._ptr(flags), self._ptr(ws), wsb, self._stream())
         check(self.lib, rc, "hmc")
+        if wsb > 0 and bool((flags & 2).any().item()):  # balanced schedule only: a hand-over timed out (segment skipped)
+            raise _lib.PbnnError("hmc: a segment of the balanced tcgen05 schedule timed out waiting for its "
+                                 "predecessor; the affected chains have bit 1 set in `flags` and are incomplete")
         return {"theta": th, "trace": trace, "flags": flags, "logp": logp, "accept_count": acc, "delta": idelta,
                 "accept": iacc}
 

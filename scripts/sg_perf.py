@@ -9,7 +9,7 @@ from pbnn_b200.ops import FlatSpec, default_ops
 
 ops = default_ops()
 names = sys.argv[1].split(",") if len(sys.argv) > 1 else ["sgld_cfg3", "psgld_cfg3", "sghmc_cfg3", "adam_cfg4", "sgld_cfg5"]
-envs = sys.argv[2].split(",") if len(sys.argv) > 2 else ["", "PBNN_NO_TC2=1"]
+envs = sys.argv[2].split(",") if len(sys.argv) > 2 else ["", "no_tc2=1"]  # library options, "a=1+b=2"
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 for name in names:
     w = dict(bench.WORKLOADS[name], name=name)
@@ -21,7 +21,7 @@ for name in names:
     for env in envs:
         for kv in filter(None, env.split("+")):
             k, v = kv.split("=")
-            os.environ[k] = v
+            ops.set_option(k, int(v))
         eng = ops.lib.pbnn_plan_engine(fs.c_struct(), op, w["B"], w["C"])
         r = step(); torch.cuda.synchronize()
         ms = []
@@ -31,7 +31,6 @@ for name in names:
             ms.append(a.elapsed_time(b))
         best = min(ms)
         fin = bool(torch.isfinite(r["theta"]).all().item())
-        print(f"{name:12s} env[{env}] engine={eng} C={w['C']} T={w['T']} L={w['L']}: {best:9.2f} ms  "
+        print(f"{name:12s} opt[{env}] engine={eng} C={w['C']} T={w['T']} L={w['L']}: {best:9.2f} ms  "
               f"{w['C'] * w['T'] / best * 1e3 / 1e6:8.3f} M chain-steps/s  finite={fin}", flush=True)
-        for kv in filter(None, env.split("+")):
-            os.environ.pop(kv.split("=")[0], None)
+        ops.reset_options()

@@ -77,7 +77,7 @@ if __name__ == "__main__":
         check_samplers((9, 100, 100, 1), 128)
         check_samplers((8, 50, 50, 1), 32)
         check_samplers((90, 256, 256, 1), 128, C=2, N=400, scale=0.03)
-        os.environ["PBNN_NO_TC2"] = "1"
+        ops.set_option("no_tc2", 1)
         print("  (FP32 engine on the same problem:)")
         check_samplers((90, 256, 256, 1), 128, C=2, N=400, scale=0.03)
-        os.environ.pop("PBNN_NO_TC2")
+        ops.reset_options()

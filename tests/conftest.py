@@ -32,15 +32,44 @@ def cuda_ops():
 @pytest.fixture(params=["emu", pytest.param("cuda", marks=pytest.mark.gpu),
                         pytest.param("cuda_notc", marks=pytest.mark.gpu),
                         pytest.param("cuda_generic", marks=pytest.mark.gpu)])
-def ops(request, monkeypatch):
+def ops(request):
     """Parity tests run against the emulator here (CPU) and against the CUDA library on the GPU box -- there three
-    times: with the default kernel selection (tcgen05 engine for HMC on one-hidden-layer relu nets, fused FP32 path
-    for the other one-hidden-layer cases), with the tensor-core engine disabled (PBNN_NO_TC=1) and with the generic
-    tiled-GEMM engine forced (PBNN_NO_H1=1; the plan is rebuilt on every call, so the environment switch is enough)."""
-    if request.param == "cuda_notc":
-        monkeypatch.setenv("PBNN_NO_TC", "1")
-        return request.getfixturevalue("cuda_ops")
-    if request.param == "cuda_generic":
-        monkeypatch.setenv("PBNN_NO_H1", "1")
-        return request.getfixturevalue("cuda_ops")
-    return request.getfixturevalue(request.param + "_ops")
+    times: with the default kernel selection (tcgen05 engines where they apply, fused FP32 path for the other
+    one-hidden-layer cases), with the tensor-core engines disabled (option "no_tc") and with the generic tiled-GEMM
+    engine forced ("no_tc" + "no_h1").  Engines are selected through the library's explicit option table
+    (pbnn_set_option; the plan is rebuilt on every call); nothing is read from the environment."""
+    if request.param in ("cuda_notc", "cuda_generic"):
+        o = request.getfixturevalue("cuda_ops")
+        o.reset_options()
+        o.set_option("no_tc", 1)
+        if request.param == "cuda_generic":
+            o.set_option("no_h1", 1)
+        yield o
+        o.reset_options()
+        return
+    o = request.getfixturevalue(request.param + "_ops")
+    o.reset_options()
+    yield o
+    o.reset_options()
+
+
+@pytest.fixture
+def options(ops):
+    """set_option with automatic reset: ``options(no_sched=1, seg_len=3)``."""
+    def set_(**kw):
+        for k, v in kw.items():
+            ops.set_option(k, v)
+    yield set_
+    ops.reset_options()
+
+
+@pytest.fixture
+def tc_options(cuda_ops):
+    """As ``options`` for tests that take the CUDA library directly."""
+    cuda_ops.reset_options()
+
+    def set_(**kw):
+        for k, v in kw.items():
+            cuda_ops.set_option(k, v)
+    yield set_
+    cuda_ops.reset_options()

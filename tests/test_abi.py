@@ -31,7 +31,7 @@ def test_header_symbols_are_exported_and_bound(cuda_lib_path):
         assert hasattr(lib, n), f"{n} declared in include/pbnn_b200.h but not exported"
     assert sorted(_lib.PROTOTYPES) == names, "ctypes prototypes out of sync with the header"
     bound = _lib.load_library(cuda_lib_path)
-    assert bound.pbnn_version() == 100
+    assert bound.pbnn_version() == 200
 
 
 def test_host_side_calls_without_gpu(cuda_lib_path):

@@ -155,6 +155,64 @@ def test_sghmc(ops, layers, act, B):
         assert rel(npy(one["trace"])[:, 0], ref[:, t]) <= RTOL_STEP
 
 
+@pytest.mark.parametrize("momentum", ["sigma_sqrt_step", "mu_sqrt_step", (0.25, 0.5, 0.125, 2.0)])
+@pytest.mark.parametrize("layers,act,B", NETS[:3])
+def test_sghmc_momentum_variants_resolve_the_drift(ops, layers, act, B, momentum):
+    """The momentum resampling of blackjax.sghmc is a parameter (the upstream body is not vendored with the reference:
+    src/pbnn/mcmc/hamiltonian.py:118-128 is only the call site).  With p ~ N(0, step) the position moves by O(sqrt(eps))
+    per inner step, so the test can run at eps = 1e-5 -- where eps * g is ~1e-2 of the increment and a wrong sign or scale
+    of the drift shows up far above the 1e-5 tolerance (the unit-variance test above needs eps = 1e-9 and is nearly blind
+    to it)."""
+    X, y, sp, fs, keys, th0 = problem(layers, act, scale=0.05)
+    coef = {"sigma_sqrt_step": o.MOMENTUM_SIGMA_SQRT_STEP, "mu_sqrt_step": o.MOMENTUM_MU_SQRT_STEP}.get(momentum, momentum)
+    eps = 1e-5 if momentum == "sigma_sqrt_step" else 1e-9
+    T, L = 3, 4
+    ref = o.sghmc(sp, X, y, th0, B, eps, T, L, keys, momentum=coef)
+    out = ops.sghmc(fs, X, y, th0, keys, B, eps, T, L, momentum_resampling=momentum)
+    assert rel(npy(out["trace"]), ref) <= RTOL_STEP
+    if momentum == "sigma_sqrt_step":
+        # the increments (drift + momentum + noise), and the drift is really in there: dropping eps * g moves them > 1e-3
+        inc_ref, inc_out = ref[:, -1] - th0, npy(out["trace"])[:, -1] - th0
+        assert rel(inc_out, inc_ref) <= 1e-4
+        nodrift = o.sghmc(sp, X, y, th0, B, eps, T, L, keys, momentum=coef, _drop_drift=True)
+        assert rel(nodrift[:, -1] - th0, inc_ref) >= 1e-3
+    for t in range(1, T):
+        one = ops.sghmc(fs, X, y, ref[:, t - 1], keys, B, eps, 1, L, t0=t, momentum_resampling=momentum)
+        assert rel(npy(one["trace"])[:, 0], ref[:, t]) <= RTOL_STEP
+
+
+def test_options_api(ops):
+    """The engine switches are an explicit option table (pbnn_set_option), not environment variables."""
+    ops.reset_options()  # (the engine-forcing fixture variants arrive with options set)
+    assert ops.get_option("no_tc") is None
+    ops.set_option("no_tc", 1)
+    assert ops.get_option("no_tc") == 1
+    ops.reset_options()
+    assert ops.get_option("no_tc") is None
+    with pytest.raises(ValueError):
+        ops.set_option("no_such_option", 1)
+    import os
+    os.environ["PBNN_NO_TC"] = "1"  # has no effect any more
+    try:
+        assert ops.get_option("no_tc") is None
+    finally:
+        os.environ.pop("PBNN_NO_TC")
+
+
+def test_out_of_range_minibatch_indices_are_clamped(ops):
+    """A JAX gather clamps; an out-of-range index must not become an out-of-bounds read (flags bit 2 reports it)."""
+    layers, act, B = NETS[0]
+    X, y, sp, fs, keys, th0 = problem(layers, act)
+    N = X.shape[0]
+    idx = np.random.default_rng(3).integers(0, N, (3, B)).astype(np.int32)
+    bad = idx.copy()
+    bad[0, 3], bad[2, 7] = N + 5, -2
+    a = ops.sgld(fs, X, y, th0, keys, B, 1e-5, 2, idx=bad)
+    b = ops.sgld(fs, X, y, th0, keys, B, 1e-5, 2, idx=bad.clip(0, N - 1))
+    assert np.array_equal(npy(a["trace"]), npy(b["trace"]))
+    assert (npy(a["flags"]) & 4).tolist() == [4, 0, 4] and not npy(b["flags"]).any()
+
+
 def test_sgld_options(ops):
     """thin / burnin / scheduled step sizes / per-step minibatches / explicit idx."""
     layers, act, B = NETS[0]
@@ -339,11 +397,10 @@ def test_edge_cases_and_errors(ops):
         ops.plan(huge, 128, 2)
 
 
-def test_streaming_tiles_path(ops, monkeypatch):
+def test_streaming_tiles_path(ops, options):
     """Row sets that do not fit shared memory are streamed tile by tile from global memory (large-N HMC, large
     minibatches); force that path and check it like the resident one."""
-    monkeypatch.setenv("PBNN_NO_RESIDENT", "1")
-    monkeypatch.setenv("PBNN_NO_H1", "1")
+    options(no_resident=1, no_h1=1, no_tc=1)
     layers, act, B = NETS[2]
     X, y, sp, fs, keys, th0 = problem(layers, act)
     ref = o.sgld(sp, X, y, th0, B, 1e-5, 4, keys)
@@ -357,10 +414,10 @@ def test_streaming_tiles_path(ops, monkeypatch):
     assert rel(npy(out["trace"]), ref) <= RTOL_STEP
 
 
-def test_global_workspace_state_path(ops, monkeypatch):
+def test_global_workspace_state_path(ops, options):
     """Models whose state does not fit shared memory keep it in a global workspace (the 90-256-256-1 case); force that
     path on small nets and check it against the oracle like the resident path."""
-    monkeypatch.setenv("PBNN_FORCE_GSTATE", "1")
+    options(force_gstate=1, no_tc2=1)
     for layers, act, B in (NETS[0], NETS[2], NETS[3]):
         X, y, sp, fs, keys, th0 = problem(layers, act)
         ref = o.sgld(sp, X, y, th0, B, 1e-5, 4, keys)

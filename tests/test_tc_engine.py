@@ -29,7 +29,7 @@ SHAPES = [((13, 50, 1), 506), ((8, 50, 1), 300), ((5, 64, 1), 100), ((15, 33, 1)
 
 
 @pytest.mark.parametrize("layers,N", SHAPES)
-def test_tc_gradient_matches_float64(cuda_ops, monkeypatch, layers, N):
+def test_tc_gradient_matches_float64(cuda_ops, tc_options, layers, N):
     """3xTF32 split operands: the gradient agrees with the float64 oracle to fp32-summation accuracy (the scalar
     FP32 engine reaches ~1e-7 on the same inputs, the tolerance here is 5e-6)."""
     X, y, sp, fs, th = problem(layers, N, 5)
@@ -37,16 +37,16 @@ def test_tc_gradient_matches_float64(cuda_ops, monkeypatch, layers, N):
     lp, g = cuda_ops.logposterior_grad(fs, X, y, th)
     assert rel(npy(g), g64) <= 5e-6
     assert rel(npy(lp), lp64) <= 5e-6
-    monkeypatch.setenv("PBNN_NO_TC", "1")
+    tc_options(no_tc=1)
     lp1, g1 = cuda_ops.logposterior_grad(fs, X, y, th)
     assert rel(npy(g), npy(g1)) <= 5e-6
 
 
-def test_tc_plan_is_selected_and_can_be_disabled(cuda_ops, monkeypatch):
+def test_tc_plan_is_selected_and_can_be_disabled(cuda_ops, tc_options):
     """The engines must actually differ: same inputs, not bit-identical results (else the switch does nothing)."""
     X, y, sp, fs, th = problem((13, 50, 1), 506, 3)
     _, g_tc = cuda_ops.logposterior_grad(fs, X, y, th)
-    monkeypatch.setenv("PBNN_NO_TC", "1")
+    tc_options(no_tc=1)
     _, g_h1 = cuda_ops.logposterior_grad(fs, X, y, th)
     assert not np.array_equal(npy(g_tc), npy(g_h1))
     assert rel(npy(g_tc), npy(g_h1)) <= 5e-6
@@ -109,7 +109,7 @@ def test_tc_many_chains_two_waves(cuda_ops):
 
 
 @pytest.mark.parametrize("seg_len", [1, 2, 3])
-def test_tc_balanced_schedule_is_bit_identical(cuda_ops, monkeypatch, seg_len):
+def test_tc_balanced_schedule_is_bit_identical(cuda_ops, tc_options, seg_len):
     """More chains than SMs: the persistent grid hands chains between CTAs through global memory; the arithmetic is
     the same, so traces, accept decisions and final states equal the one-CTA-per-chain run bit for bit."""
     X, y, sp, fs, th = problem((13, 50, 1), 506, 1, scale=0.05)
@@ -118,9 +118,9 @@ def test_tc_balanced_schedule_is_bit_identical(cuda_ops, monkeypatch, seg_len):
     th0 = (0.05 * np.random.default_rng(4).standard_normal((C, sp.num_params))).astype(np.float32)
     minv = np.ones(sp.num_params, np.float32)
     assert cuda_ops.lib.pbnn_workspace_bytes(fs.c_struct(), 5, 506, C) > 0
-    monkeypatch.setenv("PBNN_SEG_LEN", str(seg_len))
+    tc_options(seg_len=seg_len)
     a = cuda_ops.hmc(fs, X, y, th0, keys, S, 3e-4, minv, L, info=True, thin=2, burnin=1)
-    monkeypatch.setenv("PBNN_NO_SCHED", "1")
+    tc_options(no_sched=1)
     b = cuda_ops.hmc(fs, X, y, th0, keys, S, 3e-4, minv, L, info=True, thin=2, burnin=1)
     for k in ("trace", "theta", "logp", "accept_count", "delta", "accept", "flags"):
         assert np.array_equal(npy(a[k]), npy(b[k])), k
@@ -149,9 +149,9 @@ def test_tc_repeated_runs_are_bit_identical(cuda_ops):
 
 @pytest.mark.parametrize("layers,S,M", [((13, 50, 1), 37, 150), ((8, 50, 1), 70, 1024), ((3, 7, 1), 5, 129),
                                          ((15, 64, 1), 33, 700), ((1, 1, 1), 3, 1), ((6, 20, 1), 1, 2500)])
-def test_tc_predict(cuda_ops, monkeypatch, layers, S, M):
+def test_tc_predict(cuda_ops, tc_options, layers, S, M):
     """Posterior predictive on the tcgen05 engine (pb_predict_tc_kernel): predictions and moments vs the float64
-    oracle, and vs the FP32 kernel (PBNN_NO_TC=1) -- ragged tile counts, more / fewer samples than chunks."""
+    oracle, and vs the FP32 kernel (option "no_tc") -- ragged tile counts, more / fewer samples than chunks."""
     sp, fs = o.MlpSpec(tuple(layers), o.RELU, 0.1), FlatSpec(tuple(layers), o.RELU, 0.1)
     rng = np.random.default_rng(5)
     th = (0.3 * rng.standard_normal((S, sp.num_params))).astype(np.float32)
@@ -163,7 +163,7 @@ def test_tc_predict(cuda_ops, monkeypatch, layers, S, M):
     assert np.abs(npy(res["var"]) - F.var(0)).max() <= 1e-5 * max(1.0, float((F ** 2).mean(0).max()))
     only_m = cuda_ops.predict(fs, th, Xt, want_preds=False, want_moments=True)
     assert np.array_equal(npy(only_m["mean"]), npy(res["mean"]))
-    monkeypatch.setenv("PBNN_NO_TC", "1")
+    tc_options(no_tc=1)
     ref = cuda_ops.predict(fs, th, Xt, want_preds=True, want_moments=True)
     assert rel(npy(res["preds"]), npy(ref["preds"])) <= 5e-6
     assert not np.array_equal(npy(res["preds"]), npy(ref["preds"])) or S * M < 8  # the two kernels really differ
