@@ -997,14 +997,18 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
   };
 #if !defined(PB_EMU)
   // ENG 2: gradient + parameter update in one pass (pbnn_tc2.cuh); the functors own the sampler arithmetic
-  auto t2grad = [&](PbKey nkey_, bool noise_, auto pf_, auto uf_) {
-    pb_grad_tc2(pl, sm, TH, B, a.scale, nt, *static_cast<PbTc2*>(ctx), nkey_, noise_, pf_, uf_);
+  // (the engine supplies pre.a = theta from its operand images and writes the new theta to o0 / o1: trace row and
+  // final state -- W1, b1, W2 have no fp32 copy in TH while the chain runs)
+  auto t2grad = [&](PbKey nkey_, bool noise_, float* o0, float* o1, auto pf_, auto uf_) {
+    pb_grad_tc2(pl, sm, TH, B, a.scale, nt, *static_cast<PbTc2*>(ctx), nkey_, noise_, o0, o1, scu + 2, pf_, uf_);
   };
-  auto pf_theta = [&](int si, int fi) {
-    PbPre v;
-    v.a = TH[si];
-    return v;
+  auto pf_theta = [&](int si, int fi) { return PbPre(); };
+  auto trace_row = [&](int t_) -> float* {
+    return (a.trace && t_ >= a.burnin && ((t_ - a.burnin) % a.thin) == 0)
+               ? a.trace + ((size_t)c * a.T_out + (size_t)((t_ - a.burnin) / a.thin)) * P
+               : nullptr;
   };
+  auto final_dst = [&](int t_) -> float* { return (t_ == a.T - 1 && !a.no_theta_store) ? a.theta + cP : nullptr; };
 #endif
 
   pb_init_acts(pl, sm, nt);
@@ -1043,7 +1047,7 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
     if (res) load_res();
 #if !defined(PB_EMU)
     if constexpr (ENG == 2) {
-      t2grad(ck, false, pf_theta, [&](int si, int fi, const PbPre& v, float gll, float z) {
+      t2grad(ck, false, nullptr, nullptr, pf_theta, [&](int si, int fi, const PbPre& v, float gll, float z) {
         a.aux1[cP + fi] = gll - v.a * pl.inv_pv;
         return v.a;
       });
@@ -1077,7 +1081,7 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
     if (res) load_res();
 #if !defined(PB_EMU)
     if constexpr (ENG == 2) {
-      t2grad(ck, false, pf_theta, [&](int si, int fi, const PbPre& v, float gll, float z) {
+      t2grad(ck, false, nullptr, nullptr, pf_theta, [&](int si, int fi, const PbPre& v, float gll, float z) {
         const float g = gll - v.a * pl.inv_pv;
         G[si] = g;
         A1[si] = g * g;
@@ -1141,10 +1145,9 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
         const float* cve = a.cv_center ? a.cv_center_est + cP : nullptr;
         if (cvc) {
           t2grad(
-              kt, true,
+              kt, true, trace_row(t), final_dst(t),
               [&](int si, int fi) {
                 PbPre v;
-                v.a = TH[si];
                 v.c = cvc[fi];
                 v.d = cve[fi];
                 return v;
@@ -1155,10 +1158,11 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
                 return th + eps * g + ns * z;
               });
         } else {
-          t2grad(kt, true, pf_theta, [&](int si, int fi, const PbPre& v, float gll, float z) {
-            const float th = v.a;
-            return th + eps * (gll - th * pl.inv_pv) + ns * z;
-          });
+          t2grad(kt, true, trace_row(t), final_dst(t), pf_theta,
+                 [&](int si, int fi, const PbPre& v, float gll, float z) {
+                   const float th = v.a;
+                   return th + eps * (gll - th * pl.inv_pv) + ns * z;
+                 });
         }
       }
 #endif
@@ -1208,8 +1212,8 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
           PB_ENDPHASE
           pb_tc2_restage(pl, sm, *static_cast<PbTc2*>(ctx), TH, nt);
         }
-        if (a.trace && t >= a.burnin && ((t - a.burnin) % a.thin) == 0) {
-          float* dst = a.trace + ((size_t)c * a.T_out + (size_t)((t - a.burnin) / a.thin)) * P;
+        if (t == 0 && trace_row(0)) {  // (later rows are written by the drains of the step before)
+          float* dst = trace_row(0);
           PB_PHASE
           pb_for_each_param(pl, tid, nt, [&](int si, int fi) { dst[fi] = TH[si]; });
           PB_ENDPHASE
@@ -1219,10 +1223,9 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
         const float epsn =
             a.step_sizes ? a.step_sizes[t + 1 < a.n_step_sizes ? t + 1 : a.n_step_sizes - 1] : a.const_step;
         t2grad(
-            kn, more,
+            kn, more, more ? trace_row(t + 1) : nullptr, final_dst(t),
             [&](int si, int fi) {
               PbPre v;
-              v.a = TH[si];
               v.b = A1[si];
               return v;
             },
@@ -1291,10 +1294,9 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
         if constexpr (ENG == 2) {
           if (cvc) {
             t2grad(
-                kl, true,
+                kl, true, l == a.L - 1 ? trace_row(t) : nullptr, l == a.L - 1 ? final_dst(t) : nullptr,
                 [&](int si, int fi) {
                   PbPre v;
-                  v.a = TH[si];
                   v.b = A1[si];
                   v.d = cvc[fi];
                   v.e = cve[fi];
@@ -1308,10 +1310,9 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
                 });
           } else {
             t2grad(
-                kl, true,
+                kl, true, l == a.L - 1 ? trace_row(t) : nullptr, l == a.L - 1 ? final_dst(t) : nullptr,
                 [&](int si, int fi) {
                   PbPre v;
-                  v.a = TH[si];
                   v.b = A1[si];
                   return v;
                 },
@@ -1352,10 +1353,9 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
         const float cnt = (float)(a.count0 + t + 1);
         const float ibc1 = 1.0f / (1.0f - powf(a.b1, cnt)), ibc2 = 1.0f / (1.0f - powf(a.b2, cnt));
         t2grad(
-            ck, false,
+            ck, false, trace_row(t), final_dst(t),
             [&](int si, int fi) {
               PbPre p;
-              p.a = TH[si];
               p.c = A1[si];
               p.d = A2[si];
               return p;
@@ -1398,7 +1398,7 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
       PB_ENDPHASE
     }
 
-    if (a.trace && t >= a.burnin && ((t - a.burnin) % a.thin) == 0) {
+    if (ENG != 2 && a.trace && t >= a.burnin && ((t - a.burnin) % a.thin) == 0) {  // (ENG 2: written by the drains)
       float* dst = a.trace + ((size_t)c * a.T_out + (size_t)((t - a.burnin) / a.thin)) * P;
       PB_PHASE
       pb_for_each_param(pl, tid, nt, [&](int si, int fi) { dst[fi] = TH[si]; });
@@ -1406,7 +1406,8 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
     }
   }
 
-  if (!a.no_theta_store) pb_store_state(pl, TH, a.theta + cP, scu + 2, nt);
+  // (ENG 2: the drains of the last gradient evaluation have stored the final state and raised the non-finite flag)
+  if (ENG != 2 && !a.no_theta_store) pb_store_state(pl, TH, a.theta + cP, scu + 2, nt);
   if (ALGO == PB_ALGO_PSGLD || ALGO == PB_ALGO_ADAM) {
     pb_store_state(pl, ALGO == PB_ALGO_PSGLD ? G : A1, a.aux1 + cP, nullptr, nt);
     pb_store_state(pl, ALGO == PB_ALGO_PSGLD ? A1 : A2, a.aux2 + cP, nullptr, nt);

@@ -263,9 +263,25 @@ PB_DEV void pb_t2_put(uint8_t* p, int tb, float v) {
   *reinterpret_cast<uint16_t*>(p + 2 * tb) = (uint16_t)t3;
 }
 
+// the weight itself from its three bf16 terms (exact: the split is error-free, and so are the two additions); .cg:
+// the image is written with plain stores by this CTA and read through L2 by the bulk copies -- keep L1 out of it
+PB_DEV float pb_t2_get(const uint8_t* p, int tb) {
+  const uint32_t t1 = __ldcg(reinterpret_cast<const unsigned short*>(p));
+  const uint32_t t2 = __ldcg(reinterpret_cast<const unsigned short*>(p + tb));
+  const uint32_t t3 = __ldcg(reinterpret_cast<const unsigned short*>(p + 2 * tb));
+  return (__uint_as_float(t1 << 16) + __uint_as_float(t2 << 16)) + __uint_as_float(t3 << 16);
+}
+
 // ---- one gradient evaluation with the parameter update fused into the drains ------------------------------------
-//   pre = pf(resident_index, flat_index)          loads everything the update needs (pre.a MUST be theta); issued for a
-//                                                 group of elements before any of them is stored
+//   pre = pf(resident_index, flat_index)          loads what the update needs BESIDES theta (sampler state, control
+//                                                 variates); issued for a group of elements before any of them is
+//                                                 stored.  The engine fills pre.a = theta itself: the operand IMAGES are
+//                                                 the master copy of W1, b1 and W2 (three bf16 terms = the fp32 value,
+//                                                 exactly) -- no fp32 copy of them is read or written per step, which
+//                                                 keeps a 90-256-256-1 chain's working set at ~640 KB (148 chains fit the
+//                                                 L2); b2, w3, b3 stay fp32 in TH
+//   out0 / out1                                   optional flat [P] destinations of the NEW theta (trace row / final
+//                                                 state; out1 also raises bit 0 of *flagword on a non-finite value)
 //   theta_new = uf(resident_index, flat_index, pre, gll, z)   gll = d loglik / d theta of the element, z =
 //                                                 jax.random.normal(nkey, (P,))[flat_index] when `noise` (else 0); the
 //                                                 functor owns the sampler arithmetic (prior term, state arrays) and
@@ -274,7 +290,7 @@ PB_DEV void pb_t2_put(uint8_t* p, int tb, float v) {
 // compiler), then 8 x uf, then the stores.  llbuf[0..127] <- per-row log-likelihood terms.  TH is updated in place.
 template <class PF, class UF>
 PB_DEV void pb_grad_tc2(const PbPlan& pl, float* sm, float* TH, int nrows, float scale, int nt, const PbTc2& tc,
-                        PbKey nkey, bool noise, PF pf, UF uf) {
+                        PbKey nkey, bool noise, float* out0, float* out1, uint32_t* flagword, PF pf, UF uf) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
   const PbLayer& L0 = pl.L[0];
@@ -634,6 +650,14 @@ PB_DEV void pb_grad_tc2(const PbPlan& pl, float* sm, float* TH, int nrows, float
     }
     pb_tc_fence_before();
     asm volatile("bar.sync 1, 256;" ::: "memory");
+    bool bad = false;
+    auto emit = [&](int fi, float v) {
+      if (out0) out0[fi] = v;
+      if (out1) {
+        out1[fi] = v;
+        bad |= !pb_finite(v);
+      }
+    };
     auto update_w1 = [&]() {
       const int d = pl.d;
       const int tb1 = nch * Kx * 128;
@@ -650,7 +674,10 @@ PB_DEV void pb_grad_tc2(const PbPlan& pl, float* sm, float* TH, int nrows, float
         for (int j = 0; j < 4; ++j) {
           const int k = k0 + j * nkg;
           ix[j] = (uint32_t)((k < d ? L0.fw + k * H : L0.fb) + i);
-          if (own && k <= d) pre[j] = pf(L0.soff + k * L0.wp + i, (int)ix[j]);
+          if (own && k <= d) {
+            pre[j] = pf(L0.soff + k * L0.wp + i, (int)ix[j]);
+            pre[j].a = pb_t2_get(img1 + pb_t2_off(Kx, k, i), tb1);
+          }
         }
         if (noise) {
           const float4 z4 = pb_t2_normal4(nkey.k0, nkey.k1, ix[0], ix[1], ix[2], ix[3]);
@@ -668,8 +695,8 @@ PB_DEV void pb_grad_tc2(const PbPlan& pl, float* sm, float* TH, int nrows, float
         for (int j = 0; j < 4; ++j) {
           const int k = k0 + j * nkg;
           if (own && k <= d) {
-            TH[L0.soff + k * L0.wp + i] = nv[j];
             pb_t2_put(img1 + pb_t2_off(Kx, k, i), tb1, nv[j]);
+            emit((int)ix[j], nv[j]);
           }
         }
       }
@@ -709,7 +736,10 @@ PB_DEV void pb_grad_tc2(const PbPlan& pl, float* sm, float* TH, int nrows, float
             float nv[4], zz[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              if (own) pre[j] = pf(sb + (j0 + j) * L1.wp, fb + (j0 + j) * H);
+              if (own) {
+                pre[j] = pf(sb + (j0 + j) * L1.wp, fb + (j0 + j) * H);
+                pre[j].a = pb_t2_get(ib + (j0 + j) * 128 + ((cn ^ (uint32_t)(j0 + j)) << 4), tb2);
+              }
             if (noise) {
               uint32_t ix[4];
 #pragma unroll
@@ -729,8 +759,8 @@ PB_DEV void pb_grad_tc2(const PbPlan& pl, float* sm, float* TH, int nrows, float
               }
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                TH[sb + (j0 + j) * L1.wp] = nv[j];
                 pb_t2_put(ib + (j0 + j) * 128 + ((cn ^ (uint32_t)(j0 + j)) << 4), tb2, nv[j]);
+                emit(fb + (j0 + j) * H, nv[j]);
               }
             }
           }
@@ -745,7 +775,10 @@ PB_DEV void pb_grad_tc2(const PbPlan& pl, float* sm, float* TH, int nrows, float
             for (int j = 0; j < 4; ++j) {
               const int i = i0 + j0 + j;
               ix[j] = (uint32_t)(i < H ? L1.fw + i * H + n_own : L1.fb + n_own);
-              if (own && i <= H) pre[j] = pf(L1.soff + i * L1.wp + n_own, (int)ix[j]);
+              if (own && i <= H) {
+                pre[j] = pf(L1.soff + i * L1.wp + n_own, (int)ix[j]);
+                pre[j].a = i < H ? pb_t2_get(img2 + pb_t2_off(Hp, i, n_own), tb2) : TH[L1.soff + i * L1.wp + n_own];
+              }
             }
             if (noise) {
               const float4 z4 = pb_t2_normal4(nkey.k0, nkey.k1, ix[0], ix[1], ix[2], ix[3]);
@@ -767,8 +800,9 @@ PB_DEV void pb_grad_tc2(const PbPlan& pl, float* sm, float* TH, int nrows, float
             for (int j = 0; j < 4; ++j) {
               const int i = i0 + j0 + j;
               if (own && i <= H) {
-                TH[L1.soff + i * L1.wp + n_own] = nv[j];
                 if (i < H) pb_t2_put(img2 + pb_t2_off(Hp, i, n_own), tb2, nv[j]);
+                else TH[L1.soff + i * L1.wp + n_own] = nv[j];
+                emit((int)ix[j], nv[j]);
               }
             }
           }
@@ -809,18 +843,25 @@ PB_DEV void pb_grad_tc2(const PbPlan& pl, float* sm, float* TH, int nrows, float
     if ((two_tiles || g == 0) && n_own < H) {
       const float gl = two_tiles ? dw3 : dw3p[n_own] + dw3p[256 + n_own];
       const int si = L2.soff + n_own * L2.wp, fi = L2.fw + n_own;
-      const PbPre pre = pf(si, fi);
-      TH[si] = uf(si, fi, pre, gl, noise ? pb_normal_at(nkey, (uint32_t)fi) : 0.f);
+      PbPre pre = pf(si, fi);
+      pre.a = TH[si];
+      const float nv = uf(si, fi, pre, gl, noise ? pb_normal_at(nkey, (uint32_t)fi) : 0.f);
+      TH[si] = nv;
+      emit(fi, nv);
     }
     if (warp == 0) {
       float a = fp[lane] + fp[32 + lane] + fp[64 + lane] + fp[96 + lane];
       a = pb_warp_sum(a);
       if (lane == 0) {
         const int si = L2.soff + H * L2.wp, fi = L2.fb;
-        const PbPre pre = pf(si, fi);
-        TH[si] = uf(si, fi, pre, a, noise ? pb_normal_at(nkey, (uint32_t)fi) : 0.f);
+        PbPre pre = pf(si, fi);
+        pre.a = TH[si];
+        const float nv = uf(si, fi, pre, a, noise ? pb_normal_at(nkey, (uint32_t)fi) : 0.f);
+        TH[si] = nv;
+        emit(fi, nv);
       }
     }
+    if (bad && flagword) atomicOr(flagword, 1u);
     pb_tc_fence_before();
   }
 #undef PB_T2_BAR
