@@ -6,9 +6,14 @@
 One *step* = one pass of the hot path over one batch of synthetic input: a full run of the named configuration's
 job (default `hmc_cfg2`: BASELINE.json configs[1], 256 chains x 200 HMC iterations x L=20 full-batch leapfrogs on a
 13-50-1 MLP, N=506).  `value` = chain-steps/s with inputs resident in HBM (CUDA events, max over ranks);
-`e2e` = the same through the public sampler call with pinned HOST buffers (H2D of data/positions/keys and D2H of
-the positions inside the timed region).  Chains shard over ranks with no data-path collective (weak scaling); the
-only exchange is an all_gather of the predictive moments after the timed region.
+`e2e` = the same through the reference-signature call `pbnn_b200.mcmc.hmc` (pytrees in, `(positions, ravel_fn,
+predict_fn)` out) with HOST inputs and the positions copied back to pinned host memory inside the timed region
+(`e2e.ops_*`: the same through the flat C-ABI operator layer).  The metric is "SGLD & HMC": the default run also
+times the SGLD configurations (`workloads`: sgld_cfg1x, sgld_cfg3, sgld_cfg5) with their own rooflines.
+Chains shard over ranks with no data-path collective (weak scaling).  With --gpus N > 1 the run adds BASELINE
+configs[4] (`sharded_cfg5`: 1024 SGLD chains per GPU of a 90-256-256-1 net -- 8192 chains on 8 GPUs -- keys
+split(PRNGKey(0), C_total)[shard]), checks on the device that a shard's chains are bit-identical to the same chains
+run alone, and times the one exchange step (all_gather of the predictive moments over NCCL) warm.
 
 `--impl reference` times the CPU restatement of the reference (oracle/c, OpenMP over chains, all host threads) on
 the same config -- JAX / BlackJAX are not installable here, see DESIGN.md.
@@ -42,8 +47,9 @@ WORKLOADS = {
                        M=1024),
     "sgld_cfg3": dict(algo="sgld", layers=(9, 100, 100, 1), act=0, N=45730, B=128, C=1024, T=200, L=1, step=2e-8,
                       M=1024),
-    "sghmc_cfg3": dict(algo="sghmc", layers=(9, 100, 100, 1), act=0, N=45730, B=128, C=1024, T=20, L=10, step=1e-9,
-                       M=1024),
+    # (momentum ~ N(0, step): the SGHMC-paper law; the "unit" law of SURVEY.md 2b random-walks to non-finite values)
+    "sghmc_cfg3": dict(algo="sghmc", layers=(9, 100, 100, 1), act=0, N=45730, B=128, C=1024, T=20, L=10, step=1e-7,
+                       M=1024, momentum="sigma_sqrt_step"),
     # BASELINE.json configs[4], per-GPU share (1024 of the 8192 chains); state lives in the global workspace
     "sgld_cfg5": dict(algo="sgld", layers=(90, 256, 256, 1), act=0, N=515345, B=128, C=1024, T=20, L=1, step=1e-9,
                       M=4096),
@@ -51,6 +57,10 @@ WORKLOADS = {
     "adam_cfg4": dict(algo="adam", layers=(8, 50, 50, 1), act=0, N=9568, B=32, C=512, T=299 * 2, L=1, step=1e-2,
                       M=1024),
 }
+
+
+# SGHMC momentum law p = (mu0 + mu1 sqrt(step)) + (sig0 + sig1 sqrt(step)) z  (include/pbnn_b200.h)
+MOMENTUM = {"unit": (0.0, 0.0, 1.0, 0.0), "sigma_sqrt_step": (0.0, 0.0, 0.0, 1.0), "mu_sqrt_step": (0.0, 1.0, 1.0, 0.0)}
 
 
 def grad_flops(layers, B):
@@ -153,7 +163,8 @@ def cpu_run(w, n_chains, n_iters, seed_rank=0):
         co.adam_run(w["layers"], w["act"], 0.1, X, y, th0, idx, w["step"])
     else:
         co.sg_run(w["layers"], w["act"], 0.1, w["algo"], X, y, th0, w["B"], w["step"], n_iters, keys, L=w["L"],
-                  alpha=0.95 if w["algo"] == "psgld" else 0.01, trace=False)
+                  alpha=0.95 if w["algo"] == "psgld" else 0.01, trace=False,
+                  momentum=MOMENTUM[w.get("momentum", "unit")])
     return time.perf_counter() - t0
 
 
@@ -189,11 +200,77 @@ def gpu_step_fn(ops, w, fs, X, y, th0, keys, keep_trace=True):
     if a == "psgld":
         return lambda: ops.psgld(fs, X, y, th0, keys, w["B"], w["step"], w["T"], 0.95, keep_trace=False)
     if a == "sghmc":
-        return lambda: ops.sghmc(fs, X, y, th0, keys, w["B"], w["step"], w["T"], w["L"], keep_trace=False)
+        return lambda: ops.sghmc(fs, X, y, th0, keys, w["B"], w["step"], w["T"], w["L"], keep_trace=False,
+                                 momentum_resampling=w.get("momentum", "unit"))
     if a == "adam":
         idx = torch.randint(0, w["N"], (w["C"], w["T"], w["B"]), dtype=torch.int32, device="cuda")
         return lambda: ops.adam_ensemble(fs, X, y, th0, idx, w["step"])
     raise ValueError(a)
+
+
+ENGINE_NAMES = {0: "tiled_fp32", 1: "fused_h1_fp32", 2: "tcgen05_tf32x3", 3: "tiled_fp32_global_state",
+                4: "tcgen05_bf16x3_mlp2"}
+OPS = {"hmc": "OP_HMC", "sgld": "OP_SGLD", "psgld": "OP_PSGLD", "sghmc": "OP_SGHMC", "adam": "OP_ADAM"}
+
+
+def workload_config(name, w):
+    return {"workload": f"{name}: {w['algo']} MLP {'-'.join(map(str, w['layers']))} relu, N={w['N']}, batch={w['B']}, "
+                        f"{w['C']} chains/GPU x {w['T']} iterations x L={w['L']} per step, step_size={w['step']:g}"
+                        + (f", momentum={w['momentum']}" if "momentum" in w else ""),
+            "chains_per_gpu": w["C"], "iterations_per_step": w["T"], "leapfrogs": w["L"], "step_size": w["step"],
+            "l2": "flushed (256 MiB write) before every timed step"}
+
+
+def roofline_for(ops, w, fs, ms_per_step, clocks, peaks, traffic=None):
+    """Roofline object of one workload: algorithmic flops per launch / CUDA-event time against the pipe the dominant
+    kernel runs on, plus the explanatory sub-rooflines (FP32-FMA equivalent, threefry issue)."""
+    from pbnn_b200 import _lib as plib
+    flops = step_flops(w)
+    achieved = flops / (ms_per_step * 1e-3) / 1e12
+    sm_max = (clocks or {}).get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0
+    fma_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
+    engine = ops.lib.pbnn_plan_engine(fs.c_struct(), getattr(plib, OPS[w["algo"]]), w["B"], w["C"])
+    bf16_peak = peaks.get("bf16_tflops", 1590.0)
+    src = "measured (MEASURED_PEAKS.json, burst)" if peaks else "fallback (B200_PROFILING.md)"
+    fma_eq = {"achieved": achieved, "peak": fma_peak, "frac": achieved / fma_peak,
+              "note": "the same algorithmic flops against the FP32-FMA peak (148 SM x 128 lanes x 2 x clock)"}
+    # injected noise: one threefry2x32-20 block + erf_inv per parameter and noisy step, ~100 issue slots per warp-normal
+    # (SASS count, pbnn_rng.cuh); peak = every scheduler issuing nothing else
+    P = num_params(w["layers"])
+    draws = {"hmc": 1, "sgld": 1, "psgld": 1, "sghmc": w["L"] + 1, "adam": 0}[w["algo"]]
+    normals = w["C"] * w["T"] * P * draws / (ms_per_step * 1e-3)
+    rng_peak = 148 * 4 * 32 * sm_max * 1e6 / 100.0
+    rng = {"normals_per_s": normals, "peak": rng_peak, "frac": normals / rng_peak,
+           "note": "bit-exact jax.random.normal draws/s against the issue-slot bound (~100 instructions per warp-normal)"}
+    common = {"achieved": achieved, "unit": "TFLOP/s", "traffic": traffic, "algorithmic_flops_per_launch": flops,
+              "engine": ENGINE_NAMES.get(engine, engine), "fp32_fma_equivalent": fma_eq, "rng_issue": rng}
+    if engine == plib.ENGINE_TCGEN05:
+        tf32_peak = bf16_peak / 2
+        ntile = (w["B"] + 127) // 128
+        grads = w["C"] * w["T"] * (w["L"] + 1.0 / w["T"])
+        executed = grads * ntile * (6 + 8) * (128 * 64 * 8 * 2)  # 6 forward + 8 backward MMAs 128x64x8 per tile
+        return dict(common, bound="tensor", peak=tf32_peak, frac=achieved / tf32_peak, kernel="pb_hmc_tc_kernel",
+                    peak_source=f"TF32 dense tensor rate = cuBLAS bf16 {src} / 2",
+                    executed_tensor_flops_per_launch=executed,
+                    executed_tensor_tflops=executed / (ms_per_step * 1e-3) / 1e12,
+                    note="latency-bound: per gradient a dependent chain forward MMA -> epilogue -> backward MMA -> "
+                         "readout; two CTAs per SM overlap each other's waits (profiles/, DESIGN.md)")
+    if engine == plib.ENGINE_TCGEN05_MLP2:
+        B, (d, H) = 128, w["layers"][:2]
+        r16 = lambda x: (x + 15) // 16 * 16
+        Kx, Hp, Hy = r16(d + 1), r16(H), r16(H + 1)
+        nmt = (Hp + 127) // 128
+        per_grad = 2 * B * (6 * Kx * Hp + 6 * Hp * Hp + 6 * Hp * Hp + 6 * 128 * Hp + 3 * nmt * 128 * Hy)
+        executed = per_grad * w["C"] * w["T"] * w["L"]
+        return dict(common, bound="tensor", peak=bf16_peak, frac=achieved / bf16_peak, kernel="pb_sg_tc2_kernel",
+                    peak_source=f"dense bf16 tensor rate, cuBLAS {src}",
+                    executed_tensor_flops_per_launch=executed,
+                    executed_tensor_tflops=executed / (ms_per_step * 1e-3) / 1e12,
+                    note="bf16x3 products (6 passes, 3 against the exact relu masks); the step is bound by the per-"
+                         "parameter noise + update work on the CUDA cores (rng_issue), not by the tensor pipe")
+    return dict(common, bound="fma", peak=fma_peak, frac=achieved / fma_peak,
+                kernel="pb_hmc_kernel" if w["algo"] == "hmc" else "pb_sg_kernel",
+                peak_source=f"FP32 FMA: 148 SM x 128 lanes x 2 x {sm_max:.0f} MHz")
 
 
 def main():
@@ -205,6 +282,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the SGLD workloads / the sharded cfg5 run")
     ap.add_argument("--iters", type=int, default=0, help="override iterations per step (profiling runs)")
     ap.add_argument("--chains", type=int, default=0, help="override chains per GPU (profiling runs)")
     args = ap.parse_args()
@@ -215,16 +293,14 @@ def main():
         w["T"] = args.iters
     if args.chains > 0:
         w["C"] = args.chains
+    if args.iters > 0 or args.chains > 0:
+        args.no_extras = True
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     base = {"metric": "chain-steps/sec", "unit": "chain-steps/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic (UCI-shaped regression, seeded; SURVEY.md 8d)",
-            "config": {"workload": f"{args.workload}: {w['algo']} MLP {'-'.join(map(str, w['layers']))} relu, N={w['N']}, "
-                                   f"batch={w['B']}, {w['C']} chains/GPU x {w['T']} iterations x L={w['L']} per step",
-                       "chains_per_gpu": w["C"], "iterations_per_step": w["T"], "leapfrogs": w["L"],
-                       "l2": "flushed (256 MiB write) before every timed step"}}
+            "data": "synthetic (UCI-shaped regression, seeded; SURVEY.md 8d)", "config": workload_config(args.workload, w)}
 
     # ---------------------------------------------------------------- reference arm (CPU restatement)
     if args.impl == "reference":
@@ -237,8 +313,9 @@ def main():
         total = sum(t)
         v = args.steps * n_chains * iters / total
         cb = {"value": v, "unit": "chain-steps/s", "cores": cores, "kind": "port",
-              "sample": f"each step = {n_chains} chains x {iters} iterations of {args.workload} (C restatement of the "
-                        f"reference, OpenMP over chains on all host threads; JAX/BlackJAX not installable here)"}
+              "sample": f"each step = {n_chains} chains (2 per host thread, NOT the workload's {w['C']}; per-chain work is "
+                        f"identical) x {iters} iterations of {args.workload} (C restatement of the reference, OpenMP over "
+                        f"chains on all host threads; JAX/BlackJAX not installable here)"}
         out = dict(base, impl="reference", value=v, ms_per_step=1e3 * total / args.steps, cpu_baseline=cb,
                    e2e={"value": v, "unit": "chain-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                    gpu_launches=0)
@@ -254,19 +331,15 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ops = default_ops()
-    fs = FlatSpec(tuple(w["layers"]), w["act"], 0.1)
-    Xh, yh, Xth, keys, th0 = make_inputs(w, rank, world, ops)
-    X, y, Xt = (ops._as(a, torch.float32) for a in (Xh, yh, Xth))
-    keysh, th0h = keys.cpu().numpy(), th0.cpu().numpy()
-    step = gpu_step_fn(ops, w, fs, X, y, th0, keys)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    launches = [0]  # kernels of libpbnn_b200.so launched inside timed regions (counted per operator call below)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, K, W):
+    def timed(fn, K, W, kernels_per_call=1):
         for _ in range(W):
             fn()
         barrier()
@@ -279,6 +352,7 @@ def main():
             b.record()
             evs.append((a, b))
         barrier()
+        launches[0] += K * kernels_per_call
         ms = sum(a.elapsed_time(b) for a, b in evs)
         if world > 1:
             t = torch.tensor([ms], device="cuda")
@@ -286,6 +360,31 @@ def main():
             ms = float(t.item())
         return ms
 
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    traffic_db = {}
+    for fn_ in ("r2_traffic.json", "r1_traffic.json"):
+        try:
+            for k_, v_ in json.load(open(os.path.join(ROOT, "profiles", fn_))).items():
+                traffic_db.setdefault(k_, v_)
+        except (OSError, ValueError):
+            pass
+
+    def traffic_of(name):
+        tr = traffic_db.get(name)
+        if tr and not args.iters and not args.chains:
+            return tr["dram_bytes_read"] + tr["dram_bytes_write"]
+        return None
+
+    # ---- the headline workload -----------------------------------------------------------------------
+    fs = FlatSpec(tuple(w["layers"]), w["act"], 0.1)
+    Xh, yh, Xth, keys, th0 = make_inputs(w, rank, world, ops)
+    X, y, Xt = (ops._as(a, torch.float32) for a in (Xh, yh, Xth))
+    keysh, th0h = keys.cpu().numpy(), th0.cpu().numpy()
+    step = gpu_step_fn(ops, w, fs, X, y, th0, keys)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -295,79 +394,144 @@ def main():
     value = args.steps * chain_steps / (ms_total * 1e-3)
     ms_per_step = ms_total / args.steps
 
-    # end-to-end: public call with pinned host buffers; H2D of inputs and D2H of the result inside the timed region
+    # ---- end to end ------------------------------------------------------------------------------------
     e2e = None
     if not args.no_e2e:
-        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a.view(np.int32) if a.dtype == np.uint32 else a)).pin_memory()
-        hX, hy, hk, ht = pin(Xh), pin(yh), pin(keysh), pin(th0h)
         P = fs.num_params
         res_shape = (w["C"], w["T"] if w["algo"] == "hmc" else 1, P)
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a.view(np.int32) if a.dtype == np.uint32 else a)).pin_memory()
+        hX, hy, hk, ht = pin(Xh), pin(yh), pin(keysh), pin(th0h)
         hout = torch.empty(res_shape, dtype=torch.float32).pin_memory()
         h2d = sum(t.numel() * t.element_size() for t in (hX, hy, hk, ht))
         d2h = hout.numel() * 4
 
-        def e2e_step():
+        # (1) the flat operator layer (C ABI through pbnn_b200.ops), one step at a time and as a 2-stream pipeline
+        def ops_step(dst=None, stream=None):
             dX, dy = hX.to("cuda", non_blocking=True), hy.to("cuda", non_blocking=True)
             dk, dt_ = hk.to("cuda", non_blocking=True), ht.to("cuda", non_blocking=True)
             r = gpu_step_fn(ops, w, fs, dX, dy, dt_, dk)()
             src = r["trace"] if (w["algo"] == "hmc" and r.get("trace") is not None) else r["theta"].unsqueeze(1)
-            hout.copy_(src, non_blocking=True)
+            if stream is None:
+                (dst if dst is not None else hout).copy_(src, non_blocking=True)
+                return
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            stream.wait_event(ev)
+            with torch.cuda.stream(stream):
+                dst.copy_(src, non_blocking=True)
+            src.record_stream(stream)
 
-        ms_serial = timed(e2e_step, args.steps, args.warmup)
+        ms_ops_serial = timed(ops_step, args.steps, args.warmup)
 
-        # the same calls as a stream pipeline: the D2H of step i (copy stream, double-buffered pinned output) overlaps
-        # the kernel of step i+1; every step still uploads its inputs and downloads its whole result
         copy_stream = torch.cuda.Stream()
         houts = [hout, torch.empty(res_shape, dtype=torch.float32).pin_memory()]
 
-        def pipelined(K):
-            cur = torch.cuda.current_stream()
+        def pipelined(fn_, K):
             for i in range(K):
                 flush.fill_(1)
-                dX, dy = hX.to("cuda", non_blocking=True), hy.to("cuda", non_blocking=True)
-                dk, dt_ = hk.to("cuda", non_blocking=True), ht.to("cuda", non_blocking=True)
-                r = gpu_step_fn(ops, w, fs, dX, dy, dt_, dk)()
-                src = r["trace"] if (w["algo"] == "hmc" and r.get("trace") is not None) else r["theta"].unsqueeze(1)
+                fn_(houts[i % 2], copy_stream)
+            torch.cuda.current_stream().wait_stream(copy_stream)
+
+        def time_pipelined(fn_):
+            pipelined(fn_, args.warmup)
+            barrier()
+            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ea.record()
+            pipelined(fn_, args.steps)
+            eb.record()
+            barrier()
+            launches[0] += args.steps
+            ms = ea.elapsed_time(eb)
+            if world > 1:
+                t = torch.tensor([ms], device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            return ms
+
+        ms_ops_pipe = time_pipelined(ops_step)
+        to_rate = lambda ms: args.steps * chain_steps / (ms * 1e-3)
+        e2e = {"unit": "chain-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ops_value": to_rate(ms_ops_pipe), "ops_serial_value": to_rate(ms_ops_serial)}
+
+        # (2) the reference-signature call a pbnn user makes (src/pbnn/mcmc/hamiltonian.py:31-39 / langevin.py:21-33):
+        # host arrays and Flax-layout pytrees in, (positions pytree, ravel_fn, predict_fn) out, positions to the host
+        api_step = None
+        if w["algo"] in ("hmc", "sgld"):
+            from pbnn_b200 import logprobs, mcmc, pytree
+            from pbnn_b200.models import MLP
+            net = MLP.from_widths(w["layers"], "relu")
+            lik = logprobs.GaussianMLPLikelihood(net, 0.1)
+            prior = logprobs.StdNormalPrior()
+            init_tree = pytree.unravel(ht, tuple(w["layers"]))  # pinned host leaves, leading chain axis
+
+            def api_step(dst=None, stream=None):
+                if w["algo"] == "hmc":
+                    lp = logprobs.FullBatchLogPosterior(lik, prior, hX, hy)
+                    pos, ravel_fn, _ = mcmc.hmc(lp, init_tree, w["T"], w["step"], np.ones(P, np.float32), w["L"], keysh)
+                else:
+                    pos, ravel_fn, _ = mcmc.sgld(hX, hy, lik, prior, init_tree, w["B"], w["step"], w["T"], keysh)
+                src = ravel_fn(pos)
+                if w["algo"] != "hmc":
+                    src = src[:, -1:, :]
+                src = src.contiguous()
+                if stream is None:
+                    (dst if dst is not None else hout).copy_(src, non_blocking=True)
+                    return
                 ev = torch.cuda.Event()
-                ev.record(cur)
-                copy_stream.wait_event(ev)
-                with torch.cuda.stream(copy_stream):
-                    houts[i % 2].copy_(src, non_blocking=True)
-                src.record_stream(copy_stream)
-            cur.wait_stream(copy_stream)
+                ev.record(torch.cuda.current_stream())
+                stream.wait_event(ev)
+                with torch.cuda.stream(stream):
+                    dst.copy_(src, non_blocking=True)
+                src.record_stream(stream)
 
-        pipelined(args.warmup)
-        barrier()
-        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ea.record()
-        pipelined(args.steps)
-        eb.record()
-        barrier()
-        ms_e2e = ea.elapsed_time(eb)
-        if world > 1:
-            t = torch.tensor([ms_e2e], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms_e2e = float(t.item())
-        e2e = {"value": args.steps * chain_steps / (ms_e2e * 1e-3), "unit": "chain-steps/s",
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
-               "serial_value": args.steps * chain_steps / (ms_serial * 1e-3),
-               "api": "pbnn_b200.ops (C ABI) with pinned host buffers; positions returned to the host; value = steps "
-                      "issued as a 2-stream pipeline (D2H of step i overlaps the kernel of step i+1), serial_value = "
-                      "one step at a time"}
+        if api_step is not None:
+            try:
+                ms_api_serial = timed(api_step, args.steps, args.warmup)
+                ms_api_pipe = time_pipelined(api_step)
+                e2e.update(value=to_rate(ms_api_pipe), serial_value=to_rate(ms_api_serial),
+                           ms_per_step=ms_api_pipe / args.steps,
+                           api=f"pbnn_b200.mcmc.{w['algo']} (the reference's signature: pytrees in, (positions, ravel_fn, "
+                               "predict_fn) out) with host inputs; positions copied to pinned host memory; value = steps "
+                               "issued as a 2-stream pipeline (the D2H of step i overlaps the kernel of step i+1), "
+                               "serial_value = one step at a time; ops_* = the same through the flat C-ABI operators")
+            except Exception as exc:  # noqa: BLE001  (never lose the line over the wrapper layer)
+                e2e["api_error"] = f"{type(exc).__name__}: {exc}"
+        if "value" not in e2e:
+            e2e.update(value=e2e["ops_value"], serial_value=e2e["ops_serial_value"], ms_per_step=ms_ops_pipe / args.steps,
+                       api="pbnn_b200.ops (C ABI) with pinned host buffers; positions returned to the host; 2-stream "
+                           "pipeline (value) / one step at a time (serial_value)")
 
-    # the single exchange step: predictive moments of each rank's final states, all_gather'ed (not in the timed region)
+    # ---- the single exchange step: predictive moments of each rank's final states, all_gather'ed -------
+    from pbnn_b200 import dist as pdist
     last = step()
     final = last["theta"]
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
     mom = ops.predict(fs, final, Xt, want_preds=False, want_moments=True)
-    from pbnn_b200 import dist as pdist
-    pm, pv, S_tot = pdist.pooled_moments(mom["sum"], mom["sumsq"], w["C"])  # all_gather over NCCL when world > 1
-    torch.cuda.synchronize()
-    exchange_ms = 1e3 * (time.perf_counter() - t0)
+    pm, pv, S_tot = pdist.pooled_moments(mom["sum"], mom["sumsq"], w["C"])  # first call: communicator set-up included
+    payload = torch.cat([mom["sum"].reshape(-1), mom["sumsq"].reshape(-1), torch.ones(1, device="cuda")])
+    gathered = torch.empty(world * payload.numel(), device="cuda")
 
-    # posterior predictive over stored samples (north_star subsystem 4), timed on its own: every stored position of the
-    # HMC workload (C x T samples), else the final states, on the M test points
+    def exchange():
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, payload)
+        else:
+            gathered.copy_(payload)
+
+    for _ in range(5):
+        exchange()
+    barrier()
+    xa, xb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    xa.record()
+    for _ in range(20):
+        exchange()
+    xb.record()
+    barrier()
+    exchange_us = xa.elapsed_time(xb) * 1e3 / 20
+    exchange_info = {"what": "all_gather of the per-rank predictive moments (sum f, sum f^2, count), warm, CUDA events, "
+                             "20 back-to-back calls" + (" over NCCL" if world > 1 else " (one rank: a device copy)"),
+                     "us_per_exchange": exchange_us, "bytes_per_rank": int(payload.numel() * 4),
+                     "pred_mean_abs": float(pm.abs().mean()), "pred_var_mean": float(pv.mean()), "samples_pooled": S_tot}
+
+    # ---- posterior predictive over stored samples (north_star subsystem 4), timed on its own -----------
     psmp = last["trace"].reshape(-1, fs.num_params) if (w["algo"] == "hmc" and last.get("trace") is not None) else final
     ops.predict(fs, psmp, Xt, want_preds=False, want_moments=True)
     pa, pb_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -382,61 +546,93 @@ def main():
                   "engine": "tcgen05" if (len(w["layers"]) == 3 and w["act"] == 0 and w["layers"][1] <= 64
                                           and w["layers"][0] + 1 <= 16 and not ops.get_option("no_tc")) else "fp32",
                   "note": "mean / variance over the samples for every test point; not part of `value`"}
+    main_finite = bool(torch.isfinite(final).all().item())
+    accept = float(last["accept_count"].float().mean().item() / w["T"]) if w["algo"] == "hmc" else None
+    del last, final, psmp, step
+    torch.cuda.empty_cache()
+
+    # ---- the metric is "SGLD & HMC": the SGLD configurations, device-timed like the headline -------------
+    extras = {}
+    if not args.no_extras:
+        for name in ("sgld_cfg1x", "sgld_cfg3", "sgld_cfg5"):
+            if name == args.workload:
+                continue
+            we = dict(WORKLOADS[name], name=name)
+            fse = FlatSpec(tuple(we["layers"]), we["act"], 0.1)
+            Xe, ye, _, ke, the = make_inputs(we, rank, world, ops)
+            Xd, yd = ops._as(Xe, torch.float32), ops._as(ye, torch.float32)
+            fe = gpu_step_fn(ops, we, fse, Xd, yd, the, ke)
+            ks = max(3, min(args.steps, 5))
+            ms_e = timed(fe, ks, 3) / ks
+            fin = bool(torch.isfinite(fe()["theta"]).all().item())
+            extras[name] = {"value": we["C"] * we["T"] * world / (ms_e * 1e-3), "unit": "chain-steps/s",
+                            "ms_per_step": ms_e, "steps": ks, "warmup": 3, "config": workload_config(name, we),
+                            "roofline": roofline_for(ops, we, fse, ms_e, clocks, peaks, traffic_of(name)),
+                            "chains_finite": fin}
+            del Xd, yd, fe, the, ke
+            torch.cuda.empty_cache()
+
+    # ---- N > 1: BASELINE configs[4], chains sharded through pbnn_b200.dist ----------------------------
+    sharded = None
+    if world > 1 and not args.no_extras:
+        w5 = dict(WORKLOADS["sgld_cfg5"], name="sgld_cfg5")
+        fs5 = FlatSpec(tuple(w5["layers"]), w5["act"], 0.1)
+        C_total = w5["C"] * world
+        X5h, y5h, X5t = make_data(w5)
+        X5, y5, X5t = (ops._as(a, torch.float32) for a in (X5h, y5h, X5t))
+        root = np.array([[0, 0]], np.uint32)
+        k5 = pdist.shard_chain_keys(ops, root, C_total)            # split(PRNGKey(0), C_total)[lo:hi]
+        lo, hi = pdist.shard_range(C_total)
+        th5 = 0.01 * ops.normal(k5, fs5.num_params)
+        f5 = lambda: ops.sgld(fs5, X5, y5, th5, k5, w5["B"], w5["step"], w5["T"], keep_trace=False)
+        ms5 = timed(f5, 3, 3) / 3
+        out5 = f5()["theta"]
+        # sharding check on the device: every rank publishes its first 4 chains; rank r re-runs the first 4 chains of
+        # rank (r + 1) % world from the global key table, alone, and compares bit for bit
+        nchk = 4
+        mine = out5[:nchk].contiguous()
+        allfirst = torch.empty((world,) + tuple(mine.shape), device="cuda")
+        dist.all_gather_into_tensor(allfirst, mine)
+        peer = (rank + 1) % world
+        kall = ops.split(root, C_total)[0]
+        kp = kall[peer * w5["C"]:peer * w5["C"] + nchk].contiguous()
+        thp = 0.01 * ops.normal(kp, fs5.num_params)
+        solo = ops.sgld(fs5, X5, y5, thp, kp, w5["B"], w5["step"], w5["T"], keep_trace=False)["theta"]
+        same = torch.tensor([1.0 if torch.equal(solo, allfirst[peer]) else 0.0], device="cuda")
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        m5 = ops.predict(fs5, out5, X5t, want_preds=False, want_moments=True)
+        pm5, pv5, S5 = pdist.pooled_moments(m5["sum"], m5["sumsq"], w5["C"])
+        pay5 = torch.cat([m5["sum"].reshape(-1), m5["sumsq"].reshape(-1), torch.ones(1, device="cuda")])
+        g5 = torch.empty(world * pay5.numel(), device="cuda")
+        for _ in range(5):
+            dist.all_gather_into_tensor(g5, pay5)
+        barrier()
+        ya, yb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ya.record()
+        for _ in range(20):
+            dist.all_gather_into_tensor(g5, pay5)
+        yb.record()
+        barrier()
+        sharded = {"what": f"BASELINE configs[4]: {C_total} SGLD chains sharded over {world} GPUs "
+                           f"({w5['C']} per GPU, rank r owns chains [{w5['C']}r, {w5['C']}(r+1)) of split(PRNGKey(0), "
+                           f"{C_total})), MLP 90-256-256-1, N=515345, batch 128, {w5['T']} iterations per step",
+                   "value": C_total * w5["T"] / (ms5 * 1e-3), "unit": "chain-steps/s", "ms_per_step": ms5,
+                   "per_gpu_value": w5["C"] * w5["T"] / (ms5 * 1e-3), "scaling": "weak",
+                   "sharding_check": {"chains_compared_per_rank": nchk, "ranks": world,
+                                      "bit_identical_to_solo_run": bool(same.item() == 1.0),
+                                      "how": "rank r re-ran the first 4 chains of rank r+1 alone from the global key "
+                                             "table; torch.equal on the final states, MIN-reduced over ranks"},
+                   "moments_allgather_us": ya.elapsed_time(yb) * 1e3 / 20, "moments_bytes_per_rank": int(pay5.numel() * 4),
+                   "pooled_samples": S5, "pred_var_mean": float(pv5.mean()),
+                   "roofline": roofline_for(ops, w5, fs5, ms5, clocks, peaks, traffic_of("sgld_cfg5"))}
 
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except OSError:
-            pass
-        flops = step_flops(w)
-        achieved = flops / (ms_per_step * 1e-3) / 1e12
-        sm_max = (clocks or {}).get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0
-        peak_nominal = 148 * 128 * 2 * sm_max * 1e6 / 1e12
+        roofline = roofline_for(ops, w, fs, ms_per_step, clocks, peaks, traffic_of(args.workload))
         trace_bytes = w["C"] * w["T"] * fs.num_params * 4 if w["algo"] == "hmc" else 0
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        traffic = None
-        try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(args.workload)
-            if tr and not args.iters and not args.chains:
-                traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
-        except (OSError, KeyError, ValueError):
-            pass
-        from pbnn_b200 import _lib as plib
-        op = {"hmc": plib.OP_HMC, "sgld": plib.OP_SGLD, "psgld": plib.OP_PSGLD, "sghmc": plib.OP_SGHMC,
-              "adam": plib.OP_ADAM}[w["algo"]]
-        engine = ops.lib.pbnn_plan_engine(fs.c_struct(), op, w["B"], w["C"])
-        hbm = {"achieved": trace_bytes / (ms_per_step * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-               "frac": trace_bytes / (ms_per_step * 1e-3) / 1e9 / hbm_peak,
-               "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback"}
-        if engine == plib.ENGINE_TCGEN05:
-            # the two GEMMs of every gradient run on the tensor cores as split-TF32 products:
-            # achieved = ALGORITHMIC flops / time against the TF32 tensor peak (half the measured dense bf16 rate)
-            tf32_peak = peaks.get("bf16_tflops", 2250.0 * 0.73) / 2
-            ntile = (w["B"] + 127) // 128
-            grads = w["C"] * w["T"] * (w["L"] + 1.0 / w["T"])
-            executed = grads * ntile * (6 + 8) * (128 * 64 * 8 * 2)  # 6 forward + 8 backward MMAs 128x64x8 per tile
-            roofline = {"bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
-                        "frac": achieved / tf32_peak, "traffic": traffic,
-                        "peak_source": "TF32 dense tensor rate = measured cuBLAS bf16 (MEASURED_PEAKS.json burst) / 2"
-                                       if peaks else "fallback: 0.73 x 2250 / 2",
-                        "kernel": "pb_hmc_tc_kernel", "algorithmic_flops_per_launch": flops,
-                        "executed_tensor_flops_per_launch": executed,
-                        "executed_tensor_tflops": executed / (ms_per_step * 1e-3) / 1e12,
-                        "fp32_fma_equivalent": {"achieved": achieved, "peak": peak_nominal, "frac": achieved / peak_nominal,
-                                                "note": "the same algorithmic flops against the FP32-FMA peak the "
-                                                        "scalar engines are bound by (148 SM x 128 lanes x 2 x clock)"},
-                        "note": "latency-bound: per gradient a dependent chain of forward MMA -> epilogue -> backward "
-                                "MMA -> readout; two CTAs per SM overlap each other's waits; see profiles/ and DESIGN.md",
-                        "hbm": hbm}
-        else:
-            roofline = {"bound": "fma", "achieved": achieved, "peak": peak_nominal, "unit": "TFLOP/s",
-                        "frac": achieved / peak_nominal, "traffic": traffic,
-                        "peak_source": f"FP32 FMA: 148 SM x 128 lanes x 2 x {sm_max:.0f} MHz (the kernel is FP32-FMA "
-                                       f"bound, neither HBM nor tensor; DESIGN.md)",
-                        "kernel": "pb_hmc_kernel" if w["algo"] == "hmc" else "pb_sg_kernel",
-                        "algorithmic_flops_per_launch": flops, "hbm": hbm}
-        roofline["engine"] = ["tiled", "fused_h1", "tcgen05", "tiled_global_state"][engine] if 0 <= engine < 4 else engine
+        roofline["hbm"] = {"achieved": trace_bytes / (ms_per_step * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                           "frac": trace_bytes / (ms_per_step * 1e-3) / 1e9 / hbm_peak,
+                           "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback"}
         try:  # practical FP32 ceiling measured in the same run (scalar FFMA and packed FFMA2 probes)
             import ctypes
             ops.lib.pbnn_probe_fp32.argtypes = [ctypes.c_int] * 3 + [ctypes.c_void_p] * 2
@@ -451,18 +647,18 @@ def main():
                 torch.cuda.synchronize()
                 best = max(best, 148 * 8 * 256 * 10000 * 64 / (ea.elapsed_time(eb) * 1e-3) / 1e12)
             roofline["peak_measured_fp32_probe"] = best
-            roofline["frac_of_measured_fp32"] = achieved / best
-        except Exception as exc:  # noqa: BLE001
+        except Exception:  # noqa: BLE001
             roofline["peak_measured_fp32_probe"] = None
-        out = dict(base, value=value, ms_per_step=ms_per_step, clocks=clocks, roofline=roofline, gpu_launches=args.steps,
-                   predictive=predictive,
-                   exchange={"what": "predictive moments (sum, sumsq over chains) all_gather", "ms": exchange_ms,
-                             "pred_mean_abs": float(pm.abs().mean()), "pred_var_mean": float(pv.mean())},
-                   chains_finite=bool(torch.isfinite(final).all().item()))
-        if w["algo"] == "hmc":
-            out["hmc_accept_rate"] = float(last["accept_count"].float().mean().item() / w["T"])
+        out = dict(base, value=value, ms_per_step=ms_per_step, clocks=clocks, roofline=roofline,
+                   gpu_launches=launches[0], predictive=predictive, exchange=exchange_info, chains_finite=main_finite)
+        if accept is not None:
+            out["hmc_accept_rate"] = accept
         if e2e:
             out["e2e"] = e2e
+        if extras:
+            out["workloads"] = extras
+        if sharded:
+            out["sharded_cfg5"] = sharded
         if not args.no_cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_baseline(w)
         print(json.dumps(out))
