@@ -220,20 +220,18 @@ PB_DEV void pb_tc2_restage(const PbPlan& pl, float* sm, const PbTc2& tc, const f
   const PbLayer& L1 = pl.L[1];
   const int H = pl.t2_H, Hp = pl.t2_Hp, Kx = pl.t2_Kx, d = pl.d;
   PB_TAG(1)
-  for (int which = 0; which < 2; ++which) {
-    const PbLayer& Ly = which ? L1 : L0;
-    const int rows = which ? Hp : Kx, nrow = which ? H : d + 1;
-    const int tb = pl.t2_nch * rows * 128, hp2 = Hp >> 1;
-    uint8_t* base = tc.img + (which ? pl.t2_img_w2 : pl.t2_img_w1);
-    const int total = nrow * hp2;
+  {  // W1aug image: storage row = input index k (k == d: bias), columns = hidden unit
+    const int tb = pl.t2_nch * Kx * 128, hp2 = Hp >> 1;
+    uint8_t* base = tc.img + pl.t2_img_w1;
+    const int total = (d + 1) * hp2;
     for (int e0 = tid; e0 < total; e0 += 4 * nt) {
       float v0[4], v1[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int e = e0 + u * nt;
         const int k = e / hp2, n0 = 2 * (e - k * hp2);
-        v0[u] = (e < total && n0 < H) ? TH[Ly.soff + k * Ly.wp + n0] : 0.f;
-        v1[u] = (e < total && n0 + 1 < H) ? TH[Ly.soff + k * Ly.wp + n0 + 1] : 0.f;
+        v0[u] = (e < total && n0 < H) ? TH[L0.soff + k * L0.wp + n0] : 0.f;
+        v1[u] = (e < total && n0 + 1 < H) ? TH[L0.soff + k * L0.wp + n0 + 1] : 0.f;
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -242,7 +240,36 @@ PB_DEV void pb_tc2_restage(const PbPlan& pl, float* sm, const PbTc2& tc, const f
           const int k = e / hp2, n0 = 2 * (e - k * hp2);
           uint32_t t1, t2, t3;
           pb_t2_split3(v0[u], v1[u], t1, t2, t3);
-          uint8_t* p = base + pb_t2_off(rows, k, n0);
+          uint8_t* p = base + pb_t2_off(Kx, k, n0);
+          *reinterpret_cast<uint32_t*>(p) = t1;
+          *reinterpret_cast<uint32_t*>(p + tb) = t2;
+          *reinterpret_cast<uint32_t*>(p + 2 * tb) = t3;
+        }
+      }
+    }
+  }
+  {  // W2 image, TRANSPOSED: storage row = output unit n, columns = input index i (pairs i, i + 1 packed): the drain
+     // thread of output unit n (its TMEM lane) then owns one image row and moves 8 weights per 16-byte access
+    const int tb = pl.t2_nch * Hp * 128, hp2 = Hp >> 1;
+    uint8_t* base = tc.img + pl.t2_img_w2;
+    const int total = H * hp2;  // (n, pair of i)
+    for (int e0 = tid; e0 < total; e0 += 4 * nt) {
+      float v0[4], v1[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + u * nt;
+        const int ip = e / H, n = e - ip * H, i0 = 2 * ip;  // consecutive threads: consecutive n (coalesced TH reads)
+        v0[u] = (e < total && i0 < H) ? TH[L1.soff + i0 * L1.wp + n] : 0.f;
+        v1[u] = (e < total && i0 + 1 < H) ? TH[L1.soff + (i0 + 1) * L1.wp + n] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + u * nt;
+        if (e < total) {
+          const int ip = e / H, n = e - ip * H, i0 = 2 * ip;
+          uint32_t t1, t2, t3;
+          pb_t2_split3(v0[u], v1[u], t1, t2, t3);
+          uint8_t* p = base + pb_t2_off(Hp, n, i0);
           *reinterpret_cast<uint32_t*>(p) = t1;
           *reinterpret_cast<uint32_t*>(p + tb) = t2;
           *reinterpret_cast<uint32_t*>(p + 2 * tb) = t3;
@@ -360,9 +387,7 @@ PB_DEV void pb_grad_tc2(const PbPlan& pl, float* sm, float* TH, int nrows, float
         ++ause;
         row_chunk(tc.img + pl.t2_img_w1, Kx, kc, rows);
       }
-      // G2: W2 rows of chunk ic (MN-major B)
-      for (int ic = 0; ic < nch; ++ic) row_chunk(tc.img + pl.t2_img_w2, Hp, ic, (Hp - 64 * ic) < 64 ? (Hp - 64 * ic) : 64);
-      // G5: W2 column block kc, all Hp rows (K-major B)
+      // G2 (K = input index i = image COLUMNS): column block ic of the transposed W2 image, all Hp rows (K-major B)
       for (int kc = 0; kc < nch; ++kc)
         for (int t = 0; t < 3; ++t) {
           const uint32_t bytes = (uint32_t)(Hp * 128);
@@ -373,6 +398,8 @@ PB_DEV void pb_grad_tc2(const PbPlan& pl, float* sm, float* TH, int nrows, float
             pb_t2_bulk(dst + o, src + o, bytes - o < 16384u ? bytes - o : 16384u, PB_T2_BAR(PB_T2_B_WFULL + s));
           ++fill;
         }
+      // G5 (K = output unit n = image ROWS): rows of chunk kc, every column block (MN-major B)
+      for (int ic = 0; ic < nch; ++ic) row_chunk(tc.img + pl.t2_img_w2, Hp, ic, (Hp - 64 * ic) < 64 ? (Hp - 64 * ic) : 64);
       // G6: the whole X image into the ring area once every stage has been consumed
       for (int j = fill > PB_T2_NS ? fill - PB_T2_NS : 0; j < fill; ++j)
         pb_mbar_wait(PB_T2_BAR(PB_T2_B_WEMPTY + j % PB_T2_NS), (uint32_t)((j / PB_T2_NS) & 1));
@@ -433,8 +460,9 @@ PB_DEV void pb_grad_tc2(const PbPlan& pl, float* sm, float* TH, int nrows, float
       commit(PB_T2_B_ACC);
     };
     kgemm(S0, ncbx, Kx, true, false);   // G1: Z1
-    kgemm(S1, nch, Hp, false, false);   // G2: Z2
-    kgemm(S1, nch, Hp, false, true);    // G5: E = (w3 * M2) W2^T  (S1: Z2 has been consumed; Z1 stays in S0 for G4)
+    kgemm(S1, nch, Hp, false, true);    // G2: Z2 (B = transposed W2 image read K-major)
+    kgemm(S1, nch, Hp, false, false);   // G5: E = (w3 * M2) W2^T  (the same image read MN-major; S1: Z2 has been
+                                        // consumed; Z1 stays in S0 for G4)
     // G6: D1 chunks.  A = X^T (MN-major, lanes = input index k), B = dZ1 chunk (MN-major), K = 128 batch rows
     pb_mbar_wait(PB_T2_BAR(PB_T2_B_XFULL), 0u);
     pb_tc_fence_after();
@@ -658,29 +686,36 @@ PB_DEV void pb_grad_tc2(const PbPlan& pl, float* sm, float* TH, int nrows, float
         bad |= !pb_finite(v);
       }
     };
-    auto update_w1 = [&]() {
-      const int d = pl.d;
-      const int tb1 = nch * Kx * 128;
-      uint8_t* img1 = tc.img + pl.t2_img_w1;
-      const int wt = warp * 32 + lane;                       // worker thread 0..255
-      const int i = Hp > 128 ? wt : (wt & 127);              // this thread's column (hidden unit)
-      const int kg = Hp > 128 ? 0 : (wt >> 7), nkg = Hp > 128 ? 1 : 2;
-      for (int k0 = kg; k0 <= d; k0 += 4 * nkg) {
+    // ---- one block of 8 consecutive weights of ONE image row (a 16-byte chunk per bf16 term) ----------------------
+    //   p: address of the chunk in the first term image, terms tb bytes apart;  element j: resident index si0 + j sis,
+    //   flat index fi0 + j fis;  nval (1..8) valid elements (the rest are pad columns and stay zero);  dv: the eight
+    //   accumulator values, scaled by gs into d loglik / d theta;  acc += sum_j theta_j dv_j (output-layer gradient)
+    auto drain8 = [&](uint8_t* p, int tb, int si0, int sis, int fi0, int fis, int nval, const float* dv, float gs,
+                      float& acc) {
+      const uint4 q1 = __ldcg(reinterpret_cast<const uint4*>(p));
+      const uint4 q2 = __ldcg(reinterpret_cast<const uint4*>(p + tb));
+      const uint4 q3 = __ldcg(reinterpret_cast<const uint4*>(p + 2 * tb));
+      const uint32_t w1[4] = {q1.x, q1.y, q1.z, q1.w}, w2[4] = {q2.x, q2.y, q2.z, q2.w}, w3[4] = {q3.x, q3.y, q3.z, q3.w};
+      float nv[8];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {  // two groups of four: the four threefry + erf_inv chains of a group are interleaved
         PbPre pre[4];
-        float nv[4], zz[4];
-        uint32_t ix[4];
-        const bool own = i < H;
+        float zz[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int k = k0 + j * nkg;
-          ix[j] = (uint32_t)((k < d ? L0.fw + k * H : L0.fb) + i);
-          if (own && k <= d) {
-            pre[j] = pf(L0.soff + k * L0.wp + i, (int)ix[j]);
-            pre[j].a = pb_t2_get(img1 + pb_t2_off(Kx, k, i), tb1);
+          const int e = 4 * h + j, m = e >> 1;
+          if (e < nval) {
+            pre[j] = pf(si0 + e * sis, fi0 + e * fis);
+            pre[j].a = (e & 1) ? (__uint_as_float(w1[m] & 0xFFFF0000u) + __uint_as_float(w2[m] & 0xFFFF0000u)) +
+                                     __uint_as_float(w3[m] & 0xFFFF0000u)
+                               : (__uint_as_float(w1[m] << 16) + __uint_as_float(w2[m] << 16)) +
+                                     __uint_as_float(w3[m] << 16);
           }
         }
-        if (noise) {
-          const float4 z4 = pb_t2_normal4(nkey.k0, nkey.k1, ix[0], ix[1], ix[2], ix[3]);
+        if (noise && 4 * h < nval) {
+          const float4 z4 = pb_t2_normal4(nkey.k0, nkey.k1, (uint32_t)(fi0 + (4 * h) * fis),
+                                          (uint32_t)(fi0 + (4 * h + 1) * fis), (uint32_t)(fi0 + (4 * h + 2) * fis),
+                                          (uint32_t)(fi0 + (4 * h + 3) * fis));
           zz[0] = z4.x; zz[1] = z4.y; zz[2] = z4.z; zz[3] = z4.w;
         } else {
 #pragma unroll
@@ -688,17 +723,36 @@ PB_DEV void pb_grad_tc2(const PbPlan& pl, float* sm, float* TH, int nrows, float
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int k = k0 + j * nkg;
-          if (own && k <= d) nv[j] = uf(L0.soff + k * L0.wp + i, (int)ix[j], pre[j], d1buf[k * dp + i], zz[j]);
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int k = k0 + j * nkg;
-          if (own && k <= d) {
-            pb_t2_put(img1 + pb_t2_off(Kx, k, i), tb1, nv[j]);
-            emit((int)ix[j], nv[j]);
+          const int e = 4 * h + j;
+          nv[e] = 0.f;
+          if (e < nval) {
+            acc = fmaf(pre[j].a, dv[e], acc);
+            nv[e] = uf(si0 + e * sis, fi0 + e * fis, pre[j], gs * dv[e], zz[j]);
+            emit(fi0 + e * fis, nv[e]);
           }
         }
+      }
+      uint32_t t1[4], t2[4], t3[4];
+#pragma unroll
+      for (int m = 0; m < 4; ++m) pb_t2_split3(nv[2 * m], nv[2 * m + 1], t1[m], t2[m], t3[m]);
+      *reinterpret_cast<uint4*>(p) = make_uint4(t1[0], t1[1], t1[2], t1[3]);
+      *reinterpret_cast<uint4*>(p + tb) = make_uint4(t2[0], t2[1], t2[2], t2[3]);
+      *reinterpret_cast<uint4*>(p + 2 * tb) = make_uint4(t3[0], t3[1], t3[2], t3[3]);
+    };
+    // first layer: (row k, 8-column block) items of the dumped D1, dealt round-robin to the 256 workers
+    auto update_w1 = [&]() {
+      const int d = pl.d;
+      const int tb1 = nch * Kx * 128;
+      uint8_t* img1 = tc.img + pl.t2_img_w1;
+      const int wt = warp * 32 + lane, nblk = (H + 7) >> 3, items = (d + 1) * nblk;
+      float unused = 0.f;
+      for (int it = wt; it < items; it += PB_T2_WORKERS) {
+        const int k = it / nblk, i0 = 8 * (it - k * nblk);
+        const float4 a0 = *reinterpret_cast<const float4*>(d1buf + k * dp + i0);
+        const float4 a1 = *reinterpret_cast<const float4*>(d1buf + k * dp + i0 + 4);
+        const float dv[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        drain8(img1 + pb_t2_off(Kx, k, i0), tb1, L0.soff + k * L0.wp + i0, 1, (k < d ? L0.fw + k * H : L0.fb) + i0, 1,
+               H - i0 < 8 ? H - i0 : 8, dv, 1.0f, unused);
       }
     };
     pb_tc_fence_before();
@@ -706,8 +760,9 @@ PB_DEV void pb_grad_tc2(const PbPlan& pl, float* sm, float* TH, int nrows, float
     PB_MARK(9)
     // ---- G4: Y chunks = r * [relu(Z1) | 1 | 0..]; the D2 drains (fused update of W2, b2) run one chunk behind ----
     const bool two_tiles = nmt > 1;
-    const int n_own = two_tiles ? 128 * g + b : b;  // output unit (TMEM lane of D2) this thread drains
-    const float w3n = n_own < H ? w3v[n_own] : 0.f;
+    const int n_own = two_tiles ? 128 * g + b : b;  // output unit (TMEM lane of D2) this thread drains = its image row
+    const bool own = n_own < H;
+    const float w3n = own ? w3v[n_own] : 0.f;
     const int tb2 = nch * Hp * 128;
     uint8_t* img2 = tc.img + pl.t2_img_w2;
     float dw3 = 0.f;
@@ -720,92 +775,28 @@ PB_DEV void pb_grad_tc2(const PbPlan& pl, float* sm, float* TH, int nrows, float
       const int cbeg = two_tiles ? 0 : 32 * g;
       const int cend = two_tiles ? ncols : (ncols < 32 * g + 32 ? ncols : 32 * g + 32);
       for (int c0 = cbeg; c0 < cend; c0 += 8) {
-        uint32_t dv[8];
-        pb_tmem_ld8(S1 + lane_off + (uint32_t)(slot * 128 + (two_tiles ? 64 * g : 0) + c0), dv);
+        uint32_t dr[8];
+        pb_tmem_ld8(S1 + lane_off + (uint32_t)(slot * 128 + (two_tiles ? 64 * g : 0) + c0), dr);
         pb_tmem_wait_ld();
         const int i0 = 64 * ic + c0;  // input index of W2 (i == H: the bias row b2)
-        const bool own = n_own < H;
-        if (i0 + 8 <= H) {
-          // fast path: 8 kernel rows i0 .. i0 + 7 in two groups of 4 (i0 is a multiple of 8: (i & 7) == j in the swizzle)
-          const int sb = L1.soff + i0 * L1.wp + n_own, fb = L1.fw + i0 * H + n_own;
-          uint8_t* ib = img2 + (n_own >> 6) * (Hp * 128) + i0 * 128 + ((n_own & 7) << 1);
-          const uint32_t cn = (uint32_t)((n_own & 63) >> 3);
+        if (!own || i0 > H) continue;
+        float dv[8];
 #pragma unroll
-          for (int j0 = 0; j0 < 8; j0 += 4) {
-            PbPre pre[4];
-            float nv[4], zz[4];
+        for (int j = 0; j < 8; ++j) dv[j] = __uint_as_float(dr[j]);
+        if (i0 < H)  // kernel rows i0 .. : columns i0 .. of this thread's row of the transposed image
+          drain8(img2 + pb_t2_off(Hp, n_own, i0), tb2, L1.soff + i0 * L1.wp + n_own, L1.wp, L1.fw + i0 * H + n_own, H,
+                 H - i0 < 8 ? H - i0 : 8, dv, w3n, dw3);
+        if (H - i0 < 8) {  // this block holds the bias column (i == H): b2 stays fp32 in TH
+          float dd = 0.f;
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (own) {
-                pre[j] = pf(sb + (j0 + j) * L1.wp, fb + (j0 + j) * H);
-                pre[j].a = pb_t2_get(ib + (j0 + j) * 128 + ((cn ^ (uint32_t)(j0 + j)) << 4), tb2);
-              }
-            if (noise) {
-              uint32_t ix[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) ix[j] = (uint32_t)(fb + (j0 + j) * H);
-              const float4 z4 = pb_t2_normal4(nkey.k0, nkey.k1, ix[0], ix[1], ix[2], ix[3]);
-              zz[0] = z4.x; zz[1] = z4.y; zz[2] = z4.z; zz[3] = z4.w;
-            } else {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) zz[j] = 0.f;
-            }
-            if (own) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float dd = __uint_as_float(dv[j0 + j]);
-                dw3 = fmaf(pre[j].a, dd, dw3);
-                nv[j] = uf(sb + (j0 + j) * L1.wp, fb + (j0 + j) * H, pre[j], w3n * dd, zz[j]);
-              }
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                pb_t2_put(ib + (j0 + j) * 128 + ((cn ^ (uint32_t)(j0 + j)) << 4), tb2, nv[j]);
-                emit(fb + (j0 + j) * H, nv[j]);
-              }
-            }
-          }
-        } else if (i0 <= H) {
-          // ragged tail: the last kernel rows and the bias row (i == H)
-#pragma unroll
-          for (int j0 = 0; j0 < 8; j0 += 4) {
-            PbPre pre[4];
-            float nv[4], zz[4];
-            uint32_t ix[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int i = i0 + j0 + j;
-              ix[j] = (uint32_t)(i < H ? L1.fw + i * H + n_own : L1.fb + n_own);
-              if (own && i <= H) {
-                pre[j] = pf(L1.soff + i * L1.wp + n_own, (int)ix[j]);
-                pre[j].a = i < H ? pb_t2_get(img2 + pb_t2_off(Hp, i, n_own), tb2) : TH[L1.soff + i * L1.wp + n_own];
-              }
-            }
-            if (noise) {
-              const float4 z4 = pb_t2_normal4(nkey.k0, nkey.k1, ix[0], ix[1], ix[2], ix[3]);
-              zz[0] = z4.x; zz[1] = z4.y; zz[2] = z4.z; zz[3] = z4.w;
-            } else {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) zz[j] = 0.f;
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int i = i0 + j0 + j;
-              if (own && i <= H) {
-                const float dd = __uint_as_float(dv[j0 + j]);
-                dw3 = fmaf(pre[j].a, dd, dw3);
-                nv[j] = uf(L1.soff + i * L1.wp + n_own, (int)ix[j], pre[j], w3n * dd, zz[j]);
-              }
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int i = i0 + j0 + j;
-              if (own && i <= H) {
-                if (i < H) pb_t2_put(img2 + pb_t2_off(Hp, i, n_own), tb2, nv[j]);
-                else TH[L1.soff + i * L1.wp + n_own] = nv[j];
-                emit((int)ix[j], nv[j]);
-              }
-            }
-          }
+          for (int j = 0; j < 8; ++j) dd = (i0 + j == H) ? dv[j] : dd;
+          const int si = L1.soff + H * L1.wp + n_own, fi = L1.fb + n_own;
+          PbPre pre = pf(si, fi);
+          pre.a = TH[si];
+          dw3 = fmaf(pre.a, dd, dw3);
+          const float nvb = uf(si, fi, pre, w3n * dd, noise ? pb_normal_at(nkey, (uint32_t)fi) : 0.f);
+          TH[si] = nvb;
+          emit(fi, nvb);
         }
       }
       pb_tc_fence_before();

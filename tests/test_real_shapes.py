@@ -143,9 +143,11 @@ def test_sghmc_at_cfg3(eng):
     # ... and the increments themselves (theta_T - theta_0 is dominated by the momentum, so compare the drift part too)
     d_ref, d_out = refh[:, -1] - th0, npy(outh["trace"])[:, -1] - th0
     assert rel(d_out, d_ref) <= 1e-4
-    # the default ("unit") momentum law of SURVEY.md 2b as well
-    refu = o.sghmc(sp, X, y, th0, B, 1e-7, 1, 10, keys)
-    outu = eng.sghmc(fs, X, y, th0, keys, B, 1e-7, 1, 10)
+    # the default ("unit") momentum law of SURVEY.md 2b as well: theta moves by N(0, 1) per inner step, so only two inner
+    # steps stay finite (ten give NaN in the oracle too -- the reason the law is a parameter)
+    refu = o.sghmc(sp, X, y, th0, B, 1e-7, 1, 2, keys)
+    outu = eng.sghmc(fs, X, y, th0, keys, B, 1e-7, 1, 2)
+    assert np.isfinite(refu).all()
     assert rel(npy(outu["trace"]), refu) <= RTOL_STEP
 
 
