@@ -61,7 +61,7 @@ struct PbPlan {
   int t2_nch, t2_nchy, t2_ncbx, t2_nmt;    // 64-wide chunks of Hp / Hy / Kx; 128-row tiles of Hp
   int t2_wstage, t2_ring;                  // bytes of one weight-ring stage / of the whole ring
   int off_t2_vec, off_t2_bar, off_t2_big;  // float offsets: small vectors, mbarriers, 1024-byte aligned operand area
-  int t2_img_w1, t2_img_w2, t2_img_w2s, t2_img_bytes;  // byte offsets inside the image block (X image at 0)
+  int t2_img_w1, t2_img_w2, t2_img_z, t2_img_bytes;  // byte offsets inside the image block (X image at 0; z: noise ring)
   int off_act, off_scr, off_acc, off_idx, off_scal;
   int idx_cap;
   int smem_floats;
@@ -146,7 +146,9 @@ static inline void pb_plan_dw(PbPlan* pl, int nw, int bt, int kcap) {
 #define PB_PLAN_TC 4  // the caller has a tcgen05 kernel for this op (HMC): allow the tensor-core layout
 #define PB_PLAN_TC2 8  // the caller can run the two-hidden-layer tcgen05 engine (SG samplers, Adam, grad hook)
 
-#define PB_T2_NT 320       // 8 worker warps + 1 TMA warp + 1 MMA-issue warp
+#define PB_T2_NT 576       // 8 worker warps + 1 TMA warp + 1 MMA-issue warp + 8 noise warps
+#define PB_T2_NZ 16        // slots of the noise ring (one slot = 8 normals for each of the 256 worker threads)
+#define PB_T2_ZSLOT 2048   // floats per slot
 #define PB_T2_NS 3         // weight-ring stages
 #define PB_T2_TILE 16384   // bytes of one [128 rows][64 bf16] operand tile (SWIZZLE_128B)
 #define PB_T2_VEC_FLOATS 1856
@@ -194,15 +196,15 @@ static inline void pb_layout_tc2(PbPlan* pl, const pbnn_mlp_spec* sp, int rows) 
   pl->off_t2_vec = off;
   off += PB_T2_VEC_FLOATS;
   pl->off_t2_bar = off;
-  off += 64;
+  off += 160;  // up to 64 mbarriers + the TMEM base slot
   pl->off_t2_big = off;
   off += 256;  // slack for the run-time 1024-byte alignment
   off += (3 * PB_T2_TILE + pl->t2_nch * PB_T2_TILE + pl->t2_ring) / 4;
   pl->smem_floats = off;
   pl->t2_img_w1 = xi;
   pl->t2_img_w2 = pl->t2_img_w1 + 3 * pl->t2_nch * pl->t2_Kx * 128;
-  pl->t2_img_w2s = 0;
-  pl->t2_img_bytes = pl->t2_img_w2 + 3 * pl->t2_nch * pl->t2_Hp * 128;
+  pl->t2_img_z = pl->t2_img_w2 + 3 * pl->t2_nch * pl->t2_Hp * 128;
+  pl->t2_img_bytes = pl->t2_img_z + PB_T2_NZ * PB_T2_ZSLOT * 4;
 }
 
 // tcgen05 operand geometry (floats).  K-major, no swizzle: element (row x, k) at (k/4)*LBO + x*16 B + (k%4)*4 B.

@@ -113,7 +113,9 @@ enum {
   PB_T2_B_D2EMPTY = PB_T2_B_D2FULL + 2, // [2] D2 chunk slot drained by the 256 workers
   PB_T2_B_XFULL = PB_T2_B_D2EMPTY + 2,  // X image resident in the ring area (dW1)
   PB_T2_B_S1FREE,                       // D1 drained by the 256 workers: TMEM S1 may take the D2 chunk slots
-  PB_T2_NBAR
+  PB_T2_B_ZFULL,                        // [NZ] noise-ring slot written by the 256 noise threads
+  PB_T2_B_ZEMPTY = PB_T2_B_ZFULL + PB_T2_NZ,  // [NZ] noise-ring slot consumed by the 256 workers
+  PB_T2_NBAR = PB_T2_B_ZEMPTY + PB_T2_NZ
 };
 
 struct PbTc2 {
@@ -341,7 +343,8 @@ PB_DEV void pb_grad_tc2(const PbPlan& pl, float* sm, float* TH, int nrows, float
   if (tid == 0) {
     for (int i = 0; i < PB_T2_NBAR; ++i) {
       const uint32_t b = pb_t2_bar(pl, sm, i);
-      const uint32_t cnt = (i == PB_T2_B_AFULL || i == PB_T2_B_D2EMPTY || i == PB_T2_B_D2EMPTY + 1 || i == PB_T2_B_S1FREE)
+      const uint32_t cnt = (i == PB_T2_B_AFULL || i == PB_T2_B_D2EMPTY || i == PB_T2_B_D2EMPTY + 1 ||
+                            i == PB_T2_B_S1FREE || i >= PB_T2_B_ZFULL)
                                ? PB_T2_WORKERS
                                : 1u;
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(b), "r"(cnt));
@@ -511,6 +514,49 @@ PB_DEV void pb_grad_tc2(const PbPlan& pl, float* sm, float* TH, int nrows, float
       commit(PB_T2_B_AEMPTY);
       commit(PB_T2_B_D2FULL + slot);
     }
+  } else if (warp_u >= 10) {
+    // =============================== noise warps ===============================
+    // thread wt mirrors worker thread wt: it walks the SAME sequence of 8-weight blocks (first-layer items, then the
+    // D2 chunks) and writes the block's eight normals to ring slot (block number) % NZ.  The draws depend on nothing
+    // but (key, flat index), so these warps start with the evaluation and run up to NZ blocks ahead of the drains.
+    if (noise) {
+      const int wt = tid - 320, g = wt >> 7, b = wt & 127;
+      float* zr = reinterpret_cast<float*>(tc.img + pl.t2_img_z) + wt;
+      int cnt = 0;
+      auto put = [&](int fi0, int fis, bool any) {
+        const int slot = cnt % PB_T2_NZ;
+        if (cnt >= PB_T2_NZ) pb_mbar_wait(PB_T2_BAR(PB_T2_B_ZEMPTY + slot), (uint32_t)((cnt / PB_T2_NZ - 1) & 1));
+        if (any) {
+          uint32_t ix[8];
+          float z[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) ix[j] = (uint32_t)(fi0 + j * fis);
+          pb_normal_n<8>(nkey, ix, z);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) zr[slot * PB_T2_ZSLOT + j * PB_T2_WORKERS] = z[j];
+        }
+        pb_t2_arrive(PB_T2_BAR(PB_T2_B_ZFULL + slot));
+        ++cnt;
+      };
+      {
+        const int nblk = (H + 7) >> 3, items = (pl.d + 1) * nblk;
+        for (int it = wt; it - wt < items; it += PB_T2_WORKERS) {
+          const int k = it / nblk, i0 = 8 * (it - k * nblk);
+          put((k < pl.d ? L0.fw + k * H : L0.fb) + i0, 1, it < items);
+        }
+      }
+      const bool two_tiles = nmt > 1;
+      const int n_own = two_tiles ? wt : b;
+      for (int ic = 0; ic < nchy; ++ic) {
+        const int ncols = (Hy - 64 * ic) < 64 ? (Hy - 64 * ic) : 64;
+        const int nsteps = two_tiles ? (ncols >> 3) : ((ncols >> 3) < 4 ? (ncols >> 3) : 4);
+        for (int s = 0; s < nsteps; ++s) {
+          const int c0 = two_tiles ? 8 * s : 32 * g + 8 * s, i0 = 64 * ic + c0;
+          put(L1.fw + i0 * H + n_own, H, n_own < H && c0 < ncols && i0 < H);
+        }
+      }
+    }
+    __syncwarp();
   } else {
     // =============================== workers ===============================
     const int q = warp & 3, g = warp >> 2;
@@ -691,7 +737,7 @@ PB_DEV void pb_grad_tc2(const PbPlan& pl, float* sm, float* TH, int nrows, float
     //   flat index fi0 + j fis;  nval (1..8) valid elements (the rest are pad columns and stay zero);  dv: the eight
     //   accumulator values, scaled by gs into d loglik / d theta;  acc += sum_j theta_j dv_j (output-layer gradient)
     auto drain8 = [&](uint8_t* p, int tb, int si0, int sis, int fi0, int fis, int nval, const float* dv, float gs,
-                      float& acc) {
+                      float& acc, const float* zp) {
       const uint4 q1 = __ldcg(reinterpret_cast<const uint4*>(p));
       const uint4 q2 = __ldcg(reinterpret_cast<const uint4*>(p + tb));
       const uint4 q3 = __ldcg(reinterpret_cast<const uint4*>(p + 2 * tb));
@@ -712,15 +758,9 @@ PB_DEV void pb_grad_tc2(const PbPlan& pl, float* sm, float* TH, int nrows, float
                                      __uint_as_float(w3[m] << 16);
           }
         }
-        if (noise && 4 * h < nval) {
-          const float4 z4 = pb_t2_normal4(nkey.k0, nkey.k1, (uint32_t)(fi0 + (4 * h) * fis),
-                                          (uint32_t)(fi0 + (4 * h + 1) * fis), (uint32_t)(fi0 + (4 * h + 2) * fis),
-                                          (uint32_t)(fi0 + (4 * h + 3) * fis));
-          zz[0] = z4.x; zz[1] = z4.y; zz[2] = z4.z; zz[3] = z4.w;
-        } else {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) zz[j] = 0.f;
-        }
+        for (int j = 0; j < 4; ++j)  // the block's normals: written by the mirror noise thread (slot layout [j][thread])
+          zz[j] = (zp && 4 * h + j < nval) ? __ldcg(zp + (4 * h + j) * PB_T2_WORKERS) : 0.f;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int e = 4 * h + j;
@@ -739,20 +779,38 @@ PB_DEV void pb_grad_tc2(const PbPlan& pl, float* sm, float* TH, int nrows, float
       *reinterpret_cast<uint4*>(p + tb) = make_uint4(t2[0], t2[1], t2[2], t2[3]);
       *reinterpret_cast<uint4*>(p + 2 * tb) = make_uint4(t3[0], t3[1], t3[2], t3[3]);
     };
+    // noise ring: block number zcnt of this evaluation sits in slot zcnt % NZ (the noise warps walk the same sequence)
+    const int wt = warp * 32 + lane;
+    const float* zr = reinterpret_cast<const float*>(tc.img + pl.t2_img_z) + wt;
+    int zcnt = 0;
+    auto zwait = [&]() -> const float* {
+      if (!noise) return nullptr;
+      const int slot = zcnt % PB_T2_NZ;
+      pb_mbar_wait(PB_T2_BAR(PB_T2_B_ZFULL + slot), (uint32_t)((zcnt / PB_T2_NZ) & 1));
+      return zr + slot * PB_T2_ZSLOT;
+    };
+    auto zdone = [&]() {
+      if (noise) pb_t2_arrive(PB_T2_BAR(PB_T2_B_ZEMPTY + zcnt % PB_T2_NZ));
+      ++zcnt;
+    };
     // first layer: (row k, 8-column block) items of the dumped D1, dealt round-robin to the 256 workers
     auto update_w1 = [&]() {
       const int d = pl.d;
       const int tb1 = nch * Kx * 128;
       uint8_t* img1 = tc.img + pl.t2_img_w1;
-      const int wt = warp * 32 + lane, nblk = (H + 7) >> 3, items = (d + 1) * nblk;
+      const int nblk = (H + 7) >> 3, items = (d + 1) * nblk;
       float unused = 0.f;
-      for (int it = wt; it < items; it += PB_T2_WORKERS) {
-        const int k = it / nblk, i0 = 8 * (it - k * nblk);
-        const float4 a0 = *reinterpret_cast<const float4*>(d1buf + k * dp + i0);
-        const float4 a1 = *reinterpret_cast<const float4*>(d1buf + k * dp + i0 + 4);
-        const float dv[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-        drain8(img1 + pb_t2_off(Kx, k, i0), tb1, L0.soff + k * L0.wp + i0, 1, (k < d ? L0.fw + k * H : L0.fb) + i0, 1,
-               H - i0 < 8 ? H - i0 : 8, dv, 1.0f, unused);
+      for (int it = wt; it - wt < items; it += PB_T2_WORKERS) {
+        const float* zp = zwait();
+        if (it < items) {
+          const int k = it / nblk, i0 = 8 * (it - k * nblk);
+          const float4 a0 = *reinterpret_cast<const float4*>(d1buf + k * dp + i0);
+          const float4 a1 = *reinterpret_cast<const float4*>(d1buf + k * dp + i0 + 4);
+          const float dv[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+          drain8(img1 + pb_t2_off(Kx, k, i0), tb1, L0.soff + k * L0.wp + i0, 1, (k < d ? L0.fw + k * H : L0.fb) + i0, 1,
+                 H - i0 < 8 ? H - i0 : 8, dv, 1.0f, unused, zp);
+        }
+        zdone();
       }
     };
     pb_tc_fence_before();
@@ -771,33 +829,39 @@ PB_DEV void pb_grad_tc2(const PbPlan& pl, float* sm, float* TH, int nrows, float
       const int ncols = (Hy - 64 * ic) < 64 ? (Hy - 64 * ic) : 64;
       pb_mbar_wait(PB_T2_BAR(PB_T2_B_D2FULL + slot), (uint32_t)((ic >> 1) & 1));
       pb_tc_fence_after();
-      // two tiles: group g drains tile g, all columns; one tile: group g drains columns [32 g, 32 g + 32)
-      const int cbeg = two_tiles ? 0 : 32 * g;
-      const int cend = two_tiles ? ncols : (ncols < 32 * g + 32 ? ncols : 32 * g + 32);
-      for (int c0 = cbeg; c0 < cend; c0 += 8) {
-        uint32_t dr[8];
-        pb_tmem_ld8(S1 + lane_off + (uint32_t)(slot * 128 + (two_tiles ? 64 * g : 0) + c0), dr);
-        pb_tmem_wait_ld();
-        const int i0 = 64 * ic + c0;  // input index of W2 (i == H: the bias row b2)
-        if (!own || i0 > H) continue;
-        float dv[8];
+      // two tiles: group g drains tile g, all columns; one tile: group g drains columns [32 g, 32 g + 32).  Every
+      // worker walks the same number of 8-column steps (the noise ring is consumed in lock step)
+      const int nsteps = two_tiles ? (ncols >> 3) : ((ncols >> 3) < 4 ? (ncols >> 3) : 4);
+      for (int s = 0; s < nsteps; ++s) {
+        const int c0 = two_tiles ? 8 * s : 32 * g + 8 * s;
+        const float* zp = zwait();
+        if (c0 < ncols) {  // (uniform per warp)
+          uint32_t dr[8];
+          pb_tmem_ld8(S1 + lane_off + (uint32_t)(slot * 128 + (two_tiles ? 64 * g : 0) + c0), dr);
+          pb_tmem_wait_ld();
+          const int i0 = 64 * ic + c0;  // input index of W2 (i == H: the bias row b2)
+          if (own && i0 <= H) {
+            float dv[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) dv[j] = __uint_as_float(dr[j]);
-        if (i0 < H)  // kernel rows i0 .. : columns i0 .. of this thread's row of the transposed image
-          drain8(img2 + pb_t2_off(Hp, n_own, i0), tb2, L1.soff + i0 * L1.wp + n_own, L1.wp, L1.fw + i0 * H + n_own, H,
-                 H - i0 < 8 ? H - i0 : 8, dv, w3n, dw3);
-        if (H - i0 < 8) {  // this block holds the bias column (i == H): b2 stays fp32 in TH
-          float dd = 0.f;
+            for (int j = 0; j < 8; ++j) dv[j] = __uint_as_float(dr[j]);
+            if (i0 < H)  // kernel rows i0 .. : columns i0 .. of this thread's row of the transposed image
+              drain8(img2 + pb_t2_off(Hp, n_own, i0), tb2, L1.soff + i0 * L1.wp + n_own, L1.wp,
+                     L1.fw + i0 * H + n_own, H, H - i0 < 8 ? H - i0 : 8, dv, w3n, dw3, zp);
+            if (H - i0 < 8) {  // this block holds the bias column (i == H): b2 stays fp32 in TH
+              float dd = 0.f;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) dd = (i0 + j == H) ? dv[j] : dd;
-          const int si = L1.soff + H * L1.wp + n_own, fi = L1.fb + n_own;
-          PbPre pre = pf(si, fi);
-          pre.a = TH[si];
-          dw3 = fmaf(pre.a, dd, dw3);
-          const float nvb = uf(si, fi, pre, w3n * dd, noise ? pb_normal_at(nkey, (uint32_t)fi) : 0.f);
-          TH[si] = nvb;
-          emit(fi, nvb);
+              for (int j = 0; j < 8; ++j) dd = (i0 + j == H) ? dv[j] : dd;
+              const int si = L1.soff + H * L1.wp + n_own, fi = L1.fb + n_own;
+              PbPre pre = pf(si, fi);
+              pre.a = TH[si];
+              dw3 = fmaf(pre.a, dd, dw3);
+              const float nvb = uf(si, fi, pre, w3n * dd, noise ? pb_normal_at(nkey, (uint32_t)fi) : 0.f);
+              TH[si] = nvb;
+              emit(fi, nvb);
+            }
+          }
         }
+        zdone();
       }
       pb_tc_fence_before();
       pb_t2_arrive(PB_T2_BAR(PB_T2_B_D2EMPTY + slot));
