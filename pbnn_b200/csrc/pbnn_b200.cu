@@ -685,7 +685,9 @@ static int pb_launch(K kern, const PbPlan& pl, const A& a, dim3 grid, void* stre
 template <int ALGO>
 static int pb_sg_dispatch(const PbPlan& pl, const PbSgArgs& a, int C, void* stream) {
   if (pl.tc2) {
-    const int nsm = pb_backend_num_sms();
+    int nsm = pb_backend_num_sms();
+    const int cap = pb_opt(PB_OPT_TC2_CTAS, 0);  // experiments: fewer persistent CTAs (smaller L2 working set)
+    if (cap > 0 && cap < nsm) nsm = cap;
     return pb_launch(pb_sg_tc2_kernel<ALGO>, pl, a, dim3(C < nsm ? C : nsm), stream);
   }
   if (pl.gstate) {

@@ -77,11 +77,11 @@ static inline int pb_r32(int x) { return (x + 31) & ~31; }
 enum {
   PB_OPT_DW_KS = 0, PB_OPT_NW, PB_OPT_NO_RESIDENT, PB_OPT_NO_H1, PB_OPT_NO_TC, PB_OPT_BT, PB_OPT_TWO_CTA,
   PB_OPT_ONE_CTA, PB_OPT_FORCE_GSTATE, PB_OPT_NO_SCHED, PB_OPT_SEG_LEN, PB_OPT_DEBUG, PB_OPT_PRED_TPC,
-  PB_OPT_PRED_CHUNKS, PB_OPT_TC2_MIN_H, PB_OPT_TC2_MIN_ROWS, PB_OPT_NO_TC2, PB_OPT_COUNT
+  PB_OPT_PRED_CHUNKS, PB_OPT_TC2_MIN_H, PB_OPT_TC2_MIN_ROWS, PB_OPT_NO_TC2, PB_OPT_TC2_CTAS, PB_OPT_COUNT
 };
 static const char* const pb_opt_names[PB_OPT_COUNT] = {
     "dw_ks", "nw", "no_resident", "no_h1", "no_tc", "bt", "two_cta", "one_cta", "force_gstate", "no_sched", "seg_len",
-    "debug", "pred_tpc", "pred_chunks", "tc2_min_h", "tc2_min_rows", "no_tc2"};
+    "debug", "pred_tpc", "pred_chunks", "tc2_min_h", "tc2_min_rows", "no_tc2", "tc2_ctas"};
 #define PB_OPT_UNSET (-2147483647 - 1)
 inline int* pb_opt_table() {
   static int t[PB_OPT_COUNT];
