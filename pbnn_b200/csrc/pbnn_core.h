@@ -59,7 +59,7 @@ struct PbPlan {
   // streamed from a per-CTA global image block with cp.async.bulk, state arrays in the global workspace
   int tc2, t2_H, t2_Hp, t2_Hy, t2_Kx;      // hidden width, padded to 16, (H + 1) padded to 16, (d + 1) padded to 16
   int t2_nch, t2_nchy, t2_ncbx, t2_nmt;    // 64-wide chunks of Hp / Hy / Kx; 128-row tiles of Hp
-  int t2_wstage, t2_ring;                  // bytes of one weight-ring stage / of the whole ring
+  int t2_wstage, t2_ring, t2_nz;           // bytes of one weight-ring stage / of the whole ring; noise-ring slots in use
   int off_t2_vec, off_t2_bar, off_t2_big;  // float offsets: small vectors, mbarriers, 1024-byte aligned operand area
   int t2_img_w1, t2_img_w2, t2_img_z, t2_img_bytes;  // byte offsets inside the image block (X image at 0; z: noise ring)
   int off_act, off_scr, off_acc, off_idx, off_scal;
@@ -77,11 +77,11 @@ static inline int pb_r32(int x) { return (x + 31) & ~31; }
 enum {
   PB_OPT_DW_KS = 0, PB_OPT_NW, PB_OPT_NO_RESIDENT, PB_OPT_NO_H1, PB_OPT_NO_TC, PB_OPT_BT, PB_OPT_TWO_CTA,
   PB_OPT_ONE_CTA, PB_OPT_FORCE_GSTATE, PB_OPT_NO_SCHED, PB_OPT_SEG_LEN, PB_OPT_DEBUG, PB_OPT_PRED_TPC,
-  PB_OPT_PRED_CHUNKS, PB_OPT_TC2_MIN_H, PB_OPT_TC2_MIN_ROWS, PB_OPT_NO_TC2, PB_OPT_TC2_CTAS, PB_OPT_COUNT
+  PB_OPT_PRED_CHUNKS, PB_OPT_TC2_MIN_H, PB_OPT_TC2_MIN_ROWS, PB_OPT_NO_TC2, PB_OPT_TC2_CTAS, PB_OPT_TC2_NZ, PB_OPT_COUNT
 };
 static const char* const pb_opt_names[PB_OPT_COUNT] = {
     "dw_ks", "nw", "no_resident", "no_h1", "no_tc", "bt", "two_cta", "one_cta", "force_gstate", "no_sched", "seg_len",
-    "debug", "pred_tpc", "pred_chunks", "tc2_min_h", "tc2_min_rows", "no_tc2", "tc2_ctas"};
+    "debug", "pred_tpc", "pred_chunks", "tc2_min_h", "tc2_min_rows", "no_tc2", "tc2_ctas", "tc2_nz"};
 #define PB_OPT_UNSET (-2147483647 - 1)
 inline int* pb_opt_table() {
   static int t[PB_OPT_COUNT];
@@ -147,7 +147,7 @@ static inline void pb_plan_dw(PbPlan* pl, int nw, int bt, int kcap) {
 #define PB_PLAN_TC2 8  // the caller can run the two-hidden-layer tcgen05 engine (SG samplers, Adam, grad hook)
 
 #define PB_T2_NT 576       // 8 worker warps + 1 TMA warp + 1 MMA-issue warp + 8 noise warps
-#define PB_T2_NZ 16        // slots of the noise ring (one slot = 8 normals for each of the 256 worker threads)
+#define PB_T2_NZ 16        // most slots of the noise ring (one slot = 8 normals for each of the 256 worker threads)
 #define PB_T2_ZSLOT 2048   // floats per slot
 #define PB_T2_NS 3         // weight-ring stages
 #define PB_T2_TILE 16384   // bytes of one [128 rows][64 bf16] operand tile (SWIZZLE_128B)
@@ -204,7 +204,13 @@ static inline void pb_layout_tc2(PbPlan* pl, const pbnn_mlp_spec* sp, int rows) 
   pl->t2_img_w1 = xi;
   pl->t2_img_w2 = pl->t2_img_w1 + 3 * pl->t2_nch * pl->t2_Kx * 128;
   pl->t2_img_z = pl->t2_img_w2 + 3 * pl->t2_nch * pl->t2_Hp * 128;
-  pl->t2_img_bytes = pl->t2_img_z + PB_T2_NZ * PB_T2_ZSLOT * 4;
+  // noise ring: deep (16 slots = 128 normals per worker ahead) for small nets, where the whole step's noise is drawn while
+  // the forward / backward GEMMs run; shallow for wide nets, whose per-CTA working set (operand images + ring) must stay
+  // inside the L2 for 148 concurrent chains (measured, 90-256-256-1: 162 us per chain-step at 113 MB, 139 us at 83 MB)
+  pl->t2_nz = pb_opt(PB_OPT_TC2_NZ, pl->t2_Hp > 128 ? 4 : PB_T2_NZ);
+  if (pl->t2_nz < 2) pl->t2_nz = 2;
+  if (pl->t2_nz > PB_T2_NZ) pl->t2_nz = PB_T2_NZ;
+  pl->t2_img_bytes = pl->t2_img_z + pl->t2_nz * PB_T2_ZSLOT * 4;
 }
 
 // tcgen05 operand geometry (floats).  K-major, no swizzle: element (row x, k) at (k/4)*LBO + x*16 B + (k%4)*4 B.

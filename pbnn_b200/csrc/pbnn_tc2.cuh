@@ -329,6 +329,7 @@ PB_DEV void pb_grad_tc2(const PbPlan& pl, float* sm, float* TH, int nrows, float
   const int nch = pl.t2_nch, nchy = pl.t2_nchy, ncbx = pl.t2_ncbx, nmt = pl.t2_nmt;
   const uint32_t acta = tc.big, m2 = tc.big + 3u * PB_T2_TILE, ring = m2 + (uint32_t)nch * PB_T2_TILE;
   const uint32_t wstage = (uint32_t)pl.t2_wstage;
+  const int NZr = pl.t2_nz;
   const uint32_t S0 = tc.tmem, S1 = tc.tmem + 256u;
   float* b2v = sm + pl.off_t2_vec;
   float* w3v = b2v + 256;
@@ -524,8 +525,8 @@ PB_DEV void pb_grad_tc2(const PbPlan& pl, float* sm, float* TH, int nrows, float
       float* zr = reinterpret_cast<float*>(tc.img + pl.t2_img_z) + wt;
       int cnt = 0;
       auto put = [&](int fi0, int fis, bool any) {
-        const int slot = cnt % PB_T2_NZ;
-        if (cnt >= PB_T2_NZ) pb_mbar_wait(PB_T2_BAR(PB_T2_B_ZEMPTY + slot), (uint32_t)((cnt / PB_T2_NZ - 1) & 1));
+        const int slot = cnt % NZr;
+        if (cnt >= NZr) pb_mbar_wait(PB_T2_BAR(PB_T2_B_ZEMPTY + slot), (uint32_t)((cnt / NZr - 1) & 1));
         if (any) {
           uint32_t ix[8];
           float z[8];
@@ -785,12 +786,12 @@ PB_DEV void pb_grad_tc2(const PbPlan& pl, float* sm, float* TH, int nrows, float
     int zcnt = 0;
     auto zwait = [&]() -> const float* {
       if (!noise) return nullptr;
-      const int slot = zcnt % PB_T2_NZ;
-      pb_mbar_wait(PB_T2_BAR(PB_T2_B_ZFULL + slot), (uint32_t)((zcnt / PB_T2_NZ) & 1));
+      const int slot = zcnt % NZr;
+      pb_mbar_wait(PB_T2_BAR(PB_T2_B_ZFULL + slot), (uint32_t)((zcnt / NZr) & 1));
       return zr + slot * PB_T2_ZSLOT;
     };
     auto zdone = [&]() {
-      if (noise) pb_t2_arrive(PB_T2_BAR(PB_T2_B_ZEMPTY + zcnt % PB_T2_NZ));
+      if (noise) pb_t2_arrive(PB_T2_BAR(PB_T2_B_ZEMPTY + zcnt % NZr));
       ++zcnt;
     };
     // first layer: (row k, 8-column block) items of the dumped D1, dealt round-robin to the 256 workers
