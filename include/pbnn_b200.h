@@ -67,7 +67,7 @@ const char* pbnn_last_error(void);
 /* Engine-selection / tuning options (process-wide, explicit).  Names: "no_tc" (no tensor-core engines), "no_tc2"
  * (no two-hidden-layer tcgen05 engine), "no_h1" (no fused one-hidden-layer path), "no_resident", "force_gstate",
  * "no_sched" / "seg_len" (balanced HMC schedule), "nw", "bt", "dw_ks", "two_cta", "one_cta", "pred_tpc" (1, 2 or 4),
- * "pred_chunks", "tc2_min_h", "tc2_min_rows", "tc2_ctas", "tc2_nz", "debug".  pbnn_get_option returns 1 (and the sentinel INT_MIN in
+ * "pred_chunks", "tc2_min_h", "tc2_min_rows", "tc2_ctas", "tc2_nz", "tc2_nohelp", "debug".  pbnn_get_option returns 1 (and the sentinel INT_MIN in
  * *value) when the option is unset.  Every engine computes the same arithmetic contract; options never change
  * results beyond the stated tolerances. */
 int pbnn_set_option(const char* name, int value);

@@ -59,7 +59,8 @@ struct PbPlan {
   // streamed from a per-CTA global image block with cp.async.bulk, state arrays in the global workspace
   int tc2, t2_H, t2_Hp, t2_Hy, t2_Kx;      // hidden width, padded to 16, (H + 1) padded to 16, (d + 1) padded to 16
   int t2_nch, t2_nchy, t2_ncbx, t2_nmt;    // 64-wide chunks of Hp / Hy / Kx; 128-row tiles of Hp
-  int t2_wstage, t2_ring, t2_nz;           // bytes of one weight-ring stage / of the whole ring; noise-ring slots in use
+  int t2_wstage, t2_ring, t2_nz, t2_help;  // bytes of one weight-ring stage / of the whole ring; noise-ring slots in use;
+                                           // noise warps drain every other D2 step (all noise of a step fits the ring)
   int off_t2_vec, off_t2_bar, off_t2_big;  // float offsets: small vectors, mbarriers, 1024-byte aligned operand area
   int t2_img_w1, t2_img_w2, t2_img_z, t2_img_bytes;  // byte offsets inside the image block (X image at 0; z: noise ring)
   int off_act, off_scr, off_acc, off_idx, off_scal;
@@ -77,11 +78,11 @@ static inline int pb_r32(int x) { return (x + 31) & ~31; }
 enum {
   PB_OPT_DW_KS = 0, PB_OPT_NW, PB_OPT_NO_RESIDENT, PB_OPT_NO_H1, PB_OPT_NO_TC, PB_OPT_BT, PB_OPT_TWO_CTA,
   PB_OPT_ONE_CTA, PB_OPT_FORCE_GSTATE, PB_OPT_NO_SCHED, PB_OPT_SEG_LEN, PB_OPT_DEBUG, PB_OPT_PRED_TPC,
-  PB_OPT_PRED_CHUNKS, PB_OPT_TC2_MIN_H, PB_OPT_TC2_MIN_ROWS, PB_OPT_NO_TC2, PB_OPT_TC2_CTAS, PB_OPT_TC2_NZ, PB_OPT_COUNT
+  PB_OPT_PRED_CHUNKS, PB_OPT_TC2_MIN_H, PB_OPT_TC2_MIN_ROWS, PB_OPT_NO_TC2, PB_OPT_TC2_CTAS, PB_OPT_TC2_NZ, PB_OPT_TC2_NOHELP, PB_OPT_COUNT
 };
 static const char* const pb_opt_names[PB_OPT_COUNT] = {
     "dw_ks", "nw", "no_resident", "no_h1", "no_tc", "bt", "two_cta", "one_cta", "force_gstate", "no_sched", "seg_len",
-    "debug", "pred_tpc", "pred_chunks", "tc2_min_h", "tc2_min_rows", "no_tc2", "tc2_ctas", "tc2_nz"};
+    "debug", "pred_tpc", "pred_chunks", "tc2_min_h", "tc2_min_rows", "no_tc2", "tc2_ctas", "tc2_nz", "tc2_nohelp"};
 #define PB_OPT_UNSET (-2147483647 - 1)
 inline int* pb_opt_table() {
   static int t[PB_OPT_COUNT];
@@ -210,6 +211,15 @@ static inline void pb_layout_tc2(PbPlan* pl, const pbnn_mlp_spec* sp, int rows) 
   pl->t2_nz = pb_opt(PB_OPT_TC2_NZ, pl->t2_Hp > 128 ? 4 : PB_T2_NZ);
   if (pl->t2_nz < 2) pl->t2_nz = 2;
   if (pl->t2_nz > PB_T2_NZ) pl->t2_nz = PB_T2_NZ;
+  {  // 8-weight blocks of one evaluation, as the drains and the noise warps count them
+    const int items = (pl->d + 1) * ((H + 7) / 8);
+    int blocks = (items + 255) / 256;
+    for (int ic = 0; ic < pl->t2_nchy; ++ic) {
+      const int ncols = pl->t2_Hy - 64 * ic < 64 ? pl->t2_Hy - 64 * ic : 64;
+      blocks += pl->t2_nmt > 1 ? ncols / 8 : (ncols / 8 < 4 ? ncols / 8 : 4);
+    }
+    pl->t2_help = blocks <= pl->t2_nz && !pb_opt(PB_OPT_TC2_NOHELP, 0);
+  }
   pl->t2_img_bytes = pl->t2_img_z + pl->t2_nz * PB_T2_ZSLOT * 4;
 }
 

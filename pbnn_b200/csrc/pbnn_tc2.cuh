@@ -344,10 +344,11 @@ PB_DEV void pb_grad_tc2(const PbPlan& pl, float* sm, float* TH, int nrows, float
   if (tid == 0) {
     for (int i = 0; i < PB_T2_NBAR; ++i) {
       const uint32_t b = pb_t2_bar(pl, sm, i);
-      const uint32_t cnt = (i == PB_T2_B_AFULL || i == PB_T2_B_D2EMPTY || i == PB_T2_B_D2EMPTY + 1 ||
-                            i == PB_T2_B_S1FREE || i >= PB_T2_B_ZFULL)
-                               ? PB_T2_WORKERS
-                               : 1u;
+      uint32_t cnt = (i == PB_T2_B_AFULL || i == PB_T2_B_D2EMPTY || i == PB_T2_B_D2EMPTY + 1 ||
+                      i == PB_T2_B_S1FREE || i >= PB_T2_B_ZFULL)
+                         ? PB_T2_WORKERS
+                         : 1u;
+      if (pl.t2_help && (i == PB_T2_B_D2EMPTY || i == PB_T2_B_D2EMPTY + 1)) cnt = 2u * PB_T2_WORKERS;  // + helpers
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(b), "r"(cnt));
     }
     asm volatile("fence.mbarrier_init.release.cluster;");
@@ -358,6 +359,97 @@ PB_DEV void pb_grad_tc2(const PbPlan& pl, float* sm, float* TH, int nrows, float
   pb_tc_fence_after();
   const uint32_t bar0 = pb_t2_bar(pl, sm, 0);
 #define PB_T2_BAR(i) (bar0 + 8u * (uint32_t)(i))
+
+  bool bad = false;
+  auto emit = [&](int fi, float v) {
+    if (out0) out0[fi] = v;
+    if (out1) {
+      out1[fi] = v;
+      bad |= !pb_finite(v);
+    }
+  };
+  // ---- one block of 8 consecutive weights of ONE image row (a 16-byte chunk per bf16 term) ----------------------
+  //   p: address of the chunk in the first term image, terms tb bytes apart;  element j: resident index si0 + j sis,
+  //   flat index fi0 + j fis;  nval (1..8) valid elements (the rest are pad columns and stay zero);  dv: the eight
+  //   accumulator values, scaled by gs into d loglik / d theta;  acc += sum_j theta_j dv_j (output-layer gradient)
+  auto drain8 = [&](uint8_t* p, int tb, int si0, int sis, int fi0, int fis, int nval, const float* dv, float gs,
+                    float& acc, const float* zp) {
+    const uint4 q1 = __ldcg(reinterpret_cast<const uint4*>(p));
+    const uint4 q2 = __ldcg(reinterpret_cast<const uint4*>(p + tb));
+    const uint4 q3 = __ldcg(reinterpret_cast<const uint4*>(p + 2 * tb));
+    const uint32_t w1[4] = {q1.x, q1.y, q1.z, q1.w}, w2[4] = {q2.x, q2.y, q2.z, q2.w}, w3[4] = {q3.x, q3.y, q3.z, q3.w};
+    float nv[8];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {  // two groups of four: the four threefry + erf_inv chains of a group are interleaved
+      PbPre pre[4];
+      float zz[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int e = 4 * h + j, m = e >> 1;
+        if (e < nval) {
+          pre[j] = pf(si0 + e * sis, fi0 + e * fis);
+          pre[j].a = (e & 1) ? (__uint_as_float(w1[m] & 0xFFFF0000u) + __uint_as_float(w2[m] & 0xFFFF0000u)) +
+                                   __uint_as_float(w3[m] & 0xFFFF0000u)
+                             : (__uint_as_float(w1[m] << 16) + __uint_as_float(w2[m] << 16)) +
+                                   __uint_as_float(w3[m] << 16);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)  // the block's normals: written by the mirror noise thread (slot layout [j][thread])
+        zz[j] = (zp && 4 * h + j < nval) ? __ldcg(zp + (4 * h + j) * PB_T2_WORKERS) : 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int e = 4 * h + j;
+        nv[e] = 0.f;
+        if (e < nval) {
+          acc = fmaf(pre[j].a, dv[e], acc);
+          nv[e] = uf(si0 + e * sis, fi0 + e * fis, pre[j], gs * dv[e], zz[j]);
+          emit(fi0 + e * fis, nv[e]);
+        }
+      }
+    }
+    uint32_t t1[4], t2[4], t3[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) pb_t2_split3(nv[2 * m], nv[2 * m + 1], t1[m], t2[m], t3[m]);
+    *reinterpret_cast<uint4*>(p) = make_uint4(t1[0], t1[1], t1[2], t1[3]);
+    *reinterpret_cast<uint4*>(p + tb) = make_uint4(t2[0], t2[1], t2[2], t2[3]);
+    *reinterpret_cast<uint4*>(p + 2 * tb) = make_uint4(t3[0], t3[1], t3[2], t3[3]);
+  };
+  // ---- one 8-column step of a D2 chunk slot: TMEM lane n_own (= row n_own of the transposed W2 image), columns c0 .. of
+  //      chunk ic: fused update of W2[i0 .. i0 + 7][n_own] and, in the block that holds column H, of the bias b2[n_own] ----
+  const bool two_tiles = nmt > 1;
+  const bool help = pl.t2_help != 0;  // the whole evaluation's noise fits the ring: the noise warps then drain every other
+                                      // D2 step (the drains of small nets are latency-bound, not issue-bound)
+  const int tb2 = nch * Hp * 128;
+  uint8_t* img2 = tc.img + pl.t2_img_w2;
+  auto d2_step = [&](int ic, int slot, int c0, int gq, uint32_t lane_off, int n_own, float w3n, const float* zp,
+                     float& dw3) {
+    uint32_t dr[8];
+    pb_tmem_ld8(S1 + lane_off + (uint32_t)(slot * 128 + (two_tiles ? 64 * gq : 0) + c0), dr);
+    pb_tmem_wait_ld();
+    const int i0 = 64 * ic + c0;  // input index of W2 (i == H: the bias row b2)
+    if (n_own < H && i0 <= H) {
+      float dv[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dv[j] = __uint_as_float(dr[j]);
+      if (i0 < H)  // kernel rows i0 .. : columns i0 .. of this thread's row of the transposed image
+        drain8(img2 + pb_t2_off(Hp, n_own, i0), tb2, L1.soff + i0 * L1.wp + n_own, L1.wp, L1.fw + i0 * H + n_own, H,
+               H - i0 < 8 ? H - i0 : 8, dv, w3n, dw3, zp);
+      if (H - i0 < 8) {  // this block holds the bias column (i == H): b2 stays fp32 in TH
+        float dd = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dd = (i0 + j == H) ? dv[j] : dd;
+        const int si = L1.soff + H * L1.wp + n_own, fi = L1.fb + n_own;
+        PbPre pre = pf(si, fi);
+        pre.a = TH[si];
+        dw3 = fmaf(pre.a, dd, dw3);
+        const float nvb = uf(si, fi, pre, w3n * dd, noise ? pb_normal_at(nkey, (uint32_t)fi) : 0.f);
+        TH[si] = nvb;
+        emit(fi, nvb);
+      }
+    }
+  };
+  float* dw3h = b2v + 1412;  // [256] the helpers' share of the output-layer gradient (the w3 split there is dead by then)
 
   if (warp_u == 8) {
     // =============================== producer: bulk copies ===============================
@@ -520,9 +612,11 @@ PB_DEV void pb_grad_tc2(const PbPlan& pl, float* sm, float* TH, int nrows, float
     // thread wt mirrors worker thread wt: it walks the SAME sequence of 8-weight blocks (first-layer items, then the
     // D2 chunks) and writes the block's eight normals to ring slot (block number) % NZ.  The draws depend on nothing
     // but (key, flat index), so these warps start with the evaluation and run up to NZ blocks ahead of the drains.
+    // (a warp reaches the TMEM lanes 32 (warp % 4) ..: the mirror of noise warp pw is the worker with the same quadrant)
+    const int q = warp & 3, g = (warp - 10) >> 2, b = 32 * q + lane, wt = 128 * g + b;
+    const int n_own = two_tiles ? wt : b;
+    float* zr = reinterpret_cast<float*>(tc.img + pl.t2_img_z) + wt;
     if (noise) {
-      const int wt = tid - 320, g = wt >> 7, b = wt & 127;
-      float* zr = reinterpret_cast<float*>(tc.img + pl.t2_img_z) + wt;
       int cnt = 0;
       auto put = [&](int fi0, int fis, bool any) {
         const int slot = cnt % NZr;
@@ -546,8 +640,6 @@ PB_DEV void pb_grad_tc2(const PbPlan& pl, float* sm, float* TH, int nrows, float
           put((k < pl.d ? L0.fw + k * H : L0.fb) + i0, 1, it < items);
         }
       }
-      const bool two_tiles = nmt > 1;
-      const int n_own = two_tiles ? wt : b;
       for (int ic = 0; ic < nchy; ++ic) {
         const int ncols = (Hy - 64 * ic) < 64 ? (Hy - 64 * ic) : 64;
         const int nsteps = two_tiles ? (ncols >> 3) : ((ncols >> 3) < 4 ? (ncols >> 3) : 4);
@@ -556,6 +648,30 @@ PB_DEV void pb_grad_tc2(const PbPlan& pl, float* sm, float* TH, int nrows, float
           put(L1.fw + i0 * H + n_own, H, n_own < H && c0 < ncols && i0 < H);
         }
       }
+    }
+    if (help) {
+      // ---- helper drains: the odd 8-column steps of every D2 chunk (the workers take the even ones) ----
+      const uint32_t lane_off = (uint32_t)(32 * q) << 16;
+      const float w3n = n_own < H ? w3v[n_own] : 0.f;
+      float dw3 = 0.f;
+      int zc = ((pl.d + 1) * ((H + 7) >> 3) + PB_T2_WORKERS - 1) / PB_T2_WORKERS;  // ring slots of the first-layer items
+      for (int ic = 0; ic < nchy; ++ic) {
+        const int slot = ic & 1;
+        const int ncols = (Hy - 64 * ic) < 64 ? (Hy - 64 * ic) : 64;
+        const int nsteps = two_tiles ? (ncols >> 3) : ((ncols >> 3) < 4 ? (ncols >> 3) : 4);
+        pb_mbar_wait(PB_T2_BAR(PB_T2_B_D2FULL + slot), (uint32_t)((ic >> 1) & 1));
+        pb_tc_fence_after();
+        for (int s = 0; s < nsteps; ++s, ++zc) {
+          const int c0 = two_tiles ? 8 * s : 32 * g + 8 * s;
+          if ((s & 1) && c0 < ncols)  // (this thread wrote slot zc itself; the ring never wraps in this mode)
+            d2_step(ic, slot, c0, g, lane_off, n_own, w3n, noise ? zr + (zc % NZr) * PB_T2_ZSLOT : nullptr, dw3);
+        }
+        pb_tc_fence_before();
+        pb_t2_arrive(PB_T2_BAR(PB_T2_B_D2EMPTY + slot));
+      }
+      dw3h[wt] = dw3;
+      if (bad && flagword) atomicOr(flagword, 1u);
+      asm volatile("bar.sync 2, 512;" ::: "memory");
     }
     __syncwarp();
   } else {
@@ -725,61 +841,6 @@ PB_DEV void pb_grad_tc2(const PbPlan& pl, float* sm, float* TH, int nrows, float
     }
     pb_tc_fence_before();
     asm volatile("bar.sync 1, 256;" ::: "memory");
-    bool bad = false;
-    auto emit = [&](int fi, float v) {
-      if (out0) out0[fi] = v;
-      if (out1) {
-        out1[fi] = v;
-        bad |= !pb_finite(v);
-      }
-    };
-    // ---- one block of 8 consecutive weights of ONE image row (a 16-byte chunk per bf16 term) ----------------------
-    //   p: address of the chunk in the first term image, terms tb bytes apart;  element j: resident index si0 + j sis,
-    //   flat index fi0 + j fis;  nval (1..8) valid elements (the rest are pad columns and stay zero);  dv: the eight
-    //   accumulator values, scaled by gs into d loglik / d theta;  acc += sum_j theta_j dv_j (output-layer gradient)
-    auto drain8 = [&](uint8_t* p, int tb, int si0, int sis, int fi0, int fis, int nval, const float* dv, float gs,
-                      float& acc, const float* zp) {
-      const uint4 q1 = __ldcg(reinterpret_cast<const uint4*>(p));
-      const uint4 q2 = __ldcg(reinterpret_cast<const uint4*>(p + tb));
-      const uint4 q3 = __ldcg(reinterpret_cast<const uint4*>(p + 2 * tb));
-      const uint32_t w1[4] = {q1.x, q1.y, q1.z, q1.w}, w2[4] = {q2.x, q2.y, q2.z, q2.w}, w3[4] = {q3.x, q3.y, q3.z, q3.w};
-      float nv[8];
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {  // two groups of four: the four threefry + erf_inv chains of a group are interleaved
-        PbPre pre[4];
-        float zz[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int e = 4 * h + j, m = e >> 1;
-          if (e < nval) {
-            pre[j] = pf(si0 + e * sis, fi0 + e * fis);
-            pre[j].a = (e & 1) ? (__uint_as_float(w1[m] & 0xFFFF0000u) + __uint_as_float(w2[m] & 0xFFFF0000u)) +
-                                     __uint_as_float(w3[m] & 0xFFFF0000u)
-                               : (__uint_as_float(w1[m] << 16) + __uint_as_float(w2[m] << 16)) +
-                                     __uint_as_float(w3[m] << 16);
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j)  // the block's normals: written by the mirror noise thread (slot layout [j][thread])
-          zz[j] = (zp && 4 * h + j < nval) ? __ldcg(zp + (4 * h + j) * PB_T2_WORKERS) : 0.f;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int e = 4 * h + j;
-          nv[e] = 0.f;
-          if (e < nval) {
-            acc = fmaf(pre[j].a, dv[e], acc);
-            nv[e] = uf(si0 + e * sis, fi0 + e * fis, pre[j], gs * dv[e], zz[j]);
-            emit(fi0 + e * fis, nv[e]);
-          }
-        }
-      }
-      uint32_t t1[4], t2[4], t3[4];
-#pragma unroll
-      for (int m = 0; m < 4; ++m) pb_t2_split3(nv[2 * m], nv[2 * m + 1], t1[m], t2[m], t3[m]);
-      *reinterpret_cast<uint4*>(p) = make_uint4(t1[0], t1[1], t1[2], t1[3]);
-      *reinterpret_cast<uint4*>(p + tb) = make_uint4(t2[0], t2[1], t2[2], t2[3]);
-      *reinterpret_cast<uint4*>(p + 2 * tb) = make_uint4(t3[0], t3[1], t3[2], t3[3]);
-    };
     // noise ring: block number zcnt of this evaluation sits in slot zcnt % NZ (the noise warps walk the same sequence)
     const int wt = warp * 32 + lane;
     const float* zr = reinterpret_cast<const float*>(tc.img + pl.t2_img_z) + wt;
@@ -791,7 +852,7 @@ PB_DEV void pb_grad_tc2(const PbPlan& pl, float* sm, float* TH, int nrows, float
       return zr + slot * PB_T2_ZSLOT;
     };
     auto zdone = [&]() {
-      if (noise) pb_t2_arrive(PB_T2_BAR(PB_T2_B_ZEMPTY + zcnt % NZr));
+      if (noise && !help) pb_t2_arrive(PB_T2_BAR(PB_T2_B_ZEMPTY + zcnt % NZr));  // (help: the ring never wraps)
       ++zcnt;
     };
     // first layer: (row k, 8-column block) items of the dumped D1, dealt round-robin to the 256 workers
@@ -818,12 +879,8 @@ PB_DEV void pb_grad_tc2(const PbPlan& pl, float* sm, float* TH, int nrows, float
     pb_t2_arrive(PB_T2_BAR(PB_T2_B_S1FREE));
     PB_MARK(9)
     // ---- G4: Y chunks = r * [relu(Z1) | 1 | 0..]; the D2 drains (fused update of W2, b2) run one chunk behind ----
-    const bool two_tiles = nmt > 1;
     const int n_own = two_tiles ? 128 * g + b : b;  // output unit (TMEM lane of D2) this thread drains = its image row
-    const bool own = n_own < H;
-    const float w3n = own ? w3v[n_own] : 0.f;
-    const int tb2 = nch * Hp * 128;
-    uint8_t* img2 = tc.img + pl.t2_img_w2;
+    const float w3n = n_own < H ? w3v[n_own] : 0.f;
     float dw3 = 0.f;
     auto drain_d2 = [&](int ic) {
       const int slot = ic & 1;
@@ -835,33 +892,12 @@ PB_DEV void pb_grad_tc2(const PbPlan& pl, float* sm, float* TH, int nrows, float
       const int nsteps = two_tiles ? (ncols >> 3) : ((ncols >> 3) < 4 ? (ncols >> 3) : 4);
       for (int s = 0; s < nsteps; ++s) {
         const int c0 = two_tiles ? 8 * s : 32 * g + 8 * s;
-        const float* zp = zwait();
-        if (c0 < ncols) {  // (uniform per warp)
-          uint32_t dr[8];
-          pb_tmem_ld8(S1 + lane_off + (uint32_t)(slot * 128 + (two_tiles ? 64 * g : 0) + c0), dr);
-          pb_tmem_wait_ld();
-          const int i0 = 64 * ic + c0;  // input index of W2 (i == H: the bias row b2)
-          if (own && i0 <= H) {
-            float dv[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) dv[j] = __uint_as_float(dr[j]);
-            if (i0 < H)  // kernel rows i0 .. : columns i0 .. of this thread's row of the transposed image
-              drain8(img2 + pb_t2_off(Hp, n_own, i0), tb2, L1.soff + i0 * L1.wp + n_own, L1.wp,
-                     L1.fw + i0 * H + n_own, H, H - i0 < 8 ? H - i0 : 8, dv, w3n, dw3, zp);
-            if (H - i0 < 8) {  // this block holds the bias column (i == H): b2 stays fp32 in TH
-              float dd = 0.f;
-#pragma unroll
-              for (int j = 0; j < 8; ++j) dd = (i0 + j == H) ? dv[j] : dd;
-              const int si = L1.soff + H * L1.wp + n_own, fi = L1.fb + n_own;
-              PbPre pre = pf(si, fi);
-              pre.a = TH[si];
-              dw3 = fmaf(pre.a, dd, dw3);
-              const float nvb = uf(si, fi, pre, w3n * dd, noise ? pb_normal_at(nkey, (uint32_t)fi) : 0.f);
-              TH[si] = nvb;
-              emit(fi, nvb);
-            }
-          }
+        if (help && (s & 1)) {  // a helper warp drains this step
+          ++zcnt;
+          continue;
         }
+        const float* zp = zwait();
+        if (c0 < ncols) d2_step(ic, slot, c0, g, lane_off, n_own, w3n, zp, dw3);  // (uniform per warp)
         zdone();
       }
       pb_tc_fence_before();
@@ -895,9 +931,11 @@ PB_DEV void pb_grad_tc2(const PbPlan& pl, float* sm, float* TH, int nrows, float
     // output layer: dw3[n] (one tile: the two column halves are summed), db3 = sum_b r_b; fused update of w3, b3
     dw3p[g * 256 + (n_own & 255)] = dw3;
     fp[g * 128 + b] = r;
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (help) asm volatile("bar.sync 2, 512;" ::: "memory");  // workers + helpers
+    else asm volatile("bar.sync 1, 256;" ::: "memory");
     if ((two_tiles || g == 0) && n_own < H) {
-      const float gl = two_tiles ? dw3 : dw3p[n_own] + dw3p[256 + n_own];
+      float gl = two_tiles ? dw3 : dw3p[n_own] + dw3p[256 + n_own];
+      if (help) gl += two_tiles ? dw3h[n_own] : dw3h[n_own] + dw3h[128 + n_own];
       const int si = L2.soff + n_own * L2.wp, fi = L2.fw + n_own;
       PbPre pre = pf(si, fi);
       pre.a = TH[si];
