@@ -48,7 +48,7 @@ WORKLOADS = {
     "sgld_cfg3": dict(algo="sgld", layers=(9, 100, 100, 1), act=0, N=45730, B=128, C=1024, T=200, L=1, step=2e-8,
                       M=1024),
     # (momentum ~ N(0, step): the SGHMC-paper law; the "unit" law of SURVEY.md 2b random-walks to non-finite values)
-    "sghmc_cfg3": dict(algo="sghmc", layers=(9, 100, 100, 1), act=0, N=45730, B=128, C=1024, T=20, L=10, step=1e-7,
+    "sghmc_cfg3": dict(algo="sghmc", layers=(9, 100, 100, 1), act=0, N=45730, B=128, C=1024, T=20, L=10, step=3e-9,
                        M=1024, momentum="sigma_sqrt_step"),
     # BASELINE.json configs[4], per-GPU share (1024 of the 8192 chains); state lives in the global workspace
     "sgld_cfg5": dict(algo="sgld", layers=(90, 256, 256, 1), act=0, N=515345, B=128, C=1024, T=20, L=1, step=1e-9,
