@@ -18,6 +18,7 @@
 #include <utility>
 
 #include "pbnn_engine.cuh"
+#include "pbnn_tc2_pred.cuh"
 
 #if defined(PB_PROFILE)
 #define PB_PROF_START                                                  \
@@ -777,6 +778,20 @@ static int pb_backend_predict(const PbPlan& pl, const PbPredArgs& a, int mtiles,
   if (sum) {
     const int n = a.M * pl.s;
     pb_predict_reduce_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(a.part, a.nchunk, n, sum, sumsq);
+    PB_CUDA(cudaGetLastError());
+  }
+  return PBNN_OK;
+}
+
+static int pb_backend_predict_tc2(const PbPlan& pl, const PbPredTc2Args& a, int groups, float* sum, float* sumsq,
+                                  void* stream) {
+  const size_t smem = (size_t)pl.smem_floats * 4;
+  const int rc = pb_ensure_smem(reinterpret_cast<const void*>(pb_predict_tc2_kernel), smem);
+  if (rc) return rc;
+  pb_predict_tc2_kernel<<<dim3(groups, a.nchunk), PB_T2P_NT, smem, (cudaStream_t)stream>>>(pl, a);
+  PB_CUDA(cudaGetLastError());
+  if (sum) {
+    pb_predict_reduce_kernel<<<(a.M + 255) / 256, 256, 0, (cudaStream_t)stream>>>(a.part, a.nchunk, a.M, sum, sumsq);
     PB_CUDA(cudaGetLastError());
   }
   return PBNN_OK;

@@ -10,10 +10,13 @@ for layers, S, M in (((13, 50, 1), 51200, 1024), ((9, 100, 100, 1), 20000, 1024)
     smp = (0.1 * torch.randn(S, fs.num_params, device="cuda")).contiguous()
     Xt = torch.randn(M, layers[0], device="cuda")
     W = sum(layers[i] * layers[i + 1] for i in range(len(layers) - 1))
-    for want_preds in (False, True):
+    for want_preds, opts in ((False, {}), (True, {}), (False, {"no_tc2": 1})):
+        ops.reset_options()
+        for k_, v_ in opts.items():
+            ops.set_option(k_, v_)
         for it in range(3):
             torch.cuda.synchronize(); t0 = time.perf_counter()
             out = ops.predict(fs, smp, Xt, want_preds=want_preds, want_moments=True)
             torch.cuda.synchronize(); dt = time.perf_counter() - t0
         fl = 2.0 * S * M * W
-        print(f"{layers} S={S} M={M} preds={want_preds}: {dt*1e3:8.2f} ms  {fl/dt/1e12:6.2f} TFLOP/s  {S*M/dt/1e9:6.2f} G evals/s", flush=True)
+        print(f"{layers} S={S} M={M} preds={want_preds} {opts}: {dt*1e3:8.2f} ms  {fl/dt/1e12:6.2f} TFLOP/s  {S*M/dt/1e9:6.2f} G evals/s", flush=True)

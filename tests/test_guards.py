@@ -84,6 +84,8 @@ def test_tc2_engine_stays_inside_its_buffers(gops, layers, B, N, C):
     idx = np.random.default_rng(1).integers(0, N, (C, 2, B)).astype(np.int32)
     r = gops.adam_ensemble(fs, X, y, th0, idx, 1e-3)
     g, ll = gops.grad_estimator(fs, X, y, th0, idx[:, 0])
+    m = gops.predict(fs, th0, X, want_preds=True, want_moments=True)  # tcgen05 predictive (image blocks in the workspace)
+    assert torch.isfinite(m["mean"]).all()
     assert gops.check() > 10
 
 

@@ -206,3 +206,29 @@ def test_out_of_range_indices_are_clamped_and_flagged(eng):
     b = eng.sgld(fs, X, y, th0, keys, B, 1e-6, 2, idx=good)
     assert np.array_equal(npy(a["trace"]), npy(b["trace"]))
     assert (npy(a["flags"]) & 4).all() and not npy(b["flags"]).any()
+
+
+@pytest.mark.parametrize("layers,S,M", [(CFG3[0], 37, 1000), (CFG5[0], 5, 300), ((20, 64, 64, 1), 300, 130),
+                                        ((70, 160, 160, 1), 3, 64), (CFG3[0], 1, 513)])
+def test_predict_two_hidden_layers_on_tensor_cores(cuda_ops, layers, S, M):
+    """predict_fn + moments (langevin.py:75-76, metrics_prediction_intervals.py:188) for the nets pbnn's MLP produces:
+    tcgen05 kernel (pbnn_tc2_pred.cuh) vs the float64 oracle and vs the FP32 kernel; ragged tiles, one sample, more
+    sample chunks than samples.  Tolerance 1e-5 (predictions and their first two moments)."""
+    cuda_ops.reset_options()
+    rng = np.random.default_rng(5)
+    sp, fs = o.MlpSpec(tuple(layers), o.RELU, 0.1), FlatSpec(tuple(layers), 0, 0.1)
+    scale = 0.05 if layers[1] >= 160 else 0.1
+    smp = (scale * rng.standard_normal((S, sp.num_params))).astype(np.float32)
+    Xt = rng.standard_normal((M, layers[0])).astype(np.float32)
+    ref = o.predict(sp, smp, Xt, dtype=np.float64).reshape(S, M)
+    out = cuda_ops.predict(fs, smp, Xt, want_preds=True, want_moments=True)
+    assert rel(npy(out["preds"]).reshape(S, M), ref) <= 1e-5
+    assert rel(npy(out["sum"]).reshape(M), ref.sum(0)) <= 1e-5
+    assert rel(npy(out["sumsq"]).reshape(M), (ref * ref).sum(0)) <= 1e-5
+    only = cuda_ops.predict(fs, smp, Xt, want_preds=False, want_moments=True)  # moments alone: same partial sums
+    assert np.array_equal(npy(only["sum"]), npy(out["sum"])) and np.array_equal(npy(only["sumsq"]), npy(out["sumsq"]))
+    cuda_ops.set_option("no_tc2", 1)
+    fp32 = cuda_ops.predict(fs, smp, Xt, want_preds=True, want_moments=True)
+    cuda_ops.reset_options()
+    assert rel(npy(fp32["preds"]).reshape(S, M), ref) <= 1e-5
+    assert not np.array_equal(npy(fp32["preds"]), npy(out["preds"]))  # (two different engines did run)
