@@ -559,16 +559,32 @@ def main():
                 continue
             we = dict(WORKLOADS[name], name=name)
             fse = FlatSpec(tuple(we["layers"]), we["act"], 0.1)
-            Xe, ye, _, ke, the = make_inputs(we, rank, world, ops)
+            Xe, ye, Xte_h, ke, the = make_inputs(we, rank, world, ops)
             Xd, yd = ops._as(Xe, torch.float32), ops._as(ye, torch.float32)
             fe = gpu_step_fn(ops, we, fse, Xd, yd, the, ke)
             ks = max(3, min(args.steps, 5))
             ms_e = timed(fe, ks, 3) / ks
-            fin = bool(torch.isfinite(fe()["theta"]).all().item())
+            fin_theta = fe()["theta"]
+            fin = bool(torch.isfinite(fin_theta).all().item())
+            # posterior predictive moments of the final states on the workload's M test points (north_star subsystem 4)
+            Xte = ops._as(Xte_h, torch.float32)
+            ops.predict(fse, fin_theta, Xte, want_preds=False, want_moments=True)
+            qa, qb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            qa.record()
+            for _ in range(3):
+                ops.predict(fse, fin_theta, Xte, want_preds=False, want_moments=True)
+            qb.record()
+            torch.cuda.synchronize()
+            pms = qa.elapsed_time(qb) / 3
+            Wsum = sum(i * o for i, o in zip(we["layers"][:-1], we["layers"][1:]))
+            pred_e = {"samples": int(fin_theta.shape[0]), "test_points": int(Xte.shape[0]), "ms": pms,
+                      "evals_per_s": fin_theta.shape[0] * Xte.shape[0] / (pms * 1e-3),
+                      "algorithmic_tflops": 2.0 * fin_theta.shape[0] * Xte.shape[0] * Wsum / (pms * 1e-3) / 1e12}
+            del Xte, fin_theta
             extras[name] = {"value": we["C"] * we["T"] * world / (ms_e * 1e-3), "unit": "chain-steps/s",
                             "ms_per_step": ms_e, "steps": ks, "warmup": 3, "config": workload_config(name, we),
                             "roofline": roofline_for(ops, we, fse, ms_e, clocks, peaks, traffic_of(name)),
-                            "chains_finite": fin}
+                            "predictive": pred_e, "chains_finite": fin}
             del Xd, yd, fe, the, ke
             torch.cuda.empty_cache()
 
@@ -601,6 +617,13 @@ def main():
         same = torch.tensor([1.0 if torch.equal(solo, allfirst[peer]) else 0.0], device="cuda")
         dist.all_reduce(same, op=dist.ReduceOp.MIN)
         m5 = ops.predict(fs5, out5, X5t, want_preds=False, want_moments=True)
+        za, zb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        za.record()
+        for _ in range(3):
+            ops.predict(fs5, out5, X5t, want_preds=False, want_moments=True)
+        zb.record()
+        torch.cuda.synchronize()
+        pred5_ms = za.elapsed_time(zb) / 3
         pm5, pv5, S5 = pdist.pooled_moments(m5["sum"], m5["sumsq"], w5["C"])
         pay5 = torch.cat([m5["sum"].reshape(-1), m5["sumsq"].reshape(-1), torch.ones(1, device="cuda")])
         g5 = torch.empty(world * pay5.numel(), device="cuda")
@@ -623,6 +646,7 @@ def main():
                                       "how": "rank r re-ran the first 4 chains of rank r+1 alone from the global key "
                                              "table; torch.equal on the final states, MIN-reduced over ranks"},
                    "moments_allgather_us": ya.elapsed_time(yb) * 1e3 / 20, "moments_bytes_per_rank": int(pay5.numel() * 4),
+                   "predictive_ms_per_rank": pred5_ms, "predictive_test_points": int(X5t.shape[0]),
                    "pooled_samples": S5, "pred_var_mean": float(pv5.mean()),
                    "roofline": roofline_for(ops, w5, fs5, ms5, clocks, peaks, traffic_of("sgld_cfg5"))}
 
