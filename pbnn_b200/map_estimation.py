@@ -42,6 +42,11 @@ def train_fn(logposterior_fn, network, train_ds, batch_size, num_epochs, learnin
     X, y = train_ds["x"], train_ds["y"]
     n, d = int(np.shape(X)[0]), int(np.shape(X)[1])
     layers = network.widths(d)
+    if int(logposterior_fn.data_size) != n:
+        # the Adam / SGD kernels scale the minibatch log-likelihood by len(X) / batch_size; the reference would use
+        # data_size * mean(loglik) -- a different posterior.  Refuse instead of silently training on another target.
+        raise ValueError(f"build_logposterior_estimator_fn was given data_size={logposterior_fn.data_size}, but the "
+                         f"training set has {n} rows; the fused trainers support data_size == len(X) only")
     spec = logposterior_fn.spec_for(layers)
     if init_params is None:
         init_rng = ops.split(rng_key, 2)[:, 1, :]

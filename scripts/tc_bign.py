@@ -15,8 +15,8 @@ for layers, N in (((8, 50, 1), 1030), ((8, 50, 1), 768), ((11, 50, 1), 1599), ((
     th0 = 0.01 * ops.normal(keys, fs.num_params)
     minv = np.ones(fs.num_params, np.float32)
     for name, env in (("tc", None), ("fused", "1")):
-        if env: os.environ["PBNN_NO_TC"] = env
-        else: os.environ.pop("PBNN_NO_TC", None)
+        if env: ops.set_option("no_tc", int(env))
+        else: ops.reset_options()
         for it in range(3):
             torch.cuda.synchronize(); t0 = time.perf_counter()
             out = ops.hmc(fs, X, y, th0, keys, 20, 2e-4, minv, 20, keep_trace=False)

@@ -19,13 +19,13 @@ for layers, N in [((13, 50, 1), 506), ((8, 50, 1), 300), ((5, 64, 1), 100), ((15
     C = 5
     th = (0.2 * np.random.default_rng(0).standard_normal((C, sp.num_params))).astype(np.float32)
     lp64, g64 = o.logposterior_full(sp, th.astype(np.float64), X.astype(np.float64), y.astype(np.float64))
-    os.environ.pop("PBNN_NO_TC", None)
+    ops.reset_options()
     lp_tc, g_tc = ops.logposterior_grad(fs, X, y, th)
     torch.cuda.synchronize()
-    os.environ["PBNN_NO_TC"] = "1"
+    ops.set_option("no_tc", 1)
     lp_h1, g_h1 = ops.logposterior_grad(fs, X, y, th)
     torch.cuda.synchronize()
-    os.environ.pop("PBNN_NO_TC", None)
+    ops.reset_options()
     print(layers, N, "grad rel err vs f64: tc %.2e  fused %.2e | logp rel: tc %.2e fused %.2e" % (
         rel(g_tc.cpu().numpy(), g64), rel(g_h1.cpu().numpy(), g64),
         rel(lp_tc.cpu().numpy(), lp64), rel(lp_h1.cpu().numpy(), lp64)), flush=True)
@@ -53,9 +53,9 @@ keys = o.split(o.PRNGKey(1), C)
 th0 = o.init_positions(sp, keys)
 for name, env in (("tc", None), ("fused", "1")):
     if env:
-        os.environ["PBNN_NO_TC"] = env
+        ops.set_option("no_tc", int(env))
     else:
-        os.environ.pop("PBNN_NO_TC", None)
+        ops.reset_options()
     for it in range(3):
         torch.cuda.synchronize()
         t0 = time.perf_counter()

@@ -1,12 +1,12 @@
-"""Do two tcgen05 HMC CTAs share an SM?  time(C = 296) vs time(C = 148) with one CTA per chain (PBNN_NO_SCHED=1)."""
+"""Do two tcgen05 HMC CTAs share an SM?  time(C = 296) vs time(C = 148) with one CTA per chain (option no_sched)."""
 import os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
-os.environ["PBNN_NO_SCHED"] = "1"
 import torch
 from pbnn_b200.ops import FlatSpec, default_ops
 import bench
 ops = default_ops()
+ops.set_option("no_sched", 1)
 w = dict(bench.WORKLOADS["hmc_cfg2"])
 fs = FlatSpec(tuple(w["layers"]), 0, 0.1)
 X, y, Xt = bench.make_data(w)
