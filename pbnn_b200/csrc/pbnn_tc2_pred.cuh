@@ -74,30 +74,22 @@ PB_DEV void pb_tc2p_restage(const PbPlan& pl, float* sm, uint8_t* img1, uint8_t*
     }
   }
   {
-    const int tb = pl.t2_nch * Hp * 128, hp2 = Hp >> 1;
-    const int total = H * hp2;  // (pair of input indices i, output unit n): consecutive threads -> consecutive n
-    for (int e0 = tid; e0 < total; e0 += 4 * nt) {
-      float v0[4], v1[4];
+    // W2^T image: row n, 16-byte chunk = 8 consecutive input indices i.  One item = (chunk of 8 i, output unit n):
+    // consecutive threads take consecutive n (coalesced reads of the flat [i][n] kernel), each writes whole chunks
+    const int tb = pl.t2_nch * Hp * 128, nck = Hp >> 3;
+    const int total = H * nck;
+    for (int e = tid; e < total; e += nt) {
+      const int cb = e / H, n = e - cb * H, i0 = 8 * cb;
+      float v[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int e = e0 + u * nt;
-        const int ip = e / H, n = e - ip * H, i0 = 2 * ip;
-        v0[u] = (e < total && i0 < H) ? th[L1.fw + i0 * H + n] : 0.f;
-        v1[u] = (e < total && i0 + 1 < H) ? th[L1.fw + (i0 + 1) * H + n] : 0.f;
-      }
+      for (int j = 0; j < 8; ++j) v[j] = i0 + j < H ? th[L1.fw + (i0 + j) * H + n] : 0.f;
+      uint32_t t1[4], t2[4], t3[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int e = e0 + u * nt;
-        if (e < total) {
-          const int ip = e / H, n = e - ip * H, i0 = 2 * ip;
-          uint32_t t1, t2, t3;
-          pb_t2_split3(v0[u], v1[u], t1, t2, t3);
-          uint8_t* p = img2 + pb_t2_off(Hp, n, i0);
-          *reinterpret_cast<uint32_t*>(p) = t1;
-          *reinterpret_cast<uint32_t*>(p + tb) = t2;
-          *reinterpret_cast<uint32_t*>(p + 2 * tb) = t3;
-        }
-      }
+      for (int m = 0; m < 4; ++m) pb_t2_split3(v[2 * m], v[2 * m + 1], t1[m], t2[m], t3[m]);
+      uint8_t* p = img2 + pb_t2_off(Hp, n, i0);
+      *reinterpret_cast<uint4*>(p) = make_uint4(t1[0], t1[1], t1[2], t1[3]);
+      *reinterpret_cast<uint4*>(p + tb) = make_uint4(t2[0], t2[1], t2[2], t2[3]);
+      *reinterpret_cast<uint4*>(p + 2 * tb) = make_uint4(t3[0], t3[1], t3[2], t3[3]);
     }
   }
   float* b2v = sm + pl.off_t2_vec;
