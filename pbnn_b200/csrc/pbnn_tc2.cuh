@@ -9,33 +9,40 @@
 // backward GEMMs that can be written against the mask take 3 passes:
 //
 //   G1 fwd1   Z1 = Xaug W1aug                      A = X tile   (K-major)   B = W1aug (MN-major)            6 passes
-//   G2 fwd2   Z2 = relu(Z1) W2                     A = H1 chunk (K-major)   B = W2     (MN-major)            6 passes
+//   G2 fwd2   Z2 = relu(Z1) W2                     A = H1 chunk (K-major)   B = W2^T image read K-major     6 passes
 //   G3        f = w3 . relu(Z2 + b2) + b3,  r = (y - f) scale,  M2 = [Z2 + b2 > 0]           (CUDA cores)
-//   G4 dW2    D2[n][i] = sum_b M2[b][n] Y[b][i],   Y = r * [relu(Z1) | 1]   A = M2^T (MN-major)  B = Y chunk (MN-major)   3 passes
-//             dW2[i][n] = w3[n] D2[n][i],  db2[n] = w3[n] D2[n][H],
-//             dw3[n] = sum_i W2[i][n] D2[n][i] + b2[n] D2[n][H]      (relu(Z2 + b2) = M2 * (H1 W2 + b2): no extra GEMM)
-//   G5 dH1    E[b][i]  = sum_n (w3[n] M2[b][n]) W2[i][n]                  A = w3 * M2 chunk (K-major)  B = W2 (K-major)     6 passes
+//   G5 dH1    E[b][i]  = sum_n (w3[n] M2[b][n]) W2[i][n]    A = w3 * M2 chunk (K-major)  B = W2^T image read MN-major  6 passes
 //             (the chunk terms are SELECTED from a per-step 3-term split of w3: no arithmetic per element)
 //   G6 dW1    D1[k][i] = sum_b Xaug[b][k] dZ1[b][i],  dZ1 = r * E * [Z1 > 0]   A = X^T (MN-major)  B = dZ1 chunk (MN-major) 6 passes
+//   G4 dW2    D2[n][i] = sum_b M2[b][n] Y[b][i],   Y = r * [relu(Z1) | 1]   A = M2^T (MN-major)  B = Y chunk (MN-major)   3 passes
+//             (last: its drains rewrite the W2 image)  dW2[i][n] = w3[n] D2[n][i],  db2[n] = w3[n] D2[n][H],
+//             dw3[n] = sum_i W2[i][n] D2[n][i] + b2[n] D2[n][H]      (relu(Z2 + b2) = M2 * (H1 W2 + b2): no extra GEMM)
 //
 // Operand images are SWIZZLE_128B tiles: 64 bf16 (128 B) per storage row, 16-byte chunk j of row r at chunk j ^ (r & 7),
 // column blocks of 64 elements one after the other.  The SAME image is read K-major (storage row = M/N index) or
-// MN-major (storage row = K index): X, M2 and the activation chunks are written once and used both ways.
+// MN-major (storage row = K index): X, M2 and the activation chunks are written once and used both ways, and W2 is kept
+// TRANSPOSED (storage row = output unit n) so that the thread draining TMEM lane n owns one image row.
 //
-// Where things live.  Parameter-sized state (theta, momentum, ...) in the global workspace (L2 / HBM).  Per CTA a
-// global IMAGE block holds the bf16x3 operand images of X (fixed minibatch), W1aug and W2; they are streamed through
-// a 3-stage shared-memory ring with cp.async.bulk (TMA engine) + mbarriers by a dedicated producer warp.
+// Where things live.  Per CTA a global IMAGE block (L2) holds the bf16x3 operand images of X (fixed minibatch), W1aug
+// and W2^T plus the noise ring.  The images are the MASTER copy of W1, b1, W2 (three bf16 terms = the fp32 value,
+// exactly): no fp32 copy of them is read or written per step; b2, w3, b3 stay fp32 in the chain's workspace slice.
+// The images are streamed through a 3-stage shared-memory ring with cp.async.bulk (TMA engine, UBLKCP) + mbarriers by
+// a dedicated producer warp.
 //
-// Fused drains.  The weight-gradient accumulators are never written out: the thread that reads dW[i][n] from TMEM
-// also loads theta[i][n] (+ the sampler's state), draws the threefry normal, applies the caller's update functor
-// (SGLD / SGHMC / Adam / pSGLD step), stores the new theta and its three bf16 terms into the operand image.  One
-// pass over the parameters per step: no gradient array, no separate update or re-staging pass.  Shared memory: one activation chunk
-// [128 rows][64] x 3 terms (48 KB), the layer-2 mask [128][Hp] bf16, the weight ring.  TMEM (512 columns):
-// S0 = columns 0..255: Z1 -> E -> D1;  S1 = columns 256..511: Z2 -> D2 chunk slots.
+// Fused drains.  The weight-gradient accumulators are never written out: the thread that reads eight consecutive
+// dW values of its image row from TMEM also loads the eight weights (one 16-byte chunk per term), takes the eight
+// normals of the block from the noise ring, applies the caller's update functor (SGLD / SGHMC / Adam / pSGLD step),
+// splits the new values and stores the three chunks back -- and, on kept steps, the fp32 values to the trace row /
+// final state.  One pass over the parameters per step: no gradient array, no separate update, re-staging or trace pass.
+// Shared memory: one activation chunk [128 rows][64] x 3 terms (48 KB), the layer-2 mask [128][Hp] bf16, the weight
+// ring.  TMEM (512 columns): S0 = Z1 (kept for G4);  S1 = Z2 -> E -> D1 -> D2 chunk slots.
 //
-// Roles (320 threads): warps 0-7 workers (TMEM -> registers -> operand chunks / drains; warp w owns TMEM lanes
-// 32 (w % 4) .., column half w / 4), warp 8 producer (bulk copies), warp 9 MMA issue.  All mbarriers are re-initialised
-// at the start of every gradient evaluation (the evaluation is bracketed by CTA barriers), so every parity starts at 0.
+// Roles (576 threads): warps 0-7 workers (TMEM -> registers -> operand chunks / drains; warp w owns TMEM lanes
+// 32 (w % 4) .., column half w / 4), warp 8 producer (bulk copies), warp 9 MMA issue, warps 10-17 noise: thread t of
+// them mirrors worker thread t, walks the drains' block sequence and writes each block's eight jax.random.normal
+// draws into a ring (mbarrier full / empty per slot) up to t2_nz blocks ahead; when a whole step's noise fits the ring
+// (small nets) the same warps then drain every other D2 step.  All mbarriers are re-initialised at the start of every
+// gradient evaluation (the evaluation is bracketed by CTA barriers), so every parity starts at 0.
 #pragma once
 #if !defined(PB_EMU)
 
