@@ -89,6 +89,8 @@ int pbnn_plan_query(const pbnn_mlp_spec* spec, int rows, int n_state, int32_t ou
 #define PBNN_ENGINE_TILED_GLOBAL_STATE 3 /* as TILED with the parameter-sized arrays in the global workspace      */
 #define PBNN_ENGINE_TCGEN05_MLP2 4 /* SG samplers / Adam, two equal hidden relu layers, scalar output, B <= 128:
                                       bf16x3 tensor-core engine with TMA-streamed weights (pbnn_tc2.cuh)           */
+#define PBNN_ENGINE_WARP_H1 5  /* SG samplers / Adam, one hidden layer, scalar output, many chains: one warp per chain,
+                                  weights in registers for the whole run (pbnn_warp.cuh)                            */
 int pbnn_plan_engine(const pbnn_mlp_spec* spec, int op, int rows, int C);
 
 /* Workspace.  Models whose parameter-sized state does not fit shared memory (e.g. 90-256-256-1, P = 89 345) keep it in

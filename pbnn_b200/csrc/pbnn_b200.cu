@@ -18,6 +18,7 @@
 #include <utility>
 
 #include "pbnn_engine.cuh"
+#include "pbnn_warp.cuh"
 #include "pbnn_tc2_pred.cuh"
 
 #if defined(PB_PROFILE)
@@ -690,6 +691,21 @@ static int pb_sg_dispatch(const PbPlan& pl, const PbSgArgs& a, int C, void* stre
     const int cap = pb_opt(PB_OPT_TC2_CTAS, 0);  // experiments: fewer persistent CTAs (smaller L2 working set)
     if (cap > 0 && cap < nsm) nsm = cap;
     return pb_launch(pb_sg_tc2_kernel<ALGO>, pl, a, dim3(C < nsm ? C : nsm), stream);
+  }
+  if constexpr (ALGO != PB_ALGO_GRAD) {
+    if (pl.w1) {  // warp-per-chain engine: PB_W1_WPC chains per CTA, DP = float4 chunks of an augmented input row
+      const dim3 g((C + PB_W1_WPC - 1) / PB_W1_WPC);
+#define PB_W1_LAUNCH(DP_)                                                                                         \
+  return pl.act == PBNN_ACT_RELU ? pb_launch(pb_sgw_kernel<ALGO, PBNN_ACT_RELU, DP_>, pl, a, g, stream)           \
+                                 : pb_launch(pb_sgw_kernel<ALGO, PBNN_ACT_TANH, DP_>, pl, a, g, stream);
+      switch (pl.h1_dp) {
+        case 1: PB_W1_LAUNCH(1)
+        case 2: PB_W1_LAUNCH(2)
+        case 3: PB_W1_LAUNCH(3)
+        default: PB_W1_LAUNCH(4)
+      }
+#undef PB_W1_LAUNCH
+    }
   }
   if (pl.gstate) {
     if (pl.act == PBNN_ACT_RELU) return pb_launch(pb_sg_kernel<ALGO, PBNN_ACT_RELU, true, 0>, pl, a, dim3(C), stream);

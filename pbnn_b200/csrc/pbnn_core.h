@@ -52,6 +52,9 @@ struct PbPlan {
   int h1, h1_dp;                  // fused one-hidden-layer path: X row-major [rows][4*h1_dp], per-warp partial grads
   int h1_nw;                      // warps per CTA the fused path should use (0: the caller's default)
   int off_xr, off_yr, off_hpart;
+  // warp-per-chain engine (pbnn_warp.cuh; SG samplers / Adam on the same nets, many chains): float offsets inside a
+  // warp's private shared-memory block of w1_warp_floats floats -- rows [B][4 h1_dp], targets, indices, noise, aux state
+  int w1, w1_warp_floats, w1_ox, w1_oy, w1_oi, w1_oz, w1_oa;
   // tcgen05 path (one hidden relu layer, scalar output): see pbnn_tc.cuh for the operand layouts
   int tc, tc_npad;                // tc_npad = rows rounded up to the 128-row MMA tile
   int off_mk, off_z, off_wb, off_w2s, off_tcm;
@@ -78,11 +81,13 @@ static inline int pb_r32(int x) { return (x + 31) & ~31; }
 enum {
   PB_OPT_DW_KS = 0, PB_OPT_NW, PB_OPT_NO_RESIDENT, PB_OPT_NO_H1, PB_OPT_NO_TC, PB_OPT_BT, PB_OPT_TWO_CTA,
   PB_OPT_ONE_CTA, PB_OPT_FORCE_GSTATE, PB_OPT_NO_SCHED, PB_OPT_SEG_LEN, PB_OPT_DEBUG, PB_OPT_PRED_TPC,
-  PB_OPT_PRED_CHUNKS, PB_OPT_TC2_MIN_H, PB_OPT_TC2_MIN_ROWS, PB_OPT_NO_TC2, PB_OPT_TC2_CTAS, PB_OPT_TC2_NZ, PB_OPT_TC2_NOHELP, PB_OPT_COUNT
+  PB_OPT_PRED_CHUNKS, PB_OPT_TC2_MIN_H, PB_OPT_TC2_MIN_ROWS, PB_OPT_NO_TC2, PB_OPT_TC2_CTAS, PB_OPT_TC2_NZ, PB_OPT_TC2_NOHELP, PB_OPT_NO_W1,
+  PB_OPT_W1_MIN_CHAINS, PB_OPT_COUNT
 };
 static const char* const pb_opt_names[PB_OPT_COUNT] = {
     "dw_ks", "nw", "no_resident", "no_h1", "no_tc", "bt", "two_cta", "one_cta", "force_gstate", "no_sched", "seg_len",
-    "debug", "pred_tpc", "pred_chunks", "tc2_min_h", "tc2_min_rows", "no_tc2", "tc2_ctas", "tc2_nz", "tc2_nohelp"};
+    "debug", "pred_tpc", "pred_chunks", "tc2_min_h", "tc2_min_rows", "no_tc2", "tc2_ctas", "tc2_nz", "tc2_nohelp",
+    "no_w1", "w1_min_chains"};
 #define PB_OPT_UNSET (-2147483647 - 1)
 inline int* pb_opt_table() {
   static int t[PB_OPT_COUNT];
@@ -146,6 +151,8 @@ static inline void pb_plan_dw(PbPlan* pl, int nw, int bt, int kcap) {
 #define PB_PLAN_ACC 2
 #define PB_PLAN_TC 4  // the caller has a tcgen05 kernel for this op (HMC): allow the tensor-core layout
 #define PB_PLAN_TC2 8  // the caller can run the two-hidden-layer tcgen05 engine (SG samplers, Adam, grad hook)
+#define PB_PLAN_W1 16  // the caller can run the warp-per-chain engine (SG samplers, Adam)
+#define PB_W1_WARPS 4  // warps (= chains) per CTA of the warp-per-chain engine
 
 #define PB_T2_NT 576       // 8 worker warps + 1 TMA warp + 1 MMA-issue warp + 8 noise warps
 #define PB_T2_NZ 16        // most slots of the noise ring (one slot = 8 normals for each of the 256 worker threads)
@@ -436,6 +443,33 @@ static inline int pb_build_plan(const pbnn_mlp_spec* sp, int rows, int nstate, i
     if ((size_t)pl->smem_floats * 4 <= (size_t)PB_SMEM_LIMIT_BYTES) return PBNN_OK;
     pl->tc = 0;
   }
+#if !defined(PB_EMU)
+  // Warp-per-chain engine: one-hidden-layer nets, B <= 256 rows resident per warp, enough chains to fill the SMs with
+  // independent warps (below that the multi-warp fused path has the shorter step latency).
+  if (h1_ok && (flags & PB_PLAN_W1) && !pb_opt(PB_OPT_NO_W1, 0) && rows <= 256 &&
+      chains_hint >= pb_opt(PB_OPT_W1_MIN_CHAINS, 4 * 148)) {
+    pl->NT = 256;
+    pb_layout(pl, sp, rows, nstate, maxbt, 1, 1, 0, 1);
+    const int kd = 4 * pl->h1_dp, ns = 2 * kd + 3;
+    int off = 0;
+    pl->w1_ox = off;
+    off += rows * kd;
+    pl->w1_oy = off;
+    off += pb_r4(rows);
+    pl->w1_oi = off;
+    off += pb_r4(rows);
+    pl->w1_oz = off;
+    off += (P + 127) & ~127;
+    pl->w1_oa = off;
+    off += nstate > 2 ? 2 * ns * 32 : 0;
+    pl->w1_warp_floats = off;
+    pl->w1 = 1;
+    pl->NT = 32 * PB_W1_WARPS;
+    pl->smem_floats = PB_W1_WARPS * off;
+    if ((size_t)pl->smem_floats * 4 <= (size_t)(228 * 1024) / 4) return PBNN_OK;  // >= 4 CTAs (16 chains) per SM
+    pl->w1 = 0;
+  }
+#endif
   // Fused path, many chains: the warp-autonomous gradient wants >= 16 rows per warp (fewer partial-gradient arrays to
   // reduce, cheaper barriers) and the SM is filled by co-resident chains instead (measured, 8-50-1 B=32 x 4096 chains:
   // 2 warps per CTA 98 M steps/s, 4 warps 83 M, 8 warps 65 M).  Few chains: 8 warps for the latency of each one.

@@ -1,0 +1,370 @@
+// pbnn_b200: warp-per-chain engine for the SG samplers / Adam on one-hidden-layer nets with a scalar output
+// (BASELINE configs 0 / 1 family: 8-50-1, 13-50-1; H <= 64, d + 1 <= 16, B <= 256) when there are many chains.
+// Reference path: src/pbnn/mcmc/langevin.py:21-78 (sgld), :81-140 (pSGLD), src/pbnn/mcmc/hamiltonian.py:80-140 (sghmc),
+// src/pbnn/deep_ensembles.py:59-75 (Adam) over src/pbnn/models.py:16-35 and benchmark/pipelines/logprobs.py:6-17.
+//
+// One WARP owns one chain for its whole life; nothing is shared between warps, so the kernel has no CTA barrier at all
+// and an SM is kept busy by 16+ independent chains whose integer (threefry + erf_inv) and FP32 (gradient) phases
+// interleave on the two pipes.  Lane j holds the first-layer weights (and bias) of hidden units 2j, 2j + 1, their output
+// weights and a replica of the output bias IN REGISTERS for all T steps; the log-likelihood gradient of those weights
+// is lane-local too (rank-1 updates in registers), so the only cross-lane traffic of a step is one xor-butterfly per
+// data row (the network output) and the noise exchange:
+//   * noise: jax.random.normal(key_t, (P,))[i] depends on (key_t, i) only, so lane l draws i = l, l + 32, ... -- every
+//     lane does ceil(P / 32) threefry blocks instead of the 2 KD + 3 slots it owns (25 of 32 lanes hold weights at
+//     H = 50) -- into a per-warp shared-memory vector, and each lane picks up the draws of its own slots from there;
+//   * auxiliary state (pSGLD g, V; SGHMC momentum; Adam m, v) sits in per-warp shared memory as [slot][lane].
+// Same arithmetic contract as the other engines (FP32, fixed summation order, bit-exact noise); the chain's results do
+// not depend on which warp / CTA runs it.
+#pragma once
+#if !defined(PB_EMU)
+
+#define PB_W1_WPC PB_W1_WARPS  // warps (= chains) per CTA (pbnn_core.h)
+
+// register slots of a lane: u < KD first-layer row k = u of unit 2 lane; KD <= u < 2 KD the same of unit 2 lane + 1
+// (row d = bias, rows > d pads); 2 KD, 2 KD + 1 the two output weights; 2 KD + 2 the output bias (replicated in every
+// lane: all lanes apply the identical update, stores of it are same-value same-address)
+#define PB_W1_SLOT(W0_, W1_, v0_, v1_, b2_, u)                                                        \
+  (*((u) < KD ? (((u) & 1) ? &W0_[((u) >> 1) % KH].y : &W0_[((u) >> 1) % KH].x)                        \
+              : (u) < 2 * KD ? (((u) & 1) ? &W1_[(((u) - KD) >> 1) % KH].y : &W1_[(((u) - KD) >> 1) % KH].x) \
+                             : (u) == 2 * KD ? &v0_ : (u) == 2 * KD + 1 ? &v1_ : &b2_))
+
+template <int ALGO, int ACT, int DP>
+PB_DEV void pb_sgw_chain(const PbPlan& pl, const PbSgArgs& a, float* wsm, int c, int lane) {
+  constexpr int KD = 4 * DP, KH = KD / 2, NS = 2 * KD + 3, NP = 2;
+  const PbLayer& L0 = pl.L[0];
+  const PbLayer& L1 = pl.L[1];
+  const int H = L0.out, d = pl.d, P = pl.P, B = a.B;
+  float* xs = wsm + pl.w1_ox;
+  float* ys = wsm + pl.w1_oy;
+  float* zb = wsm + pl.w1_oz;
+  int* ib = reinterpret_cast<int*>(wsm + pl.w1_oi);
+  float* ax1 = wsm + pl.w1_oa + lane;  // [slot][lane]
+  float* ax2 = ax1 + NS * 32;
+  const int j0 = 2 * lane;
+  const size_t cP = (size_t)c * P;
+  uint32_t fl = 0u;
+  PbKey ck;
+  ck.k0 = a.keys ? a.keys[2 * c] : 0u;
+  ck.k1 = a.keys ? a.keys[2 * c + 1] : 0u;
+
+  // flat (ravel_pytree) index of slot u, -1 for a pad slot
+  auto slot_fi = [&](int u) -> int {
+    if (u < 2 * KD) {
+      const int unit = u >= KD ? 1 : 0, k = u - unit * KD, j = j0 + unit;
+      if (k > d || j >= H) return -1;
+      return k < d ? L0.fw + k * H + j : L0.fb + j;
+    }
+    if (u < 2 * KD + 2) {
+      const int j = j0 + (u - 2 * KD);
+      return j < H ? L1.fw + j : -1;
+    }
+    return L1.fb;
+  };
+
+  float2 W0[KH], W1[KH], a0[KH], a1[KH];
+  float v0, v1, b2, av0 = 0.f, av1 = 0.f, ab = 0.f;
+#define TH_(u) PB_W1_SLOT(W0, W1, v0, v1, b2, u)
+#define GA_(u) PB_W1_SLOT(a0, a1, av0, av1, ab, u)
+#pragma unroll
+  for (int u = 0; u < NS; ++u) {
+    const int fi = slot_fi(u);
+    TH_(u) = fi >= 0 ? a.theta[cP + fi] : 0.f;
+  }
+
+  // ---- minibatch ------------------------------------------------------------------------------------------------
+  auto gather = [&]() {  // rows ib[0..B) -> xs[b][KD] = (x_b, 1, 0...), ys[b]
+    __syncwarp();
+    for (int item = lane; item < B * KD; item += 32) {
+      const int b = item / KD, k = item - b * KD;
+      float v = k == d ? 1.f : 0.f;
+      if (k < d) v = a.X[(size_t)ib[b] * d + k];
+      xs[item] = v;
+    }
+    for (int b = lane; b < B; b += 32) ys[b] = a.y[ib[b]];
+    __syncwarp();
+  };
+  auto copy_indices = [&](const int32_t* src) {  // clamped like a JAX gather; bit 2 of the flag word records it
+    __syncwarp();
+    for (int b = lane; b < B; b += 32) {
+      int v = src ? src[b] : b;
+      if (v < 0 || v >= a.N) {
+        v = v < 0 ? 0 : a.N - 1;
+        fl |= 4u;
+      }
+      ib[b] = v;
+    }
+  };
+  PbKey gk = ck;  // minibatch generator key (utils/data.py:69-78): key <- split(key)[1]; randint(key, (B,), 0, N)
+  auto gen_advance = [&](int times) {
+    for (int i = 0; i < times; ++i) gk = pb_split_at(gk, 1u);
+  };
+  auto gen_indices = [&]() {
+    __syncwarp();
+    const PbKey k1 = pb_split_at(gk, 0u), k2 = pb_split_at(gk, 1u);
+    for (int b = lane; b < B; b += 32) ib[b] = pb_randint_at(k1, k2, (uint32_t)b, (uint32_t)a.N, a.randint_mult);
+  };
+
+  // ---- gradient of the (scaled) log-likelihood at the registers' theta: a0, a1, av0, av1, ab ----------------------
+  auto grad = [&]() {
+#pragma unroll
+    for (int k = 0; k < KH; ++k) {
+      a0[k] = make_float2(0.f, 0.f);
+      a1[k] = make_float2(0.f, 0.f);
+    }
+    av0 = av1 = ab = 0.f;
+    for (int n = 0; n < B; n += NP) {
+      float h0[NP], h1[NP], pf[NP];
+      int row[NP];
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        row[p] = pb_min(n + p, B - 1);
+        const float* xp_ = xs + row[p] * KD;
+        float2 z0 = make_float2(0.f, 0.f), z1 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int q = 0; q < DP; ++q) {
+          const float4 t = pb_ld4(xp_ + 4 * q);
+          const float2 lo = make_float2(t.x, t.y), hi = make_float2(t.z, t.w);
+          z0 = __ffma2_rn(lo, W0[2 * q], z0);
+          z1 = __ffma2_rn(lo, W1[2 * q], z1);
+          z0 = __ffma2_rn(hi, W0[2 * q + 1], z0);
+          z1 = __ffma2_rn(hi, W1[2 * q + 1], z1);
+        }
+        h0[p] = pb_act<ACT>(z0.x + z0.y);
+        h1[p] = pb_act<ACT>(z1.x + z1.y);
+        pf[p] = h0[p] * v0 + h1[p] * v1;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int p = 0; p < NP; ++p) pf[p] += __shfl_xor_sync(0xffffffffu, pf[p], o);
+      }
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        const bool valid = n + p < B;
+        const float res = ys[row[p]] - (pf[p] + b2);
+        const float r = valid ? res * a.scale : 0.f;
+        const float dz0 = r * v0 * pb_actgrad<ACT>(h0[p]), dz1 = r * v1 * pb_actgrad<ACT>(h1[p]);
+        const float2 d0 = make_float2(dz0, dz0), d1 = make_float2(dz1, dz1);
+        const float* xp_ = xs + row[p] * KD;
+#pragma unroll
+        for (int q = 0; q < DP; ++q) {
+          const float4 t = pb_ld4(xp_ + 4 * q);
+          const float2 lo = make_float2(t.x, t.y), hi = make_float2(t.z, t.w);
+          a0[2 * q] = __ffma2_rn(lo, d0, a0[2 * q]);
+          a1[2 * q] = __ffma2_rn(lo, d1, a1[2 * q]);
+          a0[2 * q + 1] = __ffma2_rn(hi, d0, a0[2 * q + 1]);
+          a1[2 * q + 1] = __ffma2_rn(hi, d1, a1[2 * q + 1]);
+        }
+        av0 += r * h0[p];
+        av1 += r * h1[p];
+        ab += r;
+      }
+    }
+  };
+
+  // ---- noise: zb[i] = jax.random.normal(key, (P,))[i], lane l draws i = l + 32 m (4 threefry chains in flight) ------
+  auto gen_noise = [&](PbKey key) {
+    __syncwarp();  // the previous step's readers are done with zb
+    for (int p0 = lane; p0 < P; p0 += 128) {
+      uint32_t idx[4];
+      float z[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) idx[j] = (uint32_t)(p0 + 32 * j);
+      pb_normal_n<4>(key, idx, z);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) zb[p0 + 32 * j] = z[j];  // (zb is padded to a multiple of 128)
+    }
+    __syncwarp();
+  };
+
+  auto trace_row = [&](int t_) -> float* {
+    return (a.trace && t_ >= a.burnin && ((t_ - a.burnin) % a.thin) == 0)
+               ? a.trace + ((size_t)c * a.T_out + (size_t)((t_ - a.burnin) / a.thin)) * P
+               : nullptr;
+  };
+  auto store_theta = [&](float* dst) {
+#pragma unroll
+    for (int u = 0; u < NS; ++u) {
+      const int fi = slot_fi(u);
+      if (fi >= 0) dst[fi] = TH_(u);
+    }
+  };
+
+  // ---- chain set-up (mirrors pb_sg_chain) -------------------------------------------------------------------------
+  if (ALGO == PB_ALGO_PSGLD || ALGO == PB_ALGO_ADAM) {
+    const bool have = ALGO == PB_ALGO_ADAM || a.has_state;
+#pragma unroll
+    for (int u = 0; u < NS; ++u) {
+      const int fi = slot_fi(u);
+      ax1[u * 32] = (have && fi >= 0) ? a.aux1[cP + fi] : 0.f;
+      ax2[u * 32] = (have && fi >= 0) ? a.aux2[cP + fi] : 0.f;
+    }
+  }
+  if (ALGO == PB_ALGO_SGHMC) {
+#pragma unroll
+    for (int u = 0; u < NS; ++u) ax1[u * 32] = 0.f;
+  }
+
+  const bool explicit_idx = a.idx != nullptr || a.contig;
+  const bool per_step =
+      explicit_idx ? (a.idx_steps > 1 || ALGO == PB_ALGO_ADAM) : (a.mb_mode == PBNN_MB_PER_STEP);
+  const int32_t* cidx = a.idx ? a.idx + (size_t)c * a.idx_steps * B : nullptr;
+  int gen_pos = 0;
+
+  // pSGLD init (psgld.py:25-29): g0 = grad(theta0, draw #init_draw), V0 = g0^2
+  if (ALGO == PB_ALGO_PSGLD && !a.has_state) {
+    if (explicit_idx) {
+      copy_indices(cidx);
+    } else {
+      gen_advance(a.init_draw - gen_pos);
+      gen_pos = a.init_draw;
+      gen_indices();
+    }
+    gather();
+    grad();
+#pragma unroll
+    for (int u = 0; u < NS; ++u) {
+      const float g = GA_(u) - TH_(u) * pl.inv_pv;
+      ax1[u * 32] = g;
+      ax2[u * 32] = g * g;
+    }
+  }
+
+  if (!per_step) {  // the minibatch the traced loop re-uses (quirk Q1)
+    if (explicit_idx) {
+      copy_indices(cidx);
+    } else {
+      gen_advance(a.which_draw - gen_pos);
+      gen_pos = a.which_draw;
+      gen_indices();
+    }
+    gather();
+  } else if (!explicit_idx) {
+    gen_advance((int)(1 + a.t0 - gen_pos));  // draw #1 belongs to kern.init, step t uses draw t0 + t + 2
+  }
+
+  for (int t = 0; t < a.T; ++t) {
+    const long long tg = a.t0 + t;
+    const PbKey kt = a.direct_key ? ck : pb_split_at(ck, (uint32_t)tg);  // split(rng_key, T)[t]
+    const float eps = a.step_sizes ? a.step_sizes[t < a.n_step_sizes ? t : a.n_step_sizes - 1] : a.const_step;
+    if (per_step) {
+      if (explicit_idx) {
+        copy_indices(cidx ? cidx + (size_t)t * B : nullptr);
+      } else {
+        gen_advance(1);
+        gen_indices();
+      }
+      gather();
+    }
+    const float* cvc = a.cv_center ? a.cv_center + cP : nullptr;
+    const float* cve = a.cv_center ? a.cv_center_est + cP : nullptr;
+
+    if (ALGO == PB_ALGO_SGLD) {
+      grad();
+      gen_noise(kt);
+      const float ns = sqrtf(2.0f * a.temperature * eps);
+#pragma unroll
+      for (int u = 0; u < NS; ++u) {
+        const int fi = slot_fi(u);
+        if (fi >= 0) {
+          const float th = TH_(u);
+          float g = GA_(u) - th * pl.inv_pv;
+          if (cvc) g = (cvc[fi] + g) - cve[fi];  // blackjax control_variates
+          TH_(u) = th + eps * g + ns * zb[fi];
+        }
+      }
+    } else if (ALGO == PB_ALGO_PSGLD) {  // diffusions.py:42-59: move with the STALE (g, V), then refresh them
+      gen_noise(kt);
+#pragma unroll
+      for (int u = 0; u < NS; ++u) {
+        const int fi = slot_fi(u);
+        if (fi >= 0) {
+          const float pre = 1.0f / (sqrtf(ax2[u * 32]) + 1e-6f);
+          TH_(u) = TH_(u) + eps * pre * ax1[u * 32] + sqrtf(2.0f * pre * eps) * zb[fi];
+        }
+      }
+      grad();
+#pragma unroll
+      for (int u = 0; u < NS; ++u) {
+        const float g = GA_(u) - TH_(u) * pl.inv_pv;
+        ax1[u * 32] = g;
+        ax2[u * 32] = a.alpha * ax2[u * 32] + (1.0f - a.alpha) * (g * g);
+      }
+    } else if (ALGO == PB_ALGO_SGHMC) {
+      const float seps = sqrtf(eps);
+      const float mom_mu = a.mom_mu0 + a.mom_mu1 * seps, mom_sig = a.mom_sig0 + a.mom_sig1 * seps;
+      gen_noise(kt);
+#pragma unroll
+      for (int u = 0; u < NS; ++u) {
+        const int fi = slot_fi(u);
+        ax1[u * 32] = fi >= 0 ? mom_mu + mom_sig * zb[fi] : 0.f;
+      }
+      const float ns = sqrtf(2.0f * eps * (a.alpha - a.beta) * a.temperature);
+      const float fric = 1.0f - a.alpha;
+      for (int l = 0; l < a.L; ++l) {
+        const PbKey kl = pb_split_at(kt, (uint32_t)l);  // split(keys[t], L)[l]
+        grad();
+        gen_noise(kl);
+#pragma unroll
+        for (int u = 0; u < NS; ++u) {
+          const int fi = slot_fi(u);
+          if (fi >= 0) {
+            const float th = TH_(u), p = ax1[u * 32];
+            float g = GA_(u) - th * pl.inv_pv;
+            if (cvc) g = (cvc[fi] + g) - cve[fi];
+            TH_(u) = th + p;
+            ax1[u * 32] = fric * p + eps * g + ns * zb[fi];
+          }
+        }
+      }
+    } else if (ALGO == PB_ALGO_ADAM) {
+      grad();
+      const float cnt = (float)(a.count0 + t + 1);
+      const float ibc1 = 1.0f / (1.0f - powf(a.b1, cnt)), ibc2 = 1.0f / (1.0f - powf(a.b2, cnt));
+#pragma unroll
+      for (int u = 0; u < NS; ++u) {
+        if (slot_fi(u) < 0) continue;
+        const float th = TH_(u);
+        const float g = -(GA_(u) - th * pl.inv_pv);  // gradient of the loss -logposterior
+        const float m = (1.0f - a.b1) * g + a.b1 * ax1[u * 32];
+        const float v = (1.0f - a.b2) * (g * g) + a.b2 * ax2[u * 32];
+        ax1[u * 32] = m;
+        ax2[u * 32] = v;
+        TH_(u) = th + (-a.lr) * __fdividef(m * ibc1, sqrtf(v * ibc2) + a.eps);
+      }
+    }
+    float* dst = trace_row(t);
+    if (dst) store_theta(dst);
+  }
+
+  if (!a.no_theta_store) {
+    store_theta(a.theta + cP);
+#pragma unroll
+    for (int u = 0; u < NS; ++u) fl |= pb_finite(TH_(u)) ? 0u : 1u;
+  }
+  if (ALGO == PB_ALGO_PSGLD || ALGO == PB_ALGO_ADAM) {
+#pragma unroll
+    for (int u = 0; u < NS; ++u) {
+      const int fi = slot_fi(u);
+      if (fi >= 0) {
+        a.aux1[cP + fi] = ax1[u * 32];
+        a.aux2[cP + fi] = ax2[u * 32];
+      }
+    }
+  }
+  fl = __reduce_or_sync(0xffffffffu, fl);
+  if (lane == 0 && a.flags) a.flags[c] = fl;
+#undef TH_
+#undef GA_
+}
+
+template <int ALGO, int ACT, int DP>
+__global__ void __launch_bounds__(32 * PB_W1_WPC)
+pb_sgw_kernel(const __grid_constant__ PbPlan pl, const __grid_constant__ PbSgArgs a) {
+  extern __shared__ __align__(16) float pb_smem[];
+  const int warp = (int)threadIdx.x >> 5, lane = (int)threadIdx.x & 31;
+  const int c = (int)blockIdx.x * PB_W1_WPC + warp;
+  if (c >= a.n_chains) return;  // (no CTA barrier anywhere in this kernel)
+  pb_sgw_chain<ALGO, ACT, DP>(pl, a, pb_smem + (size_t)warp * pl.w1_warp_floats, c, lane);
+}
+#endif

@@ -31,12 +31,14 @@ def cuda_ops():
 
 @pytest.fixture(params=["emu", pytest.param("cuda", marks=pytest.mark.gpu),
                         pytest.param("cuda_notc", marks=pytest.mark.gpu),
-                        pytest.param("cuda_generic", marks=pytest.mark.gpu)])
+                        pytest.param("cuda_generic", marks=pytest.mark.gpu),
+                        pytest.param("cuda_warp", marks=pytest.mark.gpu)])
 def ops(request):
     """Parity tests run against the emulator here (CPU) and against the CUDA library on the GPU box -- there three
     times: with the default kernel selection (tcgen05 engines where they apply, fused FP32 path for the other
     one-hidden-layer cases), with the tensor-core engines disabled (option "no_tc") and with the generic tiled-GEMM
-    engine forced ("no_tc" + "no_h1").  Engines are selected through the library's explicit option table
+    engine forced ("no_tc" + "no_h1"); a fourth pass ("w1_min_chains" = 1) sends every eligible SG / Adam call through the
+    warp-per-chain engine, which by default is only chosen for many chains.  Engines are selected through the library's explicit option table
     (pbnn_set_option; the plan is rebuilt on every call); nothing is read from the environment."""
     if request.param in ("cuda_notc", "cuda_generic"):
         o = request.getfixturevalue("cuda_ops")
@@ -44,6 +46,13 @@ def ops(request):
         o.set_option("no_tc", 1)
         if request.param == "cuda_generic":
             o.set_option("no_h1", 1)
+        yield o
+        o.reset_options()
+        return
+    if request.param == "cuda_warp":
+        o = request.getfixturevalue("cuda_ops")
+        o.reset_options()
+        o.set_option("w1_min_chains", 1)
         yield o
         o.reset_options()
         return
