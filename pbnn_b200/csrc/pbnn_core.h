@@ -54,7 +54,7 @@ struct PbPlan {
   int off_xr, off_yr, off_hpart;
   // warp-per-chain engine (pbnn_warp.cuh; SG samplers / Adam on the same nets, many chains): float offsets inside a
   // warp's private shared-memory block of w1_warp_floats floats -- rows [B][4 h1_dp], targets, indices, noise, aux state
-  int w1, w1_warp_floats, w1_ox, w1_oy, w1_oi, w1_oz, w1_oa;
+  int w1, w1_warp_floats, w1_ox, w1_oy, w1_oi, w1_ot, w1_oz, w1_oa;
   // tcgen05 path (one hidden relu layer, scalar output): see pbnn_tc.cuh for the operand layouts
   int tc, tc_npad;                // tc_npad = rows rounded up to the 128-row MMA tile
   int off_mk, off_z, off_wb, off_w2s, off_tcm;
@@ -152,7 +152,7 @@ static inline void pb_plan_dw(PbPlan* pl, int nw, int bt, int kcap) {
 #define PB_PLAN_TC 4  // the caller has a tcgen05 kernel for this op (HMC): allow the tensor-core layout
 #define PB_PLAN_TC2 8  // the caller can run the two-hidden-layer tcgen05 engine (SG samplers, Adam, grad hook)
 #define PB_PLAN_W1 16  // the caller can run the warp-per-chain engine (SG samplers, Adam)
-#define PB_W1_WARPS 4  // warps (= chains) per CTA of the warp-per-chain engine
+#define PB_W1_WARPS 1  // warps (= chains) per CTA of the warp-per-chain engine (finest balance over the SMs)
 
 #define PB_T2_NT 576       // 8 worker warps + 1 TMA warp + 1 MMA-issue warp + 8 noise warps
 #define PB_T2_NZ 16        // most slots of the noise ring (one slot = 8 normals for each of the 256 worker threads)
@@ -458,15 +458,17 @@ static inline int pb_build_plan(const pbnn_mlp_spec* sp, int rows, int nstate, i
     off += pb_r4(rows);
     pl->w1_oi = off;
     off += pb_r4(rows);
+    pl->w1_ot = off;
+    off += (P + 127) & ~127;  // flat index -> [slot][lane] table
     pl->w1_oz = off;
-    off += (P + 127) & ~127;
+    off += (ns + 1) * 32;     // noise / trace staging in slot order (+ a dump row)
     pl->w1_oa = off;
     off += nstate > 2 ? 2 * ns * 32 : 0;
     pl->w1_warp_floats = off;
     pl->w1 = 1;
     pl->NT = 32 * PB_W1_WARPS;
     pl->smem_floats = PB_W1_WARPS * off;
-    if ((size_t)pl->smem_floats * 4 <= (size_t)(228 * 1024) / 4) return PBNN_OK;  // >= 4 CTAs (16 chains) per SM
+    if ((size_t)pl->smem_floats * 4 * (12 / PB_W1_WARPS) <= (size_t)(200 * 1024)) return PBNN_OK;  // >= 12 chains per SM
     pl->w1 = 0;
   }
 #endif

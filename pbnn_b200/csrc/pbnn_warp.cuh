@@ -11,7 +11,9 @@
 // data row (the network output) and the noise exchange:
 //   * noise: jax.random.normal(key_t, (P,))[i] depends on (key_t, i) only, so lane l draws i = l, l + 32, ... -- every
 //     lane does ceil(P / 32) threefry blocks instead of the 2 KD + 3 slots it owns (25 of 32 lanes hold weights at
-//     H = 50) -- into a per-warp shared-memory vector, and each lane picks up the draws of its own slots from there;
+//     H = 50) -- and scatters them through a per-warp table (flat index -> [slot][lane], built once per chain) into a
+//     shared-memory array the owners read at immediate offsets; trace rows take the same road backwards, so the
+//     global stores are whole 128-byte lines;
 //   * auxiliary state (pSGLD g, V; SGHMC momentum; Adam m, v) sits in per-warp shared memory as [slot][lane].
 // Same arithmetic contract as the other engines (FP32, fixed summation order, bit-exact noise); the chain's results do
 // not depend on which warp / CTA runs it.
@@ -36,7 +38,8 @@ PB_DEV void pb_sgw_chain(const PbPlan& pl, const PbSgArgs& a, float* wsm, int c,
   const int H = L0.out, d = pl.d, P = pl.P, B = a.B;
   float* xs = wsm + pl.w1_ox;
   float* ys = wsm + pl.w1_oy;
-  float* zb = wsm + pl.w1_oz;
+  float* zs = wsm + pl.w1_oz;  // [NS + 1][32]: noise / trace staging in slot order (row NS: dump row for i >= P)
+  int* tab = reinterpret_cast<int*>(wsm + pl.w1_ot);  // flat index i -> slot * 32 + owner lane
   int* ib = reinterpret_cast<int*>(wsm + pl.w1_oi);
   float* ax1 = wsm + pl.w1_oa + lane;  // [slot][lane]
   float* ax2 = ax1 + NS * 32;
@@ -47,18 +50,23 @@ PB_DEV void pb_sgw_chain(const PbPlan& pl, const PbSgArgs& a, float* wsm, int c,
   ck.k0 = a.keys ? a.keys[2 * c] : 0u;
   ck.k1 = a.keys ? a.keys[2 * c + 1] : 0u;
 
-  // flat (ravel_pytree) index of slot u, -1 for a pad slot
+  // slot u -> (holds a parameter?, flat ravel_pytree index); straight-line code (u is a compile-time constant after
+  // unrolling, the row test and the base offset are warp-uniform): pad slots answer index 0 and every memory access
+  // they make is either harmless (loads) or predicated off (stores)
+  const bool ok0 = j0 < H, ok1 = j0 + 1 < H;
+  auto slot_ok = [&](int u) -> bool {
+    if (u < 2 * KD) return ((u < KD ? u : u - KD) <= d) && (u < KD ? ok0 : ok1);
+    return u == 2 * KD ? ok0 : (u == 2 * KD + 1 ? ok1 : true);
+  };
   auto slot_fi = [&](int u) -> int {
+    int fi;
     if (u < 2 * KD) {
-      const int unit = u >= KD ? 1 : 0, k = u - unit * KD, j = j0 + unit;
-      if (k > d || j >= H) return -1;
-      return k < d ? L0.fw + k * H + j : L0.fb + j;
+      const int unit = u < KD ? 0 : 1, k = u - unit * KD;
+      fi = (k < d ? L0.fw + k * H : L0.fb) + j0 + unit;
+    } else {
+      fi = u < 2 * KD + 2 ? L1.fw + j0 + (u - 2 * KD) : L1.fb;
     }
-    if (u < 2 * KD + 2) {
-      const int j = j0 + (u - 2 * KD);
-      return j < H ? L1.fw + j : -1;
-    }
-    return L1.fb;
+    return slot_ok(u) ? fi : 0;
   };
 
   float2 W0[KH], W1[KH], a0[KH], a1[KH];
@@ -67,9 +75,36 @@ PB_DEV void pb_sgw_chain(const PbPlan& pl, const PbSgArgs& a, float* wsm, int c,
 #define GA_(u) PB_W1_SLOT(a0, a1, av0, av1, ab, u)
 #pragma unroll
   for (int u = 0; u < NS; ++u) {
-    const int fi = slot_fi(u);
-    TH_(u) = fi >= 0 ? a.theta[cP + fi] : 0.f;
+    const float v = a.theta[cP + slot_fi(u)];
+    TH_(u) = slot_ok(u) ? v : 0.f;
   }
+
+  // flat index -> position in the slot-major staging array (the output bias lives in lane 0's copy; readers broadcast)
+  for (int i = lane; i < ((P + 127) & ~127); i += 32) {
+    int o = NS * 32 + lane;  // dump row
+    if (i < P) {
+      int u, j;
+      if (i >= L1.fw) {
+        j = i - L1.fw;
+        u = 2 * KD + (j & 1);
+      } else if (i == L1.fb) {
+        j = 0;
+        u = 2 * KD + 2;
+      } else if (i >= L0.fw) {
+        const int k = (i - L0.fw) / H;
+        j = (i - L0.fw) - k * H;
+        u = (j & 1) * KD + k;
+      } else {
+        j = i - L0.fb;
+        u = (j & 1) * KD + d;
+      }
+      o = u * 32 + (j >> 1);
+    }
+    tab[i] = o;
+  }
+  for (int i = lane; i < (NS + 1) * 32; i += 32) zs[i] = 0.f;  // pad slots read 0 forever
+  __syncwarp();
+#define ZS_(u) zs[(u) * 32 + ((u) == NS - 1 ? 0 : lane)]
 
   // ---- minibatch ------------------------------------------------------------------------------------------------
   auto gather = [&]() {  // rows ib[0..B) -> xs[b][KD] = (x_b, 1, 0...), ys[b]
@@ -114,6 +149,7 @@ PB_DEV void pb_sgw_chain(const PbPlan& pl, const PbSgArgs& a, float* wsm, int c,
     av0 = av1 = ab = 0.f;
     for (int n = 0; n < B; n += NP) {
       float h0[NP], h1[NP], pf[NP];
+      float4 xr[NP][DP];  // the rows stay in registers for the rank-1 update below
       int row[NP];
 #pragma unroll
       for (int p = 0; p < NP; ++p) {
@@ -122,7 +158,7 @@ PB_DEV void pb_sgw_chain(const PbPlan& pl, const PbSgArgs& a, float* wsm, int c,
         float2 z0 = make_float2(0.f, 0.f), z1 = make_float2(0.f, 0.f);
 #pragma unroll
         for (int q = 0; q < DP; ++q) {
-          const float4 t = pb_ld4(xp_ + 4 * q);
+          const float4 t = xr[p][q] = pb_ld4(xp_ + 4 * q);
           const float2 lo = make_float2(t.x, t.y), hi = make_float2(t.z, t.w);
           z0 = __ffma2_rn(lo, W0[2 * q], z0);
           z1 = __ffma2_rn(lo, W1[2 * q], z1);
@@ -134,9 +170,12 @@ PB_DEV void pb_sgw_chain(const PbPlan& pl, const PbSgArgs& a, float* wsm, int c,
         pf[p] = h0[p] * v0 + h1[p] * v1;
       }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-        for (int p = 0; p < NP; ++p) pf[p] += __shfl_xor_sync(0xffffffffu, pf[p], o);
+      for (int o = 16; o > 0; o >>= 1) {  // both rows' butterflies share one packed add per stage
+        static_assert(NP == 2, "packed butterfly");
+        const float2 got = make_float2(__shfl_xor_sync(0xffffffffu, pf[0], o), __shfl_xor_sync(0xffffffffu, pf[1], o));
+        const float2 sum = __fadd2_rn(make_float2(pf[0], pf[1]), got);
+        pf[0] = sum.x;
+        pf[1] = sum.y;
       }
 #pragma unroll
       for (int p = 0; p < NP; ++p) {
@@ -145,10 +184,9 @@ PB_DEV void pb_sgw_chain(const PbPlan& pl, const PbSgArgs& a, float* wsm, int c,
         const float r = valid ? res * a.scale : 0.f;
         const float dz0 = r * v0 * pb_actgrad<ACT>(h0[p]), dz1 = r * v1 * pb_actgrad<ACT>(h1[p]);
         const float2 d0 = make_float2(dz0, dz0), d1 = make_float2(dz1, dz1);
-        const float* xp_ = xs + row[p] * KD;
 #pragma unroll
         for (int q = 0; q < DP; ++q) {
-          const float4 t = pb_ld4(xp_ + 4 * q);
+          const float4 t = xr[p][q];
           const float2 lo = make_float2(t.x, t.y), hi = make_float2(t.z, t.w);
           a0[2 * q] = __ffma2_rn(lo, d0, a0[2 * q]);
           a1[2 * q] = __ffma2_rn(lo, d1, a1[2 * q]);
@@ -162,17 +200,21 @@ PB_DEV void pb_sgw_chain(const PbPlan& pl, const PbSgArgs& a, float* wsm, int c,
     }
   };
 
-  // ---- noise: zb[i] = jax.random.normal(key, (P,))[i], lane l draws i = l + 32 m (4 threefry chains in flight) ------
+  // ---- noise: jax.random.normal(key, (P,))[i] -> zs[tab[i]], lane l draws i = l + 32 m (4 threefry chains in flight)
   auto gen_noise = [&](PbKey key) {
-    __syncwarp();  // the previous step's readers are done with zb
+    __syncwarp();  // the previous readers are done with zs
     for (int p0 = lane; p0 < P; p0 += 128) {
       uint32_t idx[4];
+      int to[4];
       float z[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) idx[j] = (uint32_t)(p0 + 32 * j);
-      pb_normal_n<4>(key, idx, z);
+      for (int j = 0; j < 4; ++j) {
+        idx[j] = (uint32_t)(p0 + 32 * j);
+        to[j] = tab[p0 + 32 * j];  // (the table is padded to a multiple of 128: i >= P lands in the dump row)
+      }
+      pb_normal_n<4, true>(key, idx, z);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) zb[p0 + 32 * j] = z[j];  // (zb is padded to a multiple of 128)
+      for (int j = 0; j < 4; ++j) zs[to[j]] = z[j];
     }
     __syncwarp();
   };
@@ -182,12 +224,12 @@ PB_DEV void pb_sgw_chain(const PbPlan& pl, const PbSgArgs& a, float* wsm, int c,
                ? a.trace + ((size_t)c * a.T_out + (size_t)((t_ - a.burnin) / a.thin)) * P
                : nullptr;
   };
-  auto store_theta = [&](float* dst) {
+  auto store_theta = [&](float* dst) {  // registers -> slot-major staging -> flat order, coalesced
+    __syncwarp();
 #pragma unroll
-    for (int u = 0; u < NS; ++u) {
-      const int fi = slot_fi(u);
-      if (fi >= 0) dst[fi] = TH_(u);
-    }
+    for (int u = 0; u < NS; ++u) zs[u * 32 + lane] = TH_(u);  // (pad slots hold 0; the b2 replicas agree)
+    __syncwarp();
+    for (int i = lane; i < P; i += 32) dst[i] = zs[tab[i]];
   };
 
   // ---- chain set-up (mirrors pb_sg_chain) -------------------------------------------------------------------------
@@ -195,9 +237,9 @@ PB_DEV void pb_sgw_chain(const PbPlan& pl, const PbSgArgs& a, float* wsm, int c,
     const bool have = ALGO == PB_ALGO_ADAM || a.has_state;
 #pragma unroll
     for (int u = 0; u < NS; ++u) {
-      const int fi = slot_fi(u);
-      ax1[u * 32] = (have && fi >= 0) ? a.aux1[cP + fi] : 0.f;
-      ax2[u * 32] = (have && fi >= 0) ? a.aux2[cP + fi] : 0.f;
+      const bool ld = have && slot_ok(u);
+      ax1[u * 32] = ld ? a.aux1[cP + slot_fi(u)] : 0.f;
+      ax2[u * 32] = ld ? a.aux2[cP + slot_fi(u)] : 0.f;
     }
   }
   if (ALGO == PB_ALGO_SGHMC) {
@@ -265,23 +307,17 @@ PB_DEV void pb_sgw_chain(const PbPlan& pl, const PbSgArgs& a, float* wsm, int c,
       const float ns = sqrtf(2.0f * a.temperature * eps);
 #pragma unroll
       for (int u = 0; u < NS; ++u) {
-        const int fi = slot_fi(u);
-        if (fi >= 0) {
-          const float th = TH_(u);
-          float g = GA_(u) - th * pl.inv_pv;
-          if (cvc) g = (cvc[fi] + g) - cve[fi];  // blackjax control_variates
-          TH_(u) = th + eps * g + ns * zb[fi];
-        }
+        const float th = TH_(u);
+        float g = GA_(u) - th * pl.inv_pv;
+        if (cvc) g = (cvc[slot_fi(u)] + g) - cve[slot_fi(u)];  // blackjax control_variates
+        TH_(u) = th + eps * g + ns * ZS_(u);  // (pad slots: theta = g = z = 0)
       }
     } else if (ALGO == PB_ALGO_PSGLD) {  // diffusions.py:42-59: move with the STALE (g, V), then refresh them
       gen_noise(kt);
 #pragma unroll
       for (int u = 0; u < NS; ++u) {
-        const int fi = slot_fi(u);
-        if (fi >= 0) {
-          const float pre = 1.0f / (sqrtf(ax2[u * 32]) + 1e-6f);
-          TH_(u) = TH_(u) + eps * pre * ax1[u * 32] + sqrtf(2.0f * pre * eps) * zb[fi];
-        }
+        const float pre = 1.0f / (sqrtf(ax2[u * 32]) + 1e-6f);
+        TH_(u) = TH_(u) + eps * pre * ax1[u * 32] + sqrtf(2.0f * pre * eps) * ZS_(u);  // (pad slots: 0)
       }
       grad();
 #pragma unroll
@@ -296,8 +332,7 @@ PB_DEV void pb_sgw_chain(const PbPlan& pl, const PbSgArgs& a, float* wsm, int c,
       gen_noise(kt);
 #pragma unroll
       for (int u = 0; u < NS; ++u) {
-        const int fi = slot_fi(u);
-        ax1[u * 32] = fi >= 0 ? mom_mu + mom_sig * zb[fi] : 0.f;
+        ax1[u * 32] = slot_ok(u) ? mom_mu + mom_sig * ZS_(u) : 0.f;
       }
       const float ns = sqrtf(2.0f * eps * (a.alpha - a.beta) * a.temperature);
       const float fric = 1.0f - a.alpha;
@@ -307,14 +342,11 @@ PB_DEV void pb_sgw_chain(const PbPlan& pl, const PbSgArgs& a, float* wsm, int c,
         gen_noise(kl);
 #pragma unroll
         for (int u = 0; u < NS; ++u) {
-          const int fi = slot_fi(u);
-          if (fi >= 0) {
-            const float th = TH_(u), p = ax1[u * 32];
-            float g = GA_(u) - th * pl.inv_pv;
-            if (cvc) g = (cvc[fi] + g) - cve[fi];
-            TH_(u) = th + p;
-            ax1[u * 32] = fric * p + eps * g + ns * zb[fi];
-          }
+          const float th = TH_(u), p = ax1[u * 32];
+          float g = GA_(u) - th * pl.inv_pv;
+          if (cvc) g = (cvc[slot_fi(u)] + g) - cve[slot_fi(u)];
+          TH_(u) = th + p;  // (pad slots: everything 0)
+          ax1[u * 32] = fric * p + eps * g + ns * ZS_(u);
         }
       }
     } else if (ALGO == PB_ALGO_ADAM) {
@@ -323,14 +355,14 @@ PB_DEV void pb_sgw_chain(const PbPlan& pl, const PbSgArgs& a, float* wsm, int c,
       const float ibc1 = 1.0f / (1.0f - powf(a.b1, cnt)), ibc2 = 1.0f / (1.0f - powf(a.b2, cnt));
 #pragma unroll
       for (int u = 0; u < NS; ++u) {
-        if (slot_fi(u) < 0) continue;
         const float th = TH_(u);
         const float g = -(GA_(u) - th * pl.inv_pv);  // gradient of the loss -logposterior
         const float m = (1.0f - a.b1) * g + a.b1 * ax1[u * 32];
         const float v = (1.0f - a.b2) * (g * g) + a.b2 * ax2[u * 32];
         ax1[u * 32] = m;
         ax2[u * 32] = v;
-        TH_(u) = th + (-a.lr) * __fdividef(m * ibc1, sqrtf(v * ibc2) + a.eps);
+        const float tn = th + (-a.lr) * __fdividef(m * ibc1, sqrtf(v * ibc2) + a.eps);
+        TH_(u) = slot_ok(u) ? tn : 0.f;
       }
     }
     float* dst = trace_row(t);
@@ -345,10 +377,9 @@ PB_DEV void pb_sgw_chain(const PbPlan& pl, const PbSgArgs& a, float* wsm, int c,
   if (ALGO == PB_ALGO_PSGLD || ALGO == PB_ALGO_ADAM) {
 #pragma unroll
     for (int u = 0; u < NS; ++u) {
-      const int fi = slot_fi(u);
-      if (fi >= 0) {
-        a.aux1[cP + fi] = ax1[u * 32];
-        a.aux2[cP + fi] = ax2[u * 32];
+      if (slot_ok(u)) {
+        a.aux1[cP + slot_fi(u)] = ax1[u * 32];
+        a.aux2[cP + slot_fi(u)] = ax2[u * 32];
       }
     }
   }
@@ -356,10 +387,11 @@ PB_DEV void pb_sgw_chain(const PbPlan& pl, const PbSgArgs& a, float* wsm, int c,
   if (lane == 0 && a.flags) a.flags[c] = fl;
 #undef TH_
 #undef GA_
+#undef ZS_
 }
 
 template <int ALGO, int ACT, int DP>
-__global__ void __launch_bounds__(32 * PB_W1_WPC)
+__global__ void __launch_bounds__(32 * PB_W1_WPC, 16 / PB_W1_WPC)
 pb_sgw_kernel(const __grid_constant__ PbPlan pl, const __grid_constant__ PbSgArgs a) {
   extern __shared__ __align__(16) float pb_smem[];
   const int warp = (int)threadIdx.x >> 5, lane = (int)threadIdx.x & 31;

@@ -1,4 +1,3 @@
 timeout 900 python -m pytest tests/test_parity.py tests/test_api.py -m gpu -x -q -k "cuda_warp" > gpurun_out/w1_tests.log 2>&1; echo "pytest rc=$?" >> gpurun_out/w1_tests.log
-python scripts/sg_perf.py sgld_cfg1x "no_w1=1,,w1_min_chains=1" 3 > gpurun_out/w1_perf.log 2>&1
-python scripts/sg_perf.py sgld_cfg1 "no_w1=1,w1_min_chains=1" 2 >> gpurun_out/w1_perf.log 2>&1
-tail -n 15 gpurun_out/w1_tests.log; cat gpurun_out/w1_perf.log
+python scripts/sg_perf.py sgld_cfg1x "no_w1=1," 3 > gpurun_out/w1_perf.log 2>&1
+tail -n 5 gpurun_out/w1_tests.log; cat gpurun_out/w1_perf.log
