@@ -9,7 +9,8 @@ job (default `hmc_cfg2`: BASELINE.json configs[1], 256 chains x 200 HMC iteratio
 `e2e` = the same through the reference-signature call `pbnn_b200.mcmc.hmc` (pytrees in, `(positions, ravel_fn,
 predict_fn)` out) with HOST inputs and the positions copied back to pinned host memory inside the timed region
 (`e2e.ops_*`: the same through the flat C-ABI operator layer).  The metric is "SGLD & HMC": the default run also
-times the SGLD configurations (`workloads`: sgld_cfg1x, sgld_cfg3, sgld_cfg5) with their own rooflines.
+times the SGLD configurations and the Adam ensemble (`workloads`: sgld_cfg1x, sgld_cfg3, sgld_cfg5, adam_cfg4) with
+their own rooflines.
 Chains shard over ranks with no data-path collective (weak scaling).  With --gpus N > 1 the run adds BASELINE
 configs[4] (`sharded_cfg5`: 1024 SGLD chains per GPU of a 90-256-256-1 net -- 8192 chains on 8 GPUs -- keys
 split(PRNGKey(0), C_total)[shard]), checks on the device that a shard's chains are bit-identical to the same chains
@@ -209,7 +210,7 @@ def gpu_step_fn(ops, w, fs, X, y, th0, keys, keep_trace=True):
 
 
 ENGINE_NAMES = {0: "tiled_fp32", 1: "fused_h1_fp32", 2: "tcgen05_tf32x3", 3: "tiled_fp32_global_state",
-                4: "tcgen05_bf16x3_mlp2"}
+                4: "tcgen05_bf16x3_mlp2", 5: "warp_per_chain_fp32"}
 OPS = {"hmc": "OP_HMC", "sgld": "OP_SGLD", "psgld": "OP_PSGLD", "sghmc": "OP_SGHMC", "adam": "OP_ADAM"}
 
 
@@ -269,7 +270,8 @@ def roofline_for(ops, w, fs, ms_per_step, clocks, peaks, traffic=None):
                     note="bf16x3 products (6 passes, 3 against the exact relu masks); the step is bound by the per-"
                          "parameter noise + update work on the CUDA cores (rng_issue), not by the tensor pipe")
     return dict(common, bound="fma", peak=fma_peak, frac=achieved / fma_peak,
-                kernel="pb_hmc_kernel" if w["algo"] == "hmc" else "pb_sg_kernel",
+                kernel="pb_hmc_kernel" if w["algo"] == "hmc" else
+                ("pb_sgw_kernel" if engine == plib.ENGINE_WARP_H1 else "pb_sg_kernel"),
                 peak_source=f"FP32 FMA: 148 SM x 128 lanes x 2 x {sm_max:.0f} MHz")
 
 
@@ -554,7 +556,7 @@ def main():
     # ---- the metric is "SGLD & HMC": the SGLD configurations, device-timed like the headline -------------
     extras = {}
     if not args.no_extras:
-        for name in ("sgld_cfg1x", "sgld_cfg3", "sgld_cfg5"):
+        for name in ("sgld_cfg1x", "sgld_cfg3", "sgld_cfg5", "adam_cfg4"):
             if name == args.workload:
                 continue
             we = dict(WORKLOADS[name], name=name)
@@ -581,7 +583,8 @@ def main():
                       "evals_per_s": fin_theta.shape[0] * Xte.shape[0] / (pms * 1e-3),
                       "algorithmic_tflops": 2.0 * fin_theta.shape[0] * Xte.shape[0] * Wsum / (pms * 1e-3) / 1e12}
             del Xte, fin_theta
-            extras[name] = {"value": we["C"] * we["T"] * world / (ms_e * 1e-3), "unit": "chain-steps/s",
+            extras[name] = {"value": we["C"] * we["T"] * world / (ms_e * 1e-3),
+                            "unit": "member-steps/s" if we["algo"] == "adam" else "chain-steps/s",
                             "ms_per_step": ms_e, "steps": ks, "warmup": 3, "config": workload_config(name, we),
                             "roofline": roofline_for(ops, we, fse, ms_e, clocks, peaks, traffic_of(name)),
                             "predictive": pred_e, "chains_finite": fin}

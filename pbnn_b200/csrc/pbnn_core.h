@@ -459,7 +459,7 @@ static inline int pb_build_plan(const pbnn_mlp_spec* sp, int rows, int nstate, i
     pl->w1_oi = off;
     off += pb_r4(rows);
     pl->w1_ot = off;
-    off += (P + 127) & ~127;  // flat index -> [slot][lane] table
+    off += ((P + 127) & ~127) / 2;  // flat index -> [slot][lane] table (uint16)
     pl->w1_oz = off;
     off += (ns + 1) * 32;     // noise / trace staging in slot order (+ a dump row)
     pl->w1_oa = off;
@@ -468,7 +468,7 @@ static inline int pb_build_plan(const pbnn_mlp_spec* sp, int rows, int nstate, i
     pl->w1 = 1;
     pl->NT = 32 * PB_W1_WARPS;
     pl->smem_floats = PB_W1_WARPS * off;
-    if ((size_t)pl->smem_floats * 4 * (12 / PB_W1_WARPS) <= (size_t)(200 * 1024)) return PBNN_OK;  // >= 12 chains per SM
+    if ((size_t)off * 4 <= (size_t)(20 * 1024)) return PBNN_OK;  // >= 10 chains (warps) per SM
     pl->w1 = 0;
   }
 #endif

@@ -199,14 +199,15 @@ PB_DEV void pb_normal_n(PbKey k, const uint32_t* idx, float* z) {
 #undef PB_TF_ROUND_N
 #undef PB_TF_INJECT_N
 #if defined(__CUDA_ARCH__)
-  if (PACK && (N % 2) == 0) {
+  if constexpr (PACK && (N % 2) == 0) {
 #pragma unroll
     for (int j = 0; j < N; j += 2) pb_bits_to_normal2(x0[j] ^ x1[j], x0[j + 1] ^ x1[j + 1], z[j], z[j + 1]);
-    return;
-  }
+  } else
 #endif
+  {
 #pragma unroll
-  for (int j = 0; j < N; ++j) z[j] = pb_bits_to_normal(x0[j] ^ x1[j]);
+    for (int j = 0; j < N; ++j) z[j] = pb_bits_to_normal(x0[j] ^ x1[j]);
+  }
 }
 
 // jax.random.randint(key, (B,), 0, span)[b]; k1,k2 = split(key); mult = (2^16 % span)^2 % span

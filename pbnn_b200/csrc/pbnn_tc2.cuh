@@ -98,10 +98,18 @@ PB_DEV void pb_t2_arrive(uint32_t mbar) {
 PB_DEV void pb_t2_expect(uint32_t mbar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
 }
-PB_DEV void pb_t2_bulk(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(mbar)
-               : "memory");
+// Bulk copy global -> shared.  The source is (base, 32-bit byte offset) and the 64-bit sum is formed INSIDE the asm
+// block: with the offset arithmetic done in 64 bits in C++ (((size_t)t * ncbx + kc) * 16384 and the like), ptxas
+// 12.9 turned one of three unrolled copies of pb_tc2p_forward into a uniform-datapath ULEA that drops the upper
+// word of the address (SASS: UMOV UR7, URZ; ULEA UR6, UR6, UR32, 0xf; UBLKCP.S.G [..], [UR6], ..) -- an
+// illegal-address fault that came and went with unrelated changes to the translation unit (found with cuda-gdb).
+// A 32-bit product has defined wrap-around, so it cannot be folded into a 64-bit shift-add.
+PB_DEV void pb_t2_bulk(uint32_t dst, const void* base, uint32_t off, uint32_t bytes, uint32_t mbar) {
+  asm volatile(
+      "{\n\t.reg .u64 a;\n\tcvt.u64.u32 a, %2;\n\tadd.u64 a, a, %1;\n\t"
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [a], %3, [%4];\n\t}\n" ::"r"(dst),
+      "l"(base), "r"(off), "r"(bytes), "r"(mbar)
+      : "memory");
 }
 PB_DEV void pb_t2_fence_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 PB_DEV void pb_t2_st4(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -474,7 +482,7 @@ PB_DEV void pb_grad_tc2(const PbPlan& pl, float* sm, float* TH, int nrows, float
           const uint32_t dst = stage_begin((uint32_t)(nch * rows * 128));
           const int s = fill % PB_T2_NS;
           for (int cb = 0; cb < nch; ++cb)
-            pb_t2_bulk(dst + (uint32_t)cb * 8192u, img + ((size_t)(t * nch + cb) * img_rows + 64 * c) * 128,
+            pb_t2_bulk(dst + (uint32_t)cb * 8192u, img, (uint32_t)((t * nch + cb) * img_rows + 64 * c) * 128u,
                        (uint32_t)(rows * 128), PB_T2_BAR(PB_T2_B_WFULL + s));
           ++fill;
         }
@@ -485,7 +493,7 @@ PB_DEV void pb_grad_tc2(const PbPlan& pl, float* sm, float* TH, int nrows, float
         if (ause > 0) pb_mbar_wait(PB_T2_BAR(PB_T2_B_AEMPTY), (uint32_t)((ause - 1) & 1));
         pb_t2_expect(PB_T2_BAR(PB_T2_B_AXFULL), 3u * PB_T2_TILE);
         for (int t = 0; t < 3; ++t)
-          pb_t2_bulk(acta + (uint32_t)t * PB_T2_TILE, tc.img + ((size_t)t * ncbx + kc) * PB_T2_TILE, PB_T2_TILE,
+          pb_t2_bulk(acta + (uint32_t)t * PB_T2_TILE, tc.img, (uint32_t)(t * ncbx + kc) * PB_T2_TILE, PB_T2_TILE,
                      PB_T2_BAR(PB_T2_B_AXFULL));
         ++ause;
         row_chunk(tc.img + pl.t2_img_w1, Kx, kc, rows);
@@ -496,9 +504,9 @@ PB_DEV void pb_grad_tc2(const PbPlan& pl, float* sm, float* TH, int nrows, float
           const uint32_t bytes = (uint32_t)(Hp * 128);
           const uint32_t dst = stage_begin(bytes);
           const int s = fill % PB_T2_NS;
-          const uint8_t* src = tc.img + pl.t2_img_w2 + ((size_t)(t * nch + kc) * Hp) * 128;
+          const uint32_t so = (uint32_t)pl.t2_img_w2 + (uint32_t)((t * nch + kc) * Hp) * 128u;
           for (uint32_t o = 0; o < bytes; o += 16384u)
-            pb_t2_bulk(dst + o, src + o, bytes - o < 16384u ? bytes - o : 16384u, PB_T2_BAR(PB_T2_B_WFULL + s));
+            pb_t2_bulk(dst + o, tc.img, so + o, bytes - o < 16384u ? bytes - o : 16384u, PB_T2_BAR(PB_T2_B_WFULL + s));
           ++fill;
         }
       // G5 (K = output unit n = image ROWS): rows of chunk kc, every column block (MN-major B)
@@ -509,7 +517,7 @@ PB_DEV void pb_grad_tc2(const PbPlan& pl, float* sm, float* TH, int nrows, float
       const uint32_t xbytes = 3u * (uint32_t)ncbx * PB_T2_TILE;
       pb_t2_expect(PB_T2_BAR(PB_T2_B_XFULL), xbytes);
       for (uint32_t o = 0; o < xbytes; o += PB_T2_TILE)
-        pb_t2_bulk(ring + o, tc.img + o, PB_T2_TILE, PB_T2_BAR(PB_T2_B_XFULL));
+        pb_t2_bulk(ring + o, tc.img, o, PB_T2_TILE, PB_T2_BAR(PB_T2_B_XFULL));
     }
     __syncwarp();
   } else if (warp_u == 9) {
@@ -614,6 +622,11 @@ PB_DEV void pb_grad_tc2(const PbPlan& pl, float* sm, float* TH, int nrows, float
       commit(PB_T2_B_AEMPTY);
       commit(PB_T2_B_D2FULL + slot);
     }
+    // Tail: the commits nobody else waits for (last ring stages, last activation chunk) must have ARRIVED before the next
+    // evaluation re-initialises the barriers or the CTA exits.
+    for (int i = fill > PB_T2_NS ? fill - PB_T2_NS : 0; i < fill; ++i)
+      pb_mbar_wait(PB_T2_BAR(PB_T2_B_WEMPTY + i % PB_T2_NS), (uint32_t)((i / PB_T2_NS) & 1));
+    pb_mbar_wait(PB_T2_BAR(PB_T2_B_AEMPTY), (uint32_t)((ncbx + 3 * nch + nchy - 1) & 1));
   } else if (warp_u >= 10) {
     // =============================== noise warps ===============================
     // thread wt mirrors worker thread wt: it walks the SAME sequence of 8-weight blocks (first-layer items, then the

@@ -146,13 +146,13 @@ PB_DEV float pb_tc2p_forward(const PbPlan& pl, float* sm, const PbTc2& tc, const
         if (kc > 0) pb_mbar_wait(PB_T2_BAR(PB_T2_B_AEMPTY), (uint32_t)((kc - 1) & 1));
         pb_t2_expect(PB_T2_BAR(PB_T2_B_AXFULL), 3u * PB_T2_TILE);
         for (int t = 0; t < 3; ++t)
-          pb_t2_bulk(acta + (uint32_t)t * PB_T2_TILE, ximg + ((size_t)t * ncbx + kc) * PB_T2_TILE, PB_T2_TILE,
+          pb_t2_bulk(acta + (uint32_t)t * PB_T2_TILE, ximg, (uint32_t)(t * ncbx + kc) * PB_T2_TILE, PB_T2_TILE,
                      PB_T2_BAR(PB_T2_B_AXFULL));
         for (int t = 0; t < 3; ++t) {
           const uint32_t dst = stage_begin((uint32_t)(nch * rows * 128));
           const int s = fill % PB_T2_NS;
           for (int cb = 0; cb < nch; ++cb)
-            pb_t2_bulk(dst + (uint32_t)cb * 8192u, img1 + ((size_t)(t * nch + cb) * Kx + 64 * kc) * 128,
+            pb_t2_bulk(dst + (uint32_t)cb * 8192u, img1, (uint32_t)((t * nch + cb) * Kx + 64 * kc) * 128u,
                        (uint32_t)(rows * 128), PB_T2_BAR(PB_T2_B_WFULL + s));
           ++fill;
         }
@@ -163,9 +163,9 @@ PB_DEV float pb_tc2p_forward(const PbPlan& pl, float* sm, const PbTc2& tc, const
           const uint32_t bytes = (uint32_t)(Hp * 128);
           const uint32_t dst = stage_begin(bytes);
           const int s = fill % PB_T2_NS;
-          const uint8_t* src = img2 + ((size_t)(t * nch + kc) * Hp) * 128;
+          const uint32_t so = (uint32_t)((t * nch + kc) * Hp) * 128u;
           for (uint32_t o = 0; o < bytes; o += 16384u)
-            pb_t2_bulk(dst + o, src + o, bytes - o < 16384u ? bytes - o : 16384u, PB_T2_BAR(PB_T2_B_WFULL + s));
+            pb_t2_bulk(dst + o, img2, so + o, bytes - o < 16384u ? bytes - o : 16384u, PB_T2_BAR(PB_T2_B_WFULL + s));
           ++fill;
         }
     }
@@ -213,6 +213,13 @@ PB_DEV float pb_tc2p_forward(const PbPlan& pl, float* sm, const PbTc2& tc, const
     };
     kgemm(S0, ncbx, Kx, true, false);  // G1: Z1
     kgemm(S1, nch, Hp, false, true);   // G2: Z2
+    // Tail: every tcgen05.commit of this evaluation must have ARRIVED before the barriers are re-initialised by the next
+    // evaluation or the CTA exits.  The workers only wait for the accumulator barrier; the commits that free the last
+    // ring stages and the last activation chunk are separate asynchronous arrivals on other mbarriers, and nothing
+    // orders them before the accumulator's.
+    for (int i = fill > PB_T2_NS ? fill - PB_T2_NS : 0; i < fill; ++i)
+      pb_mbar_wait(PB_T2_BAR(PB_T2_B_WEMPTY + i % PB_T2_NS), (uint32_t)((i / PB_T2_NS) & 1));
+    pb_mbar_wait(PB_T2_BAR(PB_T2_B_AEMPTY), (uint32_t)((ncbx + nch - 1) & 1));
   } else {
     const int q = warp & 3, g = warp >> 2;
     const int b = 32 * q + lane;

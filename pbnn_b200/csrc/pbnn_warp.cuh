@@ -39,7 +39,7 @@ PB_DEV void pb_sgw_chain(const PbPlan& pl, const PbSgArgs& a, float* wsm, int c,
   float* xs = wsm + pl.w1_ox;
   float* ys = wsm + pl.w1_oy;
   float* zs = wsm + pl.w1_oz;  // [NS + 1][32]: noise / trace staging in slot order (row NS: dump row for i >= P)
-  int* tab = reinterpret_cast<int*>(wsm + pl.w1_ot);  // flat index i -> slot * 32 + owner lane
+  uint16_t* tab = reinterpret_cast<uint16_t*>(wsm + pl.w1_ot);  // flat index i -> slot * 32 + owner lane
   int* ib = reinterpret_cast<int*>(wsm + pl.w1_oi);
   float* ax1 = wsm + pl.w1_oa + lane;  // [slot][lane]
   float* ax2 = ax1 + NS * 32;
@@ -100,7 +100,7 @@ PB_DEV void pb_sgw_chain(const PbPlan& pl, const PbSgArgs& a, float* wsm, int c,
       }
       o = u * 32 + (j >> 1);
     }
-    tab[i] = o;
+    tab[i] = (uint16_t)o;
   }
   for (int i = lane; i < (NS + 1) * 32; i += 32) zs[i] = 0.f;  // pad slots read 0 forever
   __syncwarp();
@@ -205,7 +205,7 @@ PB_DEV void pb_sgw_chain(const PbPlan& pl, const PbSgArgs& a, float* wsm, int c,
     __syncwarp();  // the previous readers are done with zs
     for (int p0 = lane; p0 < P; p0 += 128) {
       uint32_t idx[4];
-      int to[4];
+      uint32_t to[4];
       float z[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {

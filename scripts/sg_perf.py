@@ -11,8 +11,10 @@ ops = default_ops()
 names = sys.argv[1].split(",") if len(sys.argv) > 1 else ["sgld_cfg3", "psgld_cfg3", "sghmc_cfg3", "adam_cfg4", "sgld_cfg5"]
 envs = sys.argv[2].split(",") if len(sys.argv) > 2 else ["", "no_tc2=1"]  # library options, "a=1+b=2"
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+over = dict(kv.split("=") for kv in sys.argv[4].split(",")) if len(sys.argv) > 4 else {}  # e.g. C=4096,T=500
 for name in names:
     w = dict(bench.WORKLOADS[name], name=name)
+    w.update({k: int(v) for k, v in over.items()})
     fs = FlatSpec(tuple(w["layers"]), w["act"], 0.1)
     Xh, yh, Xth, keys, th0 = bench.make_inputs(w, 0, 1, ops)
     X, y = (ops._as(a, torch.float32) for a in (Xh, yh))

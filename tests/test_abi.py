@@ -55,6 +55,14 @@ def test_host_side_calls_without_gpu(cuda_lib_path):
     assert lib.pbnn_workspace_bytes(spec, _lib.OP_SGLD, 32, 256) == 0
     assert lib.pbnn_plan_engine(spec, _lib.OP_HMC, 506, 256) == _lib.ENGINE_TCGEN05
     assert lib.pbnn_plan_engine(spec, _lib.OP_SGLD, 32, 256) == _lib.ENGINE_FUSED_H1
+    # many chains: one warp per chain (SG samplers and Adam; the gradient hook and HMC keep their engines)
+    for op in (_lib.OP_SGLD, _lib.OP_PSGLD, _lib.OP_SGHMC, _lib.OP_ADAM):
+        assert lib.pbnn_plan_engine(spec, op, 32, 2048) == _lib.ENGINE_WARP_H1
+        assert lib.pbnn_workspace_bytes(spec, op, 32, 2048) == 0
+    assert lib.pbnn_plan_engine(spec, _lib.OP_GRAD, 32, 2048) == _lib.ENGINE_FUSED_H1
+    assert lib.pbnn_plan_engine(spec, _lib.OP_HMC, 506, 2048) == _lib.ENGINE_TCGEN05
+    assert lib.pbnn_plan_engine(spec, _lib.OP_SGLD, 257, 2048) != _lib.ENGINE_WARP_H1  # rows no longer fit a warp's block
+    assert lib.pbnn_plan_engine(_lib.make_spec((13, 65, 1), 0, 0.1), _lib.OP_SGLD, 32, 2048) != _lib.ENGINE_WARP_H1
     assert lib.pbnn_plan_engine(spec, _lib.OP_HMC, 4096, 4) == _lib.ENGINE_TCGEN05     # X streams through TMEM, 4 tiles at a time
     assert lib.pbnn_plan_engine(spec, _lib.OP_HMC, 4097, 4) != _lib.ENGINE_TCGEN05     # larger data sets: FP32 engines
     assert lib.pbnn_plan_engine(_lib.make_spec((13, 65, 1), 0, 0.1), _lib.OP_HMC, 506, 4) != _lib.ENGINE_TCGEN05
