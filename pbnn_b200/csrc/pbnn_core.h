@@ -54,7 +54,7 @@ struct PbPlan {
   int off_xr, off_yr, off_hpart;
   // warp-per-chain engine (pbnn_warp.cuh; SG samplers / Adam on the same nets, many chains): float offsets inside a
   // warp's private shared-memory block of w1_warp_floats floats -- rows [B][4 h1_dp], targets, indices, noise, aux state
-  int w1, w1_warp_floats, w1_ox, w1_oy, w1_oi, w1_ot, w1_oz, w1_oa;
+  int w1, w1_warp_floats, w1_ox, w1_oy, w1_oi, w1_ot, w1_oz, w1_ow, w1_oa;
   // tcgen05 path (one hidden relu layer, scalar output): see pbnn_tc.cuh for the operand layouts
   int tc, tc_npad;                // tc_npad = rows rounded up to the 128-row MMA tile
   int off_mk, off_z, off_wb, off_w2s, off_tcm;
@@ -462,13 +462,15 @@ static inline int pb_build_plan(const pbnn_mlp_spec* sp, int rows, int nstate, i
     off += ((P + 127) & ~127) / 2;  // flat index -> [slot][lane] table (uint16)
     pl->w1_oz = off;
     off += (ns + 1) * 32;     // noise / trace staging in slot order (+ a dump row)
+    pl->w1_ow = off;
+    off += kd * 64 + 64 + 64 + 32;  // relu: published first-layer rows, output weights, ballots, residuals
     pl->w1_oa = off;
     off += nstate > 2 ? 2 * ns * 32 : 0;
     pl->w1_warp_floats = off;
     pl->w1 = 1;
     pl->NT = 32 * PB_W1_WARPS;
     pl->smem_floats = PB_W1_WARPS * off;
-    if ((size_t)off * 4 <= (size_t)(20 * 1024)) return PBNN_OK;  // >= 10 chains (warps) per SM
+    if ((size_t)off * 4 <= (size_t)(24 * 1024)) return PBNN_OK;  // >= 9 chains (warps) per SM
     pl->w1 = 0;
   }
 #endif

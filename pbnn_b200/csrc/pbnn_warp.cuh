@@ -103,6 +103,7 @@ PB_DEV void pb_sgw_chain(const PbPlan& pl, const PbSgArgs& a, float* wsm, int c,
     tab[i] = (uint16_t)o;
   }
   for (int i = lane; i < (NS + 1) * 32; i += 32) zs[i] = 0.f;  // pad slots read 0 forever
+  for (int i = lane; i < 64; i += 32) (wsm + pl.w1_ow + KD * 64 + 64)[i] = 0.f;  // ballots of units never evaluated
   __syncwarp();
 #define ZS_(u) zs[(u) * 32 + ((u) == NS - 1 ? 0 : lane)]
 
@@ -140,6 +141,13 @@ PB_DEV void pb_sgw_chain(const PbPlan& pl, const PbSgArgs& a, float* wsm, int c,
   };
 
   // ---- gradient of the (scaled) log-likelihood at the registers' theta: a0, a1, av0, av1, ab ----------------------
+  // relu nets take two layouts per 32-row block.  FORWARD with lane = data row: the weights are published to shared memory
+  // once per evaluation and read back as broadcasts, four hidden units per LDS.128, so a lane computes its own row's
+  // output with no cross-lane reduction at all (the unit-per-lane layout needs a 5-stage butterfly per row), and the relu
+  // pattern of a unit over the 32 rows is ONE ballot.  BACKWARD with lane = hidden-unit pair as before (the weight
+  // gradient must end up next to the weights): per row a broadcast of the residual and of x, the unit's ballot bit
+  // selects r or 0, rank-1 update in registers.  The output-layer gradient needs no pass over the rows:
+  // sum_b r_b relu(z_bj) = sum_k W[k][j] (sum_b r_b m_bj x_bk), the same accumulators before the factor v_j is applied.
   auto grad = [&]() {
 #pragma unroll
     for (int k = 0; k < KH; ++k) {
@@ -147,6 +155,87 @@ PB_DEV void pb_sgw_chain(const PbPlan& pl, const PbSgArgs& a, float* wsm, int c,
       a1[k] = make_float2(0.f, 0.f);
     }
     av0 = av1 = ab = 0.f;
+    if constexpr (ACT == PBNN_ACT_RELU) {
+      // [KD][64] first-layer rows (row d = bias, rows > d = the zero pads), then v[64], ballots[64], r[32]
+      float* const ws = wsm + pl.w1_ow;
+      float* const vs = ws + KD * 64;
+      uint32_t* const mt = reinterpret_cast<uint32_t*>(vs + 64);
+      float* const rs = vs + 128;
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < KD; ++k) *reinterpret_cast<float2*>(ws + k * 64 + j0) = make_float2(TH_(k), TH_(KD + k));
+      *reinterpret_cast<float2*>(vs + j0) = make_float2(v0, v1);
+      const int nq = (H + 3) >> 2;
+      float rsum = 0.f;
+      for (int rb = 0; rb < B; rb += 32) {
+        __syncwarp();
+        const int row = rb + lane;
+        const bool valid = row < B;
+        const int rowc = valid ? row : B - 1;
+        float4 xr[DP];
+#pragma unroll
+        for (int q = 0; q < DP; ++q) xr[q] = pb_ld4(xs + rowc * KD + 4 * q);
+        float f = 0.f;
+        const float* wq = ws;
+        for (int q = 0; q < nq; ++q, wq += 4) {
+          float2 z01 = make_float2(0.f, 0.f), z23 = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int k = 0; k < KD; ++k) {  // (rows > d: x = 0 times w = 0)
+            const float4 w = pb_ld4(wq + k * 64);
+            const float4 t = xr[k >> 2];
+            const float xk = (k & 3) == 0 ? t.x : (k & 3) == 1 ? t.y : (k & 3) == 2 ? t.z : t.w;
+            z01 = __ffma2_rn(make_float2(xk, xk), make_float2(w.x, w.y), z01);
+            z23 = __ffma2_rn(make_float2(xk, xk), make_float2(w.z, w.w), z23);
+          }
+          const float4 v = pb_ld4(wq + KD * 64);
+          f = fmaf(fmaxf(z01.x, 0.f), v.x, f);
+          f = fmaf(fmaxf(z01.y, 0.f), v.y, f);
+          f = fmaf(fmaxf(z23.x, 0.f), v.z, f);
+          f = fmaf(fmaxf(z23.y, 0.f), v.w, f);
+          const uint32_t m_0 = __ballot_sync(0xffffffffu, z01.x > 0.f), m_1 = __ballot_sync(0xffffffffu, z01.y > 0.f);
+          const uint32_t m_2 = __ballot_sync(0xffffffffu, z23.x > 0.f), m_3 = __ballot_sync(0xffffffffu, z23.y > 0.f);
+          if (lane == 0) *reinterpret_cast<uint4*>(mt + 4 * q) = make_uint4(m_0, m_1, m_2, m_3);
+        }
+        const float res = ys[rowc] - (f + b2);
+        const float r = valid ? res * a.scale : 0.f;
+        rs[lane] = r;
+        rsum += r;
+        __syncwarp();
+        const uint32_t m0 = mt[j0], m1 = mt[j0 + 1];
+        const int nr = pb_min(32, B - rb);
+        for (int bb = 0; bb < nr; ++bb) {
+          const float rr = rs[bb];
+          const uint32_t bit = 1u << bb;
+          const float d0s = (m0 & bit) ? rr : 0.f, d1s = (m1 & bit) ? rr : 0.f;
+          const float2 d0 = make_float2(d0s, d0s), d1 = make_float2(d1s, d1s);
+          const float* xp_ = xs + (rb + bb) * KD;
+#pragma unroll
+          for (int q = 0; q < DP; ++q) {
+            const float4 t = pb_ld4(xp_ + 4 * q);
+            const float2 lo = make_float2(t.x, t.y), hi = make_float2(t.z, t.w);
+            a0[2 * q] = __ffma2_rn(lo, d0, a0[2 * q]);
+            a1[2 * q] = __ffma2_rn(lo, d1, a1[2 * q]);
+            a0[2 * q + 1] = __ffma2_rn(hi, d0, a0[2 * q + 1]);
+            a1[2 * q + 1] = __ffma2_rn(hi, d1, a1[2 * q + 1]);
+          }
+        }
+      }
+      ab = pb_warp_sum(rsum);
+      float2 s0 = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < KH; ++k) {
+        s0 = __ffma2_rn(W0[k], a0[k], s0);
+        s1 = __ffma2_rn(W1[k], a1[k], s1);
+      }
+      av0 = s0.x + s0.y;
+      av1 = s1.x + s1.y;
+#pragma unroll
+      for (int k = 0; k < KH; ++k) {
+        a0[k] = make_float2(a0[k].x * v0, a0[k].y * v0);
+        a1[k] = make_float2(a1[k].x * v1, a1[k].y * v1);
+      }
+      return;
+    }
     for (int n = 0; n < B; n += NP) {
       float h0[NP], h1[NP], pf[NP];
       float4 xr[NP][DP];  // the rows stay in registers for the rank-1 update below
