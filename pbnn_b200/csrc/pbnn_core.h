@@ -152,6 +152,7 @@ static inline void pb_plan_dw(PbPlan* pl, int nw, int bt, int kcap) {
 #define PB_PLAN_TC 4  // the caller has a tcgen05 kernel for this op (HMC): allow the tensor-core layout
 #define PB_PLAN_TC2 8  // the caller can run the two-hidden-layer tcgen05 engine (SG samplers, Adam, grad hook)
 #define PB_PLAN_W1 16  // the caller can run the warp-per-chain engine (SG samplers, Adam)
+#define PB_PLAN_PRED 32  // posterior predictive: the MMA tile rows are test points (always full), narrower nets still pay
 #define PB_W1_WARPS 1  // warps (= chains) per CTA of the warp-per-chain engine (finest balance over the SMs)
 
 #define PB_T2_NT 576       // 8 worker warps + 1 TMA warp + 1 MMA-issue warp + 8 noise warps
@@ -427,7 +428,8 @@ static inline int pb_build_plan(const pbnn_mlp_spec* sp, int rows, int nstate, i
 #if !defined(PB_EMU)
   // two-hidden-layer tcgen05 engine: d-H-H-1 relu, one 128-row tile per gradient evaluation
   if ((flags & PB_PLAN_TC2) && pl->nl == 3 && pl->s == 1 && !hetero && sp->activation == PBNN_ACT_RELU &&
-      sp->dims[1] == sp->dims[2] && sp->dims[1] <= 256 && sp->dims[1] >= pb_opt(PB_OPT_TC2_MIN_H, 64) &&
+      sp->dims[1] == sp->dims[2] && sp->dims[1] <= 256 &&
+      sp->dims[1] >= pb_opt(PB_OPT_TC2_MIN_H, (flags & PB_PLAN_PRED) ? 32 : 64) &&
       pl->d + 1 <= 128 && rows <= 128 && rows >= pb_opt(PB_OPT_TC2_MIN_ROWS, 64) && !(flags & PB_PLAN_ACC) &&
       !pb_opt(PB_OPT_NO_TC, 0) && !pb_opt(PB_OPT_NO_TC2, 0)) {
     pb_layout_tc2(pl, sp, rows);

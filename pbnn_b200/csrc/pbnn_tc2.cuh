@@ -58,7 +58,7 @@ __device__ __noinline__ float4 pb_t2_normal4(uint32_t k0, uint32_t k1, uint32_t 
   k.k1 = k1;
   const uint32_t ix[4] = {i0, i1, i2, i3};
   float z[4];
-  pb_normal_n<4>(k, ix, z);
+  pb_normal_n<4, true>(k, ix, z);
   return make_float4(z[0], z[1], z[2], z[3]);
 }
 
@@ -646,7 +646,7 @@ PB_DEV void pb_grad_tc2(const PbPlan& pl, float* sm, float* TH, int nrows, float
           float z[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) ix[j] = (uint32_t)(fi0 + j * fis);
-          pb_normal_n<8>(nkey, ix, z);
+          pb_normal_n<8, true>(nkey, ix, z);
 #pragma unroll
           for (int j = 0; j < 8; ++j) zr[slot * PB_T2_ZSLOT + j * PB_T2_WORKERS] = z[j];
         }

@@ -209,7 +209,8 @@ def test_out_of_range_indices_are_clamped_and_flagged(eng):
 
 
 @pytest.mark.parametrize("layers,S,M", [(CFG3[0], 37, 1000), (CFG5[0], 5, 300), ((20, 64, 64, 1), 300, 130),
-                                        ((70, 160, 160, 1), 3, 64), (CFG3[0], 1, 513)])
+                                        ((70, 160, 160, 1), 3, 64), (CFG3[0], 1, 513), (CFG4[0], 64, 700),
+                                        ((5, 32, 32, 1), 9, 129), ((8, 33, 33, 1), 40, 200)])
 def test_predict_two_hidden_layers_on_tensor_cores(cuda_ops, layers, S, M):
     """predict_fn + moments (langevin.py:75-76, metrics_prediction_intervals.py:188) for the nets pbnn's MLP produces:
     tcgen05 kernel (pbnn_tc2_pred.cuh) vs the float64 oracle and vs the FP32 kernel; ragged tiles, one sample, more
