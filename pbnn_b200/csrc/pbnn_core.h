@@ -446,10 +446,12 @@ static inline int pb_build_plan(const pbnn_mlp_spec* sp, int rows, int nstate, i
     pl->tc = 0;
   }
 #if !defined(PB_EMU)
-  // Warp-per-chain engine: one-hidden-layer nets, B <= 256 rows resident per warp, enough chains to fill the SMs with
-  // independent warps (below that the multi-warp fused path has the shorter step latency).
+  // Warp-per-chain engine: one-hidden-layer nets, B <= 256 rows resident per warp, more chains than the multi-warp
+  // fused path can keep co-resident (two CTAs per SM).  Measured, 8-50-1 B = 32 (M chain-steps/s, fused | warp):
+  // 148 chains 39 | 30, 296 chains 62 | 59, 444 chains 55 | 88, 2048 chains 91-101 | 186: a lone warp advances a chain in
+  // ~5 us per step against ~3.8 us for eight co-operating warps, but sixteen of them share an SM.
   if (h1_ok && (flags & PB_PLAN_W1) && !pb_opt(PB_OPT_NO_W1, 0) && rows <= 256 &&
-      chains_hint >= pb_opt(PB_OPT_W1_MIN_CHAINS, 4 * 148)) {
+      chains_hint >= pb_opt(PB_OPT_W1_MIN_CHAINS, 2 * 148 + 1)) {
     pl->NT = 256;
     pb_layout(pl, sp, rows, nstate, maxbt, 1, 1, 0, 1);
     const int kd = 4 * pl->h1_dp, ns = 2 * kd + 3;

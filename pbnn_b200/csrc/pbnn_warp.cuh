@@ -234,8 +234,7 @@ PB_DEV void pb_sgw_chain(const PbPlan& pl, const PbSgArgs& a, float* wsm, int c,
         a0[k] = make_float2(a0[k].x * v0, a0[k].y * v0);
         a1[k] = make_float2(a1[k].x * v1, a1[k].y * v1);
       }
-      return;
-    }
+    } else {
     for (int n = 0; n < B; n += NP) {
       float h0[NP], h1[NP], pf[NP];
       float4 xr[NP][DP];  // the rows stay in registers for the rank-1 update below
@@ -287,6 +286,7 @@ PB_DEV void pb_sgw_chain(const PbPlan& pl, const PbSgArgs& a, float* wsm, int c,
         ab += r;
       }
     }
+    }  // (other activations: the unit-per-lane forward, one butterfly per row pair)
   };
 
   // ---- noise: jax.random.normal(key, (P,))[i] -> zs[tab[i]], lane l draws i = l + 32 m (4 threefry chains in flight)
