@@ -91,6 +91,8 @@ int pbnn_plan_query(const pbnn_mlp_spec* spec, int rows, int n_state, int32_t ou
                                       bf16x3 tensor-core engine with TMA-streamed weights (pbnn_tc2.cuh)           */
 #define PBNN_ENGINE_WARP_H1 5  /* SG samplers / Adam, one hidden layer, scalar output, many chains: one warp per chain,
                                   weights in registers for the whole run (pbnn_warp.cuh)                            */
+#define PBNN_ENGINE_WARP_MLP2 6 /* Adam (deep ensembles, MAP), two equal hidden relu layers, H <= 64, d + 1 <= 16,
+                                   B <= 32: one warp per member, weights in its shared-memory block (pbnn_warp2.cuh) */
 int pbnn_plan_engine(const pbnn_mlp_spec* spec, int op, int rows, int C);
 
 /* Workspace.  Models whose parameter-sized state does not fit shared memory (e.g. 90-256-256-1, P = 89 345) keep it in

@@ -19,6 +19,7 @@
 
 #include "pbnn_engine.cuh"
 #include "pbnn_warp.cuh"
+#include "pbnn_warp2.cuh"
 #include "pbnn_tc2_pred.cuh"
 
 #if defined(PB_PROFILE)
@@ -691,6 +692,18 @@ static int pb_sg_dispatch(const PbPlan& pl, const PbSgArgs& a, int C, void* stre
     const int cap = pb_opt(PB_OPT_TC2_CTAS, 0);  // experiments: fewer persistent CTAs (smaller L2 working set)
     if (cap > 0 && cap < nsm) nsm = cap;
     return pb_launch(pb_sg_tc2_kernel<ALGO>, pl, a, dim3(C < nsm ? C : nsm), stream);
+  }
+  if constexpr (ALGO == PB_ALGO_ADAM) {
+    if (pl.w2) {  // Adam for small two-hidden-layer relu nets: one four-warp CTA per member
+#define PB_W2_LAUNCH(DP_) return pb_launch(pb_adam_w2_kernel<DP_>, pl, a, dim3(C), stream);
+      switch (pl.w2_dp) {
+        case 1: PB_W2_LAUNCH(1)
+        case 2: PB_W2_LAUNCH(2)
+        case 3: PB_W2_LAUNCH(3)
+        default: PB_W2_LAUNCH(4)
+      }
+#undef PB_W2_LAUNCH
+    }
   }
   if constexpr (ALGO != PB_ALGO_GRAD) {
     if (pl.w1) {  // warp-per-chain engine: PB_W1_WPC chains per CTA, DP = float4 chunks of an augmented input row

@@ -55,6 +55,9 @@ struct PbPlan {
   // warp-per-chain engine (pbnn_warp.cuh; SG samplers / Adam on the same nets, many chains): float offsets inside a
   // warp's private shared-memory block of w1_warp_floats floats -- rows [B][4 h1_dp], targets, indices, noise, aux state
   int w1, w1_warp_floats, w1_ox, w1_oy, w1_oi, w1_ot, w1_oz, w1_ow, w1_oa;
+  // Adam for small two-hidden-layer relu nets, four warps per member (pbnn_warp2.cuh): float offsets inside the CTA's block;
+  // w2_jr = roundup4(H + 1) rows of the layer-2 weights, w2_pa = activation pitch (= 4 mod 8: conflict-free LDS.128)
+  int w2, w2_warp_floats, w2_dp, w2_jr, w2_pa, w2_ox, w2_ow1, w2_ow2, w2_ow3, w2_oh, w2_os, w2_oz, w2_od;
   // tcgen05 path (one hidden relu layer, scalar output): see pbnn_tc.cuh for the operand layouts
   int tc, tc_npad;                // tc_npad = rows rounded up to the 128-row MMA tile
   int off_mk, off_z, off_wb, off_w2s, off_tcm;
@@ -82,12 +85,12 @@ enum {
   PB_OPT_DW_KS = 0, PB_OPT_NW, PB_OPT_NO_RESIDENT, PB_OPT_NO_H1, PB_OPT_NO_TC, PB_OPT_BT, PB_OPT_TWO_CTA,
   PB_OPT_ONE_CTA, PB_OPT_FORCE_GSTATE, PB_OPT_NO_SCHED, PB_OPT_SEG_LEN, PB_OPT_DEBUG, PB_OPT_PRED_TPC,
   PB_OPT_PRED_CHUNKS, PB_OPT_TC2_MIN_H, PB_OPT_TC2_MIN_ROWS, PB_OPT_NO_TC2, PB_OPT_TC2_CTAS, PB_OPT_TC2_NZ, PB_OPT_TC2_NOHELP, PB_OPT_NO_W1,
-  PB_OPT_W1_MIN_CHAINS, PB_OPT_COUNT
+  PB_OPT_W1_MIN_CHAINS, PB_OPT_NO_W2, PB_OPT_COUNT
 };
 static const char* const pb_opt_names[PB_OPT_COUNT] = {
     "dw_ks", "nw", "no_resident", "no_h1", "no_tc", "bt", "two_cta", "one_cta", "force_gstate", "no_sched", "seg_len",
     "debug", "pred_tpc", "pred_chunks", "tc2_min_h", "tc2_min_rows", "no_tc2", "tc2_ctas", "tc2_nz", "tc2_nohelp",
-    "no_w1", "w1_min_chains"};
+    "no_w1", "w1_min_chains", "no_w2"};
 #define PB_OPT_UNSET (-2147483647 - 1)
 inline int* pb_opt_table() {
   static int t[PB_OPT_COUNT];
@@ -152,6 +155,7 @@ static inline void pb_plan_dw(PbPlan* pl, int nw, int bt, int kcap) {
 #define PB_PLAN_TC 4  // the caller has a tcgen05 kernel for this op (HMC): allow the tensor-core layout
 #define PB_PLAN_TC2 8  // the caller can run the two-hidden-layer tcgen05 engine (SG samplers, Adam, grad hook)
 #define PB_PLAN_W1 16  // the caller can run the warp-per-chain engine (SG samplers, Adam)
+#define PB_PLAN_W2 64  // the caller is the Adam trainer: small two-hidden-layer relu nets may run one warp per member
 #define PB_PLAN_PRED 32  // posterior predictive: the MMA tile rows are test points (always full), narrower nets still pay
 #define PB_W1_WARPS 1  // warps (= chains) per CTA of the warp-per-chain engine (finest balance over the SMs)
 
@@ -426,6 +430,37 @@ static inline int pb_build_plan(const pbnn_mlp_spec* sp, int rows, int nstate, i
 #endif
   const int nw_env = pb_opt(PB_OPT_NW, 0);
 #if !defined(PB_EMU)
+  // four-warps-per-member Adam (pbnn_warp2.cuh): d-H-H-1 relu, H <= 64, d + 1 <= 16, B <= 32 (BASELINE configs[3])
+  if ((flags & PB_PLAN_W2) && pl->nl == 3 && pl->s == 1 && !hetero && sp->activation == PBNN_ACT_RELU &&
+      sp->dims[1] == sp->dims[2] && sp->dims[1] <= 64 && pl->d + 1 <= 16 && rows <= 32 && !pb_opt(PB_OPT_NO_W2, 0)) {
+    const int H = sp->dims[1], kd = pb_r4(pl->d + 1);
+    pl->w2 = 1;
+    pl->w2_dp = kd / 4;
+    pl->w2_jr = pb_r4(H + 1);
+    pl->w2_pa = (pl->w2_jr % 8) == 4 ? pl->w2_jr : pl->w2_jr + 4;
+    int off = 0;
+    pl->w2_ox = off;
+    off += 32 * kd;
+    pl->w2_ow1 = off;
+    off += kd * 64;
+    pl->w2_ow2 = off;
+    off += pl->w2_jr * 64;
+    pl->w2_ow3 = off;
+    off += 64 + 4 * 32 + 36;  // w3, per-warp partial outputs, residuals (+ the broadcast slot of b3)
+    pl->w2_oh = off;
+    off += 32 * pl->w2_pa;
+    pl->w2_os = off;
+    off += 32 * pl->w2_pa;
+    pl->w2_oz = off;
+    off += 32 * pl->w2_pa;
+    pl->w2_od = off;
+    off += 32 * pl->w2_pa + 64;  // (+ slack: lanes of the last row read a pair beyond the padded width)
+    pl->w2_warp_floats = off;
+    pl->NT = 128;
+    pl->BT = 32;
+    pl->smem_floats = off;
+    return PBNN_OK;
+  }
   // two-hidden-layer tcgen05 engine: d-H-H-1 relu, one 128-row tile per gradient evaluation
   if ((flags & PB_PLAN_TC2) && pl->nl == 3 && pl->s == 1 && !hetero && sp->activation == PBNN_ACT_RELU &&
       sp->dims[1] == sp->dims[2] && sp->dims[1] <= 256 &&

@@ -57,7 +57,8 @@ def test_engines_selected_for_the_baseline_shapes(cuda_ops):
     for op in (_lib.OP_SGLD, _lib.OP_PSGLD, _lib.OP_SGHMC, _lib.OP_GRAD):
         assert e(CFG3[0], op, 128, 1024) == _lib.ENGINE_TCGEN05_MLP2
         assert e(CFG5[0], op, 128, 1024) == _lib.ENGINE_TCGEN05_MLP2
-    assert e(CFG4[0], _lib.OP_ADAM, 32, 512) == _lib.ENGINE_TILED  # too small for a 128-row MMA tile to pay
+    assert e(CFG4[0], _lib.OP_ADAM, 32, 512) == _lib.ENGINE_WARP_MLP2  # too small for a 128-row MMA tile: one warp per member
+    assert e(CFG4[0], _lib.OP_SGLD, 32, 512) == _lib.ENGINE_TILED
     cuda_ops.set_option("no_tc2", 1)
     assert e(CFG3[0], _lib.OP_SGLD, 128, 1024) == _lib.ENGINE_TILED
     assert e(CFG5[0], _lib.OP_SGLD, 128, 1024) == _lib.ENGINE_TILED_GLOBAL_STATE
