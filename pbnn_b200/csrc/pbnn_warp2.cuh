@@ -77,7 +77,12 @@ PB_DEV void pb_adam_w2_member(const PbPlan& pl, const PbSgArgs& a, float* sm, in
     const float g = -(gll - th * pl.inv_pv);  // gradient of the loss -logposterior
     m = (1.0f - a.b1) * g + a.b1 * m;
     v = (1.0f - a.b2) * (g * g) + a.b2 * v;
-    const float tn = th + (-a.lr) * __fdividef(m * ibc1, sqrtf(v * ibc2) + a.eps);
+    // (sqrt.approx / rcp.approx: 2^-22 relative each, on a step of relative size lr -- the IEEE sqrtf + the range
+    //  handling of __fdividef cost ~30 of the 45 instructions of this update, 3 051 times per step)
+    float sq, rc;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(v * ibc2));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(sq + a.eps));
+    const float tn = th + (-a.lr) * ((m * ibc1) * rc);
     return ok ? tn : th;
   };
 
@@ -98,8 +103,11 @@ PB_DEV void pb_adam_w2_member(const PbPlan& pl, const PbSgArgs& a, float* sm, in
     float xr[KD];
     {
       const float* xp = a.X + (size_t)v * d;
+      float xl[KD];
 #pragma unroll
-      for (int k = 0; k < KD; ++k) xr[k] = k < d ? xp[k] : (k == d ? 1.f : 0.f);
+      for (int k = 0; k < KD; ++k) xl[k] = xp[k < d ? k : 0];  // (all loads first, the selects after: see phase G)
+#pragma unroll
+      for (int k = 0; k < KD; ++k) xr[k] = k < d ? xl[k] : (k == d ? 1.f : 0.f);
     }
     const float yb = a.y[v];
     if (warp == 0) {
@@ -108,6 +116,7 @@ PB_DEV void pb_adam_w2_member(const PbPlan& pl, const PbSgArgs& a, float* sm, in
         pb_st4(xs + lane * KD + 4 * q, float4{xr[4 * q], xr[4 * q + 1], xr[4 * q + 2], xr[4 * q + 3]});
     }
 
+    PB_MARK(1)
     // ---- B. layer 1 (row layout; warp w: output quads w, w + 4, ..): H1s[b][j] = relu(x_b . W1[:, j] + b1_j) -----------
     for (int q = warp; q < nq; q += NW) {
       const float* wq = W1s + 4 * q;
@@ -124,6 +133,7 @@ PB_DEV void pb_adam_w2_member(const PbPlan& pl, const PbSgArgs& a, float* sm, in
     if (warp == (H >> 2) % NW) h1row[H] = 1.f;  // bias input of layer 2, after the quad that covers column H (if any)
     __syncthreads();
 
+    PB_MARK(2)
     // ---- C. layer 2 (row layout; warp w: output quads w, w + 4, w + 8, w + 12): S2s = relu(z2), partial w3 . relu(z2) ---
     {
       float2 acc[4][2];
@@ -163,6 +173,7 @@ PB_DEV void pb_adam_w2_member(const PbPlan& pl, const PbSgArgs& a, float* sm, in
     }
     __syncthreads();
 
+    PB_MARK(3)
     // ---- D. residual (every warp), dZ2 = r w3 [z2 > 0] for ALL units in registers (the next phase contracts over them);
     //         warp w publishes its own quads of it ------------------------------------------------------------------------
     const float f = ((fps[lane] + fps[32 + lane]) + fps[64 + lane]) + fps[96 + lane];
@@ -183,6 +194,7 @@ PB_DEV void pb_adam_w2_member(const PbPlan& pl, const PbSgArgs& a, float* sm, in
       }
     }
 
+    PB_MARK(4)
     // ---- F. dZ1 (row layout; warp w: input quads w, w + 4, ..): D1s[b][j] = [h1_bj > 0] sum_n dZ2_bn W2[j][n] -------------
     for (int jq = warp; jq < nq; jq += NW) {
       const float4 h4 = pb_ld4(h1row + 4 * jq);
@@ -191,19 +203,23 @@ PB_DEV void pb_adam_w2_member(const PbPlan& pl, const PbSgArgs& a, float* sm, in
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj, wr += 64) {
         const float hv = jj == 0 ? h4.x : jj == 1 ? h4.y : jj == 2 ? h4.z : h4.w;
-        float2 s = make_float2(0.f, 0.f);
+        float2 s0 = make_float2(0.f, 0.f), s1 = s0, s2 = s0, s3 = s0;  // (four chains: 32 dependent FFMA2 otherwise)
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          const float4 w = pb_ld4(wr + 4 * q);
-          s = __ffma2_rn(make_float2(w.x, w.y), dz[q][0], s);
-          s = __ffma2_rn(make_float2(w.z, w.w), dz[q][1], s);
+        for (int q = 0; q < 16; q += 2) {
+          const float4 w = pb_ld4(wr + 4 * q), w2 = pb_ld4(wr + 4 * q + 4);
+          s0 = __ffma2_rn(make_float2(w.x, w.y), dz[q][0], s0);
+          s1 = __ffma2_rn(make_float2(w.z, w.w), dz[q][1], s1);
+          s2 = __ffma2_rn(make_float2(w2.x, w2.y), dz[q + 1][0], s2);
+          s3 = __ffma2_rn(make_float2(w2.z, w2.w), dz[q + 1][1], s3);
         }
+        const float2 s = __fadd2_rn(__fadd2_rn(s0, s1), __fadd2_rn(s2, s3));
         e4[jj] = (4 * jq + jj < H && hv > 0.f) ? s.x + s.y : 0.f;  // (row H of W2s is the bias, not an input unit)
       }
       pb_st4(d1row + 4 * jq, float4{e4[0], e4[1], e4[2], e4[3]});
     }
     __syncthreads();  // Z2s, D1s, rs complete; every read of the OLD W2 is done
 
+    PB_MARK(5)
     // ---- G. dW2, db2 (unit layout, 8 input units per pass, pass p by warp p % NW) + Adam on exactly those weights --------
     for (int j0 = 8 * warp; j0 <= H; j0 += 8 * NW) {
       float2 acc[8], mo[8], vo[8];
@@ -211,15 +227,18 @@ PB_DEV void pb_adam_w2_member(const PbPlan& pl, const PbSgArgs& a, float* sm, in
       for (int i = 0; i < 8; ++i) {  // the moments of this pass: in flight during the row loop
         const int j = j0 + i;
         const int fi = (j < H ? L1.fw + j * H : L1.fb) + n0;
-        const bool l0 = ok0 && j <= H, l1 = ok1 && j <= H;
-        mo[i] = make_float2(l0 ? M[fi] : 0.f, l1 ? M[fi + 1] : 0.f);
-        vo[i] = make_float2(l0 ? V[fi] : 0.f, l1 ? V[fi + 1] : 0.f);
+        // (a weight that does not exist reads slot 0 and never stores: a select on the loaded value would make the
+        //  loads wait for each other -- the zero would be written to the register the load is still filling)
+        const int f0 = (ok0 && j <= H) ? fi : 0, f1 = (ok1 && j <= H) ? fi + 1 : 0;
+        mo[i] = make_float2(M[f0], M[f1]);
+        vo[i] = make_float2(V[f0], V[f1]);
         acc[i] = make_float2(0.f, 0.f);
       }
       const bool two = j0 + 4 < JR;  // (the pass covers one or two quads of input units)
       const float* hp = H1s + j0;
       const float* zp = Z2s + n0c;
-      for (int b = 0; b < 32; ++b, hp += PA, zp += PA) {
+#pragma unroll 4
+      for (int b = 0; b < 32; ++b, hp += PA, zp += PA) {  // (unrolled: the loads of four rows are in flight together)
         const float2 d2 = *reinterpret_cast<const float2*>(zp);
         const float4 h4 = pb_ld4(hp);
         acc[0] = __ffma2_rn(make_float2(h4.x, h4.x), d2, acc[0]);
@@ -259,36 +278,24 @@ PB_DEV void pb_adam_w2_member(const PbPlan& pl, const PbSgArgs& a, float* sm, in
       }
     }
 
-    // ---- H. (last warp, whose dW2 pass is the short one) dW1, db1, dw3, db3 (unit layout) + Adam ------------------------
+    PB_MARK(6)
+    // ---- H. dW1, db1 (unit layout, warp NW - 1) and dw3, db3 (warp NW - 2: its last dW2 pass is the short one) + Adam ----
     if (warp == NW - 1) {
       float2 a0[KH], a1[KH], mo[KD], vo[KD];
-      float m3[3], v3[3];
 #pragma unroll
       for (int k = 0; k < KH; ++k) a0[k] = a1[k] = make_float2(0.f, 0.f);
 #pragma unroll
       for (int k = 0; k < KD; ++k) {
         const int fi = (k < d ? L0.fw + k * H : L0.fb) + n0;
-        const bool l0 = ok0 && k <= d, l1 = ok1 && k <= d;
-        mo[k] = make_float2(l0 ? M[fi] : 0.f, l1 ? M[fi + 1] : 0.f);
-        vo[k] = make_float2(l0 ? V[fi] : 0.f, l1 ? V[fi + 1] : 0.f);
+        const int f0 = (ok0 && k <= d) ? fi : 0, f1 = (ok1 && k <= d) ? fi + 1 : 0;
+        mo[k] = make_float2(M[f0], M[f1]);
+        vo[k] = make_float2(V[f0], V[f1]);
       }
-      m3[0] = ok0 ? M[L2.fw + n0] : 0.f;
-      v3[0] = ok0 ? V[L2.fw + n0] : 0.f;
-      m3[1] = ok1 ? M[L2.fw + n0 + 1] : 0.f;
-      v3[1] = ok1 ? V[L2.fw + n0 + 1] : 0.f;
-      m3[2] = M[L2.fb];
-      v3[2] = V[L2.fb];
-      float2 g3 = make_float2(0.f, 0.f);
-      float gb3 = 0.f;
       const float* dp = D1s + n0c;
-      const float* sp = S2s + n0c;
       const float* xp = xs;
-      for (int b = 0; b < 32; ++b, dp += PA, sp += PA, xp += KD) {
+#pragma unroll 4
+      for (int b = 0; b < 32; ++b, dp += PA, xp += KD) {
         const float2 d1 = *reinterpret_cast<const float2*>(dp);
-        const float2 h2 = *reinterpret_cast<const float2*>(sp);
-        const float rb = rs[b];
-        g3 = __ffma2_rn(make_float2(rb, rb), h2, g3);  // dw3_n = sum_b r_b relu(z2_bn)
-        gb3 += rb;                                      // db3   = sum_b r_b
         const float2 dx = make_float2(d1.x, d1.x), dy = make_float2(d1.y, d1.y);
 #pragma unroll
         for (int q = 0; q < DP; ++q) {
@@ -307,14 +314,6 @@ PB_DEV void pb_adam_w2_member(const PbPlan& pl, const PbSgArgs& a, float* sm, in
           th.y = adam(th.y, (k & 1) ? a1[k >> 1].y : a1[k >> 1].x, mo[k].y, vo[k].y, ok1);
           *reinterpret_cast<float2*>(W1s + k * 64 + n0) = th;
         }
-      {
-        float2 th = *reinterpret_cast<const float2*>(w3s + n0);
-        th.x = adam(th.x, g3.x, m3[0], v3[0], ok0);
-        th.y = adam(th.y, g3.y, m3[1], v3[1], ok1);
-        *reinterpret_cast<float2*>(w3s + n0) = th;
-      }
-      const float b3n = adam(b3, gb3, m3[2], v3[2], true);
-      if (lane == 0) rs[32] = b3n;  // (published to the other warps behind the barrier below)
 #pragma unroll
       for (int k = 0; k < KD; ++k) {
         const int fi = (k < d ? L0.fw + k * H : L0.fb) + n0;
@@ -327,6 +326,31 @@ PB_DEV void pb_adam_w2_member(const PbPlan& pl, const PbSgArgs& a, float* sm, in
           V[fi + 1] = vo[k].y;
         }
       }
+    }
+    if (warp == NW - 2) {
+      float m3[3], v3[3];
+      m3[0] = M[ok0 ? L2.fw + n0 : 0];
+      v3[0] = V[ok0 ? L2.fw + n0 : 0];
+      m3[1] = M[ok1 ? L2.fw + n0 + 1 : 0];
+      v3[1] = V[ok1 ? L2.fw + n0 + 1 : 0];
+      m3[2] = M[L2.fb];
+      v3[2] = V[L2.fb];
+      float2 g3 = make_float2(0.f, 0.f);
+      float gb3 = 0.f;
+      const float* sp = S2s + n0c;
+#pragma unroll 4
+      for (int b = 0; b < 32; ++b, sp += PA) {
+        const float2 h2 = *reinterpret_cast<const float2*>(sp);
+        const float rb = rs[b];
+        g3 = __ffma2_rn(make_float2(rb, rb), h2, g3);  // dw3_n = sum_b r_b relu(z2_bn)
+        gb3 += rb;                                      // db3   = sum_b r_b
+      }
+      float2 th = *reinterpret_cast<const float2*>(w3s + n0);
+      th.x = adam(th.x, g3.x, m3[0], v3[0], ok0);
+      th.y = adam(th.y, g3.y, m3[1], v3[1], ok1);
+      *reinterpret_cast<float2*>(w3s + n0) = th;
+      const float b3n = adam(b3, gb3, m3[2], v3[2], true);
+      if (lane == 0) rs[32] = b3n;  // (published to the other warps behind the barrier below)
       if (ok0) {
         M[L2.fw + n0] = m3[0];
         V[L2.fw + n0] = v3[0];
@@ -342,6 +366,7 @@ PB_DEV void pb_adam_w2_member(const PbPlan& pl, const PbSgArgs& a, float* sm, in
     }
     __syncthreads();  // the new weights are visible to the next step
     b3 = rs[32];
+    PB_MARK(7)
   }
 
   // ---- final state ----------------------------------------------------------------------------------------------------
@@ -376,6 +401,9 @@ __global__ void __launch_bounds__(32 * PB_W2_NW, 4)
 pb_adam_w2_kernel(const __grid_constant__ PbPlan pl, const __grid_constant__ PbSgArgs a) {
   extern __shared__ __align__(16) float pb_smem[];
   const int c = (int)blockIdx.x;
+#if defined(PB_PROFILE)
+  if (blockIdx.x == 0 && threadIdx.x == 0) pb_prof_last = clock64();
+#endif
   if (threadIdx.x == 0 && a.flags) a.flags[c] = 0u;
   __syncthreads();
   pb_adam_w2_member<DP>(pl, a, pb_smem, c);
