@@ -87,9 +87,11 @@ PB_DEV void pb_adam_w2_member(const PbPlan& pl, const PbSgArgs& a, float* sm, in
   };
 
   for (int t = 0; t < a.T; ++t) {
-    const float cnt = (float)(a.count0 + t + 1);
-    ibc1 = 1.0f / (1.0f - powf(a.b1, cnt));
-    ibc2 = 1.0f / (1.0f - powf(a.b2, cnt));
+    if (tid == 0) {  // bias corrections of this step (published behind the first barrier)
+      const float cnt = (float)(a.count0 + t + 1);
+      rs[33] = 1.0f / (1.0f - powf(a.b1, cnt));
+      rs[34] = 1.0f / (1.0f - powf(a.b2, cnt));
+    }
 
     // ---- A. this step's minibatch row of the lane (every warp keeps it in registers; clamped like a JAX gather) ------
     int v = 0;
@@ -131,6 +133,8 @@ PB_DEV void pb_adam_w2_member(const PbPlan& pl, const PbSgArgs& a, float* sm, in
     }
     __syncthreads();
     if (warp == (H >> 2) % NW) h1row[H] = 1.f;  // bias input of layer 2, after the quad that covers column H (if any)
+    ibc1 = rs[33];
+    ibc2 = rs[34];
     __syncthreads();
 
     PB_MARK(2)
@@ -222,21 +226,20 @@ PB_DEV void pb_adam_w2_member(const PbPlan& pl, const PbSgArgs& a, float* sm, in
     PB_MARK(5)
     // ---- G. dW2, db2 (unit layout, 8 input units per pass, pass p by warp p % NW) + Adam on exactly those weights --------
     for (int j0 = 8 * warp; j0 <= H; j0 += 8 * NW) {
+      if (!ok0) continue;  // (lanes beyond the net's width own no weights; nothing below is warp-collective)
       float2 acc[8], mo[8], vo[8];
+      const int o1 = ok1 ? 1 : 0;  // (odd H: the last lane's second unit does not exist -- it reads its first one twice)
 #pragma unroll
       for (int i = 0; i < 8; ++i) {  // the moments of this pass: in flight during the row loop
-        const int j = j0 + i;
+        const int j = j0 + i <= H ? j0 + i : H;  // (rows beyond the bias row re-read it and never store)
         const int fi = (j < H ? L1.fw + j * H : L1.fb) + n0;
-        // (a weight that does not exist reads slot 0 and never stores: a select on the loaded value would make the
-        //  loads wait for each other -- the zero would be written to the register the load is still filling)
-        const int f0 = (ok0 && j <= H) ? fi : 0, f1 = (ok1 && j <= H) ? fi + 1 : 0;
-        mo[i] = make_float2(M[f0], M[f1]);
-        vo[i] = make_float2(V[f0], V[f1]);
+        mo[i] = make_float2(M[fi], M[fi + o1]);
+        vo[i] = make_float2(V[fi], V[fi + o1]);
         acc[i] = make_float2(0.f, 0.f);
       }
       const bool two = j0 + 4 < JR;  // (the pass covers one or two quads of input units)
       const float* hp = H1s + j0;
-      const float* zp = Z2s + n0c;
+      const float* zp = Z2s + n0;
 #pragma unroll 4
       for (int b = 0; b < 32; ++b, hp += PA, zp += PA) {  // (unrolled: the loads of four rows are in flight together)
         const float2 d2 = *reinterpret_cast<const float2*>(zp);
@@ -256,24 +259,19 @@ PB_DEV void pb_adam_w2_member(const PbPlan& pl, const PbSgArgs& a, float* sm, in
       float* wp = W2s + j0 * 64 + n0;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        if (j0 + i <= H) {
+        if (j0 + i <= H) {  // (uniform)
+          const int j = j0 + i;
+          const int fi = (j < H ? L1.fw + j * H : L1.fb) + n0;
           float2 th = *reinterpret_cast<const float2*>(wp + i * 64);
-          th.x = adam(th.x, acc[i].x, mo[i].x, vo[i].x, ok0);
+          th.x = adam(th.x, acc[i].x, mo[i].x, vo[i].x, true);
           th.y = adam(th.y, acc[i].y, mo[i].y, vo[i].y, ok1);
           *reinterpret_cast<float2*>(wp + i * 64) = th;
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int j = j0 + i;
-        const int fi = (j < H ? L1.fw + j * H : L1.fb) + n0;
-        if (ok0 && j <= H) {
           M[fi] = mo[i].x;
           V[fi] = vo[i].x;
-        }
-        if (ok1 && j <= H) {
-          M[fi + 1] = mo[i].y;
-          V[fi + 1] = vo[i].y;
+          if (ok1) {
+            M[fi + 1] = mo[i].y;
+            V[fi + 1] = vo[i].y;
+          }
         }
       }
     }
