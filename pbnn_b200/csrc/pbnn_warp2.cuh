@@ -145,17 +145,19 @@ PB_DEV void pb_adam_w2_member(const PbPlan& pl, const PbSgArgs& a, float* sm, in
       for (int u = 0; u < 4; ++u) acc[u][0] = acc[u][1] = make_float2(0.f, 0.f);
       const float* wr = W2s + 4 * warp;
       const float* hp = h1row;
+      const int nqw = (nq - warp + NW - 1) / NW;
       for (int jq = 0; jq < (JR >> 2); ++jq, hp += 4) {
         const float4 h4 = pb_ld4(hp);
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj, wr += 64) {
           const float hv = jj == 0 ? h4.x : jj == 1 ? h4.y : jj == 2 ? h4.z : h4.w;
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {  // (quads beyond the net's width multiply zero weights)
-            const float4 w = pb_ld4(wr + 16 * u);
-            acc[u][0] = __ffma2_rn(make_float2(hv, hv), make_float2(w.x, w.y), acc[u][0]);
-            acc[u][1] = __ffma2_rn(make_float2(hv, hv), make_float2(w.z, w.w), acc[u][1]);
-          }
+          for (int u = 0; u < 4; ++u)
+            if (u < nqw) {  // (warp-uniform: this warp's quads w, w + 4, .. below the net's width)
+              const float4 w = pb_ld4(wr + 16 * u);
+              acc[u][0] = __ffma2_rn(make_float2(hv, hv), make_float2(w.x, w.y), acc[u][0]);
+              acc[u][1] = __ffma2_rn(make_float2(hv, hv), make_float2(w.z, w.w), acc[u][1]);
+            }
         }
       }
       float fpart = 0.f;

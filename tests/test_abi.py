@@ -63,6 +63,15 @@ def test_host_side_calls_without_gpu(cuda_lib_path):
     assert lib.pbnn_plan_engine(spec, _lib.OP_HMC, 506, 2048) == _lib.ENGINE_TCGEN05
     assert lib.pbnn_plan_engine(spec, _lib.OP_SGLD, 257, 2048) != _lib.ENGINE_WARP_H1  # rows no longer fit a warp's block
     assert lib.pbnn_plan_engine(_lib.make_spec((13, 65, 1), 0, 0.1), _lib.OP_SGLD, 32, 2048) != _lib.ENGINE_WARP_H1
+    # Adam on small two-hidden-layer relu nets (BASELINE configs[3]): four warps per member; everything else as before
+    ens = _lib.make_spec((8, 50, 50, 1), 0, 0.1)
+    assert lib.pbnn_plan_engine(ens, _lib.OP_ADAM, 32, 512) == _lib.ENGINE_WARP_MLP2
+    assert lib.pbnn_workspace_bytes(ens, _lib.OP_ADAM, 32, 512) == 0
+    assert lib.pbnn_plan_engine(ens, _lib.OP_ADAM, 33, 512) == _lib.ENGINE_TILED           # more than 32 rows
+    assert lib.pbnn_plan_engine(ens, _lib.OP_SGLD, 32, 512) == _lib.ENGINE_TILED           # samplers keep their engines
+    assert lib.pbnn_plan_engine(_lib.make_spec((8, 50, 50, 1), 1, 0.1), _lib.OP_ADAM, 32, 512) == _lib.ENGINE_TILED  # tanh
+    assert lib.pbnn_plan_engine(_lib.make_spec((8, 50, 40, 1), 0, 0.1), _lib.OP_ADAM, 32, 512) == _lib.ENGINE_TILED
+    assert lib.pbnn_plan_engine(_lib.make_spec((8, 65, 65, 1), 0, 0.1), _lib.OP_ADAM, 32, 512) == _lib.ENGINE_TILED
     assert lib.pbnn_plan_engine(spec, _lib.OP_HMC, 4096, 4) == _lib.ENGINE_TCGEN05     # X streams through TMEM, 4 tiles at a time
     assert lib.pbnn_plan_engine(spec, _lib.OP_HMC, 4097, 4) != _lib.ENGINE_TCGEN05     # larger data sets: FP32 engines
     assert lib.pbnn_plan_engine(_lib.make_spec((13, 65, 1), 0, 0.1), _lib.OP_HMC, 506, 4) != _lib.ENGINE_TCGEN05

@@ -90,3 +90,65 @@ def test_diverged_chain_raises_the_flag(cuda_ops, tc_options):
     bad = ~np.isfinite(npy(out["theta"])).all(axis=1)
     assert bad.any()
     assert np.array_equal((npy(out["flags"]) & 1).astype(bool), bad)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Adam for small two-hidden-layer relu nets, four warps per member (pbnn_b200/csrc/pbnn_warp2.cuh)
+# ------------------------------------------------------------------------------------------------------------------
+def _adam_reference(sp, X, y, th0, idx, lr, steps):
+    th, m, v, cnt = th0.copy(), np.zeros_like(th0), np.zeros_like(th0), 0
+    for s_ in range(steps):
+        g = -o.grad_estimator(sp, th, X[idx[:, s_]], y[idx[:, s_]], X.shape[0])
+        th, m, v, cnt = o.adam_step(th, g.astype(np.float32), m, v, cnt, lr)
+    return th, m, v
+
+
+@pytest.mark.parametrize("layers,B", [((8, 50, 50, 1), 32), ((15, 64, 64, 1), 32), ((3, 33, 33, 1), 17), ((1, 1, 1, 1), 1),
+                                      ((12, 7, 7, 1), 5), ((4, 16, 16, 1), 32), ((9, 57, 57, 1), 31)])
+def test_adam_two_hidden_layers_edge_shapes(cuda_ops, tc_options, layers, B):
+    """Widest / narrowest / odd widths (the last lane's second unit does not exist), ragged batches, one to four float4
+    chunks per input row: final parameters and both Adam moments against the numpy oracle; the tiled FP32 engine (option
+    no_w2) agrees to rounding and is a different kernel."""
+    C, N, steps, lr = 3, 200, 6, 1e-2
+    X, y = o.synthetic_regression(N, layers[0], 4)
+    sp, fs = o.MlpSpec(tuple(layers), o.RELU, 0.1), FlatSpec(tuple(layers), o.RELU, 0.1)
+    th0 = (0.1 * np.random.default_rng(4).standard_normal((C, sp.num_params))).astype(np.float32)
+    idx = np.random.default_rng(5).integers(0, N, (C, steps, B)).astype(np.int32)
+    assert cuda_ops.lib.pbnn_plan_engine(fs.c_struct(), _lib.OP_ADAM, B, C) == _lib.ENGINE_WARP_MLP2
+    th, m, v = _adam_reference(sp, X, y, th0, idx, lr, steps)
+    out = cuda_ops.adam_ensemble(fs, X, y, th0, idx, lr)
+    assert not npy(out["flags"]).any()
+    assert rel(npy(out["theta"]), th) <= 5e-5  # six free-running Adam steps (the first moves every weight by ~lr)
+    assert rel(npy(out["m"]), m) <= 5e-5 and rel(npy(out["v"]), v) <= 1e-4
+    one = cuda_ops.adam_ensemble(fs, X, y, th0, idx[:, :1], lr)
+    th1, _, _ = _adam_reference(sp, X, y, th0, idx, lr, 1)
+    assert rel(npy(one["theta"]), th1) <= 1e-5
+    tc_options(no_w2=1)
+    assert cuda_ops.lib.pbnn_plan_engine(fs.c_struct(), _lib.OP_ADAM, B, C) != _lib.ENGINE_WARP_MLP2
+    tiled = cuda_ops.adam_ensemble(fs, X, y, th0, idx, lr)
+    assert rel(npy(tiled["theta"]), npy(out["theta"])) <= 5e-5
+
+
+def test_adam_two_hidden_layers_members_are_independent_and_resumable(cuda_ops):
+    """A member's result is bit-identical alone and among 300; two halves with the carried moments equal one run."""
+    layers, B, N, C, steps = (8, 50, 50, 1), 32, 9568, 300, 8
+    X, y = o.synthetic_regression(N, layers[0], 6)
+    sp, fs = o.MlpSpec(layers, o.RELU, 0.1), FlatSpec(layers, o.RELU, 0.1)
+    th0 = (0.05 * np.random.default_rng(6).standard_normal((C, sp.num_params))).astype(np.float32)
+    idx = np.random.default_rng(7).integers(0, N, (C, steps, B)).astype(np.int32)
+    out = cuda_ops.adam_ensemble(fs, X, y, th0, idx, 1e-2)
+    pick = np.array([0, 1, 149, C - 1])
+    solo = cuda_ops.adam_ensemble(fs, X, y, th0[pick], idx[pick], 1e-2)
+    for k in ("theta", "m", "v"):
+        assert np.array_equal(npy(solo[k]), npy(out[k])[pick])
+    th, m, v = _adam_reference(sp, X, y, th0[pick], idx[pick], 1e-2, steps)
+    assert rel(npy(solo["theta"]), th) <= 5e-5
+    a = cuda_ops.adam_ensemble(fs, X, y, th0[pick], idx[pick][:, :3], 1e-2)
+    b = cuda_ops.adam_ensemble(fs, X, y, a["theta"], idx[pick][:, 3:], 1e-2, m=a["m"], v=a["v"], count0=a["count"])
+    assert np.array_equal(npy(b["theta"]), npy(solo["theta"]))
+    bad = idx[pick].copy()
+    bad[0, 2, 5], bad[1, 0, 0] = N + 3, -1
+    c = cuda_ops.adam_ensemble(fs, X, y, th0[pick], bad, 1e-2)
+    d = cuda_ops.adam_ensemble(fs, X, y, th0[pick], bad.clip(0, N - 1), 1e-2)
+    assert np.array_equal(npy(c["theta"]), npy(d["theta"]))
+    assert (npy(c["flags"])[:2] & 4).all() and not npy(d["flags"]).any()
