@@ -210,7 +210,7 @@ def gpu_step_fn(ops, w, fs, X, y, th0, keys, keep_trace=True):
 
 
 ENGINE_NAMES = {0: "tiled_fp32", 1: "fused_h1_fp32", 2: "tcgen05_tf32x3", 3: "tiled_fp32_global_state",
-                4: "tcgen05_bf16x3_mlp2", 5: "warp_per_chain_fp32", 6: "warp_per_member_fp32_mlp2"}
+                4: "tcgen05_bf16x3_mlp2", 5: "warp_per_chain_fp32", 6: "four_warps_per_member_fp32_mlp2"}
 OPS = {"hmc": "OP_HMC", "sgld": "OP_SGLD", "psgld": "OP_PSGLD", "sghmc": "OP_SGHMC", "adam": "OP_ADAM"}
 
 
