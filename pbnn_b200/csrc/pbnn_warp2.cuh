@@ -86,6 +86,21 @@ PB_DEV void pb_adam_w2_member(const PbPlan& pl, const PbSgArgs& a, float* sm, in
     return ok ? tn : th;
   };
 
+  // minibatch row index of step t for this lane (clamped like a JAX gather; bit 2 of the flag word records a clamp)
+  int vn = 0;
+  auto fetch_index = [&](int t) {
+    int v = 0;
+    if (valid && t < a.T) {
+      v = a.contig ? lane : cidx[(size_t)(a.idx_steps > 1 ? t : 0) * B + lane];
+      if (v < 0 || v >= a.N) {
+        v = v < 0 ? 0 : a.N - 1;
+        fl |= 4u;
+      }
+    }
+    vn = v;
+  };
+  fetch_index(0);
+
   for (int t = 0; t < a.T; ++t) {
     if (tid == 0) {  // bias corrections of this step (published behind the first barrier)
       const float cnt = (float)(a.count0 + t + 1);
@@ -93,25 +108,18 @@ PB_DEV void pb_adam_w2_member(const PbPlan& pl, const PbSgArgs& a, float* sm, in
       rs[34] = 1.0f / (1.0f - powf(a.b2, cnt));
     }
 
-    // ---- A. this step's minibatch row of the lane (every warp keeps it in registers; clamped like a JAX gather) ------
-    int v = 0;
-    if (valid) {
-      v = a.contig ? lane : cidx[(size_t)(a.idx_steps > 1 ? t : 0) * B + lane];
-      if (v < 0 || v >= a.N) {
-        v = v < 0 ? 0 : a.N - 1;
-        fl |= 4u;
-      }
-    }
+    // ---- A. this step's minibatch row of the lane (every warp keeps it in registers); its index was fetched while the
+    //         previous step finished (index -> row would be two dependent L2 round trips here) ------------------------------
     float xr[KD];
     {
-      const float* xp = a.X + (size_t)v * d;
+      const float* xp = a.X + (size_t)vn * d;
       float xl[KD];
 #pragma unroll
       for (int k = 0; k < KD; ++k) xl[k] = xp[k < d ? k : 0];  // (all loads first, the selects after: see phase G)
 #pragma unroll
       for (int k = 0; k < KD; ++k) xr[k] = k < d ? xl[k] : (k == d ? 1.f : 0.f);
     }
-    const float yb = a.y[v];
+    const float yb = a.y[vn];
     if (warp == 0) {
 #pragma unroll
       for (int q = 0; q < DP; ++q)
@@ -131,11 +139,11 @@ PB_DEV void pb_adam_w2_member(const PbPlan& pl, const PbSgArgs& a, float* sm, in
       }
       pb_st4(h1row + 4 * q, float4{fmaxf(z01.x, 0.f), fmaxf(z01.y, 0.f), fmaxf(z23.x, 0.f), fmaxf(z23.y, 0.f)});
     }
+    if (warp == (H >> 2) % NW) h1row[H] = 1.f;  // bias input of layer 2: column H belongs to a quad of THIS warp (stored
+                                                //  above, same thread) or to none
     __syncthreads();
-    if (warp == (H >> 2) % NW) h1row[H] = 1.f;  // bias input of layer 2, after the quad that covers column H (if any)
     ibc1 = rs[33];
     ibc2 = rs[34];
-    __syncthreads();
 
     PB_MARK(2)
     // ---- C. layer 2 (row layout; warp w: output quads w, w + 4, w + 8, w + 12): S2s = relu(z2), partial w3 . relu(z2) ---
@@ -224,6 +232,7 @@ PB_DEV void pb_adam_w2_member(const PbPlan& pl, const PbSgArgs& a, float* sm, in
       pb_st4(d1row + 4 * jq, float4{e4[0], e4[1], e4[2], e4[3]});
     }
     __syncthreads();  // Z2s, D1s, rs complete; every read of the OLD W2 is done
+    fetch_index(t + 1);  // (in flight behind the weight-gradient passes)
 
     PB_MARK(5)
     // ---- G. dW2, db2 (unit layout, 8 input units per pass, pass p by warp p % NW) + Adam on exactly those weights --------
