@@ -382,7 +382,7 @@ PB_DEV void pb_tc_grad_core(const PbPlan& pl, float* sm, float* TH, float* G, in
       pb_tc_fence_before();
       if (round + 1 < ntiles)  // the accumulator is free: the issue warp may start the next tile's forward MMAs
         asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(mb_h) : "memory");
-      float f0 = 0.f, f1 = 0.f;
+      float2 f01 = make_float2(0.f, 0.f);  // (.x: even units, .y: odd units -- packed FMA, same sums as two scalar chains)
       // blocks of 8 hidden units behind a (uniform) branch: units >= H are skipped at that granularity
 #pragma unroll
       for (int c8 = 0; c8 < 8; ++c8)
@@ -390,12 +390,13 @@ PB_DEV void pb_tc_grad_core(const PbPlan& pl, float* sm, float* TH, float* G, in
 #pragma unroll
           for (int j4 = 2 * c8; j4 < 2 * c8 + 2; ++j4) {
             const float4 w = pb_ld4(w2s + 4 * j4);
-            f0 = fmaf(fmaxf(__uint_as_float(h[4 * j4]), 0.f), w.x, f0);
-            f1 = fmaf(fmaxf(__uint_as_float(h[4 * j4 + 1]), 0.f), w.y, f1);
-            f0 = fmaf(fmaxf(__uint_as_float(h[4 * j4 + 2]), 0.f), w.z, f0);
-            f1 = fmaf(fmaxf(__uint_as_float(h[4 * j4 + 3]), 0.f), w.w, f1);
+            f01 = __ffma2_rn(make_float2(fmaxf(__uint_as_float(h[4 * j4]), 0.f), fmaxf(__uint_as_float(h[4 * j4 + 1]), 0.f)),
+                             make_float2(w.x, w.y), f01);
+            f01 = __ffma2_rn(make_float2(fmaxf(__uint_as_float(h[4 * j4 + 2]), 0.f), fmaxf(__uint_as_float(h[4 * j4 + 3]), 0.f)),
+                             make_float2(w.z, w.w), f01);
           }
         }
+      const float f0 = f01.x, f1 = f01.y;
       const int row = round * 128 + tid;
       const bool valid = row < nrows;
       const float res = yr[row] - ((f0 + f1) + b2);
@@ -416,10 +417,13 @@ PB_DEV void pb_tc_grad_core(const PbPlan& pl, float* sm, float* TH, float* G, in
         }
       float* zr = sm + pl.off_z + (kk >> 2) * PB_TC_Z_LBO + (half * 32) * 4 + (kk & 3);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float z = r * __uint_as_float(xr[i]);
-        zr[i * 4] = z;
-        zr[(16 + i) * 4] = z - pb_trunc_tf32(z);
+      for (int i = 0; i < 16; i += 2) {  // (packed multiply / subtract: per component the same arithmetic)
+        const float2 z = __fmul2_rn(make_float2(r, r), make_float2(__uint_as_float(xr[i]), __uint_as_float(xr[i + 1])));
+        const float2 lo = __ffma2_rn(make_float2(pb_trunc_tf32(z.x), pb_trunc_tf32(z.y)), make_float2(-1.f, -1.f), z);
+        zr[i * 4] = z.x;
+        zr[(i + 1) * 4] = z.y;
+        zr[(16 + i) * 4] = lo.x;
+        zr[(17 + i) * 4] = lo.y;
       }
       PB_MARK(22)
       pb_fence_async_smem();

@@ -177,10 +177,19 @@ PB_DEV void pb_sgw_chain(const PbPlan& pl, const PbSgArgs& a, float* wsm, int c,
         for (int q = 0; q < DP; ++q) xr[q] = pb_ld4(xs + rowc * KD + 4 * q);
         float f = 0.f;
         const float* wq = ws;
+        // d a multiple of 4 (8-50-1): the bias is the only live row of the last float4 chunk -- it starts the sums
+        // and the chunk is skipped (rows > d: x = 0 times w = 0 otherwise)
+        const bool bias_first = KD > 4 && d == KD - 4;
         for (int q = 0; q < nq; ++q, wq += 4) {
           float2 z01 = make_float2(0.f, 0.f), z23 = make_float2(0.f, 0.f);
+          if (bias_first) {
+            const float4 w = pb_ld4(wq + (KD - 4) * 64);
+            z01 = make_float2(w.x, w.y);
+            z23 = make_float2(w.z, w.w);
+          }
 #pragma unroll
-          for (int k = 0; k < KD; ++k) {  // (rows > d: x = 0 times w = 0)
+          for (int k = 0; k < KD; ++k) {
+            if (k >= KD - 4 && bias_first) break;
             const float4 w = pb_ld4(wq + k * 64);
             const float4 t = xr[k >> 2];
             const float xk = (k & 3) == 0 ? t.x : (k & 3) == 1 ? t.y : (k & 3) == 2 ? t.z : t.w;
