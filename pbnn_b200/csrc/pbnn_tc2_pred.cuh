@@ -64,7 +64,10 @@ PB_DEV void pb_tc2p_restage(const PbPlan& pl, float* sm, uint8_t* img1, uint8_t*
     for (int e = tid; e < total; e += nt) {
       const int k = e / hp2, n0 = 2 * (e - k * hp2);
       const float* row = k < d ? th + L0.fw + k * H : th + L0.fb;
-      const float v0 = n0 < H ? row[n0] : 0.f, v1 = n0 + 1 < H ? row[n0 + 1] : 0.f;
+      // (loads from clamped addresses, selects AFTER: a zero written to the register a load is still filling makes the
+      //  loads of a thread wait for each other -- measured in pbnn_warp2.cuh)
+      const float l0 = row[n0 < H ? n0 : 0], l1 = row[n0 + 1 < H ? n0 + 1 : 0];
+      const float v0 = n0 < H ? l0 : 0.f, v1 = n0 + 1 < H ? l1 : 0.f;
       uint32_t t1, t2, t3;
       pb_t2_split3(v0, v1, t1, t2, t3);
       uint8_t* p = img1 + pb_t2_off(Kx, k, n0);
@@ -80,9 +83,11 @@ PB_DEV void pb_tc2p_restage(const PbPlan& pl, float* sm, uint8_t* img1, uint8_t*
     const int total = H * nck;
     for (int e = tid; e < total; e += nt) {
       const int cb = e / H, n = e - cb * H, i0 = 8 * cb;
-      float v[8];
+      float v[8], l[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = i0 + j < H ? th[L1.fw + (i0 + j) * H + n] : 0.f;
+      for (int j = 0; j < 8; ++j) l[j] = th[L1.fw + (i0 + j < H ? i0 + j : 0) * H + n];  // (all eight loads in flight)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = i0 + j < H ? l[j] : 0.f;
       uint32_t t1[4], t2[4], t3[4];
 #pragma unroll
       for (int m = 0; m < 4; ++m) pb_t2_split3(v[2 * m], v[2 * m + 1], t1[m], t2[m], t3[m]);
@@ -95,8 +100,9 @@ PB_DEV void pb_tc2p_restage(const PbPlan& pl, float* sm, uint8_t* img1, uint8_t*
   float* b2v = sm + pl.off_t2_vec;
   float* w3v = b2v + 256;
   for (int n = tid; n < 256; n += nt) {
-    b2v[n] = n < H ? th[L1.fb + n] : 0.f;
-    w3v[n] = n < H ? th[L2.fw + n] : 0.f;
+    const float lb = th[L1.fb + (n < H ? n : 0)], lw = th[L2.fw + (n < H ? n : 0)];
+    b2v[n] = n < H ? lb : 0.f;
+    w3v[n] = n < H ? lw : 0.f;
   }
   if (tid == 0) sm[pl.off_t2_vec + 1408] = th[L2.fb];
   pb_t2_fence_async_global();
