@@ -109,3 +109,32 @@ def test_fp32_engines_and_helpers_stay_inside_their_buffers(gops):
     gops.permutation(keys, 1030)
     gops.minibatch_indices(keys, 2, 32, 1030)
     assert gops.check() > 10
+
+
+@pytest.mark.parametrize("layers,B,C", [((8, 50, 1), 32, 300), ((13, 50, 1), 40, 5), ((15, 64, 1), 96, 3), ((3, 7, 1), 33, 4)])
+def test_warp_per_chain_engine_stays_inside_its_buffers(gops, layers, B, C):
+    """pbnn_warp.cuh: trace rows leave through a staging array in whole lines, the state arrays of pSGLD / Adam are read
+    and written per slot -- every one of those global accesses must stay inside the caller's buffers."""
+    gops.set_option("w1_min_chains", 1)
+    fs, X, y, keys, th0 = problem(gops, layers, 400, C)
+    r = gops.sgld(fs, X, y, th0, keys, B, 1e-6, 5, thin=2, burnin=1)
+    assert torch.isfinite(r["trace"]).all()
+    gops.sgld(fs, X, y, th0, keys, B, 1e-6, 3, minibatch_mode="per_step", keep_trace=False)
+    gops.psgld(fs, X, y, th0, keys, B, 1e-7, 3, 0.95)
+    gops.sghmc(fs, X, y, th0, keys, B, 1e-7, 2, 2, momentum_resampling="sigma_sqrt_step")
+    idx = np.random.default_rng(1).integers(0, 400, (C, 2, B)).astype(np.int32)
+    gops.adam_ensemble(fs, X, y, th0, idx, 1e-3)
+    assert gops.check() > 10
+    gops.reset_options()
+
+
+@pytest.mark.parametrize("layers,B,C", [((8, 50, 50, 1), 32, 7), ((15, 64, 64, 1), 32, 3), ((3, 33, 33, 1), 17, 4),
+                                        ((1, 1, 1, 1), 1, 2)])
+def test_four_warp_adam_kernel_stays_inside_its_buffers(gops, layers, B, C):
+    """pbnn_warp2.cuh: the moments are updated in place in global memory, pair by pair; lanes beyond the net's width and
+    the second unit of an odd width must neither read nor write outside theta / m / v."""
+    fs, X, y, keys, th0 = problem(gops, layers, 300, C)
+    idx = np.random.default_rng(2).integers(0, 300, (C, 4, B)).astype(np.int32)
+    r = gops.adam_ensemble(fs, X, y, th0, idx, 1e-2)
+    assert torch.isfinite(r["theta"]).all() and torch.isfinite(r["m"]).all() and torch.isfinite(r["v"]).all()
+    assert gops.check() > 5
