@@ -440,7 +440,7 @@ static inline int pb_build_plan(const pbnn_mlp_spec* sp, int rows, int nstate, i
     pl->w2_pa = (pl->w2_jr % 8) == 4 ? pl->w2_jr : pl->w2_jr + 4;
     int off = 0;
     pl->w2_ox = off;
-    off += 32 * kd;
+    off += 2 * 32 * kd + 64;  // rows of this step and of the next one (cp.async), then y of both
     pl->w2_ow1 = off;
     off += kd * 64;
     pl->w2_ow2 = off;

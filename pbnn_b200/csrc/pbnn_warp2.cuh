@@ -13,7 +13,7 @@
 //   unit layout (lane = output pair)    the weight gradients (reductions over the rows: rank-1 updates in registers,
 //                                       8 input units per pass, the passes dealt over the warps), each followed at once by the
 //                                       Adam update of exactly those weights -- no gradient array, no update pass.
-// Four CTA barriers per step.  Same arithmetic contract as the other engines (FP32, fixed summation order); a member's
+// Four CTA barriers per step; the next step's minibatch rows arrive by cp.async behind the weight-gradient passes.  Same arithmetic contract as the other engines (FP32, fixed summation order); a member's
 // result does not depend on the launch it runs in.
 #pragma once
 #if !defined(PB_EMU)
@@ -29,7 +29,8 @@ PB_DEV void pb_adam_w2_member(const PbPlan& pl, const PbSgArgs& a, float* sm, in
   const PbLayer& L2 = pl.L[2];
   const int H = L0.out, d = pl.d, P = pl.P, B = a.B;
   const int JR = pl.w2_jr, PA = pl.w2_pa, nq = (H + 3) >> 2;
-  float* const xs = sm + pl.w2_ox;    // [32][KD]  minibatch rows (x, 1, 0..)
+  float* const xs0 = sm + pl.w2_ox;   // [2][32][KD]  minibatch rows (x, 1, 0..) of this step / the next one, then y [2][32]
+  float* const ys0 = xs0 + 2 * 32 * KD;
   float* const W1s = sm + pl.w2_ow1;  // [KD][64]  row k < d: kernel row, row d: bias, else 0
   float* const W2s = sm + pl.w2_ow2;  // [JR][64]  row j < H: kernel row, row H: bias, else 0
   float* const w3s = sm + pl.w2_ow3;  // [64] w3, then [NW][32] partial outputs, [32] residuals
@@ -86,9 +87,10 @@ PB_DEV void pb_adam_w2_member(const PbPlan& pl, const PbSgArgs& a, float* sm, in
     return ok ? tn : th;
   };
 
-  // minibatch row index of step t for this lane (clamped like a JAX gather; bit 2 of the flag word records a clamp)
-  int vn = 0;
-  auto fetch_index = [&](int t) {
+  // Minibatch rows.  Warp 0 fetches them a step ahead with cp.async straight into shared memory (double-buffered), the
+  // row INDEX two steps ahead: index -> row are two dependent L2 round trips (~3 k cycles) that no phase has to wait
+  // for any more.  Indices are clamped like a JAX gather; bit 2 of the flag word records a clamp.
+  auto fetch_index = [&](int t) -> int {
     int v = 0;
     if (valid && t < a.T) {
       v = a.contig ? lane : cidx[(size_t)(a.idx_steps > 1 ? t : 0) * B + lane];
@@ -97,9 +99,30 @@ PB_DEV void pb_adam_w2_member(const PbPlan& pl, const PbSgArgs& a, float* sm, in
         fl |= 4u;
       }
     }
-    vn = v;
+    return v;
   };
-  fetch_index(0);
+  auto issue_row = [&](int v, int buf) {  // lane's row -> xs[buf][lane][0..d), y -> ys[buf][lane] (asynchronous)
+    const float* xp = a.X + (size_t)v * d;
+    const uint32_t dst = pb_smem_u32(xs0 + (buf * 32 + lane) * KD);
+    if ((d & 3) == 0 && (reinterpret_cast<uintptr_t>(a.X) & 15) == 0) {
+      for (int k = 0; k < d; k += 4)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 4u * (uint32_t)k), "l"(xp + k) : "memory");
+    } else {
+      for (int k = 0; k < d; ++k)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4u * (uint32_t)k), "l"(xp + k) : "memory");
+    }
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(pb_smem_u32(ys0 + buf * 32 + lane)), "l"(a.y + v)
+                 : "memory");
+  };
+  int vn = 0;
+  if (warp == 0) {
+    for (int buf = 0; buf < 2; ++buf)  // the constant tail of an augmented row: (1, 0, ..)
+      for (int k = d; k < KD; ++k) xs0[(buf * 32 + lane) * KD + k] = k == d ? 1.f : 0.f;
+    issue_row(fetch_index(0), 0);
+    vn = fetch_index(1);
+    asm volatile("cp.async.wait_all;" ::: "memory");
+  }
+  __syncthreads();
 
   for (int t = 0; t < a.T; ++t) {
     if (tid == 0) {  // bias corrections of this step (published behind the first barrier)
@@ -108,23 +131,18 @@ PB_DEV void pb_adam_w2_member(const PbPlan& pl, const PbSgArgs& a, float* sm, in
       rs[34] = 1.0f / (1.0f - powf(a.b2, cnt));
     }
 
-    // ---- A. this step's minibatch row of the lane (every warp keeps it in registers); its index was fetched while the
-    //         previous step finished (index -> row would be two dependent L2 round trips here) ------------------------------
+    // ---- A. this step's minibatch row of the lane (every warp keeps it in registers), fetched during the previous step ---
+    const float* const xs = xs0 + (t & 1) * 32 * KD;
     float xr[KD];
-    {
-      const float* xp = a.X + (size_t)vn * d;
-      float xl[KD];
 #pragma unroll
-      for (int k = 0; k < KD; ++k) xl[k] = xp[k < d ? k : 0];  // (all loads first, the selects after: see phase G)
-#pragma unroll
-      for (int k = 0; k < KD; ++k) xr[k] = k < d ? xl[k] : (k == d ? 1.f : 0.f);
+    for (int q = 0; q < DP; ++q) {
+      const float4 x4 = pb_ld4(xs + lane * KD + 4 * q);
+      xr[4 * q] = x4.x;
+      xr[4 * q + 1] = x4.y;
+      xr[4 * q + 2] = x4.z;
+      xr[4 * q + 3] = x4.w;
     }
-    const float yb = a.y[vn];
-    if (warp == 0) {
-#pragma unroll
-      for (int q = 0; q < DP; ++q)
-        pb_st4(xs + lane * KD + 4 * q, float4{xr[4 * q], xr[4 * q + 1], xr[4 * q + 2], xr[4 * q + 3]});
-    }
+    const float yb = ys0[(t & 1) * 32 + lane];
 
     PB_MARK(1)
     // ---- B. layer 1 (row layout; warp w: output quads w, w + 4, ..): H1s[b][j] = relu(x_b . W1[:, j] + b1_j) -----------
@@ -232,7 +250,11 @@ PB_DEV void pb_adam_w2_member(const PbPlan& pl, const PbSgArgs& a, float* sm, in
       pb_st4(d1row + 4 * jq, float4{e4[0], e4[1], e4[2], e4[3]});
     }
     __syncthreads();  // Z2s, D1s, rs complete; every read of the OLD W2 is done
-    fetch_index(t + 1);  // (in flight behind the weight-gradient passes)
+    int vn2 = 0;
+    if (warp == 0) {  // next step's rows and the index after that: in flight behind the weight-gradient passes
+      issue_row(vn, (t + 1) & 1);
+      vn2 = fetch_index(t + 2);
+    }
 
     PB_MARK(5)
     // ---- G. dW2, db2 (unit layout, 8 input units per pass, pass p by warp p % NW) + Adam on exactly those weights --------
@@ -373,7 +395,11 @@ PB_DEV void pb_adam_w2_member(const PbPlan& pl, const PbSgArgs& a, float* sm, in
         V[L2.fb] = v3[2];
       }
     }
-    __syncthreads();  // the new weights are visible to the next step
+    if (warp == 0) {
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      vn = vn2;
+    }
+    __syncthreads();  // the new weights and the next rows are visible to the next step
     b3 = rs[32];
     PB_MARK(7)
   }
