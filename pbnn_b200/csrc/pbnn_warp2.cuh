@@ -13,8 +13,9 @@
 //   unit layout (lane = output pair)    the weight gradients (reductions over the rows: rank-1 updates in registers,
 //                                       8 input units per pass, the passes dealt over the warps), each followed at once by the
 //                                       Adam update of exactly those weights -- no gradient array, no update pass.
-// Four CTA barriers per step; the next step's minibatch rows arrive by cp.async behind the weight-gradient passes.  Same arithmetic contract as the other engines (FP32, fixed summation order); a member's
-// result does not depend on the launch it runs in.
+// Four CTA barriers per step; the next step's minibatch rows arrive by cp.async behind the weight-gradient passes.
+// Same arithmetic contract as the other engines (FP32, fixed summation order); a member's result does not depend on
+// the launch it runs in.
 #pragma once
 #if !defined(PB_EMU)
 
