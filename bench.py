@@ -43,6 +43,10 @@ WORKLOADS = {
     # BASELINE.json configs[0] shape, many chains
     "sgld_cfg1": dict(algo="sgld", layers=(8, 50, 1), act=0, N=1030, B=32, C=1, T=100_000, L=1, step=1e-5, M=1024),
     "sgld_cfg1x": dict(algo="sgld", layers=(8, 50, 1), act=0, N=1030, B=32, C=2048, T=2000, L=1, step=1e-5, M=1024),
+    # the same shape on the other samplers (warp-per-chain engine; not part of the default line)
+    "psgld_cfg1x": dict(algo="psgld", layers=(8, 50, 1), act=0, N=1030, B=32, C=2048, T=2000, L=1, step=1e-6, M=1024),
+    "sghmc_cfg1x": dict(algo="sghmc", layers=(8, 50, 1), act=0, N=1030, B=32, C=2048, T=200, L=10, step=1e-7, M=1024,
+                        momentum="sigma_sqrt_step"),
     # BASELINE.json configs[2]
     "psgld_cfg3": dict(algo="psgld", layers=(9, 100, 100, 1), act=0, N=45730, B=128, C=1024, T=200, L=1, step=2e-8,
                        M=1024),
