@@ -79,6 +79,27 @@ PB_DEV void pb_st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 PB_DEV int pb_min(int a, int b) { return a < b ? a : b; }
 PB_DEV int pb_r4dev(int x) { return (x + 3) & ~3; }
 PB_DEV bool pb_finite(float x) { return fabsf(x) <= 3.402823466e+38f; }
+// Per-parameter square roots / reciprocals of the pSGLD and Adam updates: MUFU approximations on the device (2^-22
+// relative each, on terms the parity contract resolves to 1e-5; the IEEE sqrtf and division are ~100 instructions per
+// parameter and step -- as much as the bit-exact normal the same parameter draws), the exact ones in the emulator.
+PB_DEV float pb_sqrt_fast(float x) {
+#if defined(__CUDA_ARCH__)
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#else
+  return sqrtf(x);
+#endif
+}
+PB_DEV float pb_rcp_fast(float x) {
+#if defined(__CUDA_ARCH__)
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#else
+  return 1.0f / x;
+#endif
+}
 #if defined(PB_EMU)
 static inline float __fdividef(float a, float b) { return a / b; }
 #endif
@@ -1206,8 +1227,8 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
                 return v;
               },
               [&](int si, int fi, float z, const PbPre& v) {
-                const float pre = 1.0f / (sqrtf(v.a) + 1e-6f);
-                TH[si] = v.b + eps * pre * v.c + sqrtf(2.0f * pre * eps) * z;
+                const float pre = pb_rcp_fast(pb_sqrt_fast(v.a) + 1e-6f);
+                TH[si] = v.b + eps * pre * v.c + pb_sqrt_fast(2.0f * pre * eps) * z;
               });
           PB_ENDPHASE
           pb_tc2_restage(pl, sm, *static_cast<PbTc2*>(ctx), TH, nt);
@@ -1235,8 +1256,8 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
               G[si] = g;
               A1[si] = V;
               if (!more) return v.a;
-              const float pre = 1.0f / (sqrtf(V) + 1e-6f);
-              return v.a + epsn * pre * g + sqrtf(2.0f * pre * epsn) * z;
+              const float pre = pb_rcp_fast(pb_sqrt_fast(V) + 1e-6f);
+              return v.a + epsn * pre * g + pb_sqrt_fast(2.0f * pre * epsn) * z;
             });
         continue;  // (the trace of this step has been written above)
       }
@@ -1253,8 +1274,8 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
             return v;
           },
           [&](int si, int fi, float z, const PbPre& v) {
-            const float pre = 1.0f / (sqrtf(v.a) + 1e-6f);
-            TH[si] = v.b + eps * pre * v.c + sqrtf(2.0f * pre * eps) * z;
+            const float pre = pb_rcp_fast(pb_sqrt_fast(v.a) + 1e-6f);
+            TH[si] = v.b + eps * pre * v.c + pb_sqrt_fast(2.0f * pre * eps) * z;
           });
       PB_ENDPHASE
       grad(tile_loaded);
@@ -1367,7 +1388,7 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
               const float v = (1.0f - a.b2) * (g * g) + a.b2 * p.d;
               A1[si] = m;
               A2[si] = v;
-              return th + (-a.lr) * __fdividef(m * ibc1, sqrtf(v * ibc2) + a.eps);
+              return th + (-a.lr) * ((m * ibc1) * pb_rcp_fast(pb_sqrt_fast(v * ibc2) + a.eps));
             });
       }
 #endif
@@ -1393,7 +1414,7 @@ PB_DEV void pb_sg_chain(const PbPlan& pl, const PbSgArgs& a, float* sm, int c, i
             const float v = (1.0f - a.b2) * (g * g) + a.b2 * p.d;
             A1[i] = m;
             A2[i] = v;
-            TH[i] = th + (-a.lr) * __fdividef(m * ibc1, sqrtf(v * ibc2) + a.eps);
+            TH[i] = th + (-a.lr) * ((m * ibc1) * pb_rcp_fast(pb_sqrt_fast(v * ibc2) + a.eps));
           });
       PB_ENDPHASE
     }

@@ -22,16 +22,6 @@
 
 #define PB_W1_WPC PB_W1_WARPS  // warps (= chains) per CTA (pbnn_core.h)
 
-PB_DEV float pb_sqrt_approx(float x) {
-  float r;
-  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
-PB_DEV float pb_rcp_approx(float x) {
-  float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
 
 // register slots of a lane: u < KD first-layer row k = u of unit 2 lane; KD <= u < 2 KD the same of unit 2 lane + 1
 // (row d = bias, rows > d pads); 2 KD, 2 KD + 1 the two output weights; 2 KD + 2 the output bias (replicated in every
@@ -427,8 +417,8 @@ PB_DEV void pb_sgw_chain(const PbPlan& pl, const PbSgArgs& a, float* wsm, int c,
       for (int u = 0; u < NS; ++u) {
         // (sqrt.approx / rcp.approx, 2^-22 relative each: the IEEE sqrtf and division cost ~100 instructions per slot --
         //  more than the slot's share of the noise generation)
-        const float pre = pb_rcp_approx(pb_sqrt_approx(ax2[u * 32]) + 1e-6f);
-        TH_(u) = TH_(u) + eps * pre * ax1[u * 32] + pb_sqrt_approx(2.0f * pre * eps) * ZS_(u);  // (pad slots: 0)
+        const float pre = pb_rcp_fast(pb_sqrt_fast(ax2[u * 32]) + 1e-6f);
+        TH_(u) = TH_(u) + eps * pre * ax1[u * 32] + pb_sqrt_fast(2.0f * pre * eps) * ZS_(u);  // (pad slots: 0)
       }
       grad();
 #pragma unroll
@@ -472,7 +462,7 @@ PB_DEV void pb_sgw_chain(const PbPlan& pl, const PbSgArgs& a, float* wsm, int c,
         const float v = (1.0f - a.b2) * (g * g) + a.b2 * ax2[u * 32];
         ax1[u * 32] = m;
         ax2[u * 32] = v;
-        const float tn = th + (-a.lr) * ((m * ibc1) * pb_rcp_approx(pb_sqrt_approx(v * ibc2) + a.eps));
+        const float tn = th + (-a.lr) * ((m * ibc1) * pb_rcp_fast(pb_sqrt_fast(v * ibc2) + a.eps));
         TH_(u) = slot_ok(u) ? tn : 0.f;
       }
     }
