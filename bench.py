@@ -9,8 +9,9 @@ job (default `hmc_cfg2`: BASELINE.json configs[1], 256 chains x 200 HMC iteratio
 `e2e` = the same through the reference-signature call `pbnn_b200.mcmc.hmc` (pytrees in, `(positions, ravel_fn,
 predict_fn)` out) with HOST inputs and the positions copied back to pinned host memory inside the timed region
 (`e2e.ops_*`: the same through the flat C-ABI operator layer).  The metric is "SGLD & HMC": the default run also
-times the other BASELINE configurations (`workloads`: sgld_cfg1x, sgld_cfg3, psgld_cfg3, sghmc_cfg3 -- configs[2] --,
-sgld_cfg5, adam_cfg4) with their own rooflines.
+times the other BASELINE configurations (`workloads`: sgld_cfg1 -- configs[0], one chain --, sgld_cfg1x, sgld_cfg3,
+psgld_cfg3, sghmc_cfg3 -- configs[2] --, sgld_cfg5 -- configs[4], one GPU's share --, adam_cfg4 -- configs[3]) with their
+own rooflines.
 Chains shard over ranks with no data-path collective (weak scaling).  With --gpus N > 1 the run adds BASELINE
 configs[4] (`sharded_cfg5`: 1024 SGLD chains per GPU of a 90-256-256-1 net -- 8192 chains on 8 GPUs -- keys
 split(PRNGKey(0), C_total)[shard]), checks on the device that a shard's chains are bit-identical to the same chains
@@ -561,7 +562,7 @@ def main():
     # ---- the metric is "SGLD & HMC": the SGLD configurations, device-timed like the headline -------------
     extras = {}
     if not args.no_extras:
-        for name in ("sgld_cfg1x", "sgld_cfg3", "psgld_cfg3", "sghmc_cfg3", "sgld_cfg5", "adam_cfg4"):
+        for name in ("sgld_cfg1", "sgld_cfg1x", "sgld_cfg3", "psgld_cfg3", "sghmc_cfg3", "sgld_cfg5", "adam_cfg4"):
             if name == args.workload:
                 continue
             we = dict(WORKLOADS[name], name=name)
