@@ -215,7 +215,7 @@ def gpu_step_fn(ops, w, fs, X, y, th0, keys, keep_trace=True):
 
 
 ENGINE_NAMES = {0: "tiled_fp32", 1: "fused_h1_fp32", 2: "tcgen05_tf32x3", 3: "tiled_fp32_global_state",
-                4: "tcgen05_bf16x3_mlp2", 5: "warp_per_chain_fp32", 6: "four_warps_per_member_fp32_mlp2"}
+                4: "tcgen05_bf16x3_mlp2", 5: "warp_per_chain_fp32", 6: "four_warps_per_member_fp32_mlp2", 7: "four_warps_per_chain_fp32"}
 OPS = {"hmc": "OP_HMC", "sgld": "OP_SGLD", "psgld": "OP_PSGLD", "sghmc": "OP_SGHMC", "adam": "OP_ADAM"}
 
 
@@ -276,7 +276,7 @@ def roofline_for(ops, w, fs, ms_per_step, clocks, peaks, traffic=None):
                          "parameter noise + update work on the CUDA cores (rng_issue), not by the tensor pipe")
     return dict(common, bound="fma", peak=fma_peak, frac=achieved / fma_peak,
                 kernel="pb_hmc_kernel" if w["algo"] == "hmc" else
-                ("pb_sgw_kernel" if engine == plib.ENGINE_WARP_H1 else
+                ("pb_sgw_kernel" if engine == plib.ENGINE_WARP_H1 else "pb_sgc_kernel" if engine == plib.ENGINE_CTA4_H1 else
                  "pb_adam_w2_kernel" if engine == plib.ENGINE_WARP_MLP2 else "pb_sg_kernel"),
                 peak_source=f"FP32 FMA: 148 SM x 128 lanes x 2 x {sm_max:.0f} MHz")
 

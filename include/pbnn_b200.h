@@ -92,6 +92,8 @@ int pbnn_plan_query(const pbnn_mlp_spec* spec, int rows, int n_state, int32_t ou
                                       bf16x3 tensor-core engine with TMA-streamed weights (pbnn_tc2.cuh)           */
 #define PBNN_ENGINE_WARP_H1 5  /* SG samplers / Adam, one hidden layer, scalar output, many chains: one warp per chain,
                                   weights in registers for the whole run (pbnn_warp.cuh)                            */
+#define PBNN_ENGINE_CTA4_H1 7   /* SGLD, one hidden relu layer, scalar output, FEW chains: the warp engine with a CTA of four
+                                   warps per chain (replicated weights, split forward / backward / noise)            */
 #define PBNN_ENGINE_WARP_MLP2 6 /* Adam (deep ensembles, MAP), two equal hidden relu layers, H <= 64, d + 1 <= 16,
                                    B <= 32: one warp per member, weights in its shared-memory block (pbnn_warp2.cuh) */
 int pbnn_plan_engine(const pbnn_mlp_spec* spec, int op, int rows, int C);

@@ -12,7 +12,7 @@ from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
 PBNN_MAX_LAYERS = 8
 ACT_RELU, ACT_TANH = 0, 1
 OP_SGLD, OP_PSGLD, OP_SGHMC, OP_ADAM, OP_GRAD, OP_HMC = range(6)
-ENGINE_TILED, ENGINE_FUSED_H1, ENGINE_TCGEN05, ENGINE_TILED_GLOBAL_STATE, ENGINE_TCGEN05_MLP2, ENGINE_WARP_H1, ENGINE_WARP_MLP2 = range(7)
+ENGINE_TILED, ENGINE_FUSED_H1, ENGINE_TCGEN05, ENGINE_TILED_GLOBAL_STATE, ENGINE_TCGEN05_MLP2, ENGINE_WARP_H1, ENGINE_WARP_MLP2, ENGINE_CTA4_H1 = range(8)
 MB_REFERENCE_FIXED, MB_PER_STEP = 0, 1
 
 _HERE = os.path.dirname(os.path.abspath(__file__))

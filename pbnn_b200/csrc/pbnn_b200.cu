@@ -705,8 +705,18 @@ static int pb_sg_dispatch(const PbPlan& pl, const PbSgArgs& a, int C, void* stre
 #undef PB_W2_LAUNCH
     }
   }
+  if constexpr (ALGO == PB_ALGO_SGLD) {
+    if (pl.w1 == 2) {  // few chains: a CTA of four warps per chain (pbnn_warp.cuh, NWC = 4)
+      switch (pl.h1_dp) {
+        case 1: return pb_launch(pb_sgc_kernel<1>, pl, a, dim3(C), stream);
+        case 2: return pb_launch(pb_sgc_kernel<2>, pl, a, dim3(C), stream);
+        case 3: return pb_launch(pb_sgc_kernel<3>, pl, a, dim3(C), stream);
+        default: return pb_launch(pb_sgc_kernel<4>, pl, a, dim3(C), stream);
+      }
+    }
+  }
   if constexpr (ALGO != PB_ALGO_GRAD) {
-    if (pl.w1) {  // warp-per-chain engine: PB_W1_WPC chains per CTA, DP = float4 chunks of an augmented input row
+    if (pl.w1 == 1) {  // warp-per-chain engine: PB_W1_WPC chains per CTA, DP = float4 chunks of an augmented input row
       const dim3 g((C + PB_W1_WPC - 1) / PB_W1_WPC);
 #define PB_W1_LAUNCH(DP_)                                                                                         \
   return pl.act == PBNN_ACT_RELU ? pb_launch(pb_sgw_kernel<ALGO, PBNN_ACT_RELU, DP_>, pl, a, g, stream)           \

@@ -85,12 +85,12 @@ enum {
   PB_OPT_DW_KS = 0, PB_OPT_NW, PB_OPT_NO_RESIDENT, PB_OPT_NO_H1, PB_OPT_NO_TC, PB_OPT_BT, PB_OPT_TWO_CTA,
   PB_OPT_ONE_CTA, PB_OPT_FORCE_GSTATE, PB_OPT_NO_SCHED, PB_OPT_SEG_LEN, PB_OPT_DEBUG, PB_OPT_PRED_TPC,
   PB_OPT_PRED_CHUNKS, PB_OPT_TC2_MIN_H, PB_OPT_TC2_MIN_ROWS, PB_OPT_NO_TC2, PB_OPT_TC2_CTAS, PB_OPT_TC2_NZ, PB_OPT_TC2_NOHELP, PB_OPT_NO_W1,
-  PB_OPT_W1_MIN_CHAINS, PB_OPT_NO_W2, PB_OPT_COUNT
+  PB_OPT_W1_MIN_CHAINS, PB_OPT_NO_W2, PB_OPT_NO_W1C, PB_OPT_COUNT
 };
 static const char* const pb_opt_names[PB_OPT_COUNT] = {
     "dw_ks", "nw", "no_resident", "no_h1", "no_tc", "bt", "two_cta", "one_cta", "force_gstate", "no_sched", "seg_len",
     "debug", "pred_tpc", "pred_chunks", "tc2_min_h", "tc2_min_rows", "no_tc2", "tc2_ctas", "tc2_nz", "tc2_nohelp",
-    "no_w1", "w1_min_chains", "no_w2"};
+    "no_w1", "w1_min_chains", "no_w2", "no_w1c"};
 #define PB_OPT_UNSET (-2147483647 - 1)
 inline int* pb_opt_table() {
   static int t[PB_OPT_COUNT];
@@ -155,6 +155,7 @@ static inline void pb_plan_dw(PbPlan* pl, int nw, int bt, int kcap) {
 #define PB_PLAN_TC 4  // the caller has a tcgen05 kernel for this op (HMC): allow the tensor-core layout
 #define PB_PLAN_TC2 8  // the caller can run the two-hidden-layer tcgen05 engine (SG samplers, Adam, grad hook)
 #define PB_PLAN_W1 16  // the caller can run the warp-per-chain engine (SG samplers, Adam)
+#define PB_PLAN_W1C 128  // the caller is SGLD: with few chains a CTA of four warps per chain may run (pbnn_warp.cuh, NWC = 4)
 #define PB_PLAN_W2 64  // the caller is the Adam trainer: small two-hidden-layer relu nets may run one warp per member
 #define PB_PLAN_PRED 32  // posterior predictive: the MMA tile rows are test points (always full), narrower nets still pay
 #define PB_W1_WARPS 1  // warps (= chains) per CTA of the warp-per-chain engine (finest balance over the SMs)
@@ -485,11 +486,13 @@ static inline int pb_build_plan(const pbnn_mlp_spec* sp, int rows, int nstate, i
   // fused path can keep co-resident (two CTAs per SM).  Measured, 8-50-1 B = 32 (M chain-steps/s, fused | warp):
   // 148 chains 39 | 30, 296 chains 62 | 59, 444 chains 55 | 88, 2048 chains 91-101 | 186: a lone warp advances a chain in
   // ~5 us per step against ~3.8 us for eight co-operating warps, but sixteen of them share an SM.
-  if (h1_ok && (flags & PB_PLAN_W1) && !pb_opt(PB_OPT_NO_W1, 0) && rows <= 256 &&
-      chains_hint >= pb_opt(PB_OPT_W1_MIN_CHAINS, 2 * 148 + 1)) {
+  const int w1_many = chains_hint >= pb_opt(PB_OPT_W1_MIN_CHAINS, 2 * 148 + 1);
+  // (fewer chains, SGLD on a relu net: the same engine with a CTA of FOUR warps per chain -- w1 = 2)
+  const int w1_few = !w1_many && (flags & PB_PLAN_W1C) && sp->activation == PBNN_ACT_RELU && !pb_opt(PB_OPT_NO_W1C, 0);
+  if (h1_ok && (flags & PB_PLAN_W1) && !pb_opt(PB_OPT_NO_W1, 0) && rows <= 256 && (w1_many || w1_few)) {
     pl->NT = 256;
     pb_layout(pl, sp, rows, nstate, maxbt, 1, 1, 0, 1);
-    const int kd = 4 * pl->h1_dp, ns = 2 * kd + 3;
+    const int kd = 4 * pl->h1_dp, ns = 2 * kd + 3, nwc = w1_few ? 4 : 1;
     int off = 0;
     pl->w1_ox = off;
     off += rows * kd;
@@ -498,18 +501,19 @@ static inline int pb_build_plan(const pbnn_mlp_spec* sp, int rows, int nstate, i
     pl->w1_oi = off;
     off += pb_r4(rows);
     pl->w1_ot = off;
-    off += ((P + 127) & ~127) / 2;  // flat index -> [slot][lane] table (uint16)
+    off += (((P + 128 * nwc - 1) / (128 * nwc)) * (128 * nwc)) / 2;  // flat index -> [slot][lane] table (uint16)
     pl->w1_oz = off;
     off += (ns + 1) * 32;     // noise / trace staging in slot order (+ a dump row)
     pl->w1_ow = off;
     off += kd * 64 + 64 + 64 + 32;  // relu: published first-layer rows, output weights, ballots, residuals
+    if (nwc > 1) off += nwc * 32 + nwc * (kd / 2) * 128;  // partial outputs and partial gradients of the warps
     pl->w1_oa = off;
     off += nstate > 2 ? 2 * ns * 32 : 0;
     pl->w1_warp_floats = off;
-    pl->w1 = 1;
-    pl->NT = 32 * PB_W1_WARPS;
-    pl->smem_floats = PB_W1_WARPS * off;
-    if ((size_t)off * 4 <= (size_t)(24 * 1024)) return PBNN_OK;  // >= 9 chains (warps) per SM
+    pl->w1 = w1_few ? 2 : 1;
+    pl->NT = w1_few ? 128 : 32 * PB_W1_WARPS;
+    pl->smem_floats = w1_few ? off : PB_W1_WARPS * off;
+    if ((size_t)off * 4 <= (size_t)((w1_few ? 56 : 24) * 1024)) return PBNN_OK;  // >= 9 warps / >= 4 four-warp CTAs per SM
     pl->w1 = 0;
   }
 #endif

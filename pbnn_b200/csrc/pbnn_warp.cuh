@@ -31,9 +31,20 @@
               : (u) < 2 * KD ? (((u) & 1) ? &W1_[(((u) - KD) >> 1) % KH].y : &W1_[(((u) - KD) >> 1) % KH].x) \
                              : (u) == 2 * KD ? &v0_ : (u) == 2 * KD + 1 ? &v1_ : &b2_))
 
-template <int ALGO, int ACT, int DP>
+// NWC warps per chain: 1 (many chains: every warp its own chain) or 4 (few chains, SGLD on relu nets: a CTA per chain --
+// every warp keeps a replica of the weights and applies the identical update, the warps split the hidden units of the
+// forward, the rows of the backward (partial gradients summed through shared memory) and the noise draws: a quarter of
+// the step latency of a lone warp for BASELINE configs[0], one chain)
+template <int ALGO, int ACT, int DP, int NWC = 1>
 PB_DEV void pb_sgw_chain(const PbPlan& pl, const PbSgArgs& a, float* wsm, int c, int lane) {
-  constexpr int KD = 4 * DP, KH = KD / 2, NS = 2 * KD + 3, NP = 2;
+  constexpr int KD = 4 * DP, KH = KD / 2, NS = 2 * KD + 3, NP = 2, CT = 32 * NWC;
+  static_assert(NWC == 1 || (ALGO == PB_ALGO_SGLD && ACT == PBNN_ACT_RELU), "the CTA-per-chain variant: SGLD, relu");
+  const int wc = NWC == 1 ? 0 : (int)(threadIdx.x >> 5);  // warp within the chain
+  const int ctid = 32 * wc + lane;
+  auto csync = [&]() {
+    if constexpr (NWC == 1) __syncwarp();
+    else __syncthreads();
+  };
   const PbLayer& L0 = pl.L[0];
   const PbLayer& L1 = pl.L[1];
   const int H = L0.out, d = pl.d, P = pl.P, B = a.B;
@@ -81,7 +92,7 @@ PB_DEV void pb_sgw_chain(const PbPlan& pl, const PbSgArgs& a, float* wsm, int c,
   }
 
   // flat index -> position in the slot-major staging array (the output bias lives in lane 0's copy; readers broadcast)
-  for (int i = lane; i < ((P + 127) & ~127); i += 32) {
+  for (int i = ctid; i < ((P + 4 * CT - 1) / (4 * CT)) * (4 * CT); i += CT) {
     int o = NS * 32 + lane;  // dump row
     if (i < P) {
       int u, j;
@@ -103,26 +114,26 @@ PB_DEV void pb_sgw_chain(const PbPlan& pl, const PbSgArgs& a, float* wsm, int c,
     }
     tab[i] = (uint16_t)o;
   }
-  for (int i = lane; i < (NS + 1) * 32; i += 32) zs[i] = 0.f;  // pad slots read 0 forever
-  for (int i = lane; i < 64; i += 32) (wsm + pl.w1_ow + KD * 64 + 64)[i] = 0.f;  // ballots of units never evaluated
-  __syncwarp();
+  for (int i = ctid; i < (NS + 1) * 32; i += CT) zs[i] = 0.f;  // pad slots read 0 forever
+  for (int i = ctid; i < 64; i += CT) (wsm + pl.w1_ow + KD * 64 + 64)[i] = 0.f;  // ballots of units never evaluated
+  csync();
 #define ZS_(u) zs[(u) * 32 + ((u) == NS - 1 ? 0 : lane)]
 
   // ---- minibatch ------------------------------------------------------------------------------------------------
   auto gather = [&]() {  // rows ib[0..B) -> xs[b][KD] = (x_b, 1, 0...), ys[b]
-    __syncwarp();
-    for (int item = lane; item < B * KD; item += 32) {
+    csync();
+    for (int item = ctid; item < B * KD; item += CT) {
       const int b = item / KD, k = item - b * KD;
       float v = k == d ? 1.f : 0.f;
       if (k < d) v = a.X[(size_t)ib[b] * d + k];
       xs[item] = v;
     }
-    for (int b = lane; b < B; b += 32) ys[b] = a.y[ib[b]];
-    __syncwarp();
+    for (int b = ctid; b < B; b += CT) ys[b] = a.y[ib[b]];
+    csync();
   };
   auto copy_indices = [&](const int32_t* src) {  // clamped like a JAX gather; bit 2 of the flag word records it
-    __syncwarp();
-    for (int b = lane; b < B; b += 32) {
+    csync();
+    for (int b = ctid; b < B; b += CT) {
       int v = src ? src[b] : b;
       if (v < 0 || v >= a.N) {
         v = v < 0 ? 0 : a.N - 1;
@@ -136,9 +147,9 @@ PB_DEV void pb_sgw_chain(const PbPlan& pl, const PbSgArgs& a, float* wsm, int c,
     for (int i = 0; i < times; ++i) gk = pb_split_at(gk, 1u);
   };
   auto gen_indices = [&]() {
-    __syncwarp();
+    csync();
     const PbKey k1 = pb_split_at(gk, 0u), k2 = pb_split_at(gk, 1u);
-    for (int b = lane; b < B; b += 32) ib[b] = pb_randint_at(k1, k2, (uint32_t)b, (uint32_t)a.N, a.randint_mult);
+    for (int b = ctid; b < B; b += CT) ib[b] = pb_randint_at(k1, k2, (uint32_t)b, (uint32_t)a.N, a.randint_mult);
   };
 
   // ---- gradient of the (scaled) log-likelihood at the registers' theta: a0, a1, av0, av1, ab ----------------------
@@ -162,14 +173,18 @@ PB_DEV void pb_sgw_chain(const PbPlan& pl, const PbSgArgs& a, float* wsm, int c,
       float* const vs = ws + KD * 64;
       uint32_t* const mt = reinterpret_cast<uint32_t*>(vs + 64);
       float* const rs = vs + 128;
-      __syncwarp();
+      float* const fps = rs + 32;                  // [NWC][32] partial outputs        (NWC > 1)
+      float* const gps = fps + NWC * 32;           // [NWC][NS][32] partial gradients  (NWC > 1)
+      csync();
+      if (wc == 0) {  // (the replicas agree: one warp publishes)
 #pragma unroll
-      for (int k = 0; k < KD; ++k) *reinterpret_cast<float2*>(ws + k * 64 + j0) = make_float2(TH_(k), TH_(KD + k));
-      *reinterpret_cast<float2*>(vs + j0) = make_float2(v0, v1);
+        for (int k = 0; k < KD; ++k) *reinterpret_cast<float2*>(ws + k * 64 + j0) = make_float2(TH_(k), TH_(KD + k));
+        *reinterpret_cast<float2*>(vs + j0) = make_float2(v0, v1);
+      }
       const int nq = (H + 3) >> 2;
       float rsum = 0.f;
       for (int rb = 0; rb < B; rb += 32) {
-        __syncwarp();
+        csync();
         const int row = rb + lane;
         const bool valid = row < B;
         const int rowc = valid ? row : B - 1;
@@ -177,11 +192,11 @@ PB_DEV void pb_sgw_chain(const PbPlan& pl, const PbSgArgs& a, float* wsm, int c,
 #pragma unroll
         for (int q = 0; q < DP; ++q) xr[q] = pb_ld4(xs + rowc * KD + 4 * q);
         float f = 0.f;
-        const float* wq = ws;
+        const float* wq = ws + 4 * wc;
         // d a multiple of 4 (8-50-1): the bias is the only live row of the last float4 chunk -- it starts the sums
         // and the chunk is skipped (rows > d: x = 0 times w = 0 otherwise)
         const bool bias_first = KD > 4 && d == KD - 4;
-        for (int q = 0; q < nq; ++q, wq += 4) {
+        for (int q = wc; q < nq; q += NWC, wq += 4 * NWC) {  // (NWC > 1: the warps split the hidden units)
           float2 z01 = make_float2(0.f, 0.f), z23 = make_float2(0.f, 0.f);
           if (bias_first) {
             const float4 w = pb_ld4(wq + (KD - 4) * 64);
@@ -206,14 +221,21 @@ PB_DEV void pb_sgw_chain(const PbPlan& pl, const PbSgArgs& a, float* wsm, int c,
           const uint32_t m_2 = __ballot_sync(0xffffffffu, z23.x > 0.f), m_3 = __ballot_sync(0xffffffffu, z23.y > 0.f);
           if (lane == 0) *reinterpret_cast<uint4*>(mt + 4 * q) = make_uint4(m_0, m_1, m_2, m_3);
         }
+        if constexpr (NWC > 1) {
+          fps[wc * 32 + lane] = f;
+          __syncthreads();
+          f = 0.f;
+#pragma unroll
+          for (int w = 0; w < NWC; ++w) f += fps[w * 32 + lane];  // (fixed order: every warp gets the same bits)
+        }
         const float res = ys[rowc] - (f + b2);
         const float r = valid ? res * a.scale : 0.f;
-        rs[lane] = r;
+        if (wc == 0) rs[lane] = r;
         rsum += r;
-        __syncwarp();
+        csync();
         const uint32_t m0 = mt[j0], m1 = mt[j0 + 1];
         const int nr = pb_min(32, B - rb);
-        for (int bb = 0; bb < nr; ++bb) {
+        for (int bb = wc * (32 / NWC); bb < pb_min(nr, (wc + 1) * (32 / NWC)); ++bb) {  // (NWC > 1: the warps split the rows)
           const float rr = rs[bb];
           const uint32_t bit = 1u << bb;
           const float d0s = (m0 & bit) ? rr : 0.f, d1s = (m1 & bit) ? rr : 0.f;
@@ -231,6 +253,26 @@ PB_DEV void pb_sgw_chain(const PbPlan& pl, const PbSgArgs& a, float* wsm, int c,
         }
       }
       ab = pb_warp_sum(rsum);
+      if constexpr (NWC > 1) {  // partial first-layer gradients of the warps -> every warp sums all of them, same order
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < KH; ++k) {
+          *reinterpret_cast<float2*>(gps + ((wc * KH + k) * 32 + lane) * 4) = a0[k];
+          *reinterpret_cast<float2*>(gps + ((wc * KH + k) * 32 + lane) * 4 + 2) = a1[k];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < KH; ++k) {
+          float2 t0 = make_float2(0.f, 0.f), t1 = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int w = 0; w < NWC; ++w) {
+            t0 = __fadd2_rn(t0, *reinterpret_cast<const float2*>(gps + ((w * KH + k) * 32 + lane) * 4));
+            t1 = __fadd2_rn(t1, *reinterpret_cast<const float2*>(gps + ((w * KH + k) * 32 + lane) * 4 + 2));
+          }
+          a0[k] = t0;
+          a1[k] = t1;
+        }
+      }
       float2 s0 = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f);
 #pragma unroll
       for (int k = 0; k < KH; ++k) {
@@ -301,21 +343,21 @@ PB_DEV void pb_sgw_chain(const PbPlan& pl, const PbSgArgs& a, float* wsm, int c,
 
   // ---- noise: jax.random.normal(key, (P,))[i] -> zs[tab[i]], lane l draws i = l + 32 m (4 threefry chains in flight)
   auto gen_noise = [&](PbKey key) {
-    __syncwarp();  // the previous readers are done with zs
-    for (int p0 = lane; p0 < P; p0 += 128) {
+    csync();  // the previous readers are done with zs
+    for (int p0 = ctid; p0 < P; p0 += 4 * CT) {
       uint32_t idx[4];
       uint32_t to[4];
       float z[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        idx[j] = (uint32_t)(p0 + 32 * j);
-        to[j] = tab[p0 + 32 * j];  // (the table is padded to a multiple of 128: i >= P lands in the dump row)
+        idx[j] = (uint32_t)(p0 + CT * j);
+        to[j] = tab[p0 + CT * j];  // (the table is padded to a multiple of 4 CT: i >= P lands in the dump row)
       }
       pb_normal_n<4, true>(key, idx, z);
 #pragma unroll
       for (int j = 0; j < 4; ++j) zs[to[j]] = z[j];
     }
-    __syncwarp();
+    csync();
   };
 
   auto trace_row = [&](int t_) -> float* {
@@ -324,11 +366,13 @@ PB_DEV void pb_sgw_chain(const PbPlan& pl, const PbSgArgs& a, float* wsm, int c,
                : nullptr;
   };
   auto store_theta = [&](float* dst) {  // registers -> slot-major staging -> flat order, coalesced
-    __syncwarp();
+    csync();
+    if (wc == 0) {
 #pragma unroll
-    for (int u = 0; u < NS; ++u) zs[u * 32 + lane] = TH_(u);  // (pad slots hold 0; the b2 replicas agree)
-    __syncwarp();
-    for (int i = lane; i < P; i += 32) dst[i] = zs[tab[i]];
+      for (int u = 0; u < NS; ++u) zs[u * 32 + lane] = TH_(u);  // (pad slots hold 0; the b2 replicas agree)
+    }
+    csync();
+    for (int i = ctid; i < P; i += CT) dst[i] = zs[tab[i]];
   };
 
   // ---- chain set-up (mirrors pb_sg_chain) -------------------------------------------------------------------------
@@ -485,10 +529,25 @@ PB_DEV void pb_sgw_chain(const PbPlan& pl, const PbSgArgs& a, float* wsm, int c,
     }
   }
   fl = __reduce_or_sync(0xffffffffu, fl);
-  if (lane == 0 && a.flags) a.flags[c] = fl;
+  if constexpr (NWC == 1) {
+    if (lane == 0 && a.flags) a.flags[c] = fl;
+  } else {
+    if (lane == 0 && a.flags && fl) atomicOr(a.flags + c, fl);  // (zeroed by the kernel before the chain starts)
+  }
 #undef TH_
 #undef GA_
 #undef ZS_
+}
+
+// few chains (SGLD, relu): one CTA of four warps per chain
+template <int DP>
+__global__ void __launch_bounds__(128, 4)
+pb_sgc_kernel(const __grid_constant__ PbPlan pl, const __grid_constant__ PbSgArgs a) {
+  extern __shared__ __align__(16) float pb_smem[];
+  const int c = (int)blockIdx.x;
+  if (threadIdx.x == 0 && a.flags) a.flags[c] = 0u;
+  __syncthreads();
+  pb_sgw_chain<PB_ALGO_SGLD, PBNN_ACT_RELU, DP, 4>(pl, a, pb_smem, c, (int)threadIdx.x & 31);
 }
 
 template <int ALGO, int ACT, int DP>

@@ -44,6 +44,7 @@ def ops(request):
         o = request.getfixturevalue("cuda_ops")
         o.reset_options()
         o.set_option("no_tc", 1)
+        o.set_option("no_w1c", 1)  # (few-chain SGLD on relu nets: the fused path, not the four-warp variant of the warp engine)
         if request.param == "cuda_generic":
             o.set_option("no_h1", 1)
         yield o

@@ -54,7 +54,9 @@ def test_host_side_calls_without_gpu(cuda_lib_path):
     assert lib.pbnn_workspace_bytes(spec, _lib.OP_HMC, 506, 256) == 256 * (751 + 4) * 4 + 16
     assert lib.pbnn_workspace_bytes(spec, _lib.OP_SGLD, 32, 256) == 0
     assert lib.pbnn_plan_engine(spec, _lib.OP_HMC, 506, 256) == _lib.ENGINE_TCGEN05
-    assert lib.pbnn_plan_engine(spec, _lib.OP_SGLD, 32, 256) == _lib.ENGINE_FUSED_H1
+    assert lib.pbnn_plan_engine(spec, _lib.OP_SGLD, 32, 256) == _lib.ENGINE_CTA4_H1   # few chains, relu: four warps per chain
+    assert lib.pbnn_plan_engine(spec, _lib.OP_PSGLD, 32, 256) == _lib.ENGINE_FUSED_H1
+    assert lib.pbnn_plan_engine(_lib.make_spec((13, 50, 1), 1, 0.1), _lib.OP_SGLD, 32, 256) == _lib.ENGINE_FUSED_H1  # tanh
     # many chains: one warp per chain (SG samplers and Adam; the gradient hook and HMC keep their engines)
     for op in (_lib.OP_SGLD, _lib.OP_PSGLD, _lib.OP_SGHMC, _lib.OP_ADAM):
         assert lib.pbnn_plan_engine(spec, op, 32, 2048) == _lib.ENGINE_WARP_H1

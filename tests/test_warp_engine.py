@@ -44,7 +44,7 @@ def test_default_selection_and_chain_independence(cuda_ops, tc_options):
     tc_options(w1_min_chains=1)
     solo = cuda_ops.sgld(fs, X, y, th0[pick], keys[pick], B, eps, T)
     assert np.array_equal(npy(solo["trace"]), npy(out["trace"])[pick])
-    # and the multi-warp fused path (what few chains get by default) agrees to rounding, not bit for bit
+    # and the multi-warp fused path agrees to rounding, not bit for bit
     tc_options(no_w1=1)
     fused = cuda_ops.sgld(fs, X, y, th0[pick], keys[pick], B, eps, T)
     assert rel(npy(fused["trace"]), npy(solo["trace"])) <= 1e-5
@@ -152,3 +152,29 @@ def test_adam_two_hidden_layers_members_are_independent_and_resumable(cuda_ops):
     d = cuda_ops.adam_ensemble(fs, X, y, th0[pick], bad.clip(0, N - 1), 1e-2)
     assert np.array_equal(npy(c["theta"]), npy(d["theta"]))
     assert (npy(c["flags"])[:2] & 4).all() and not npy(d["flags"]).any()
+
+
+@pytest.mark.parametrize("layers,B,C", [((8, 50, 1), 32, 1), ((13, 50, 1), 40, 5), ((15, 64, 1), 96, 3), ((3, 7, 1), 33, 2),
+                                        ((1, 1, 1), 1, 1), ((4, 50, 1), 256, 2)])
+def test_four_warps_per_chain_variant(cuda_ops, tc_options, layers, B, C):
+    """Few chains, SGLD, relu: the warp engine with a CTA of four warps per chain (replicated weights, split forward /
+    backward / noise).  Default selection, parity with the oracle (trace, thinning, per-step minibatches, control
+    variates through the API tests), bit-identical repeats, and the fused path as the second opinion."""
+    X, y, sp, fs, keys, th0 = problem(layers, o.RELU, C, N=400)
+    assert cuda_ops.lib.pbnn_plan_engine(fs.c_struct(), _lib.OP_SGLD, B, C) == _lib.ENGINE_CTA4_H1
+    T, eps = 6, 1e-6
+    ref = o.sgld(sp, X, y, th0, B, eps, T, keys)
+    out = cuda_ops.sgld(fs, X, y, th0, keys, B, eps, T)
+    assert rel(npy(out["trace"]), ref) <= 1e-5 and not npy(out["flags"]).any()
+    assert np.array_equal(npy(out["theta"]), npy(out["trace"])[:, -1])
+    again = cuda_ops.sgld(fs, X, y, th0, keys, B, eps, T)
+    assert np.array_equal(npy(again["trace"]), npy(out["trace"]))
+    thin = cuda_ops.sgld(fs, X, y, th0, keys, B, eps, T, thin=2, burnin=1)
+    assert np.array_equal(npy(thin["trace"]), npy(out["trace"])[:, 1::2])
+    refp = o.sgld(sp, X, y, th0, B, eps, 4, keys, minibatch_mode="per_step")
+    outp = cuda_ops.sgld(fs, X, y, th0, keys, B, eps, 4, minibatch_mode="per_step")
+    assert rel(npy(outp["trace"]), refp) <= 1e-5
+    tc_options(no_w1c=1)
+    assert cuda_ops.lib.pbnn_plan_engine(fs.c_struct(), _lib.OP_SGLD, B, C) == _lib.ENGINE_FUSED_H1
+    fused = cuda_ops.sgld(fs, X, y, th0, keys, B, eps, T)
+    assert rel(npy(fused["trace"]), npy(out["trace"])) <= 1e-5
