@@ -68,7 +68,8 @@ const char* pbnn_last_error(void);
  * (no two-hidden-layer tcgen05 engine), "no_h1" (no fused one-hidden-layer path), "no_resident", "force_gstate",
  * "no_sched" / "seg_len" (balanced HMC schedule), "nw", "bt", "dw_ks", "two_cta", "one_cta", "pred_tpc" (1, 2 or 4),
  * "pred_chunks", "tc2_min_h", "tc2_min_rows", "tc2_ctas", "tc2_nz", "tc2_nohelp", "no_w1" (no warp-per-chain engine),
- * "w1_min_chains" (chain count from which that engine is chosen; default 297), "no_w2" (no four-warp Adam kernel),
+ * "w1_min_chains" (chain count from which that engine is chosen; default 297, 520 for SGLD on relu nets), "no_w1c" (no
+ * four-warps-per-chain variant for few chains), "no_w2" (no four-warp Adam kernel),
  * "debug".  pbnn_get_option returns 1 (and the sentinel INT_MIN in *value) when the option is unset.  Every engine computes the same arithmetic contract; options never change
  * results beyond the stated tolerances. */
 int pbnn_set_option(const char* name, int value);

@@ -486,9 +486,11 @@ static inline int pb_build_plan(const pbnn_mlp_spec* sp, int rows, int nstate, i
   // fused path can keep co-resident (two CTAs per SM).  Measured, 8-50-1 B = 32 (M chain-steps/s, fused | warp):
   // 148 chains 39 | 30, 296 chains 62 | 59, 444 chains 55 | 88, 2048 chains 91-101 | 186: a lone warp advances a chain in
   // ~5 us per step against ~3.8 us for eight co-operating warps, but sixteen of them share an SM.
-  const int w1_many = chains_hint >= pb_opt(PB_OPT_W1_MIN_CHAINS, 2 * 148 + 1);
-  // (fewer chains, SGLD on a relu net: the same engine with a CTA of FOUR warps per chain -- w1 = 2)
-  const int w1_few = !w1_many && (flags & PB_PLAN_W1C) && sp->activation == PBNN_ACT_RELU && !pb_opt(PB_OPT_NO_W1C, 0);
+  // (fewer chains, SGLD on a relu net: the same engine with a CTA of FOUR warps per chain -- w1 = 2.  Measured against
+  //  one warp per chain, 8-50-1 B = 32, M chain-steps/s: 296 chains 76 | 60, 444 chains 102 | 89, 592 chains 108 | 118)
+  const int w1c_ok = (flags & PB_PLAN_W1C) && sp->activation == PBNN_ACT_RELU && !pb_opt(PB_OPT_NO_W1C, 0);
+  const int w1_many = chains_hint >= pb_opt(PB_OPT_W1_MIN_CHAINS, w1c_ok ? 520 : 2 * 148 + 1);
+  const int w1_few = !w1_many && w1c_ok;
   if (h1_ok && (flags & PB_PLAN_W1) && !pb_opt(PB_OPT_NO_W1, 0) && rows <= 256 && (w1_many || w1_few)) {
     pl->NT = 256;
     pb_layout(pl, sp, rows, nstate, maxbt, 1, 1, 0, 1);
